@@ -1,0 +1,138 @@
+/*
+ * quip_b200.h -- C ABI of libquipb200.so: the B200 (sm_100a) replacement for the native layer under
+ * the reference's `torch.ops.quip_lib.*` operator registry (chu-tianxiang/QuIP-for-all @ 04754a4).
+ *
+ * Drop-in boundary.  The reference binds its native code through a pybind11 module `quiptools_cuda`
+ * (quip_cuda/quiptools_wrapper.cpp:87-100) plus the third-party `fast_hadamard_transform_cuda`
+ * (register_lib.py:5,18-20).  Every entry point below names the reference interface it replaces.
+ * Conventions (all entry points):
+ *   - plain pointers + sizes, no torch/ATen types; every buffer is CALLER-OWNED device memory,
+ *     contiguous row-major, 16-byte aligned;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), never synchronised, never
+ *     allocates -> CUDA-graph capturable (the reference relies on this: origin_order.cu:608-609);
+ *   - returns 0 on success, a positive cudaError_t value for CUDA failures, or a negative QUIPB200_E*
+ *     code for argument errors.  Never throws, never exits (contrast e8p_gemv.cu:36-43 `exit()`).
+ *   - `Qidxs` tensors are the reference's on-disk format unchanged: (q_out, q_in/(codesz*packsz))
+ *     (qlinear.py:52-57); signed storage is reinterpreted as unsigned (origin_order.cu:268, :841).
+ */
+#ifndef QUIP_B200_H
+#define QUIP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QUIPB200_ABI_VERSION 1
+
+/* argument-error codes (negative); CUDA errors are returned as positive cudaError_t values */
+#define QUIPB200_EINVAL     (-1)  /* bad shape / null pointer / unsupported combination */
+#define QUIPB200_EALIGN     (-2)  /* pointer or row pitch not 16-byte aligned */
+#define QUIPB200_EWORKSPACE (-3)  /* workspace too small (see quipb200_linear_workspace_bytes) */
+#define QUIPB200_EUNSUPPORTED (-4) /* shape outside what the fused path covers; caller uses the dense path */
+
+/* codebooks: codebook/__init__.py:7-13 (codebook_id) */
+enum quipb200_codebook {
+  QUIPB200_CB_E8P12 = 0,      /* codebook/e8p12.py      int16 codes, 8 weights / code, 2 bit */
+  QUIPB200_CB_E8P12RVQ4B = 1, /* codebook/e8p12_rvq4.py int32 codes (hi16 main | lo16 residual), 4 bit */
+  QUIPB200_CB_D4 = 2,         /* codebook/d4.py         uint8 codes, 4 weights / code, 2 bit */
+  QUIPB200_CB_E8P12RVQ3B = 3, /* codebook/e8p12_rvq3.py 3-byte codes, 3 bit */
+  QUIPB200_CB_HI = 4          /* codebook/hi.py         int32 = 8 nibbles, 4 bit scalar */
+};
+
+int quipb200_abi_version(void);
+/* Human-readable text for a code returned by any entry point (static storage). */
+const char* quipb200_strerror(int code);
+/* Number of SMs of the current device (cached); <0 on error. */
+int quipb200_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * quip_lib::hadamard(Tensor x, float scale) -> Tensor        register_lib.py:10-20
+ *   replaces fast_hadamard_transform_cuda.fast_hadamard_transform: unnormalised Sylvester-order
+ *   Walsh-Hadamard transform over the last dim (n = power of two, <= 32768), fp32 internal math,
+ *   y = H_n x * scale, output dtype = input dtype.  dtype: 0 = fp16, 1 = bf16, 2 = fp32.
+ * ------------------------------------------------------------------------------------------- */
+int quipb200_hadamard(const void* x, void* y, int64_t rows, int n, float scale, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense dequantisation: quip_lib::decompress_*_origorder       register_lib.py:109-185
+ *   replaces quiptools_cuda.decompress_{e8p,e8prvq4,d4,e8prvq3,hi}_origorder
+ *   (origin_order.cu:837-885, :956-1024, :794-833, :887-954, :1028-1074).  Bit-exact with those kernels.
+ *   out: fp16 [rows, cols] with cols = 8*codes_per_row (4* for D4).  Unlike the reference (which
+ *   silently requires rows*cols % 2048 == 0) any size is handled.
+ * ------------------------------------------------------------------------------------------- */
+int quipb200_decompress_e8p(const int16_t* qidxs, const int64_t* grid_packed_abs, void* out_f16,
+                            int64_t rows, int64_t codes_per_row, void* stream);
+int quipb200_decompress_e8prvq4(const int32_t* qidxs, const int64_t* grid_packed_abs, void* out_f16,
+                                int64_t rows, int64_t codes_per_row, float resid_scale, void* stream);
+int quipb200_decompress_d4(const uint8_t* qidxs, const void* grid_f16_256x4, void* out_f16,
+                           int64_t rows, int64_t codes_per_row, void* stream);
+/* qidxs: int32 [rows, 3*codes_per_row/4] viewed as byte triplets */
+int quipb200_decompress_e8prvq3(const int32_t* qidxs, const int64_t* grid_packed_abs,
+                                const int32_t* e81b_packed, void* out_f16,
+                                int64_t rows, int64_t codes_per_row, float resid_scale, void* stream);
+int quipb200_decompress_hi(const int32_t* qidxs, void* out_f16, int64_t rows, int64_t codes_per_row,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Decode + matmul: quip_lib::{e8p,e8prvq4,d4}_mm_origorder       register_lib.py:22-38, :58-92
+ *   replaces quiptools_cuda.*_mm_origorder (origin_order.cu:557-743):
+ *     out[M,N] (fp16) = x[M,K] (fp16) . decode(Qidxs[N, K/codesz])^T
+ *   Small-M (decode) path: activations are quantised per row to 16-bit fixed point, the dot products
+ *   run as exact integer dp4a on CUDA cores, one fp16 rounding at the end (tolerance: DESIGN.md).
+ *   Requires the packed row pitch to be a multiple of 16 bytes (K % 64 == 0; RVQ4B: K % 32 == 0)
+ *   and M <= QUIPB200_MM_MAX_M; otherwise returns QUIPB200_EUNSUPPORTED and the caller takes the
+ *   decompress + dense-GEMM path (exactly what the reference does for M >= 32, e8p12.py:153-155).
+ *   workspace: >= quipb200_mm_workspace_bytes(M, N, K) bytes of device scratch.
+ * ------------------------------------------------------------------------------------------- */
+#define QUIPB200_MM_MAX_M 16
+size_t quipb200_mm_workspace_bytes(int M, int N, int K);
+int quipb200_mm(int codebook, const void* x_f16, const void* qidxs, const void* grid,
+                float resid_scale, void* out_f16, int M, int N, int K,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused QuantLinear.forward (eval branch)                          qlinear.py:87-115
+ *   y = [(hadK_R (x) H) ( decode(Qidxs) . ((hadK_L^T (x) H) (SU . x)) * wscale ) * Wscale_pc][:out] . SV + bias
+ *   i.e. the whole chain  x*SU -> matmul_hadUt_cuda -> codebook(x, Qidxs) -> [*Wscale] ->
+ *   matmul_hadU_cuda -> [:out_features] -> *SV -> +bias  (quant.py:72-88) in three launches
+ *   (prologue / GEMV / epilogue) instead of the reference's 5-9 launches + library calls.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct quipb200_linear {
+  int32_t codebook;          /* enum quipb200_codebook (E8P12, E8P12RVQ4B, D4 on the fused path) */
+  int32_t in_features;       /* qlinear.py:20 */
+  int32_t out_features;      /* qlinear.py:21 */
+  int32_t q_in;              /* padded in  dim (qlinear.py:29) */
+  int32_t q_out;             /* padded out dim (qlinear.py:30) */
+  int32_t K_left;            /* qlinear.py:29  (1 => pure FWHT) */
+  int32_t K_right;           /* qlinear.py:30 */
+  float wscale_float;        /* qlinear.py:75, quantizer.py:837 */
+  float resid_scale;         /* codebook.opt_resid_scale (RVQ only) */
+  const void* qidxs;         /* Qidxs buffer, reference layout (qlinear.py:52-57) */
+  const void* grid;          /* E8P*: int64[256] grid_packed_abs; D4: fp16 [256,4] */
+  const void* SU;            /* fp16 [in_features]  or NULL (qlinear.py:90, quantizer.py:840-844) */
+  const void* SV;            /* fp16 [out_features] or NULL */
+  const void* bias;          /* fp16 [out_features] or NULL */
+  const void* had_left;      /* fp16 [K_left, K_left]   or NULL when K_left == 1 */
+  const void* had_right;     /* fp16 [K_right, K_right] or NULL when K_right == 1 */
+  const void* wscale_pc;     /* fp16 [q_out] per-channel Wscale (already mean-normalised) or NULL */
+} quipb200_linear_t;
+
+size_t quipb200_linear_workspace_bytes(const quipb200_linear_t* layer, int M);
+/* x: fp16 [M, in_features] with row pitch ldx elements; y: fp16 [M, out_features] pitch ldy. */
+int quipb200_linear_forward(const quipb200_linear_t* layer, const void* x_f16, int64_t ldx,
+                            void* y_f16, int64_t ldy, int M,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Tuning / introspection hooks used by bench.py and the tests (not part of the reference surface). */
+int quipb200_set_option(const char* name, int value);   /* e.g. "gemv_table_repl" = 1|16 */
+int quipb200_get_option(const char* name);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches evidence) */
+int64_t quipb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUIP_B200_H */

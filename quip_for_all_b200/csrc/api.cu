@@ -1,0 +1,74 @@
+// C-ABI glue: version / error strings / device info / tuning options.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace qb {
+int64_t g_launch_count = 0;
+extern int g_opt_table_repl;
+extern int g_opt_gemv_warps;
+extern int g_opt_gemv_ctas_per_sm;
+extern int g_opt_stage_mask;
+}  // namespace qb
+
+extern "C" int quipb200_abi_version(void) { return QUIPB200_ABI_VERSION; }
+
+extern "C" const char* quipb200_strerror(int code) {
+  if (code == 0) return "success";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  switch (code) {
+    case QUIPB200_EINVAL: return "quipb200: invalid argument (shape / null pointer / unsupported combination)";
+    case QUIPB200_EALIGN: return "quipb200: pointer or row pitch is not 16-byte aligned";
+    case QUIPB200_EWORKSPACE: return "quipb200: workspace too small";
+    case QUIPB200_EUNSUPPORTED: return "quipb200: shape not covered by the fused path (use the dense path)";
+  }
+  return "quipb200: unknown error";
+}
+
+extern "C" int quipb200_sm_count(void) {
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+extern "C" int quipb200_set_option(const char* name, int value) {
+  if (!name) return QUIPB200_EINVAL;
+  if (!strcmp(name, "gemv_table_repl")) {
+    if (value != 1 && value != 16) return QUIPB200_EINVAL;
+    qb::g_opt_table_repl = value;
+    return 0;
+  }
+  if (!strcmp(name, "gemv_warps")) {
+    if (value < 0 || value > 24) return QUIPB200_EINVAL;
+    qb::g_opt_gemv_warps = value;
+    return 0;
+  }
+  if (!strcmp(name, "gemv_ctas_per_sm")) {
+    if (value < 1 || value > 4) return QUIPB200_EINVAL;
+    qb::g_opt_gemv_ctas_per_sm = value;
+    return 0;
+  }
+  if (!strcmp(name, "stage_mask")) {
+    if (value < 0 || value > 7) return QUIPB200_EINVAL;
+    qb::g_opt_stage_mask = value;
+    return 0;
+  }
+  return QUIPB200_EINVAL;
+}
+
+extern "C" int quipb200_get_option(const char* name) {
+  if (!name) return QUIPB200_EINVAL;
+  if (!strcmp(name, "gemv_table_repl")) return qb::g_opt_table_repl;
+  if (!strcmp(name, "gemv_warps")) return qb::g_opt_gemv_warps;
+  if (!strcmp(name, "gemv_ctas_per_sm")) return qb::g_opt_gemv_ctas_per_sm;
+  if (!strcmp(name, "stage_mask")) return qb::g_opt_stage_mask;
+  return QUIPB200_EINVAL;
+}
+
+extern "C" int64_t quipb200_launch_count(void) { return qb::g_launch_count; }

@@ -1,0 +1,161 @@
+// Shared device helpers for libquipb200 (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/quip_b200.h"
+
+namespace qb {
+
+extern int64_t g_launch_count;
+
+// Enqueue-side error check: returns the cudaError_t as a positive int.
+#define QB_LAUNCH_CHECK()                              \
+  do {                                                 \
+    ::qb::g_launch_count++;                            \
+    cudaError_t e__ = cudaGetLastError();              \
+    if (e__ != cudaSuccess) return (int)e__;           \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// memory helpers
+// ---------------------------------------------------------------------------------------------
+// streaming 128-bit load: weights are read exactly once per call -> keep them out of L1
+__device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream_v4(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+// prmt with the sign-replicate selector bit (PTX ISA prmt default mode, selector bit 3)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+// dp4a: 4 x int8 multiply-accumulate.  ss: signed x signed, su: signed a x unsigned b.
+__device__ __forceinline__ int dp4a_ss(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp4a_su(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+__device__ __forceinline__ float f16_round(float v) { return __half2float(__float2half_rn(v)); }
+
+// ---------------------------------------------------------------------------------------------
+// E8P decode (bit-exact restatement of the codebook definition, codebook/e8p12.py:82-103):
+// code c: abs index c>>8 into the 256-entry packed-int8 table, sign byte c&0xff.
+// Returns 8 packed int8 in units of 1/4 (lo = packed bytes 0..3, hi = bytes 4..7);
+// weight i of the 8-vector is packed byte {0,2,1,3,4,6,5,7}[i].
+// `tab1` entries are the reference table OR 0x01 per byte ("+1/4" pre-applied).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint2 e8p_apply_signs(uint2 t1, uint32_t sign_byte, uint32_t& parity) {
+  parity = __popc(sign_byte) & 1u;
+  const uint32_t s = sign_byte ^ parity;  // bit0 (-> packed byte 7) carries the parity fix
+  // bit (7-j) of s -> msb of byte j  (lo: bytes 0..3 <- bits 7..4 ; hi: bytes 4..7 <- bits 3..0)
+  const uint32_t m_lo = prmt(s * 0x08040201u, 0u, 0xba98u);  // 0xff where the byte is negated
+  const uint32_t m_hi = prmt(s * 0x80402010u, 0u, 0xba98u);
+  uint2 v;
+  // negate a value whose low two bits are '11' (a|1): xor with 0xfc gives -(a)+1 ... i.e. s*a + 1
+  v.x = t1.x ^ (m_lo & 0xfcfcfcfcu);
+  v.y = t1.y ^ (m_hi & 0xfcfcfcfcu);
+  return v;  // still needs "- 2 per byte" when parity == 1
+}
+
+// full decode to packed int8 (quarter units), bytes in packed order
+__device__ __forceinline__ uint2 e8p_decode_q(uint2 t1, uint32_t code16) {
+  uint32_t par;
+  uint2 v = e8p_apply_signs(t1, code16 & 0xffu, par);
+  // every byte is >= 2 as unsigned (values 3,7,11,15 or 0xf3..0xff) so no borrow crosses bytes
+  v.x -= par * 0x02020202u;
+  v.y -= par * 0x02020202u;
+  return v;
+}
+
+// packed int8 (units 1/4) -> fp16 pairs, exact: 0x5c80 ^ byte == 288 + int8/4 in fp16, then -288.
+// out[0]=(b0,b2) out[1]=(b1,b3) of the 32-bit word, as half2 bit patterns.
+__device__ __forceinline__ void q4_to_half2(uint32_t w, __half2& even, __half2& odd) {
+  const uint32_t e = (w & 0x00ff00ffu) ^ 0x5c805c80u;
+  const uint32_t o = ((w >> 8) & 0x00ff00ffu) ^ 0x5c805c80u;
+  const __half2 adj = __float2half2_rn(-288.0f);
+  even = __hadd2(*reinterpret_cast<const __half2*>(&e), adj);
+  odd = __hadd2(*reinterpret_cast<const __half2*>(&o), adj);
+}
+
+// ---------------------------------------------------------------------------------------------
+// In-CTA Walsh-Hadamard butterflies on a padded fp32 shared-memory array.
+// Layout: element i lives at s[spad(i)] (8 floats of padding every 64 -> radix-8 passes with
+// strides 8, 64, 512.. are bank-conflict free).  The array holds `total` = K*L elements organised
+// as K contiguous blocks of L = 2^log2L; butterflies never cross a block.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int spad(int i) { return i + ((i >> 6) << 3); }
+static inline size_t spad_host(size_t n) { return n + ((n >> 6) << 3) + 8; }
+
+template <int R>
+__device__ __forceinline__ void butterfly_regs(float (&v)[1 << R]) {
+#pragma unroll
+  for (int h = 1; h < (1 << R); h <<= 1) {
+#pragma unroll
+    for (int j = 0; j < (1 << R); j++) {
+      if (!(j & h)) {
+        const float a = v[j], c = v[j | h];
+        v[j] = a + c;
+        v[j | h] = a - c;
+      }
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void fwht_pass(float* s, int total, int b, int tid, int nthreads) {
+  const int ngroups = total >> R;
+  const int lomask = (1 << b) - 1;
+  for (int g = tid; g < ngroups; g += nthreads) {
+    const int lo = g & lomask, hi = g >> b;
+    const int base = (hi << (b + R)) | lo;
+    float v[1 << R];
+#pragma unroll
+    for (int j = 0; j < (1 << R); j++) v[j] = s[spad(base + (j << b))];
+    butterfly_regs<R>(v);
+#pragma unroll
+    for (int j = 0; j < (1 << R); j++) s[spad(base + (j << b))] = v[j];
+  }
+}
+
+// all butterfly stages for bits [b0, log2L); ends with a __syncthreads()
+__device__ __forceinline__ void fwht_smem(float* s, int total, int log2L, int b0, int tid, int nthreads) {
+  int b = b0;
+  while (b < log2L) {
+    const int r = (log2L - b >= 3) ? 3 : (log2L - b);
+    if (r == 3) fwht_pass<3>(s, total, b, tid, nthreads);
+    else if (r == 2) fwht_pass<2>(s, total, b, tid, nthreads);
+    else fwht_pass<1>(s, total, b, tid, nthreads);
+    b += r;
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace qb

@@ -1,0 +1,265 @@
+"""Model-level harness around the QuantLinear hot path.
+
+* `make_random_quantized_llama` -- a HF `LlamaForCausalLM` whose block linears are `QuantLinear`s
+  with random-init packed weights (BASELINE configs 2-5: no checkpoints / network are available).
+  Synthetic-input recipe: SURVEY.md section 8(d) / BASELINE.md section 4.
+* `LlamaDecodeEngine` -- bs=1 greedy decode loop over such a model (or one loaded with
+  `load_quantized_model`): static KV cache + whole-step CUDA graph, the stand-in for the reference's
+  `example_generate.py --compile` (StaticCache + torch.compile(reduce-overhead), example_generate.py:62-70).
+  It can own a contiguous slice of the decoder layers, which is the unit of the multi-GPU layer pipeline.
+"""
+import math
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .codebook import codebook_id
+from .qlinear import QuantLinear
+from .quantizer import QuipQuantizer, apply_load_time_tricks
+
+LLAMA2_SHAPES = {
+    # hidden, intermediate, layers, heads, kv_heads
+    "llama2-7b": dict(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                      num_attention_heads=32, num_key_value_heads=32),
+    "llama2-13b": dict(hidden_size=5120, intermediate_size=13824, num_hidden_layers=40,
+                       num_attention_heads=40, num_key_value_heads=40),
+    "llama2-70b": dict(hidden_size=8192, intermediate_size=28672, num_hidden_layers=80,
+                       num_attention_heads=64, num_key_value_heads=8),
+    "tiny": dict(hidden_size=256, intermediate_size=704, num_hidden_layers=2,
+                 num_attention_heads=4, num_key_value_heads=4),
+}
+
+
+def llama_config(name_or_cfg, vocab_size=32000, **overrides):
+    from transformers import LlamaConfig
+    if not isinstance(name_or_cfg, str):
+        return name_or_cfg
+    kw = dict(LLAMA2_SHAPES[name_or_cfg], vocab_size=vocab_size, max_position_embeddings=4096,
+              rms_norm_eps=1e-5, tie_word_embeddings=False)
+    kw.update(overrides)
+    return LlamaConfig(**kw)
+
+
+E8P_GRID_RMS = 1.09375 ** 0.5 * 1.09375 ** 0.5  # E8P grid mean square per element = 1.09375
+
+
+@torch.no_grad()
+def randomize_quantlinear(layer: QuantLinear, gen: torch.Generator, weight_std: float = 0.02):
+    """Random packed weights: codes uniform over the full index range, SU/SV random signs,
+    Wscale chosen so that the effective weight std is `weight_std`."""
+    dev = layer.Qidxs.device
+    info = torch.iinfo(layer.Qidxs.dtype)
+    q = torch.randint(info.min, info.max + 1, layer.Qidxs.shape, dtype=torch.int64, device=dev, generator=gen)
+    layer.Qidxs.copy_(q.to(layer.Qidxs.dtype))
+    for p in (layer.SU, layer.SV):
+        s = torch.randint(0, 2, p.shape, device=dev, generator=gen).to(p.dtype) * 2 - 1
+        p.data.copy_(s)
+    rms = {"E8P12": 1.09375 ** 0.5, "E8P12RVQ4B": 1.09375 ** 0.5 * 1.04, "E8P12RVQ3B": 1.09375 ** 0.5 * 1.06,
+           "D4": 1.2990, "HI": 4.61}[layer.codebook.id]
+    layer.Wscale.fill_(weight_std / rms)
+    if layer.bias is not None:
+        layer.bias.zero_()
+    for name in ("had_left", "had_right"):
+        h = getattr(layer, name)
+        if h is not None and layer.use_rand:
+            k = h.shape[0]
+            a = torch.randn(k, k, device=dev, generator=gen, dtype=torch.float32)
+            qm, r = torch.linalg.qr(a)
+            qm = qm * torch.sign(torch.diagonal(r)).unsqueeze(0)
+            h.copy_(qm.to(h.dtype))
+
+
+@torch.no_grad()
+def make_random_quantized_llama(config="llama2-7b", codebook="E8P12", seed=0, device="cuda",
+                                dtype=torch.float16, use_rand=True, per_channel=False,
+                                layer_range: Optional[range] = None):
+    """LlamaForCausalLM with random-init QuantLinear blocks, built directly on `device`.
+    `layer_range` keeps only a slice of the decoder layers (pipeline stage); embeddings / final norm /
+    lm_head are always created (they are small) so any stage can be first or last."""
+    from transformers import LlamaForCausalLM
+    cfg = llama_config(config)
+    if layer_range is not None:
+        import copy
+        cfg = copy.deepcopy(cfg)
+        cfg.num_hidden_layers = len(layer_range)
+    with torch.device("meta"):
+        model = LlamaForCausalLM(cfg).to(dtype)
+    quantizer = QuipQuantizer(codebook=codebook, use_rand=use_rand, per_channel=per_channel, inference=True,
+                              ft_epochs=0)
+    model = quantizer.convert_model(model)
+    from .quantizer import _materialize
+    _materialize(model, device, dtype)
+    model = model.to(device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    std = getattr(cfg, "initializer_range", 0.02)
+    for name, mod in model.named_modules():
+        if isinstance(mod, QuantLinear):
+            randomize_quantlinear(mod, gen)
+        elif isinstance(mod, nn.Embedding):
+            mod.weight.normal_(0.0, std, generator=gen)
+        elif isinstance(mod, nn.Linear):
+            mod.weight.normal_(0.0, std, generator=gen)
+            if mod.bias is not None:
+                mod.bias.zero_()
+        elif mod.__class__.__name__.endswith("RMSNorm"):
+            mod.weight.fill_(1.0)
+    apply_load_time_tricks(model, merge_suv=False)
+    model.is_quantized = True
+    model.eval()
+    return model
+
+
+def quantized_bytes(model) -> int:
+    """Packed code bytes of all QuantLinears = the algorithmic HBM bytes of one bs=1 decode step."""
+    return sum(m.Qidxs.numel() * m.Qidxs.element_size() for m in model.modules() if isinstance(m, QuantLinear))
+
+
+class LlamaDecodeEngine:
+    """bs=1 greedy decoding over (a slice of) a Llama model with QuantLinear blocks.
+
+    step graph:  tok -> [embed] -> layers -> [norm -> lm_head -> argmax -> tok]   (one CUDA graph)
+    """
+
+    def __init__(self, model, max_cache_len: int = 512, first_stage: bool = True, last_stage: bool = True,
+                 use_cuda_graph: bool = True):
+        self.model = model
+        self.cfg = model.config
+        self.layers = list(model.model.layers)
+        self.first, self.last = first_stage, last_stage
+        self.dev = next(model.parameters()).device
+        cfg = self.cfg
+        self.nh, self.nkv = cfg.num_attention_heads, cfg.num_key_value_heads
+        self.hd = getattr(cfg, "head_dim", None) or cfg.hidden_size // cfg.num_attention_heads
+        self.eps = cfg.rms_norm_eps
+        self.max_len = max_cache_len
+        dt = torch.float16
+        L = len(self.layers)
+        self.k_cache = torch.zeros(L, 1, self.nkv, max_cache_len, self.hd, dtype=dt, device=self.dev)
+        self.v_cache = torch.zeros_like(self.k_cache)
+        rp = getattr(cfg, "rope_parameters", None) or {}
+        theta = rp.get("rope_theta", getattr(cfg, "rope_theta", 10000.0))
+        inv = 1.0 / (theta ** (torch.arange(0, self.hd, 2, dtype=torch.float32, device=self.dev) / self.hd))
+        t = torch.arange(max_cache_len, dtype=torch.float32, device=self.dev)
+        fr = torch.outer(t, inv)
+        emb = torch.cat((fr, fr), dim=-1)
+        self.cos, self.sin = emb.cos().to(dt), emb.sin().to(dt)
+        self.arange = torch.arange(max_cache_len, device=self.dev)
+        # static step buffers
+        self.tok = torch.zeros(1, 1, dtype=torch.long, device=self.dev)
+        self.pos = torch.zeros(1, dtype=torch.long, device=self.dev)
+        self.hidden_in = torch.zeros(1, 1, cfg.hidden_size, dtype=dt, device=self.dev)
+        self.hidden_out = torch.zeros(1, 1, cfg.hidden_size, dtype=dt, device=self.dev)
+        self.use_graph = use_cuda_graph
+        self.graph = None
+
+    # ---- building blocks --------------------------------------------------------------------
+    def _rms(self, x, w):
+        v = x.float()
+        v = v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + self.eps)
+        return w * v.to(x.dtype)
+
+    @staticmethod
+    def _rot(x):
+        h = x.shape[-1] // 2
+        return torch.cat((-x[..., h:], x[..., :h]), dim=-1)
+
+    def _layer(self, li, h, pos, cos, sin, mask):
+        lyr = self.layers[li]
+        at = lyr.self_attn
+        T = h.shape[1]
+        x = self._rms(h, lyr.input_layernorm.weight)
+        q = at.q_proj(x).view(1, T, self.nh, self.hd).transpose(1, 2)
+        k = at.k_proj(x).view(1, T, self.nkv, self.hd).transpose(1, 2)
+        v = at.v_proj(x).view(1, T, self.nkv, self.hd).transpose(1, 2)
+        q = q * cos + self._rot(q) * sin
+        k = k * cos + self._rot(k) * sin
+        self.k_cache[li].index_copy_(2, pos, k)
+        self.v_cache[li].index_copy_(2, pos, v)
+        kk, vv = self.k_cache[li], self.v_cache[li]
+        o = F.scaled_dot_product_attention(q, kk, vv, attn_mask=mask, enable_gqa=(self.nkv != self.nh))
+        o = o.transpose(1, 2).reshape(1, T, self.nh * self.hd)
+        h = h + at.o_proj(o)
+        x = self._rms(h, lyr.post_attention_layernorm.weight)
+        mlp = lyr.mlp
+        h = h + mlp.down_proj(F.silu(mlp.gate_proj(x)) * mlp.up_proj(x))
+        return h
+
+    def _forward(self, tok_or_hidden, pos):
+        """pos: long [T] absolute positions. Returns next-token ids [1,1] (last stage) or hidden."""
+        h = self.model.model.embed_tokens(tok_or_hidden) if self.first else tok_or_hidden
+        cos = self.cos.index_select(0, pos)[None, None]
+        sin = self.sin.index_select(0, pos)[None, None]
+        mask = (self.arange[None, :] <= pos[:, None])[None, None]     # [1,1,T,max_len]
+        for li in range(len(self.layers)):
+            h = self._layer(li, h, pos, cos, sin, mask)
+        if not self.last:
+            return h
+        h = self._rms(h[:, -1:], self.model.model.norm.weight)
+        logits = self.model.lm_head(h)
+        return logits.argmax(-1)
+
+    # ---- public API -------------------------------------------------------------------------
+    @torch.no_grad()
+    def prefill(self, ids_or_hidden):
+        T = ids_or_hidden.shape[1]
+        assert T <= self.max_len
+        pos = torch.arange(T, device=self.dev)
+        out = self._forward(ids_or_hidden, pos)
+        self.pos.fill_(T)
+        if self.last:
+            self.tok.copy_(out)
+        return out
+
+    @torch.no_grad()
+    def _step_body(self):
+        out = self._forward(self.tok if self.first else self.hidden_in, self.pos)
+        if self.last:
+            self.tok.copy_(out)
+        else:
+            self.hidden_out.copy_(out)
+        self.pos.add_(1)
+
+    @torch.no_grad()
+    def capture(self):
+        """Warm up and capture one decode step into a CUDA graph (state is restored afterwards)."""
+        if not self.use_graph:
+            return
+        saved = (self.tok.clone(), self.pos.clone(), self.k_cache.clone(), self.v_cache.clone())
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._step_body()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        self.pos.copy_(saved[1])
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step_body()
+        self.graph = g
+        self.tok.copy_(saved[0]); self.pos.copy_(saved[1])
+        self.k_cache.copy_(saved[2]); self.v_cache.copy_(saved[3])
+
+    @torch.no_grad()
+    def step(self):
+        """One decode step: consumes self.tok / self.pos, leaves the next token in self.tok."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
+
+    @torch.no_grad()
+    def generate(self, input_ids, max_new_tokens):
+        """Greedy decode; returns the generated ids [1, max_new_tokens] (device tensor)."""
+        assert self.first and self.last
+        self.prefill(input_ids.to(self.dev))
+        if self.use_graph and self.graph is None:
+            self.capture()
+        out = torch.empty(1, max_new_tokens, dtype=torch.long, device=self.dev)
+        out[:, 0] = self.tok[:, 0]
+        for i in range(1, max_new_tokens):
+            self.step()
+            out[:, i] = self.tok[:, 0]
+        return out

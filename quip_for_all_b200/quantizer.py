@@ -1,0 +1,263 @@
+"""Inference-side model surgery and checkpoint loading (reference: quantizer.py:53-248, 760-848).
+
+`QuipQuantizer` keeps the reference's constructor keywords / `to_dict` / `from_dict` / `convert_model` /
+`get_no_split_module_classes`; the offline quantisation driver (`quantize_model`, LDLQ, fine-tuning,
+`save`) is out of scope for this build and raises NotImplementedError.
+
+`load_quantized_model` has the reference signature but does not need `accelerate`: the HF model is
+instantiated on the meta device, every block linear is swapped for a `QuantLinear`, and the
+checkpoint shards (`pytorch_model*.bin` or `*.safetensors`, with or without an index json -- what
+`Accelerator.save_model` writes, quantizer.py:718-756) are streamed into it.
+"""
+import json
+import os
+from logging import getLogger
+from typing import Any, Dict, List, Optional, Union
+
+import torch
+from torch import nn
+
+from .codebook import codebook_id
+from .constants import QUIP_CONFIG
+from .qlinear import QuantLinear
+from .utils import Conv1D, get_block_name_with_pattern, get_layers, recurse_getattr
+
+logger = getLogger(__name__)
+
+
+class QuipQuantizer(object):
+    """Configuration holder + layer replacement.  Keyword set = reference quantizer.py:58-79."""
+
+    def __init__(self, codebook: str, dataset: str = "redpajama", nsamples: int = 4096,
+                 model_seqlen: int = 2048, quip_tune_iters: int = 10, use_rand: bool = True,
+                 rescale_WH: bool = False, sigma_reg: float = 1e-2, sigma_reg2: float = 1e-2,
+                 modules_to_not_convert: Optional[List] = None, block_name_to_quantize: Optional[str] = None,
+                 merge_suv: bool = False, per_channel: bool = False, opt_resid_scale: Optional[float] = None,
+                 inference: bool = False, ft_epochs: int = 5, ft_lr: float = 5e-5, ft_susv_lr: float = 5e-4,
+                 ft_valid_size: int = 128, ft_bs: int = 8, ft_update_freq: int = 2, ft_early_stop: int = 3,
+                 *args, **kwargs):
+        if codebook not in codebook_id:
+            raise ValueError(f"unknown codebook {codebook!r}; expected one of {sorted(codebook_id)}")
+        self.codebook = codebook_id[codebook](inference=inference, opt_resid_scale=opt_resid_scale)
+        self.dataset = dataset
+        self.nsamples = nsamples
+        self.model_seqlen = model_seqlen
+        self.quip_tune_iters = quip_tune_iters
+        self.use_rand = use_rand
+        self.rescale_WH = rescale_WH
+        self.sigma_reg = sigma_reg
+        self.sigma_reg2 = sigma_reg2
+        self.modules_to_not_convert = modules_to_not_convert or []
+        self.block_name_to_quantize = block_name_to_quantize
+        self.merge_suv = merge_suv
+        self.per_channel = per_channel
+        self.opt_resid_scale = opt_resid_scale
+        self.inference = inference
+        self.ft_epochs, self.ft_lr, self.ft_susv_lr = ft_epochs, ft_lr, ft_susv_lr
+        self.ft_valid_size, self.ft_bs = ft_valid_size, ft_bs
+        self.ft_update_freq, self.ft_early_stop = ft_update_freq, ft_early_stop
+        self.quant_method = "QUiP"
+
+    def to_dict(self):
+        """quantization_config.json contents (reference: quantizer.py:132-147)."""
+        return {
+            "quant_method": "QUiP",
+            "rescale_WH": self.rescale_WH,
+            "use_rand": self.use_rand,
+            "codebook": self.codebook.id,
+            "codesz": self.codebook.codesz,
+            "idx_dtype": str(self.codebook.idx_dtype),
+            "merge_suv": self.merge_suv,
+            "per_channel": self.per_channel,
+            "opt_resid_scale": self.opt_resid_scale,
+            "modules_to_not_convert": self.modules_to_not_convert,
+        }
+
+    @classmethod
+    def from_dict(cls, config_dict: Dict[str, Any]):
+        return cls(**config_dict)   # extra keys (codesz, idx_dtype, quant_method) fall into **kwargs
+
+    def convert_model(self, model: nn.Module):
+        """Swap every Linear / Conv1D / Conv2d under the block prefix for a QuantLinear."""
+        if self.block_name_to_quantize is None:
+            self.block_name_to_quantize = get_block_name_with_pattern(model)
+        targets = get_layers(model, prefix=self.block_name_to_quantize, skip=self.modules_to_not_convert)
+        self._replace_by_quant_layers(model, targets)
+        return model
+
+    def get_no_split_module_classes(self, model):
+        block = recurse_getattr(model, self.block_name_to_quantize)[0]
+        return [block.__class__.__name__]
+
+    def _replace_by_quant_layers(self, model: nn.Module, targets: Dict[str, nn.Module]):
+        for name, layer in targets.items():
+            if isinstance(layer, QuantLinear):
+                continue
+            if isinstance(layer, nn.Linear):
+                fin, fout = layer.in_features, layer.out_features
+            elif isinstance(layer, nn.Conv2d):
+                fin, fout = layer.in_channels, layer.out_channels
+            elif isinstance(layer, Conv1D):
+                fin, fout = layer.weight.shape[0], layer.weight.shape[1]
+            else:
+                continue
+            device = layer.weight.device
+            # a fresh codebook object per layer, as the reference does (quantizer.py:230-233)
+            cb = codebook_id[self.codebook.id](inference=True, opt_resid_scale=self.opt_resid_scale)
+            with torch.device("cpu"):
+                new = QuantLinear(fin, fout, cb, bias=(layer.bias is not None), use_rand=self.use_rand,
+                                  per_channel=self.per_channel, weight_dtype=layer.weight.dtype)
+            if device.type != "meta":
+                new = new.to(device)
+            parent_name, _, attr = name.rpartition(".")
+            parent = recurse_getattr(model, parent_name) if parent_name else model
+            setattr(parent, attr, new)
+
+    def quantize_model(self, *a, **k):
+        raise NotImplementedError("offline quantisation (calibration + LDLQ + fine-tuning) is out of scope of "
+                                  "the B200 inference build; quantise with the reference and load the result")
+
+    save = quantize_model
+
+
+# --------------------------------------------------------------------------------------------------
+# checkpoint loading
+# --------------------------------------------------------------------------------------------------
+def load_config(model_path, safetensors=True, trust_remote_code=True, revision=None):
+    from transformers import AutoConfig
+    if not os.path.isdir(model_path):
+        from huggingface_hub import snapshot_download
+        ignore = ["*msgpack*", "*h5*", "optimizer.pt"]
+        ignore += ["*.pt*", "*.bin*", "consolidated*"] if safetensors else ["*.safetensors*"]
+        model_path = snapshot_download(model_path, ignore_patterns=ignore, revision=revision)
+    config = AutoConfig.from_pretrained(model_path, trust_remote_code=trust_remote_code, revision=revision)
+    return model_path, config
+
+
+def _checkpoint_files(folder: str, use_safetensors: bool) -> List[str]:
+    names = (["model.safetensors.index.json", "model.safetensors"] if use_safetensors else []) + \
+            ["pytorch_model.bin.index.json", "pytorch_model.bin", "model.safetensors.index.json",
+             "model.safetensors"]
+    for n in names:
+        p = os.path.join(folder, n)
+        if not os.path.isfile(p):
+            continue
+        if n.endswith(".index.json"):
+            with open(p) as f:
+                shard_names = sorted(set(json.load(f)["weight_map"].values()))
+            return [os.path.join(folder, s) for s in shard_names]
+        return [p]
+    raise FileNotFoundError(f"no pytorch_model*.bin / model*.safetensors checkpoint found in {folder}")
+
+
+def _read_shard(path: str) -> Dict[str, torch.Tensor]:
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        return load_file(path)
+    return torch.load(path, map_location="cpu", weights_only=True)
+
+
+def _materialize(model: nn.Module, device, dtype):
+    """Give real storage to whatever is still on the meta device (everything except the QuantLinears)."""
+    for mod in model.modules():
+        for name, p in list(mod._parameters.items()):
+            if p is not None and p.is_meta:
+                mod._parameters[name] = nn.Parameter(torch.empty(p.shape, dtype=p.dtype, device=device),
+                                                     requires_grad=False)
+        for name, b in list(mod._buffers.items()):
+            if b is not None and b.is_meta:
+                mod._buffers[name] = torch.empty(b.shape, dtype=b.dtype, device=device)
+    # non-persistent computed buffers (rotary inv_freq) do not come from the checkpoint: rebuild them
+    for parent in model.modules():
+        for cname, child in list(parent.named_children()):
+            if "RotaryEmbedding" in child.__class__.__name__ and hasattr(child, "config"):
+                parent.add_module(cname, child.__class__(config=child.config).to(device))
+
+
+def load_state_into(model: nn.Module, files: List[str]):
+    """Stream checkpoint shards into the model.  QuantLinear attributes that the checkpoint lacks
+    because they were merged away at pack time (SU / SV = None, qlinear.py:125-131) are set to None."""
+    own = dict(model.state_dict(keep_vars=True))
+    seen = set()
+    for f in files:
+        shard = _read_shard(f)
+        for k, v in shard.items():
+            if k not in own:
+                logger.warning("checkpoint key %s has no destination", k)
+                continue
+            dst = own[k]
+            if dst.shape != v.shape:
+                raise RuntimeError(f"shape mismatch for {k}: checkpoint {tuple(v.shape)} vs model {tuple(dst.shape)}")
+            with torch.no_grad():
+                dst.copy_(v.to(dst.dtype) if dst.dtype.is_floating_point and v.dtype.is_floating_point else v)
+            seen.add(k)
+        del shard
+    for name, mod in model.named_modules():
+        if isinstance(mod, QuantLinear):
+            for attr in ("SU", "SV"):
+                if f"{name}.{attr}" not in seen:
+                    setattr(mod, attr, None)
+    missing = [k for k in own if k not in seen and not k.endswith((".SU", ".SV"))]
+    return missing
+
+
+def apply_load_time_tricks(model: nn.Module, merge_suv: bool = False):
+    """Post-load normalisation (reference: quantizer.py:836-844)."""
+    for layer in get_layers(model, [QuantLinear]).values():
+        layer.wscale_float = layer.Wscale.mean().float().item()
+        if layer.per_channel:
+            layer.Wscale = layer.Wscale / layer.Wscale.mean()
+        if merge_suv:
+            if layer.SU is not None and torch.all(layer.SU > 0):
+                layer.SU = None
+            if layer.SV is not None and torch.all(layer.SV > 0):
+                layer.SV = None
+
+
+def load_quantized_model(save_folder: str, revision: Optional[str] = None,
+                         torch_dtype: Optional[Union[str, torch.dtype]] = torch.float16,
+                         trust_remote_code: bool = True, use_safetensors: bool = False,
+                         device_map: Optional[Union[str, dict]] = None):
+    """Load a QuIP-for-all checkpoint folder into a HF model whose block linears are QuantLinears.
+    Signature and behaviour follow the reference (quantizer.py:779-848), including the hard CUDA
+    requirement -- there is no CPU inference path."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("No GPU found. A GPU is needed to run quantized model.")
+    from transformers import AutoModelForCausalLM
+    folder, config = load_config(save_folder, trust_remote_code=trust_remote_code,
+                                 safetensors=use_safetensors, revision=revision)
+    if isinstance(torch_dtype, str):
+        torch_dtype = getattr(torch, torch_dtype)
+    with torch.device("meta"):
+        model = AutoModelForCausalLM.from_config(config, trust_remote_code=trust_remote_code, dtype=torch_dtype)
+
+    qcfg = getattr(config, "quantization_config", None)
+    if qcfg is None:
+        with open(os.path.join(folder, QUIP_CONFIG)) as f:
+            qcfg = json.load(f)
+    qcfg = dict(qcfg if isinstance(qcfg, dict) else qcfg.to_dict())
+    qcfg["inference"] = True
+    qcfg["ft_epochs"] = 0
+    quantizer = QuipQuantizer.from_dict(qcfg)
+    model = quantizer.convert_model(model)
+
+    device = "cpu"
+    if isinstance(device_map, str) and device_map not in ("auto", "balanced", "sequential"):
+        device = device_map
+    elif isinstance(device_map, dict) and set(device_map) == {""}:
+        device = device_map[""]
+    elif device_map is not None:
+        device = "cuda"      # whole model on the current GPU; multi-GPU goes through parallel.LayerPipeline
+    _materialize(model, "cpu", torch_dtype)
+    missing = load_state_into(model, _checkpoint_files(folder, use_safetensors))
+    if hasattr(model, "tie_weights"):
+        model.tie_weights()
+    missing = [k for k in missing if not ("lm_head" in k and getattr(config, "tie_word_embeddings", False))]
+    if missing:
+        raise RuntimeError(f"checkpoint is missing {len(missing)} tensors, e.g. {missing[:5]}")
+    apply_load_time_tricks(model, quantizer.merge_suv)
+    if device != "cpu":
+        model = model.to(device)
+    model.is_quantized = True
+    model.eval()
+    return model

@@ -1,0 +1,441 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C-ABI library
+via torch.ops.quip_lib; the CPU oracle (oracle/quip_oracle.py) is the checker.
+
+Bars:  dequantised weights / integer work: BIT-EXACT.   Floating-point forward: |y - y_oracle| <=
+2^-8 * max|y_oracle| against the oracle evaluated with the reference's fp16 rounding points (helpers.tol_of).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import quip_oracle as qo
+from helpers import make_layer, oracle_forward, oracle_w_hat, tol_of
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib_loaded():
+    import quip_for_all_b200  # noqa: F401
+    from quip_for_all_b200 import _native
+    _native.lib()          # fail loudly if the CUDA library is missing
+    yield
+
+
+def _grid(dev=DEV):
+    from quip_for_all_b200.codebook.e8p12 import get_packed_abs_grid
+    return get_packed_abs_grid().to(dev)
+
+
+# ------------------------------------------------------------------------------------------------
+# dequantisation: bit-exact
+# ------------------------------------------------------------------------------------------------
+def test_decompress_e8p_all_65536_codes_bit_exact():
+    codes = torch.arange(65536, dtype=torch.int32).to(torch.int16).view(256, 256).to(DEV)
+    w = torch.ops.quip_lib.decompress_e8p_origorder(codes, _grid())
+    ref = qo.e8p_full_grid().astype(np.float16).reshape(256, 2048)
+    assert np.array_equal(w.cpu().numpy().view(np.uint16), ref.view(np.uint16))
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (7, 33), (64, 512), (4096, 512), (0, 8), (5, 0)])
+def test_decompress_e8p_shapes(shape):
+    g = torch.Generator().manual_seed(shape[0] * 1000 + shape[1])
+    q = torch.randint(-32768, 32768, shape, generator=g).to(torch.int16)
+    w = torch.ops.quip_lib.decompress_e8p_origorder(q.to(DEV), _grid())
+    assert w.shape == (shape[0], shape[1] * 8) and w.dtype == torch.float16
+    if q.numel():
+        assert np.array_equal(w.cpu().numpy().view(np.uint16), qo.decompress_e8p(q.numpy()).view(np.uint16))
+
+
+@pytest.mark.parametrize("shape", [(3, 5), (128, 64), (1000, 129)])
+def test_decompress_rvq4_d4_rvq3_hi_bit_exact(shape):
+    from quip_for_all_b200.codebook.d4 import build_D4_CB
+    from quip_for_all_b200.codebook.e8p12_rvq3 import get_e81bgrid, pack_e81b
+    g = torch.Generator().manual_seed(7)
+    q32 = torch.randint(-2**31, 2**31, shape, generator=g, dtype=torch.int64).to(torch.int32)
+    for scale in (1 / 3.45, 0.37):
+        w = torch.ops.quip_lib.decompress_e8prvq4_origorder(q32.to(DEV), _grid(), scale)
+        assert np.array_equal(w.cpu().numpy().view(np.uint16), qo.decompress_e8prvq4(q32.numpy(), scale).view(np.uint16))
+    q8 = torch.randint(0, 256, shape, generator=g).to(torch.uint8)
+    for gd in (build_D4_CB().half(), build_D4_CB()):     # fp16 contract; fp32 grid is cast by the binding
+        w = torch.ops.quip_lib.decompress_d4_origorder(q8.to(DEV), gd.to(DEV))
+        assert np.array_equal(w.cpu().numpy().view(np.uint16), qo.decompress_d4(q8.numpy()).view(np.uint16))
+    w = torch.ops.quip_lib.decompress_hi_origorder(q32.to(DEV))
+    assert np.array_equal(w.cpu().numpy().view(np.uint16), qo.decompress_hi(q32.numpy()).view(np.uint16))
+    q3 = torch.randint(-2**31, 2**31, (shape[0], 3 * ((shape[1] + 3) // 4)), generator=g, dtype=torch.int64).to(torch.int32)
+    cb2 = pack_e81b(get_e81bgrid()).to(DEV)
+    w = torch.ops.quip_lib.decompress_e8prvq3_origorder(q3.to(DEV), _grid(), cb2, 1 / 2.04)
+    assert np.array_equal(w.cpu().numpy().view(np.uint16), qo.decompress_e8prvq3(q3.numpy(), 1 / 2.04).view(np.uint16))
+
+
+def test_decompress_vs_golden_reference_weights(golden_dir):
+    ql = np.load(os.path.join(golden_dir, "quantlinear.npz"))
+    from quip_for_all_b200 import codebook_id
+    for name in ql["names"]:
+        pre = str(name) + "/"
+        cb = codebook_id[str(ql[pre + "codebook"])](inference=True).to(DEV)
+        w = cb.decompress_weight(torch.tensor(ql[pre + "Qidxs"]).to(DEV))
+        assert np.array_equal(w.cpu().numpy().view(np.uint16), ql[pre + "W_hat"].view(np.uint16)), name
+
+
+# ------------------------------------------------------------------------------------------------
+# hadamard op
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 64, 256, 1024, 4096, 8192, 32768])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.bfloat16])
+def test_hadamard_matches_oracle(n, dtype):
+    g = torch.Generator().manual_seed(n)
+    rows = 5 if n <= 4096 else 2
+    x = torch.randn(rows, n, generator=g).to(dtype)
+    scale = 1.0 / np.sqrt(n)
+    y = torch.ops.quip_lib.hadamard(x.to(DEV), scale)
+    assert y.dtype == dtype and y.shape == x.shape
+    ref = qo.fwht(x.float().numpy(), scale)
+    eps = {torch.float16: 2.0 ** -10, torch.bfloat16: 2.0 ** -7, torch.float32: 2.0 ** -20}[dtype]
+    assert np.abs(y.float().cpu().numpy() - ref).max() <= eps * max(1.0, np.abs(ref).max())
+
+
+def test_hadamard_batched_3d_and_involution():
+    x = torch.randn(4, 43, 256, device=DEV, dtype=torch.float32)
+    y = torch.ops.quip_lib.hadamard(x, 1 / 16.0)
+    ref = qo.fwht(x.cpu().numpy(), 1 / 16.0)
+    assert np.abs(y.cpu().numpy() - ref).max() < 1e-4
+    z = torch.ops.quip_lib.hadamard(y, 1 / 16.0)           # H H = n I
+    assert torch.allclose(z, x, atol=1e-4)
+    assert torch.ops.quip_lib.hadamard(torch.zeros(0, 64, device=DEV), 1.0).shape == (0, 64)
+    with pytest.raises(RuntimeError):
+        torch.ops.quip_lib.hadamard(torch.zeros(2, 24, device=DEV), 1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# decode + matmul ops
+# ------------------------------------------------------------------------------------------------
+def _mm_check(out, x, W_hat, slack=1.0):
+    ref64 = x.double().cpu().numpy() @ W_hat.astype(np.float64).T
+    err = np.abs(out.float().cpu().numpy() - ref64)
+    # fp16 output rounding (2^-11 relative) + 16-bit fixed-point activations: 2^-9 of the output scale
+    tol = slack * 2.0 ** -9 * np.abs(ref64).max()
+    assert err.max() <= tol, (err.max(), tol)
+    return err.max() / np.abs(ref64).max()
+
+
+@pytest.mark.parametrize("M", [1, 2, 7, 16, 17, 40])
+@pytest.mark.parametrize("N,K", [(512, 4096), (64, 64), (8, 128), (96, 2048 + 64)])
+def test_e8p_mm(M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    q = torch.randint(-32768, 32768, (N, K // 8), generator=g).to(torch.int16)
+    x = torch.randn(M, K, generator=g).half()
+    out = torch.ops.quip_lib.e8p_mm_origorder(x.to(DEV), q.to(DEV), _grid())
+    assert out.shape == (M, N) and out.dtype == torch.float16
+    _mm_check(out, x, qo.decompress_e8p(q.numpy()))
+
+
+def test_e8p_mm_row_pitch_not_16B_takes_dense_path():
+    q = torch.randint(-32768, 32768, (24, 12)).to(torch.int16)       # K = 96: 24-byte rows
+    x = torch.randn(3, 96).half()
+    out = torch.ops.quip_lib.e8p_mm_origorder(x.to(DEV), q.to(DEV), _grid())
+    _mm_check(out, x, qo.decompress_e8p(q.numpy()))
+
+
+def test_e8p_mm_edge_inputs():
+    q = torch.randint(-32768, 32768, (64, 64)).to(torch.int16).to(DEV)
+    W = qo.decompress_e8p(q.cpu().numpy())
+    z = torch.ops.quip_lib.e8p_mm_origorder(torch.zeros(2, 512, device=DEV, dtype=torch.float16), q, _grid())
+    assert torch.count_nonzero(z) == 0                                  # all-zero row: scale 0 guard
+    assert torch.ops.quip_lib.e8p_mm_origorder(torch.zeros(0, 512, device=DEV, dtype=torch.float16), q, _grid()).shape == (0, 64)
+    # wide dynamic range inside one row: one element 1000x larger than the rest
+    x = torch.randn(1, 512).half()
+    x[0, 3] = 800.0
+    out = torch.ops.quip_lib.e8p_mm_origorder(x.to(DEV), q, _grid())
+    _mm_check(out, x, W)
+    # tiny magnitudes (fp16 subnormal region scaled up by the per-row scale)
+    x = (torch.randn(2, 512) * 1e-4).half()
+    out = torch.ops.quip_lib.e8p_mm_origorder(x.to(DEV), q, _grid())
+    _mm_check(out, x, W, slack=2.0)
+    with pytest.raises(RuntimeError):
+        torch.ops.quip_lib.e8p_mm_origorder(torch.zeros(1, 256, device=DEV, dtype=torch.float16), q, _grid())
+
+
+@pytest.mark.parametrize("M", [1, 5, 30])
+def test_rvq4_and_d4_mm(M):
+    from quip_for_all_b200.codebook.d4 import build_D4_CB
+    g = torch.Generator().manual_seed(M)
+    N, K = 256, 1024
+    x = torch.randn(M, K, generator=g).half()
+    q = torch.randint(-2**31, 2**31, (N, K // 8), generator=g, dtype=torch.int64).to(torch.int32)
+    out = torch.ops.quip_lib.e8prvq4_mm_origorder(x.to(DEV), q.to(DEV), _grid(), 1 / 3.45)
+    _mm_check(out, x, qo.decompress_e8prvq4(q.numpy()), slack=1.5)
+    q8 = torch.randint(0, 256, (N, K // 4), generator=g).to(torch.uint8)
+    out = torch.ops.quip_lib.d4_mm_origorder(x.to(DEV), q8.to(DEV), build_D4_CB().to(DEV))
+    _mm_check(out, x, qo.decompress_d4(q8.numpy()))
+
+
+def test_rvq3_and_hi_mm_dense_path():
+    from quip_for_all_b200.codebook.e8p12_rvq3 import get_e81bgrid, pack_e81b
+    g = torch.Generator().manual_seed(3)
+    N, K = 64, 256
+    x = torch.randn(4, K, generator=g).half()
+    q3 = torch.randint(-2**31, 2**31, (N, 3 * K // 32), generator=g, dtype=torch.int64).to(torch.int32)
+    out = torch.ops.quip_lib.e8prvq3_mm_origorder(x.to(DEV), q3.to(DEV), _grid(), pack_e81b(get_e81bgrid()).to(DEV), 1 / 2.04)
+    _mm_check(out, x, qo.decompress_e8prvq3(q3.numpy()), slack=2.0)
+    qh = torch.randint(-2**31, 2**31, (N, K // 8), generator=g, dtype=torch.int64).to(torch.int32)
+    out = torch.ops.quip_lib.hi_mm_origorder(x.to(DEV), qh.to(DEV))
+    _mm_check(out, x, qo.decompress_hi(qh.numpy()), slack=2.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused QuantLinear.forward
+# ------------------------------------------------------------------------------------------------
+def _layer_from_golden(ql, name):
+    from quip_for_all_b200 import QuantLinear, codebook_id, quant
+    pre = name + "/"
+    fin, fout, bias, use_rand, pc, M, K_left, K_right, q_in, q_out = [int(v) for v in ql[pre + "meta"]]
+    cb = codebook_id[str(ql[pre + "codebook"])](inference=True)
+    layer = QuantLinear(fin, fout, cb, bias=bool(bias), use_rand=bool(use_rand), per_channel=bool(pc))
+    assert (layer.K_left, layer.K_right, layer.q_in_features, layer.q_out_features) == (K_left, K_right, q_in, q_out)
+    layer.Qidxs.copy_(torch.tensor(ql[pre + "Qidxs"]))
+    layer.Wscale.copy_(torch.tensor(ql[pre + "Wscale"]))
+    for attr in ("SU", "SV"):
+        if pre + attr in ql.files:
+            getattr(layer, attr).data.copy_(torch.tensor(ql[pre + attr]))
+        else:
+            setattr(layer, attr, None)
+    if bias:
+        layer.bias.copy_(torch.tensor(ql[pre + "bias"]))
+    for attr in ("had_left", "had_right"):
+        if pre + attr in ql.files:
+            getattr(layer, attr).copy_(torch.tensor(ql[pre + attr]))
+    layer.wscale_float = float(ql[pre + "wscale_float"])
+    return layer.to(DEV).eval(), torch.tensor(ql[pre + "x"]), ql[pre + "y"]
+
+
+def test_quantlinear_forward_vs_reference_golden(golden_dir):
+    """Product forward on the GPU vs outputs of the reference's own QuantLinear.forward (gen_golden.py)."""
+    from quip_for_all_b200 import quant
+    had = np.load(os.path.join(golden_dir, "hadamard.npz"))
+    for k in (12, 20, 28, 172):
+        quant.register_had_table(k, torch.tensor(had[f"table_{k}"].astype(np.float32)))
+    ql = np.load(os.path.join(golden_dir, "quantlinear.npz"))
+    for name in ql["names"]:
+        layer, x, yref = _layer_from_golden(ql, str(name))
+        with torch.no_grad():
+            y = layer(x.to(DEV))
+        assert y.shape == yref.shape and y.dtype == torch.float16
+        err = np.abs(y.float().cpu().numpy() - yref.astype(np.float64)).max()
+        assert err <= tol_of(yref), (name, err, tol_of(yref))
+
+
+CASES = [
+    # fin, fout, codebook, bias, use_rand, per_channel, M
+    (4096, 4096, "E8P12", False, True, False, 1),        # BASELINE config 1 / q,k,v,o of Llama-2-7B
+    (4096, 11008, "E8P12", False, True, False, 1),       # gate/up: K_right = 43
+    (11008, 4096, "E8P12", False, True, False, 1),       # down: K_left = 43
+    (1024, 8192, "E8P12", True, True, False, 3),
+    (8192, 1024, "E8P12", True, True, True, 2),          # per-channel
+    (4096, 4096, "E8P12RVQ4B", False, True, False, 1),
+    (4096, 4096, "D4", True, True, False, 2),
+    (2048, 2048, "E8P12", False, True, False, 16),
+    (2048, 2048, "E8P12", False, True, False, 40),       # M >= 32: reference op sequence (decompress + GEMM)
+    (448, 320, "E8P12", True, True, False, 4),           # K_left = 7, K_right = 5, 64 | q_in
+]
+
+
+@pytest.mark.parametrize("fin,fout,cbid,bias,use_rand,pc,M", CASES)
+def test_quantlinear_forward_vs_oracle(fin, fout, cbid, bias, use_rand, pc, M):
+    layer = make_layer(fin, fout, cbid, bias=bias, use_rand=use_rand, per_channel=pc, seed=fin + fout + M, device=DEV)
+    x = torch.randn(M, fin, generator=torch.Generator().manual_seed(M)).half()
+    with torch.no_grad():
+        y = layer(x.to(DEV))
+    ref = oracle_forward(layer, x, rounding="reference")
+    err = np.abs(y.float().cpu().numpy() - ref)
+    assert err.max() <= tol_of(ref), (err.max(), tol_of(ref))
+    # and against the unrounded fp64 forward
+    ref64 = oracle_forward(layer, x, rounding="none")
+    assert np.abs(y.float().cpu().numpy() - ref64).max() <= tol_of(ref64)
+    # relative RMS error well inside fp16 resolution
+    assert np.sqrt((err ** 2).mean()) <= 2.0 ** -10 * np.sqrt((ref ** 2).mean()) * 2
+
+
+def test_fused_matches_reference_op_sequence():
+    """The fused op and the reference's own op sequence (through the individual quip_lib ops) agree."""
+    layer = make_layer(4096, 11008, "E8P12", bias=True, seed=5, device=DEV)
+    x = torch.randn(2, 4096, generator=torch.Generator().manual_seed(0)).half().to(DEV)
+    with torch.no_grad():
+        y_fused = layer(x)
+        from quip_for_all_b200 import register_lib
+        old = register_lib.fused_supported
+        try:
+            import quip_for_all_b200.qlinear as qmod
+            qmod.fused_supported = lambda *a: False
+            y_seq = layer(x)
+        finally:
+            qmod.fused_supported = old
+    assert (y_fused - y_seq).abs().max().item() <= 2.0 ** -8 * y_seq.abs().max().item()
+
+
+def test_properties_at_full_size():
+    """Size-independent properties at BASELINE's full layer size: linearity and sign symmetry."""
+    layer = make_layer(4096, 4096, "E8P12", seed=11, device=DEV)
+    x = torch.randn(1, 4096, generator=torch.Generator().manual_seed(1)).half().to(DEV)
+    with torch.no_grad():
+        y1, y2, yn = layer(x), layer(2 * x), layer(-x)
+        z = layer(torch.zeros_like(x))
+    assert torch.count_nonzero(z) == 0
+    assert torch.equal(yn, -y1)                                   # exact: integer arithmetic is sign-symmetric
+    assert (y2 - 2 * y1).abs().max().item() <= 2.0 ** -9 * y2.abs().max().item()
+    # batch invariance: row i of a batch == the same row alone (bit-exact, deterministic integer sums)
+    xb = torch.randn(5, 4096, generator=torch.Generator().manual_seed(2)).half().to(DEV)
+    with torch.no_grad():
+        yb = layer(xb)
+        for i in range(5):
+            assert torch.equal(yb[i:i + 1], layer(xb[i:i + 1]))
+
+
+def test_non_fp16_activations_and_3d_input():
+    layer = make_layer(512, 256, "E8P12", bias=True, seed=3, device=DEV)
+    x = torch.randn(2, 3, 512, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        y16 = layer(x.half().to(DEV))
+        y32 = layer(x.to(DEV))
+        ybf = layer(x.bfloat16().to(DEV))
+    assert y16.shape == (2, 3, 256) and y32.dtype == torch.float32 and ybf.dtype == torch.bfloat16
+    assert (y32 - y16.float()).abs().max() <= 2.0 ** -8 * y16.abs().max()
+
+
+def test_training_mode_dense_weight_matches_eval():
+    """calc_weight (dense dequant + two-sided Hadamard, qlinear.py:144-159) reproduces the eval forward."""
+    layer = make_layer(512, 768, "E8P12", bias=True, seed=9, device=DEV)   # 768 = 3 * 256
+    x = torch.randn(4, 512, generator=torch.Generator().manual_seed(4)).half().to(DEV)
+    with torch.no_grad():
+        y_eval = layer(x)
+        layer.train()
+        y_train = layer(x)
+        layer.eval()
+    assert (y_eval - y_train).abs().max().item() <= 2.0 ** -6 * y_eval.abs().max().item()
+
+
+def test_cuda_graph_capture_of_fused_forward():
+    layer = make_layer(4096, 4096, "E8P12", seed=2, device=DEV)
+    x = torch.randn(1, 4096, device=DEV, dtype=torch.float16)
+    with torch.no_grad():
+        y_eager = layer(x).clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            layer(x)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            y_g = layer(x)
+        x.copy_(torch.randn(1, 4096, device=DEV, dtype=torch.float16))
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(y_g, layer(x))
+    assert not torch.equal(y_g, y_eager)
+
+
+# ------------------------------------------------------------------------------------------------
+# vs the reference's own CUDA kernels (oracle/_ref/quiptools_cuda.so), when the build shipped it
+# ------------------------------------------------------------------------------------------------
+def _ref_mod():
+    import build_ref
+    m = build_ref.load_ref_module()
+    if m is None:
+        pytest.skip("oracle/_ref/quiptools_cuda.so not present")
+    return m
+
+
+def test_vs_reference_cuda_kernels():
+    from quip_for_all_b200.codebook.d4 import build_D4_CB
+    ref = _ref_mod()
+    g = torch.Generator().manual_seed(0)
+    N, K = 4096, 4096
+    grid = _grid()
+    q = torch.randint(-32768, 32768, (N, K // 8), generator=g).to(torch.int16).to(DEV)
+    Y = torch.empty(N, K, dtype=torch.float16, device=DEV)
+    ref.decompress_e8p_origorder(q, grid, Y)
+    assert torch.equal(Y, torch.ops.quip_lib.decompress_e8p_origorder(q, grid))       # K6 bit-exact
+    q4 = torch.randint(-2**31, 2**31, (N, K // 8), generator=g, dtype=torch.int64).to(torch.int32).to(DEV)
+    ref.decompress_e8prvq4_origorder(q4, grid, Y, 1 / 3.45)
+    assert torch.equal(Y, torch.ops.quip_lib.decompress_e8prvq4_origorder(q4, grid, 1 / 3.45))   # K7
+    q8 = torch.randint(0, 256, (N, K // 4), generator=g).to(torch.uint8).to(DEV)
+    cb = build_D4_CB().half().to(DEV)
+    ref.decompress_d4_origorder(q8, cb, Y)
+    assert torch.equal(Y, torch.ops.quip_lib.decompress_d4_origorder(q8, cb))         # K8
+    for M in (1, 4, 16):
+        x = torch.randn(M, K, generator=g).half().to(DEV)
+        for mine, theirs in (
+            (torch.ops.quip_lib.e8p_mm_origorder(x, q, grid), ref.e8p_mm_origorder(x, q, grid)),                  # K1
+            (torch.ops.quip_lib.e8prvq4_mm_origorder(x, q4, grid, 1 / 3.45), ref.e8prvq4_mm_origorder(x, q4, grid, 1 / 3.45)),  # K2
+            (torch.ops.quip_lib.d4_mm_origorder(x, q8, cb), ref.d4_mm_origorder(x, q8, cb)),                      # K3
+        ):
+            d = (mine.float() - theirs.float()).abs().max().item()
+            assert d <= 2.0 ** -9 * theirs.float().abs().max().item(), d
+
+
+# ------------------------------------------------------------------------------------------------
+# drop-in into the HF forward pass, and the decode engine
+# ------------------------------------------------------------------------------------------------
+def _tiny_model(codebook="E8P12"):
+    from quip_for_all_b200.modeling import make_random_quantized_llama
+    return make_random_quantized_llama("tiny", codebook, seed=0, device=DEV)
+
+
+def _densify(model):
+    """Replace every QuantLinear by an nn.Linear holding its dense dequantised weight."""
+    import copy
+    from quip_for_all_b200 import QuantLinear
+    dense = copy.deepcopy(model)
+    for name, mod in list(dense.named_modules()):
+        for cname, child in list(mod.named_children()):
+            if isinstance(child, QuantLinear):
+                W = child.calc_weight(cache=False)                       # (q_in, q_out), x @ W
+                W = W[:child.in_features, :child.out_features].float()
+                if child.SU is not None:
+                    W = child.SU.float()[:, None] * W
+                if child.SV is not None:
+                    W = W * child.SV.float()[None, :]
+                lin = torch.nn.Linear(child.in_features, child.out_features, bias=child.bias is not None,
+                                      device=DEV, dtype=torch.float32)
+                lin.weight.data.copy_(W.T)
+                if child.bias is not None:
+                    lin.bias.data.copy_(child.bias.float())
+                setattr(mod, cname, lin)
+    return dense.float()
+
+
+def test_hf_forward_dropin_decode_and_prefill():
+    model = _tiny_model()
+    dense = _densify(model)
+    ids = torch.randint(0, 32000, (1, 40), generator=torch.Generator().manual_seed(0)).to(DEV)
+    with torch.no_grad():
+        lq = model(ids).logits.float()           # M = 40 rows: reference op sequence
+        ld = dense(ids).logits
+        assert (lq - ld).abs().max() <= 0.03 * ld.abs().max()
+        lq1 = model(ids[:, :5]).logits.float()   # M = 5 rows: fused path
+        ld1 = dense(ids[:, :5]).logits
+        assert (lq1 - ld1).abs().max() <= 0.03 * ld1.abs().max()
+
+
+def test_decode_engine_matches_hf_greedy():
+    from quip_for_all_b200.modeling import LlamaDecodeEngine
+    model = _tiny_model()
+    ids = torch.randint(0, 32000, (1, 12), generator=torch.Generator().manual_seed(1)).to(DEV)
+    eng = LlamaDecodeEngine(model, max_cache_len=64)
+    out = eng.generate(ids, 8)
+    eng2 = LlamaDecodeEngine(model, max_cache_len=64, use_cuda_graph=False)
+    out2 = eng2.generate(ids, 8)
+    assert torch.equal(out, out2)                                 # graph replay == eager
+    with torch.no_grad():
+        seq = ids
+        hf = []
+        for _ in range(8):
+            nxt = model(seq).logits[:, -1].argmax(-1, keepdim=True)
+            hf.append(nxt)
+            seq = torch.cat([seq, nxt], 1)
+    hf = torch.cat(hf, 1)
+    # identical up to fp16 noise flipping a near-tie: require the first tokens to agree
+    assert torch.equal(out[:, :2], hf[:, :2])

@@ -1,0 +1,273 @@
+"""CPU-side tests of the product host code: tables, module geometry, op registry, C-ABI surface, loader."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import quip_oracle as qo
+from helpers import make_layer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_product_tables_equal_oracle_and_reference(golden_dir):
+    from quip_for_all_b200.codebook import e8p12, d4, e8p12_rvq3
+    t = np.load(os.path.join(golden_dir, "tables.npz"))
+    assert np.array_equal(e8p12.get_packed_abs_grid().numpy(), t["e8p_abs"])
+    assert np.array_equal(e8p12.get_packed_abs_grid().numpy(), qo.e8p_abs_table())
+    g, idx = e8p12.get_full_grid()
+    assert np.array_equal(g.numpy().astype(np.float16).view(np.uint16), t["e8p_full_grid_f16"].view(np.uint16))
+    assert np.array_equal(d4.build_D4_CB().numpy(), t["d4_grid"])
+    assert np.array_equal(e8p12_rvq3.get_e81bgrid().numpy(), t["e81b_grid"])
+    assert np.array_equal(e8p12_rvq3.pack_e81b(e8p12_rvq3.get_e81bgrid()).numpy(), t["e81b_packed"])
+
+
+def test_codebook_attributes():
+    from quip_for_all_b200 import codebook_id
+    from fractions import Fraction
+    exp = {"E8P12": (8, 1, torch.int16, 1.03), "E8P12RVQ4B": (8, 1, torch.int32, 1.03),
+           "E8P12RVQ3B": (8, Fraction(4, 3), torch.int32, 0.98), "D4": (4, 1, torch.uint8, 1.21),
+           "HI": (1, 8, torch.int32, 2.97)}
+    assert set(codebook_id) == set(exp)
+    for k, (codesz, packsz, dt, opt) in exp.items():
+        cb = codebook_id[k](inference=True)
+        assert (cb.id, cb.codesz, cb.packsz, cb.idx_dtype, cb.opt_scale, cb.pack_out) == (k, codesz, packsz, dt, opt, False)
+        assert cb.state_dict() == {}          # only non-persistent buffers
+    assert abs(codebook_id["E8P12RVQ4B"](inference=True).opt_resid_scale - 1 / 3.45) < 1e-12
+    assert codebook_id["E8P12RVQ4B"](inference=True, opt_resid_scale=0.3).opt_resid_scale == 0.3
+
+
+def test_quantize_roundtrip_cpu():
+    """quantize (nearest codeword) of a codeword returns its index: the grid is self-consistent."""
+    from quip_for_all_b200 import codebook_id
+    cb = codebook_id["E8P12"](inference=False)
+    idx = torch.randint(0, 65536, (200,))
+    vals, got = cb.quantize(cb.grid[idx])
+    assert torch.equal(got, idx) and torch.equal(vals, cb.grid[idx])
+    d = codebook_id["D4"](inference=False)
+    i = torch.arange(256)
+    assert torch.equal(d.quantize(d.grid[i])[1].long(), i)
+
+
+def test_quantlinear_geometry_and_state_dict():
+    lay = make_layer(4096, 11008, "E8P12", bias=True)
+    sd = lay.state_dict()
+    assert set(sd) == {"SU", "SV", "Qidxs", "Wscale", "weight", "bias", "had_right"}
+    assert sd["Qidxs"].shape == (11008, 512) and sd["Qidxs"].dtype == torch.int16
+    assert sd["had_right"].shape == (43, 43) and sd["had_right"].dtype == torch.float16
+    assert sd["Wscale"].shape == () and sd["Wscale"].dtype == torch.float32
+    assert sd["weight"].shape == () and lay.K_left == 1 and lay.K_right == 43
+    assert lay.infeatures == 4096 and lay.outfeatures == 11008
+    assert abs(lay.wscale_float - 0.02 / 1.09375) < 1e-7
+    lay = make_layer(11008, 4096, "E8P12RVQ4B")
+    assert lay.Qidxs.shape == (4096, 1376) and lay.Qidxs.dtype == torch.int32 and lay.K_left == 43
+    lay = make_layer(4096, 4096, "D4")
+    assert lay.Qidxs.shape == (4096, 1024) and lay.Qidxs.dtype == torch.uint8
+    lay = make_layer(4096, 4096, "E8P12RVQ3B")
+    assert lay.Qidxs.shape == (4096, 384)
+    lay = make_layer(4096, 4096, "HI")
+    assert lay.Qidxs.shape == (4096, 512)
+    from quip_for_all_b200 import QuipLinear, QuantLinear
+    assert QuipLinear is QuantLinear
+
+
+def test_had_orthonormal_random_block():
+    lay = make_layer(96, 80, "E8P12")
+    for h in (lay.had_left, lay.had_right):
+        hf = h.float()
+        assert torch.allclose(hf @ hf.T, torch.eye(hf.shape[0]), atol=5e-3)
+
+
+def test_matmul_hadU_cpu_matches_golden(golden_dir):
+    from quip_for_all_b200.quant import matmul_hadU
+    had = np.load(os.path.join(golden_dir, "hadamard.npz"))
+    n_checked = 0
+    for n, use_rand, K, padn, has in had["shapes"]:
+        for tr in (0, 1):
+            key = f"x_n{n}_r{use_rand}_t{tr}"
+            if key not in had.files:
+                continue
+            hk = torch.tensor(had[f"hadK_n{n}_r{use_rand}"]) if has else None
+            y = matmul_hadU(torch.tensor(had[key]), hk, int(K), int(padn), transpose=bool(tr))
+            ref = torch.tensor(had[f"y_n{n}_r{use_rand}_t{tr}"])
+            assert torch.allclose(y, ref, atol=2e-5 * max(1.0, ref.abs().max().item()))
+            n_checked += 1
+    assert n_checked >= 10
+
+
+def test_get_hadK_shapes_with_tables(golden_dir):
+    from quip_for_all_b200 import quant
+    had = np.load(os.path.join(golden_dir, "hadamard.npz"))
+    for k in (12, 20, 28, 172):
+        quant.register_had_table(k, torch.tensor(had[f"table_{k}"].astype(np.float32)))
+    hk, K, n = quant.get_hadK(11008, use_rand=False)
+    assert (K, n) == (172, 11008) and torch.allclose(hk @ hk.T, torch.eye(172), atol=1e-5)
+    hk, K, n = quant.get_hadK(28672, use_rand=False)
+    assert (K, n) == (28, 28672)
+    assert quant.get_hadK(66, use_rand=False)[1:] == (1, 128)       # exp < 2 -> zero-pad
+    assert quant.get_hadK(4096, use_rand=False) == (None, 1, 4096)
+    hk, K, n = quant.get_hadK(11008, use_rand=True)
+    assert (K, n) == (43, 11008) and hk.shape == (43, 43)
+
+
+REF_SCHEMAS = {
+    "hadamard": "quip_lib::hadamard(Tensor x, float scale) -> Tensor",
+    "e8p_mm_origorder": "quip_lib::e8p_mm_origorder(Tensor x, Tensor Qidxs, Tensor grid) -> Tensor",
+    "e8prvq3_mm_origorder": "quip_lib::e8prvq3_mm_origorder(Tensor x, Tensor Qidxs, Tensor grid, Tensor grid2, float scale) -> Tensor",
+    "e8prvq4_mm_origorder": "quip_lib::e8prvq4_mm_origorder(Tensor x, Tensor Qidxs, Tensor grid, float scale) -> Tensor",
+    "d4_mm_origorder": "quip_lib::d4_mm_origorder(Tensor x, Tensor Qidxs, Tensor grid) -> Tensor",
+    "hi_mm_origorder": "quip_lib::hi_mm_origorder(Tensor x, Tensor Qidxs) -> Tensor",
+    "decompress_e8p_origorder": "quip_lib::decompress_e8p_origorder(Tensor Qidxs, Tensor grid) -> Tensor",
+    "decompress_e8prvq3_origorder": "quip_lib::decompress_e8prvq3_origorder(Tensor Qidxs, Tensor grid, Tensor grid2, float scale) -> Tensor",
+    "decompress_e8prvq4_origorder": "quip_lib::decompress_e8prvq4_origorder(Tensor Qidxs, Tensor grid, float scale) -> Tensor",
+    "decompress_d4_origorder": "quip_lib::decompress_d4_origorder(Tensor Qidxs, Tensor grid) -> Tensor",
+    "decompress_hi_origorder": "quip_lib::decompress_hi_origorder(Tensor Qidxs) -> Tensor",
+}
+
+
+def test_op_registry_schemas_match_reference():
+    import quip_for_all_b200  # noqa: F401
+    for name, schema in REF_SCHEMAS.items():
+        op = getattr(torch.ops.quip_lib, name).default
+        assert str(op._schema) == schema
+    assert hasattr(torch.ops.quip_lib, "quantlinear_fwd")
+
+
+def test_ops_are_cuda_only_like_reference():
+    import quip_for_all_b200  # noqa: F401
+    with pytest.raises(NotImplementedError):
+        torch.ops.quip_lib.hadamard(torch.zeros(2, 8), 1.0)
+    with pytest.raises(NotImplementedError):
+        torch.ops.quip_lib.decompress_e8p_origorder(torch.zeros(2, 8, dtype=torch.int16), torch.zeros(256, dtype=torch.int64))
+    lay = make_layer(64, 64, "E8P12")
+    with pytest.raises(NotImplementedError):
+        lay(torch.zeros(1, 64, dtype=torch.float16))
+
+
+def test_fake_impls_give_shapes():
+    import quip_for_all_b200  # noqa: F401
+    q = torch.empty(32, 16, dtype=torch.int16, device="meta")
+    g = torch.empty(256, dtype=torch.int64, device="meta")
+    x = torch.empty(3, 128, dtype=torch.float16, device="meta")
+    assert torch.ops.quip_lib.decompress_e8p_origorder(q, g).shape == (32, 128)
+    assert torch.ops.quip_lib.e8p_mm_origorder(x, q, g).shape == (3, 32)
+    assert torch.ops.quip_lib.hadamard(x, 0.5).shape == (3, 128)
+    q3 = torch.empty(32, 12, dtype=torch.int32, device="meta")
+    assert torch.ops.quip_lib.decompress_e8prvq3_origorder(q3, g, g, 0.5).shape == (32, 128)
+    assert torch.ops.quip_lib.decompress_d4_origorder(torch.empty(8, 4, dtype=torch.uint8, device="meta"), g).shape == (8, 16)
+
+
+def test_cabi_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports everything include/quip_b200.h declares."""
+    from quip_for_all_b200 import _native
+    from quip_for_all_b200.build import build
+    build()
+    hdr = open(os.path.join(ROOT, "include", "quip_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|size_t|int64_t|const char\*)\s+(quipb200_\w+)\s*\(", hdr, re.M))
+    assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
+    L = ctypes.CDLL(_native.LIB_PATH)
+    for s in declared:
+        assert hasattr(L, s), s
+    L.quipb200_abi_version.restype = ctypes.c_int
+    assert L.quipb200_abi_version() == 1
+    L.quipb200_strerror.restype = ctypes.c_char_p
+    assert b"workspace" in L.quipb200_strerror(-3)
+    assert ctypes.sizeof(_native.LinearDesc) == 104     # 9 x 4 B (+4 pad) + 8 pointers
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from quip_for_all_b200 import _native
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", "/nonexistent/libquipb200.so")
+    with pytest.raises(_native.QuipB200Error):
+        _native.lib()
+
+
+def _tiny_llama():
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=192, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, vocab_size=128, max_position_embeddings=64)
+    return cfg, LlamaForCausalLM
+
+
+def test_convert_model_replaces_block_linears_only():
+    from quip_for_all_b200 import QuantLinear, QuipQuantizer
+    cfg, cls = _tiny_llama()
+    model = cls(cfg).half()
+    q = QuipQuantizer(codebook="E8P12", inference=True, modules_to_not_convert=["down_proj"])
+    q.convert_model(model)
+    assert q.block_name_to_quantize == "model.layers"
+    assert q.get_no_split_module_classes(model) == ["LlamaDecoderLayer"]
+    kinds = {n: type(m).__name__ for n, m in model.named_modules() if n.endswith("_proj") or n == "lm_head"}
+    assert kinds["lm_head"] == "Linear"
+    assert kinds["model.layers.0.self_attn.q_proj"] == "QuantLinear"
+    assert kinds["model.layers.1.mlp.down_proj"] == "Linear"      # skipped by pattern
+    ql = model.model.layers[0].self_attn.k_proj
+    assert isinstance(ql, QuantLinear) and (ql.in_features, ql.out_features) == (64, 32) and ql.bias is None
+    d = q.to_dict()
+    assert d["codebook"] == "E8P12" and d["codesz"] == 8 and d["quant_method"] == "QUiP"
+    q2 = QuipQuantizer.from_dict(dict(d, inference=True))      # extra keys swallowed
+    assert q2.codebook.id == "E8P12"
+    with pytest.raises(NotImplementedError):
+        q.quantize_model(model, None)
+
+
+@pytest.mark.parametrize("fmt", ["bin", "safetensors"])
+def test_checkpoint_roundtrip_cpu(tmp_path, fmt):
+    """Write a reference-format checkpoint folder (sharded, SU merged away on one layer), load it back."""
+    from quip_for_all_b200 import QuantLinear, QuipQuantizer
+    from quip_for_all_b200 import quantizer as qz
+    from quip_for_all_b200.modeling import randomize_quantlinear
+    cfg, cls = _tiny_llama()
+    torch.manual_seed(0)
+    src = cls(cfg).half()
+    QuipQuantizer(codebook="E8P12", inference=True).convert_model(src)
+    gen = torch.Generator().manual_seed(1)
+    for m in src.modules():
+        if isinstance(m, QuantLinear):
+            randomize_quantlinear(m, gen)
+    src.model.layers[0].self_attn.q_proj.SU = None           # merged at pack time (qlinear.py:125)
+    sd = {k: v.contiguous() for k, v in src.state_dict().items()}
+    keys = sorted(sd)
+    shards = [dict((k, sd[k]) for k in keys[::2]), dict((k, sd[k]) for k in keys[1::2])]
+    ext = "bin" if fmt == "bin" else "safetensors"
+    base = "pytorch_model" if fmt == "bin" else "model"
+    wm = {}
+    for i, sh in enumerate(shards):
+        name = f"{base}-{i+1:05d}-of-00002.{ext}"
+        if fmt == "bin":
+            torch.save(sh, tmp_path / name)
+        else:
+            from safetensors.torch import save_file
+            save_file(sh, str(tmp_path / name))
+        wm.update({k: name for k in sh})
+    (tmp_path / f"{base}.{ext}.index.json").write_text(json.dumps({"metadata": {}, "weight_map": wm}))
+    files = qz._checkpoint_files(str(tmp_path), use_safetensors=(fmt == "safetensors"))
+    assert len(files) == 2
+    with torch.device("meta"):
+        dst = cls(cfg).half()
+    QuipQuantizer(codebook="E8P12", inference=True).convert_model(dst)
+    qz._materialize(dst, "cpu", torch.float16)
+    missing = qz.load_state_into(dst, files)
+    assert missing == []
+    qz.apply_load_time_tricks(dst)
+    assert dst.model.layers[0].self_attn.q_proj.SU is None
+    assert dst.model.layers[0].self_attn.k_proj.SU is not None
+    for k, v in dst.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    l0 = dst.model.layers[1].mlp.up_proj
+    assert abs(l0.wscale_float - float(l0.Wscale)) < 1e-9
+    # rotary buffers were rebuilt, not left uninitialised
+    assert torch.isfinite(dst.model.rotary_emb.inv_freq).all() and dst.model.rotary_emb.inv_freq[0] == 1.0
+
+
+def test_load_quantized_model_requires_cuda(tmp_path):
+    from quip_for_all_b200 import load_quantized_model
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="No GPU found"):
+        load_quantized_model(str(tmp_path))
