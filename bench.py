@@ -196,7 +196,9 @@ def kernel_bench(model, torch, peak, peak_src, reps=5):
             xs[L.in_features] = torch.randn(1, L.in_features, device=dev, dtype=torch.float16)
     bytes_total = sum(L.Qidxs.numel() * L.Qidxs.element_size() for L in layers)
     out = {}
-    for name, mask in (("gemv", 2), ("prologue", 1), ("epilogue", 4), ("fused_op", 7)):
+    for name, fuse, mask in (("fused_op", 3, 7), ("gemv_only", 0, 2), ("prologue_only", 0, 1),
+                             ("epilogue_only", 0, 4)):
+        _native.set_option("fuse", fuse)
         _native.set_option("stage_mask", mask)
         try:
             with torch.no_grad():
@@ -221,13 +223,15 @@ def kernel_bench(model, torch, peak, peak_src, reps=5):
                 ms = e0.elapsed_time(e1) / reps
         finally:
             _native.set_option("stage_mask", 7)
+            _native.set_option("fuse", 3)
         out[name] = {"us_per_launch_avg": 1000.0 * ms / len(layers), "launches": len(layers), "ms_per_sweep": ms}
-    us = out["gemv"]["us_per_launch_avg"]
+    us = out["fused_op"]["us_per_launch_avg"]
     achieved = bytes_total / len(layers) / (us * 1e-6) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "ql_gemv_kernel<E8P12>",
+            "traffic": None, "kernel": "ql_gemv_kernel<E8P12> (fused: x rotation + GEMV + last-CTA output rotation; "
+                                       "down_proj adds a 1-CTA prologue launch, included in the time)",
             "bytes_per_launch": bytes_total / len(layers), "us_per_launch": us, "peak_source": peak_src,
-            "how": f"CUDA events around a graph of {len(layers)} back-to-back GEMV-only launches over all "
+            "how": f"CUDA events around a graph of {len(layers)} back-to-back fused QuantLinear calls over all "
                    f"QuantLinears of the model ({bytes_total/1e9:.3f} GB of distinct codes, >> L2), {reps} replays"}
     return roof, out
 
@@ -254,15 +258,24 @@ def ref_cuda_bench(model, torch, reps=3):
         for L in layers[:4]:
             ref.e8p_mm_origorder(xs[L.q_in_features], L.Qidxs, L.codebook.grid_packed_abs)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            for L in layers:
-                ref.e8p_mm_origorder(xs[L.q_in_features], L.Qidxs, L.codebook.grid_packed_abs)
-        e1.record()
-        e1.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for L in layers:
+                    ref.e8p_mm_origorder(xs[L.q_in_features], L.Qidxs, L.codebook.grid_packed_abs)
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s)
+            for _ in range(reps):
+                g.replay()
+            e1.record(s)
+            e1.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    return {"kernel": "tinygemm_m16n8k16_chunk_kernel<BLayout_E8> via quiptools_cuda.e8p_mm_origorder (M=1, mm only, eager launches)",
+    return {"kernel": "tinygemm_m16n8k16_chunk_kernel<BLayout_E8> via quiptools_cuda.e8p_mm_origorder (M=1, mm ONLY -- no "
+                      "Hadamards / scalings --, CUDA-graph replay)",
             "us_per_launch_avg": 1000.0 * ms / len(layers), "gbs": bytes_total / (ms * 1e-3) / 1e9,
             "launches": len(layers)}
 
@@ -306,11 +319,13 @@ def run_ours(a):
     clocks = ClockSampler(local)
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()          # ncu --profile-from-start off captures only the timed region
     e0.record()
     for _ in range(a.steps):
         eng.step()
     e1.record()
     e1.synchronize()
+    torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     ck = clocks.stop()
     tok_s = a.steps / (ms * 1e-3)

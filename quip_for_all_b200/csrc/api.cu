@@ -9,6 +9,7 @@ extern int g_opt_table_repl;
 extern int g_opt_gemv_warps;
 extern int g_opt_gemv_ctas_per_sm;
 extern int g_opt_stage_mask;
+extern int g_opt_fuse;
 }  // namespace qb
 
 extern "C" int quipb200_abi_version(void) { return QUIPB200_ABI_VERSION; }
@@ -59,6 +60,11 @@ extern "C" int quipb200_set_option(const char* name, int value) {
     qb::g_opt_stage_mask = value;
     return 0;
   }
+  if (!strcmp(name, "fuse")) {
+    if (value < 0 || value > 3) return QUIPB200_EINVAL;
+    qb::g_opt_fuse = value;
+    return 0;
+  }
   return QUIPB200_EINVAL;
 }
 
@@ -68,6 +74,7 @@ extern "C" int quipb200_get_option(const char* name) {
   if (!strcmp(name, "gemv_warps")) return qb::g_opt_gemv_warps;
   if (!strcmp(name, "gemv_ctas_per_sm")) return qb::g_opt_gemv_ctas_per_sm;
   if (!strcmp(name, "stage_mask")) return qb::g_opt_stage_mask;
+  if (!strcmp(name, "fuse")) return qb::g_opt_fuse;
   return QUIPB200_EINVAL;
 }
 

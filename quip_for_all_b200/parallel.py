@@ -1,0 +1,187 @@
+"""Multi-GPU layer pipeline: one process per GPU, whole decoder layers per stage, activations shipped
+between stages with NCCL point-to-point over NVLink (torch.distributed).
+
+Why layers and not intra-linear shards: the Hadamard rotations of a QuantLinear span its full input
+and output dimensions, so a linear cannot be row/column sharded (the reference says the same,
+README.md:84); the reference's only multi-device facility keeps whole decoder blocks on one device
+(`no_split_module_classes`, quantizer.py:180-191, :831).  There is no collective on the data path --
+only the [1, 1, hidden] fp16 hand-off (8-16 KiB) per stage boundary and the 8-byte token id back to
+stage 0.
+
+Schedule.  P stages keep S = P independent bs=1 sequences in flight.  Time is cut into ticks; at tick
+t stage r runs one decode step of sequence (t - r) mod S, then ALL ranks do one ring exchange
+(rank r -> r+1, last -> 0) issued as a single grouped isend/irecv, which is deadlock-free under strict
+rendezvous semantics.  The token sampled by the last stage at tick t reaches stage 0 for tick t+1, which
+is exactly when stage 0 is due to run that sequence again.  One token leaves the pipeline per tick.
+"""
+import os
+import time
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+
+def partition_layers(n_layers: int, world: int) -> List[range]:
+    """Contiguous, near-equal slices of the decoder layers (earlier stages get the remainder)."""
+    base, rem = divmod(n_layers, world)
+    out, start = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append(range(start, start + n))
+        start += n
+    return out
+
+
+class RingPipeline:
+    """Tick driver.  `stage` must provide, for slot s in [0, S):
+         step(s)                      run one decode step of slot s in place
+         out_buffer(s) / in_buffer(s) tensors sent to the next stage / received from the previous one
+         scratch_in()                 a tensor shaped like in_buffer for discarded fill-phase traffic
+    """
+
+    def __init__(self, stage, rank: int, world: int, n_slots: int = None, group=None):
+        self.stage, self.rank, self.world = stage, rank, world
+        self.S = n_slots or world
+        assert world % self.S == 0 or self.S == world, "token feedback needs S | P"
+        self.group = group
+        self.nxt, self.prv = (rank + 1) % world, (rank - 1) % world
+        self.t = 0
+
+    def exchange(self, send_t: torch.Tensor, recv_t: torch.Tensor):
+        if self.world == 1:
+            recv_t.copy_(send_t)
+            return
+        ops = [dist.P2POp(dist.isend, send_t, self.nxt, self.group),
+               dist.P2POp(dist.irecv, recv_t, self.prv, self.group)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def tick(self):
+        t, r, S = self.t, self.rank, self.S
+        active = t >= r
+        s = (t - r) % S
+        if active:
+            self.stage.step(s)
+        s_next = (t + 1 - r) % S
+        sender_active = t >= ((r - 1) % self.world)      # was my upstream neighbour active this tick?
+        recv_t = self.stage.in_buffer(s_next) if sender_active else self.stage.scratch_in()
+        self.exchange(self.stage.out_buffer(s), recv_t)
+        self.t += 1
+        return active and r == self.world - 1            # True when this tick emitted a token
+
+
+# --------------------------------------------------------------------------------------------------
+# the real stage: a slice of a random-init quantised Llama, one decode engine per in-flight sequence
+# --------------------------------------------------------------------------------------------------
+class LlamaStage:
+    def __init__(self, model_name, codebook, rank, world, device, n_slots, cache_len, seed=0, use_graph=True):
+        from .modeling import LlamaDecodeEngine, llama_config, make_random_quantized_llama
+        cfg = llama_config(model_name)
+        self.layers = partition_layers(cfg.num_hidden_layers, world)[rank]
+        self.first, self.last = rank == 0, rank == world - 1
+        self.model = make_random_quantized_llama(cfg, codebook, seed=seed + rank, device=device,
+                                                 layer_range=self.layers)
+        self.engines = [LlamaDecodeEngine(self.model, max_cache_len=cache_len, first_stage=self.first,
+                                          last_stage=self.last, use_cuda_graph=use_graph)
+                        for _ in range(n_slots)]
+        e = self.engines[0]
+        self._scratch = torch.zeros_like(e.tok if self.first else e.hidden_in)
+        self.hidden = cfg.hidden_size
+        self.device = device
+
+    def step(self, s):
+        self.engines[s].step()
+
+    def out_buffer(self, s):
+        e = self.engines[s]
+        return e.tok if self.last else e.hidden_out
+
+    def in_buffer(self, s):
+        e = self.engines[s]
+        return e.tok if self.first else e.hidden_in
+
+    def scratch_in(self):
+        return self._scratch
+
+    @torch.no_grad()
+    def prefill_all(self, prompts, pipe: RingPipeline):
+        """Sequential prefill of every slot through the stages (one-time, not timed)."""
+        T = prompts[0].shape[1]
+        world, r = pipe.world, pipe.rank
+        hid = torch.zeros(1, T, self.hidden, dtype=torch.float16, device=self.device)
+        tokbuf = torch.zeros(1, 1, dtype=torch.long, device=self.device)
+        for s, ids in enumerate(prompts):
+            e = self.engines[s]
+            for stage in range(world):
+                if stage == r:
+                    out = e.prefill(ids.to(self.device) if self.first else hid)
+                    if not self.last:
+                        hid_out = out.contiguous()
+                if stage < world - 1:                     # ship [1,T,H] from `stage` to `stage+1`
+                    if r == stage:
+                        dist.send(hid_out, stage + 1)
+                    elif r == stage + 1:
+                        dist.recv(hid, stage)
+            # first token: last stage -> stage 0
+            if world > 1:
+                if self.last:
+                    dist.send(e.tok, 0)
+                elif self.first:
+                    dist.recv(tokbuf, world - 1)
+                    e.tok.copy_(tokbuf)
+        for e in self.engines:
+            e.capture()
+
+
+def run_pipeline_bench(a, metric):
+    """bench.py body for WORLD_SIZE > 1 (launched by torchrun, one rank per GPU)."""
+    import json
+    world = int(os.environ["WORLD_SIZE"])
+    rank = int(os.environ["RANK"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    S = world
+    cache_len = a.cache_len or (a.prompt_len + (a.steps + a.warmup) // S * 2 + 3 * S + 32)
+    stage = LlamaStage(a.model, a.codebook, rank, world, dev, S, cache_len, use_graph=not a.no_graph)
+    pipe = RingPipeline(stage, rank, world, S)
+    g = torch.Generator().manual_seed(0)
+    vocab = stage.model.config.vocab_size
+    prompts = [torch.randint(0, vocab, (1, a.prompt_len), generator=g) for _ in range(S)]
+    stage.prefill_all(prompts, pipe)
+    # fill + warm-up ticks
+    for _ in range(world - 1 + max(a.warmup, 3)):
+        pipe.tick()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        pipe.tick()                                       # one token leaves the pipeline per tick
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    if rank == 0:
+        from .modeling import LLAMA2_SHAPES
+        line = {
+            "metric": metric, "value": a.steps / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8 weights x int16 fixed-point activations (exact int32 dp4a), fp16 in/out",
+            "data": "synthetic",
+            "config": {"workload": f"{a.model} {a.codebook} bs=1 greedy decode, layer pipeline over {world} GPUs "
+                                   f"({world} independent bs=1 sequences in flight, one per stage), random-init "
+                                   f"packed weights, synthetic {a.prompt_len}-token prompts",
+                       "parallelism": f"pp{world} (whole decoder layers per stage, NCCL p2p ring exchange per tick)",
+                       "l2": "inputs larger than L2 (each stage streams its slice of the 1.6 GB of codes per tick)"},
+            "e2e": None, "gpu_launches": None, "clocks": None,
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()

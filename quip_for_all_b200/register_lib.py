@@ -50,6 +50,8 @@ def _hadamard_cuda(x: Tensor, scale: float) -> Tensor:
     xc = _contig(x)
     y = torch.empty_like(xc)
     rows = xc.numel() // n if n else 0
+    if rows == 0:
+        return y
     with torch.cuda.device(x.device):
         check(lib().quipb200_hadamard(_ptr(xc), _ptr(y), rows, n, float(scale), _DT[x.dtype], _stream()),
               "hadamard")
@@ -71,6 +73,8 @@ def _decompress_e8p(Qidxs: Tensor, grid: Tensor) -> Tensor:
     _check_q(Qidxs, torch.int16, "decompress_e8p_origorder")
     q = _contig(Qidxs)
     out = torch.empty((q.shape[0], q.shape[1] * 8), dtype=torch.float16, device=q.device)
+    if out.numel() == 0:
+        return out
     with torch.cuda.device(q.device):
         check(lib().quipb200_decompress_e8p(_ptr(q), _ptr(grid), _ptr(out), q.shape[0], q.shape[1], _stream()),
               "decompress_e8p_origorder")
@@ -81,6 +85,8 @@ def _decompress_e8prvq4(Qidxs: Tensor, grid: Tensor, scale: float) -> Tensor:
     _check_q(Qidxs, torch.int32, "decompress_e8prvq4_origorder")
     q = _contig(Qidxs)
     out = torch.empty((q.shape[0], q.shape[1] * 8), dtype=torch.float16, device=q.device)
+    if out.numel() == 0:
+        return out
     with torch.cuda.device(q.device):
         check(lib().quipb200_decompress_e8prvq4(_ptr(q), _ptr(grid), _ptr(out), q.shape[0], q.shape[1],
                                                 float(scale), _stream()), "decompress_e8prvq4_origorder")
@@ -92,6 +98,8 @@ def _decompress_e8prvq3(Qidxs: Tensor, grid: Tensor, grid2: Tensor, scale: float
     q = _contig(Qidxs)
     cols = q.shape[1] * 32 // 3
     out = torch.empty((q.shape[0], cols), dtype=torch.float16, device=q.device)
+    if out.numel() == 0:
+        return out
     with torch.cuda.device(q.device):
         check(lib().quipb200_decompress_e8prvq3(_ptr(q), _ptr(grid), _ptr(grid2), _ptr(out), q.shape[0],
                                                 cols // 8, float(scale), _stream()),
@@ -104,6 +112,8 @@ def _decompress_d4(Qidxs: Tensor, grid: Tensor) -> Tensor:
     q = _contig(Qidxs)
     g = _d4_grid_f16(grid)
     out = torch.empty((q.shape[0], q.shape[1] * 4), dtype=torch.float16, device=q.device)
+    if out.numel() == 0:
+        return out
     with torch.cuda.device(q.device):
         check(lib().quipb200_decompress_d4(_ptr(q), _ptr(g), _ptr(out), q.shape[0], q.shape[1], _stream()),
               "decompress_d4_origorder")
@@ -114,6 +124,8 @@ def _decompress_hi(Qidxs: Tensor) -> Tensor:
     _check_q(Qidxs, torch.int32, "decompress_hi_origorder")
     q = _contig(Qidxs)
     out = torch.empty((q.shape[0], q.shape[1] * 8), dtype=torch.float16, device=q.device)
+    if out.numel() == 0:
+        return out
     with torch.cuda.device(q.device):
         check(lib().quipb200_decompress_hi(_ptr(q), _ptr(out), q.shape[0], q.shape[1], _stream()),
               "decompress_hi_origorder")

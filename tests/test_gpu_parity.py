@@ -389,6 +389,7 @@ def _densify(model):
     import copy
     from quip_for_all_b200 import QuantLinear
     dense = copy.deepcopy(model)
+    dense.is_quantized = False
     for name, mod in list(dense.named_modules()):
         for cname, child in list(mod.named_children()):
             if isinstance(child, QuantLinear):
