@@ -126,6 +126,40 @@ int quipb200_linear_forward(const quipb200_linear_t* layer, const void* x_f16, i
                             void* y_f16, int64_t ldy, int M,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Grouped / hooked variant used by the decode engine (no reference counterpart: the reference leaves
+ * these element-wise ops to HF modules and hides their launches behind torch.compile CUDA graphs,
+ * example_generate.py:68-70).  Up to QUIPB200_MAX_GROUP QuantLinears that read the SAME input
+ * (q/k/v or gate/up of a decoder layer) run in ONE launch, optionally with the ops that surround them
+ * folded in:
+ *   pre_norm_weight : x <- LlamaRMSNorm(x) (fp32 statistics, fp16 result times fp16 weight)   before SU
+ *   gate            : x <- silu(gate) * x   (LlamaMLP: act_fn(gate_proj(h)) * up_proj(h))      before SU
+ *   residual        : y <- residual + y     (decoder-layer skip connection)                    after bias
+ * ------------------------------------------------------------------------------------------- */
+#define QUIPB200_MAX_GROUP 3
+typedef struct quipb200_fusion {
+  const void* pre_norm_weight;   /* fp16 [in_features] or NULL */
+  float pre_norm_eps;
+  int32_t reserved;
+  const void* gate;              /* fp16 [M, in_features] (row pitch ldgate) or NULL */
+  int64_t ldgate;
+  const void* residual;          /* fp16 [M, out_features] (row pitch ldres) or NULL; may alias y */
+  int64_t ldres;
+} quipb200_fusion_t;
+
+size_t quipb200_linear_group_workspace_bytes(const quipb200_linear_t* layers, int n_layers, int M);
+int quipb200_linear_group_forward(const quipb200_linear_t* layers, int n_layers,
+                                  const quipb200_fusion_t* fusion /* may be NULL */,
+                                  const void* x_f16, int64_t ldx, void* const* y_f16, const int64_t* ldy,
+                                  int M, void* workspace, size_t workspace_bytes, void* stream);
+
+/* RoPE (HF rotate_half convention) + KV-cache append + single-query attention, one CTA per head.
+ * q [n_heads*head_dim], k/v [n_kv_heads*head_dim] fp16; caches [n_kv_heads, max_len, head_dim] fp16;
+ * cos/sin [max_len, head_dim] fp16; *pos = index of the new token (device memory, graph-replayable). */
+int quipb200_attn_decode(const void* q, const void* k, const void* v, void* k_cache, void* v_cache,
+                         const void* cos_t, const void* sin_t, const int64_t* pos, void* out,
+                         int n_heads, int n_kv_heads, int head_dim, int max_len, void* stream);
+
 /* Tuning / introspection hooks used by bench.py and the tests (not part of the reference surface). */
 int quipb200_set_option(const char* name, int value);   /* e.g. "gemv_table_repl" = 1|16 */
 int quipb200_get_option(const char* name);

@@ -22,6 +22,7 @@ EXPORTS = [
     "quipb200_decompress_e8prvq3", "quipb200_decompress_hi",
     "quipb200_mm_workspace_bytes", "quipb200_mm",
     "quipb200_linear_workspace_bytes", "quipb200_linear_forward",
+    "quipb200_linear_group_workspace_bytes", "quipb200_linear_group_forward", "quipb200_attn_decode",
     "quipb200_set_option", "quipb200_get_option", "quipb200_launch_count",
 ]
 
@@ -35,6 +36,12 @@ class LinearDesc(Structure):
         ("qidxs", c_void_p), ("grid", c_void_p), ("SU", c_void_p), ("SV", c_void_p), ("bias", c_void_p),
         ("had_left", c_void_p), ("had_right", c_void_p), ("wscale_pc", c_void_p),
     ]
+
+
+class Fusion(Structure):
+    """struct quipb200_fusion (include/quip_b200.h)."""
+    _fields_ = [("pre_norm_weight", c_void_p), ("pre_norm_eps", c_float), ("reserved", c_int32),
+                ("gate", c_void_p), ("ldgate", c_int64), ("residual", c_void_p), ("ldres", c_int64)]
 
 
 class QuipB200Error(RuntimeError):
@@ -70,12 +77,18 @@ def lib():
     L.quipb200_linear_workspace_bytes.restype = c_size_t
     L.quipb200_linear_workspace_bytes.argtypes = [POINTER(LinearDesc), c_int]
     L.quipb200_linear_forward.argtypes = [POINTER(LinearDesc), vp, c_int64, vp, c_int64, c_int, vp, c_size_t, vp]
+    L.quipb200_linear_group_workspace_bytes.restype = c_size_t
+    L.quipb200_linear_group_workspace_bytes.argtypes = [POINTER(LinearDesc), c_int, c_int]
+    L.quipb200_linear_group_forward.argtypes = [POINTER(LinearDesc), c_int, POINTER(Fusion), vp, c_int64,
+                                                POINTER(c_void_p), POINTER(c_int64), c_int, vp, c_size_t, vp]
+    L.quipb200_attn_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp]
     L.quipb200_set_option.argtypes = [c_char_p, c_int]
     L.quipb200_get_option.argtypes = [c_char_p]
     L.quipb200_launch_count.restype = c_int64
     for fn in ("quipb200_hadamard", "quipb200_decompress_e8p", "quipb200_decompress_e8prvq4",
                "quipb200_decompress_d4", "quipb200_decompress_e8prvq3", "quipb200_decompress_hi",
-               "quipb200_mm", "quipb200_linear_forward", "quipb200_set_option", "quipb200_get_option"):
+               "quipb200_mm", "quipb200_linear_forward", "quipb200_linear_group_forward", "quipb200_attn_decode",
+               "quipb200_set_option", "quipb200_get_option"):
         getattr(L, fn).restype = c_int
     if L.quipb200_abi_version() != 1:
         raise QuipB200Error("libquipb200.so ABI version mismatch")

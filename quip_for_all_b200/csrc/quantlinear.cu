@@ -1,14 +1,15 @@
 // Fused QuantLinear.forward for the decode regime (small M) -- the hot path.
 //
-//   ONE kernel per call when the input dim is a power of two (q,k,v,o,gate,up of Llama-2):
+//   ONE kernel per call (or per group of up to 3 linears sharing an input: q/k/v, gate/up):
 //     phase 0  every warp issues the 128-bit loads of its first packed-code rows (HBM latency starts now)
 //     phase 1  every CTA redundantly computes x' = H (SU.x) * wscale/sqrt(n) in shared memory and
 //              quantises it to 16-bit fixed point (hidden behind the phase-0 loads)
 //     phase 2  GEMV: int8-decode(Qidxs) . x_q as exact integer dp4a on CUDA cores, full rows per CTA
 //     phase 3  the last CTA to finish (atomic ticket) runs the output side:
-//              *scale -> [*Wscale_pc] -> (hadK (x) H)/sqrt(L) -> [:out] -> *SV -> +bias
-//   Non power-of-two input dims (down_proj: 11008 = 43 * 256) run the input rotation in a 1-CTA
-//   prologue kernel first (2 launches).
+//              *scale -> [*Wscale_pc] -> (hadK (x) H)/sqrt(L) -> [:out] -> *SV -> +bias [-> +residual]
+//   Non power-of-two input dims (down_proj: 11008 = 43 * 256) run the input rotation -- FWHT blocks
+//   plus a 43x43 orthogonal mix on the legacy tensor path (mma.sync) -- in a 1-CTA prologue kernel
+//   first (2 launches).
 //
 // Reference chain replaced: qlinear.py:87-115 -> quant.py:72-88 -> register_lib.py:18-38 ->
 // origin_order.cu:388-555 (K1) / fast_hadamard_transform_cuda: 5-9 launches per call.
@@ -37,100 +38,173 @@ constexpr int PRO_THREADS = 512;
 constexpr int GEMV_MAX_WARPS = 16;
 constexpr int GEMV_UNROLL = 4;
 constexpr int COUNTER_SLOTS = 4096;
+constexpr int CH = 2;        // octets (8 elements) a thread keeps in flight per round in the rotations
 
 // tickets for the last-CTA-done epilogue: zero at module load, reset by the CTA that consumes them.
-// One slot per launch, handed out round-robin by the host; launches that share a slot must not
-// overlap in time (4096 slots; a captured 7B decode step uses 224).
+// One slot per launched linear, handed out round-robin by the host; launches that share a slot must
+// not overlap in time (4096 slots; a captured 7B decode step uses 224).
 __device__ unsigned int g_counters[COUNTER_SLOTS * QUIPB200_MM_MAX_M];
 static unsigned int g_next_slot = 0;
 
 // ---------------------------------------------------------------------------------------------
-// shared layout helpers for the rotations
+// rotation workspace in shared memory
+//   s  : fp32 butterfly array, padded (spad)
+//   t  : fp16 result.  K == 1: t[i].  K > 1: K rows of stride Ls = L + 8 halfs (+ one zero row) --
+//        the layout ldmatrix wants; the orthogonal mix runs IN PLACE on it.
+//   hk : fp16 [Kp][Kp] coefficient matrix M[k_out][k_in], zero padded to Kp = roundup16(K)
 // ---------------------------------------------------------------------------------------------
 struct RotSmem {
-  float* s;      // spad(q) floats (butterfly workspace)
-  __half* t;     // q halves (rotated vector, fp16-rounded)
-  __half* hk;    // K*K halves, laid out [k_in][k_out]
-  float* red;    // 32 floats
+  float* s;
+  __half* t;
+  __half* hk;
+  float* red;
+  int Ls;       // row stride of t (halfs)
+  int log2L;
 };
 
+static inline int kpad(int K) { return (K + 15) / 16 * 16; }
+static inline size_t rot_t_halfs(int q, int K) { return K > 1 ? (size_t)(K + 1) * (q / K + 8) : (size_t)q; }
 static inline size_t rot_smem_bytes(int q, int K) {
-  size_t b = spad_host((size_t)q) * sizeof(float);
-  b += ((size_t)q * sizeof(__half) + 15) / 16 * 16;
-  b += ((size_t)K * K * sizeof(__half) + 15) / 16 * 16;
+  size_t b = (spad_host((size_t)q) * sizeof(float) + 15) / 16 * 16;
+  b += (rot_t_halfs(q, K) * sizeof(__half) + 15) / 16 * 16;
+  if (K > 1) b += (size_t)kpad(K) * kpad(K) * sizeof(__half);
   b += 32 * sizeof(float);
   return (b + 15) / 16 * 16;
 }
 
-__device__ __forceinline__ RotSmem rot_carve(unsigned char* base, int q, int K) {
+__device__ __forceinline__ RotSmem rot_carve(unsigned char* base, int q, int K, int log2L) {
   RotSmem r;
   r.s = reinterpret_cast<float*>(base);
-  size_t off = ((size_t)(q + ((q >> 6) << 3) + 8)) * sizeof(float);
+  size_t off = (((size_t)(q + ((q >> 6) << 3) + 8)) * sizeof(float) + 15) / 16 * 16;
   r.t = reinterpret_cast<__half*>(base + off);
-  off += ((size_t)q * sizeof(__half) + 15) / 16 * 16;
+  const size_t th = K > 1 ? (size_t)(K + 1) * ((q / K) + 8) : (size_t)q;
+  off += (th * sizeof(__half) + 15) / 16 * 16;
   r.hk = reinterpret_cast<__half*>(base + off);
-  off += ((size_t)K * K * sizeof(__half) + 15) / 16 * 16;
+  if (K > 1) {
+    const int Kp = (K + 15) / 16 * 16;
+    off += (size_t)Kp * Kp * sizeof(__half);
+  }
   r.red = reinterpret_cast<float*>(base + off);
+  r.Ls = K > 1 ? (q / K) + 8 : q;
+  r.log2L = log2L;
   return r;
 }
 
-// Rotation: in: s[spad(i)] (fp32), out: t[i] (fp16) = round( (hadK' (x) H_L) s * scale ).
-// Rounding points follow the reference: fp16 after the FWHT*scale (register_lib.py:20), fp16 after
-// hadK@ (quant.py:83).  `hk` holds coef[k_in][k_out].  transform == 0: t = round(s).
-__device__ __forceinline__ void rotate_smem(const RotSmem& sm, int q, int K, int log2L, float scale,
-                                            int transform, int tid, int nt) {
+__device__ __forceinline__ int t_index(const RotSmem& sm, int K, int i) {
+  return K > 1 ? (i >> sm.log2L) * sm.Ls + (i & ((1 << sm.log2L) - 1)) : i;
+}
+
+// coefficient matrix M[k_out][k_in] = hadK[k_out][k_in] (output side) or hadK[k_in][k_out] (input side,
+// hadK^T; quant.py:79-80), zero padded
+__device__ __forceinline__ void load_hadK(const RotSmem& sm, const __half* hadK, int K, int transpose, int tid,
+                                          int nt) {
+  if (K <= 1 || hadK == nullptr) return;
+  const int Kp = (K + 15) / 16 * 16;
+  for (int i = tid; i < Kp * Kp; i += nt) {
+    const int ko = i / Kp, ki = i - ko * Kp;
+    __half v = __float2half_rn(0.f);
+    if (ko < K && ki < K) v = transpose ? hadK[ki * K + ko] : hadK[ko * K + ki];
+    sm.hk[i] = v;
+  }
+}
+
+// In-place mix t <- M t on the tensor path.  One warp owns an 8-column tile: it reads every B fragment
+// of that tile before it writes, so in-place is safe.  fp16 operands, fp32 accumulate, one fp16
+// rounding -- the arithmetic of the reference's `hadK @ input` fp16 GEMM (quant.py:83).
+template <int MT>   // MT = Kp / 16 (1..4); larger blocks (use_rand=False K=172) take the CUDA-core mix
+__device__ __forceinline__ void mix_mma_tiles(const RotSmem& sm, int K, int warp, int lane, int nwarps) {
+  const int L = 1 << sm.log2L, Kp = MT * 16;
+  const int g = lane >> 2, tq = lane & 3;
+  for (int nt_i = warp; nt_i < (L >> 3); nt_i += nwarps) {
+    const int c0 = nt_i << 3;
+    uint32_t bf[MT][2];
+#pragma unroll
+    for (int kt = 0; kt < MT; kt++) {
+      int r = kt * 16 + (lane & 15);
+      if (r >= K) r = K;                                   // the zero row
+      ldmatrix_x2_trans(bf[kt], sm.t + (size_t)r * sm.Ls + c0);
+    }
+    float acc[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[mt][j] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < MT; kt++) {
+        uint32_t af[4];
+        ldmatrix_x4(af, sm.hk + (size_t)(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * Kp + kt * 16 + (lane >> 4) * 8);
+        mma_16816(acc[mt], af, bf[kt]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      if (r0 < K)
+        *reinterpret_cast<__half2*>(sm.t + (size_t)r0 * sm.Ls + c0 + tq * 2) = __floats2half2_rn(acc[mt][0], acc[mt][1]);
+      if (r1 < K)
+        *reinterpret_cast<__half2*>(sm.t + (size_t)r1 * sm.Ls + c0 + tq * 2) = __floats2half2_rn(acc[mt][2], acc[mt][3]);
+    }
+  }
+}
+
+// Rotation: in: s[spad(i)] (fp32) with butterfly stages [0, b0) already applied;
+// out: t (fp16) = round( (M (x) H_L) s * scale ).  Rounding points follow the reference: fp16 after
+// the FWHT*scale (register_lib.py:20), fp16 after hadK@ (quant.py:83).  transform == 0: t = round(s).
+__device__ __forceinline__ void rotate_smem(const RotSmem& sm, int q, int K, float scale, int transform, int b0,
+                                            int tid, int nt) {
   if (!transform) {
     for (int i = tid; i < q; i += nt) sm.t[i] = __float2half_rn(sm.s[spad(i)]);
     __syncthreads();
     return;
   }
-  fwht_smem(sm.s, q, log2L, 0, tid, nt);
+  fwht_smem(sm.s, q, sm.log2L, b0, tid, nt);
   if (K == 1) {
     for (int i = tid; i < q; i += nt) sm.t[i] = __float2half_rn(sm.s[spad(i)] * scale);
     __syncthreads();
     return;
   }
+  const int L = 1 << sm.log2L;
+  const int Kp = (K + 15) / 16 * 16;
+  if (L >= 8 && Kp <= 64) {
+    for (int i = tid; i < q; i += nt) sm.t[t_index(sm, K, i)] = __float2half_rn(sm.s[spad(i)] * scale);
+    for (int i = tid; i < sm.Ls; i += nt) sm.t[(size_t)K * sm.Ls + i] = __float2half_rn(0.f);
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+    switch (Kp >> 4) {
+      case 1: mix_mma_tiles<1>(sm, K, warp, lane, nwarps); break;
+      case 2: mix_mma_tiles<2>(sm, K, warp, lane, nwarps); break;
+      case 3: mix_mma_tiles<3>(sm, K, warp, lane, nwarps); break;
+      default: mix_mma_tiles<4>(sm, K, warp, lane, nwarps); break;
+    }
+    __syncthreads();
+    return;
+  }
+  // generic CUDA-core mix (tiny blocks / very large K): out-of-place from s into t
   for (int i = tid; i < q; i += nt) sm.s[spad(i)] = f16_round(sm.s[spad(i)] * scale);
   __syncthreads();
-  const int L = 1 << log2L;
-  const int ktiles = (K + 7) >> 3;
-  const int ntasks = ktiles << log2L;
-  for (int task = tid; task < ntasks; task += nt) {
-    const int c = task & (L - 1);
-    const int k0 = (task >> log2L) << 3;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = 0.f;
-    for (int kp = 0; kp < K; kp++) {
-      const float tv = sm.s[spad((kp << log2L) + c)];
-      const __half* row = sm.hk + kp * K + k0;
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-        if (k0 + j < K) acc[j] = fmaf(__half2float(row[j]), tv, acc[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; j++)
-      if (k0 + j < K) sm.t[((k0 + j) << log2L) + c] = __float2half_rn(acc[j]);
+  for (int i = tid; i < q; i += nt) {
+    const int ko = i >> sm.log2L, c = i & (L - 1);
+    float acc = 0.f;
+    for (int kp = 0; kp < K; kp++)
+      acc = fmaf(__half2float(sm.hk[ko * Kp + kp]), sm.s[spad((kp << sm.log2L) + c)], acc);
+    sm.t[t_index(sm, K, i)] = __float2half_rn(acc);
   }
   __syncthreads();
 }
 
-__device__ __forceinline__ void load_hadK(const RotSmem& sm, const __half* hadK, int K, int transpose,
-                                          int tid, int nt) {
-  // want coef[k_in][k_out]; y[k_out] = sum_kin M[k_out][k_in] t[k_in], M = hadK (or hadK^T)
-  if (K <= 1 || hadK == nullptr) return;
-  for (int i = tid; i < K * K; i += nt) {
-    const int kin = i / K, kout = i - kin * K;
-    sm.hk[i] = transpose ? hadK[kin * K + kout] : hadK[kout * K + kin];
-  }
-}
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 
 // ---------------------------------------------------------------------------------------------
-// input side: x*SU -> rotation -> 16-bit fixed point records
+// input side: [rmsnorm] [silu(gate)*x] x*SU -> rotation -> 16-bit fixed point records
 // ---------------------------------------------------------------------------------------------
 struct PrologueArgs {
   const __half* x;
   int64_t ldx;
+  const __half* gate;     // optional: x <- silu(gate) * x
+  int64_t ldgate;
+  const __half* norm_w;   // optional: x <- rmsnorm(x) * norm_w
+  float norm_eps;
   const __half* SU;
   const __half* hadK;
   int K, in_features, q_in, log2L, transform;
@@ -139,55 +213,162 @@ struct PrologueArgs {
   float* xscale;   // [M]
 };
 
+__device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// element-wise pre-ops on 8 consecutive inputs (rounding points = the fp16 tensor ops HF / the reference issue)
+__device__ __forceinline__ void pre_ops(float (&f)[8], const float (&g)[8], bool has_gate, const float (&w)[8],
+                                        bool has_norm, float rstd, const float (&su)[8], bool has_su) {
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    float v = f[j];
+    if (has_gate) v = f16_round(f16_round(silu_f(g[j])) * v);   // LlamaMLP: act_fn(gate) * up
+    if (has_norm) v = f16_round(__half2float(__float2half_rn(v * rstd)) * w[j]);   // LlamaRMSNorm
+    if (has_su) v = f16_round(v * su[j]);                        // qlinear.py:91
+    f[j] = v;
+  }
+}
+
 // Computes the records into `dst` (shared or global) and returns the fixed-point scale.
 __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned char* rot_base, uint4* dst, int m,
                                                int tid, int nt) {
-  const RotSmem sm = rot_carve(rot_base, a.q_in, a.K);
+  const RotSmem sm = rot_carve(rot_base, a.q_in, a.K, a.log2L);
   const __half* xr = a.x + (size_t)m * a.ldx;
+  const __half* gr = a.gate ? a.gate + (size_t)m * a.ldgate : nullptr;
   load_hadK(sm, a.hadK, a.K, /*transpose=*/1, tid, nt);
-  for (int i = tid; i < a.q_in; i += nt) {
-    float v = 0.f;
-    if (i < a.in_features) {
-      v = __half2float(xr[i]);
-      if (a.SU) v = f16_round(v * __half2float(a.SU[i]));  // qlinear.py:91 (fp16 tensor op)
+  const int noct = a.q_in >> 3;
+  const int noct_in = a.in_features >> 3;
+  const bool vec = (a.in_features & 7) == 0 && al16(xr) && (!gr || al16(gr)) && (!a.SU || al16(a.SU)) &&
+                   (!a.norm_w || al16(a.norm_w));
+  const bool reg_pass = a.transform && a.log2L >= 3;   // first radix-8 butterfly in registers
+  float rstd = 1.f;
+  const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (vec) {
+    const bool single = noct <= nt * CH;    // everything fits one round: no re-read for the norm
+    uint4 xv[CH];
+    if (a.norm_w) {
+      float ss = 0.f;
+      for (int base = 0; base < noct_in; base += nt * CH) {
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+          const int idx = base + c * nt + tid;
+          xv[c] = make_uint4(0, 0, 0, 0);
+          if (idx < noct_in) xv[c] = *reinterpret_cast<const uint4*>(xr + (size_t)idx * 8);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+          float f[8];
+          unpack_h8(xv[c], f);
+          if (gr) {   // the norm never follows a gate in Llama; keep the generic order anyway
+            const int idx = base + c * nt + tid;
+            float g[8];
+            if (idx < noct_in) {
+              unpack_h8(*reinterpret_cast<const uint4*>(gr + (size_t)idx * 8), g);
+#pragma unroll
+              for (int j = 0; j < 8; j++) f[j] = f16_round(f16_round(silu_f(g[j])) * f[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) ss = fmaf(f[j], f[j], ss);
+        }
+      }
+      ss = block_sum(ss, sm.red, tid, nt);
+      rstd = rsqrtf(ss / (float)a.in_features + a.norm_eps);
     }
-    sm.s[spad(i)] = v;
+    for (int base = 0; base < noct; base += nt * CH) {
+      uint4 gv[CH], wv[CH], sv[CH];
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        const int idx = base + c * nt + tid;
+        const bool in = idx < noct_in;
+        if (!(a.norm_w && single)) {
+          xv[c] = make_uint4(0, 0, 0, 0);
+          if (in) xv[c] = *reinterpret_cast<const uint4*>(xr + (size_t)idx * 8);
+        }
+        gv[c] = wv[c] = sv[c] = make_uint4(0, 0, 0, 0);
+        if (in && gr) gv[c] = *reinterpret_cast<const uint4*>(gr + (size_t)idx * 8);
+        if (in && a.norm_w) wv[c] = *reinterpret_cast<const uint4*>(a.norm_w + (size_t)idx * 8);
+        if (in && a.SU) sv[c] = *reinterpret_cast<const uint4*>(a.SU + (size_t)idx * 8);
+      }
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        const int idx = base + c * nt + tid;
+        if (idx < noct) {
+          float f[8], g[8], w[8], su[8];
+          unpack_h8(xv[c], f);
+          unpack_h8(gv[c], g);
+          unpack_h8(wv[c], w);
+          unpack_h8(sv[c], su);
+          if (idx < noct_in) pre_ops(f, g, gr != nullptr, w, a.norm_w != nullptr, rstd, su, a.SU != nullptr);
+          if (reg_pass) butterfly_regs<3>(f);
+          float4* d = reinterpret_cast<float4*>(sm.s + spad(idx * 8));
+          d[0] = make_float4(f[0], f[1], f[2], f[3]);
+          d[1] = make_float4(f[4], f[5], f[6], f[7]);
+        }
+      }
+    }
+  } else {
+    if (a.norm_w) {
+      float ss = 0.f;
+      for (int i = tid; i < a.in_features; i += nt) {
+        float v = __half2float(xr[i]);
+        if (gr) v = f16_round(f16_round(silu_f(__half2float(gr[i]))) * v);
+        ss = fmaf(v, v, ss);
+      }
+      ss = block_sum(ss, sm.red, tid, nt);
+      rstd = rsqrtf(ss / (float)a.in_features + a.norm_eps);
+    }
+    for (int i = tid; i < a.q_in; i += nt) {
+      float v = 0.f;
+      if (i < a.in_features) {
+        v = __half2float(xr[i]);
+        if (gr) v = f16_round(f16_round(silu_f(__half2float(gr[i]))) * v);
+        if (a.norm_w) v = f16_round(__half2float(__float2half_rn(v * rstd)) * __half2float(a.norm_w[i]));
+        if (a.SU) v = f16_round(v * __half2float(a.SU[i]));
+      }
+      sm.s[spad(i)] = v;
+    }
   }
+  (void)zero8;
   __syncthreads();
-  rotate_smem(sm, a.q_in, a.K, a.log2L, a.scale, a.transform, tid, nt);
+  rotate_smem(sm, a.q_in, a.K, a.scale, a.transform, (vec && reg_pass) ? 3 : 0, tid, nt);
 
-  // abs-max -> 16-bit fixed-point scale
+  // abs-max -> 16-bit fixed-point scale, then the records
+  const int L = 1 << a.log2L;
+  const bool rowvec = (a.K == 1) || (L >= 8);    // 8 consecutive outputs are contiguous (and 16-B aligned) in t
   float mx = 0.f;
-  for (int i = tid; i < a.q_in; i += nt) mx = fmaxf(mx, fabsf(__half2float(sm.t[i])));
-  mx = warp_max(mx);
-  if ((tid & 31) == 0) sm.red[tid >> 5] = mx;
-  __syncthreads();
-  if (tid < 32) {
-    float v = (tid < (nt >> 5)) ? sm.red[tid] : 0.f;
-    v = warp_max(v);
-    if (tid == 0) sm.red[0] = v;
+  if (rowvec) {
+    for (int sgi = tid; sgi < noct; sgi += nt) {
+      float f[8];
+      unpack_h8(*reinterpret_cast<const uint4*>(sm.t + t_index(sm, a.K, sgi * 8)), f);
+#pragma unroll
+      for (int j = 0; j < 8; j++) mx = fmaxf(mx, fabsf(f[j]));
+    }
+  } else {
+    for (int i = tid; i < a.q_in; i += nt) mx = fmaxf(mx, fabsf(__half2float(sm.t[t_index(sm, a.K, i)])));
   }
-  __syncthreads();
-  mx = sm.red[0];
+  mx = block_max(mx, sm.red, tid, nt);
   const float inv = (mx > 0.f) ? 32767.0f / mx : 0.f;
-
-  const int nseg = a.q_in >> 3;
-  for (int sgi = tid; sgi < nseg; sgi += nt) {
-    int qv[8];
+  for (int sgi = tid; sgi < noct; sgi += nt) {
+    float f[8];
+    if (rowvec) {
+      unpack_h8(*reinterpret_cast<const uint4*>(sm.t + t_index(sm, a.K, sgi * 8)), f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) f[j] = __half2float(sm.t[t_index(sm, a.K, sgi * 8 + j)]);
+    }
+    uint32_t hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      int v = __float2int_rn(__half2float(sm.t[sgi * 8 + j]) * inv);
-      qv[j] = max(-32767, min(32767, v));
+      int v = __float2int_rn(f[j] * inv);
+      v = max(-32767, min(32767, v));
+      hi[j] = (uint32_t)(v >> 8) & 0xffu;
+      lo[j] = (uint32_t)v & 0xffu;
     }
     uint4 r;
-    r.x = ((uint32_t)(qv[0] >> 8) & 0xffu) | (((uint32_t)(qv[1] >> 8) & 0xffu) << 8) |
-          (((uint32_t)(qv[2] >> 8) & 0xffu) << 16) | (((uint32_t)(qv[3] >> 8) & 0xffu) << 24);
-    r.y = ((uint32_t)(qv[4] >> 8) & 0xffu) | (((uint32_t)(qv[5] >> 8) & 0xffu) << 8) |
-          (((uint32_t)(qv[6] >> 8) & 0xffu) << 16) | (((uint32_t)(qv[7] >> 8) & 0xffu) << 24);
-    r.z = ((uint32_t)qv[0] & 0xffu) | (((uint32_t)qv[1] & 0xffu) << 8) | (((uint32_t)qv[2] & 0xffu) << 16) |
-          (((uint32_t)qv[3] & 0xffu) << 24);
-    r.w = ((uint32_t)qv[4] & 0xffu) | (((uint32_t)qv[5] & 0xffu) << 8) | (((uint32_t)qv[6] & 0xffu) << 16) |
-          (((uint32_t)qv[7] & 0xffu) << 24);
+    r.x = hi[0] | (hi[1] << 8) | (hi[2] << 16) | (hi[3] << 24);
+    r.y = hi[4] | (hi[5] << 8) | (hi[6] << 16) | (hi[7] << 24);
+    r.z = lo[0] | (lo[1] << 8) | (lo[2] << 16) | (lo[3] << 24);
+    r.w = lo[4] | (lo[5] << 8) | (lo[6] << 16) | (lo[7] << 24);
     dst[sgi] = r;
   }
   return (mx > 0.f) ? mx / 32767.0f : 0.f;
@@ -215,32 +396,119 @@ struct EpilogueArgs {
   float scale;           // 1/sqrt(L)
   const __half* SV;
   const __half* bias;
+  const __half* residual;   // optional skip connection added after the bias (may alias y)
+  int64_t ldres;
   __half* y;
   int64_t ldy;
 };
 
 __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned char* rot_base, int m, float xscale,
                                               int tid, int nt) {
-  const RotSmem sm = rot_carve(rot_base, a.q_out, a.K);
+  const RotSmem sm = rot_carve(rot_base, a.q_out, a.K, a.log2L);
   load_hadK(sm, a.hadK, a.K, /*transpose=*/0, tid, nt);
   const float xs = xscale * a.unit;
   const float* ar = a.acc + (size_t)m * a.q_out;
   const float* ar2 = a.acc2 ? a.acc2 + (size_t)m * a.q_out : nullptr;
-  for (int i = tid; i < a.q_out; i += nt) {
-    float v = __ldcg(ar + i);
-    if (ar2) v = fmaf(a.resid_scale, __ldcg(ar2 + i), v);
-    v = f16_round(v * xs);                                             // mm output is fp16 (origin_order.cu:129)
-    if (a.wscale_pc) v = f16_round(v * __half2float(a.wscale_pc[i]));  // qlinear.py:107
-    sm.s[spad(i)] = v;
+  const int noct = a.q_out >> 3;
+  const bool reg_pass = a.transform && a.log2L >= 3;
+  const bool vec_in = (a.q_out & 7) == 0 && al16(ar) && (!ar2 || al16(ar2));
+  if (vec_in) {
+    for (int base = 0; base < noct; base += nt * CH) {
+      float4 v0[CH], v1[CH], w0[CH], w1[CH];
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        const int idx = base + c * nt + tid;
+        v0[c] = v1[c] = w0[c] = w1[c] = make_float4(0, 0, 0, 0);
+        if (idx < noct) {
+          v0[c] = __ldcg(reinterpret_cast<const float4*>(ar + (size_t)idx * 8));
+          v1[c] = __ldcg(reinterpret_cast<const float4*>(ar + (size_t)idx * 8) + 1);
+          if (ar2) {
+            w0[c] = __ldcg(reinterpret_cast<const float4*>(ar2 + (size_t)idx * 8));
+            w1[c] = __ldcg(reinterpret_cast<const float4*>(ar2 + (size_t)idx * 8) + 1);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        const int idx = base + c * nt + tid;
+        if (idx < noct) {
+          float f[8] = {v0[c].x, v0[c].y, v0[c].z, v0[c].w, v1[c].x, v1[c].y, v1[c].z, v1[c].w};
+          const float r[8] = {w0[c].x, w0[c].y, w0[c].z, w0[c].w, w1[c].x, w1[c].y, w1[c].z, w1[c].w};
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float v = f[j];
+            if (ar2) v = fmaf(a.resid_scale, r[j], v);
+            v = f16_round(v * xs);                                                          // origin_order.cu:129
+            if (a.wscale_pc) v = f16_round(v * __half2float(a.wscale_pc[idx * 8 + j]));   // qlinear.py:107
+            f[j] = v;
+          }
+          if (reg_pass) butterfly_regs<3>(f);
+          float4* d = reinterpret_cast<float4*>(sm.s + spad(idx * 8));
+          d[0] = make_float4(f[0], f[1], f[2], f[3]);
+          d[1] = make_float4(f[4], f[5], f[6], f[7]);
+        }
+      }
+    }
+  } else {
+    for (int i = tid; i < a.q_out; i += nt) {
+      float v = __ldcg(ar + i);
+      if (ar2) v = fmaf(a.resid_scale, __ldcg(ar2 + i), v);
+      v = f16_round(v * xs);
+      if (a.wscale_pc) v = f16_round(v * __half2float(a.wscale_pc[i]));
+      sm.s[spad(i)] = v;
+    }
   }
   __syncthreads();
-  rotate_smem(sm, a.q_out, a.K, a.log2L, a.scale, a.transform, tid, nt);
+  rotate_smem(sm, a.q_out, a.K, a.scale, a.transform, (vec_in && reg_pass) ? 3 : 0, tid, nt);
+
   __half* yr = a.y + (size_t)m * a.ldy;
-  for (int i = tid; i < a.out_features; i += nt) {
-    float v = __half2float(sm.t[i]);
-    if (a.SV) v = f16_round(v * __half2float(a.SV[i]));  // qlinear.py:112
-    if (a.bias) v = v + __half2float(a.bias[i]);         // qlinear.py:114
-    yr[i] = __float2half_rn(v);
+  const __half* rr = a.residual ? a.residual + (size_t)m * a.ldres : nullptr;
+  const int L = 1 << a.log2L;
+  const bool vec_out = (a.out_features & 7) == 0 && al16(yr) && (!a.SV || al16(a.SV)) && (!a.bias || al16(a.bias)) &&
+                       (!rr || al16(rr)) && ((a.K == 1) || L >= 8);
+  if (vec_out) {
+    const int noct_out = a.out_features >> 3;
+    for (int base = 0; base < noct_out; base += nt * CH) {
+      uint4 sv[CH], bv[CH], rv[CH];
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        const int idx = base + c * nt + tid;
+        sv[c] = bv[c] = rv[c] = make_uint4(0, 0, 0, 0);
+        if (idx < noct_out) {
+          if (a.SV) sv[c] = *reinterpret_cast<const uint4*>(a.SV + (size_t)idx * 8);
+          if (a.bias) bv[c] = *reinterpret_cast<const uint4*>(a.bias + (size_t)idx * 8);
+          if (rr) rv[c] = *reinterpret_cast<const uint4*>(rr + (size_t)idx * 8);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        const int idx = base + c * nt + tid;
+        if (idx < noct_out) {
+          float f[8], s8[8], b8[8], r8[8];
+          unpack_h8(*reinterpret_cast<const uint4*>(sm.t + t_index(sm, a.K, idx * 8)), f);
+          unpack_h8(sv[c], s8);
+          unpack_h8(bv[c], b8);
+          unpack_h8(rv[c], r8);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float v = f[j];
+            if (a.SV) v = f16_round(v * s8[j]);      // qlinear.py:112
+            if (a.bias) v = f16_round(v + b8[j]);    // qlinear.py:114
+            if (rr) v = v + r8[j];                   // decoder-layer residual (fusion hook)
+            f[j] = v;
+          }
+          *reinterpret_cast<uint4*>(yr + (size_t)idx * 8) = pack_h8(f);
+        }
+      }
+    }
+  } else {
+    for (int i = tid; i < a.out_features; i += nt) {
+      float v = __half2float(sm.t[t_index(sm, a.K, i)]);
+      if (a.SV) v = f16_round(v * __half2float(a.SV[i]));
+      if (a.bias) v = f16_round(v + __half2float(a.bias[i]));
+      if (rr) v = v + __half2float(rr[i]);
+      yr[i] = __float2half_rn(v);
+    }
   }
 }
 
@@ -257,12 +525,17 @@ struct GemvArgs {
   int64_t row_bytes;
   const void* table;           // E8P: uint2[256]; D4: fp16 [256][4]
   int N, nseg, C, g;           // rows, 8-element segments per row, chunks per row, warps per chunk
-  int rows_per_cta_max;
   int fuse_pro, fuse_epi;
   PrologueArgs pro;            // fuse_pro: computed in-kernel; else pro.xq / pro.xscale are read
   EpilogueArgs epi;            // epi.acc / epi.acc2 are this kernel's outputs
   unsigned int* counters;      // [M] tickets (fuse_epi)
   uint32_t xq_off, rot_off;    // shared-memory byte offsets of the x records / rotation workspace
+};
+
+struct GroupArgs {
+  int n;
+  int cta_begin[QUIPB200_MAX_GROUP + 1];
+  GemvArgs a[QUIPB200_MAX_GROUP];
 };
 
 // element order inside a 4-byte x word after this permute matches the packed-byte order of the
@@ -312,11 +585,11 @@ __device__ __forceinline__ void e8p_dot2(uint32_t w, const unsigned char* tab, c
 }
 
 template <int CB>
-__global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(GemvArgs a) {
+__global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const __grid_constant__ GroupArgs ga) {
   using T = CbTraits<CB>;
   constexpr int UNROLL = GEMV_UNROLL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // [table][red: rows_per_cta_max * C * ACCS ints][x records][rotation workspace]
+  // [table][red: rows_per_cta * C * ACCS ints][x records][rotation workspace]
   unsigned char* tab = smem_raw;
   int* red = reinterpret_cast<int*>(smem_raw + T::TAB_BYTES);
   __shared__ float s_xscale;
@@ -325,10 +598,15 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(GemvArg
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   const int m = blockIdx.y;
 
-  // ---- rows of this CTA ----
-  const int G = gridDim.x;
-  const int row_begin = (int)(((int64_t)blockIdx.x * a.N) / G);
-  const int row_end = (int)(((int64_t)(blockIdx.x + 1) * a.N) / G);
+  // ---- which member of the group, which rows ----
+  int j = 0;
+  if (ga.n > 1 && (int)blockIdx.x >= ga.cta_begin[1]) j = 1;
+  if (ga.n > 2 && (int)blockIdx.x >= ga.cta_begin[2]) j = 2;
+  const GemvArgs& a = ga.a[j];
+  const int G = ga.cta_begin[j + 1] - ga.cta_begin[j];
+  const int bx = blockIdx.x - ga.cta_begin[j];
+  const int row_begin = (int)(((int64_t)bx * a.N) / G);
+  const int row_end = (int)(((int64_t)(bx + 1) * a.N) / G);
   const int nrows = row_end - row_begin;
   const int units = a.C * a.g;
 
@@ -354,7 +632,7 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(GemvArg
     for (int i = tid; i < 256; i += nt) {
       int v[4];
 #pragma unroll
-      for (int j = 0; j < 4; j++) v[j] = __float2int_rn(__half2float(g[i * 4 + j]) * 2.0f) & 0xff;
+      for (int jj = 0; jj < 4; jj++) v[jj] = __float2int_rn(__half2float(g[i * 4 + jj]) * 2.0f) & 0xff;
       reinterpret_cast<uint32_t*>(tab)[i] = (uint32_t)v[0] | ((uint32_t)v[2] << 8) | ((uint32_t)v[1] << 16) |
                                             ((uint32_t)v[3] << 24);
     }
@@ -375,7 +653,7 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(GemvArg
     uint4* xq_s = reinterpret_cast<uint4*>(smem_raw + a.xq_off);
     xscale = prologue_body(a.pro, smem_raw + a.rot_off, xq_s, m, tid, nt);
     xq = xq_s;
-    if (!a.fuse_epi && blockIdx.x == 0 && tid == 0) a.pro.xscale[m] = xscale;   // for the epilogue kernel
+    if (!a.fuse_epi && bx == 0 && tid == 0) a.pro.xscale[m] = xscale;   // for the epilogue kernel
   } else {
     xq = a.pro.xq + (size_t)m * a.nseg;
     xscale = a.pro.xscale[m];
@@ -487,7 +765,7 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(GemvArg
     if (T::ACCS == 2) __stcg(acc2 + (size_t)m * a.N + row_begin + r, (float)s2);
   }
 
-  // ---- phase 3: the last CTA of this row of the grid runs the output side ----
+  // ---- phase 3: the last CTA of this member runs the output side ----
   if (!a.fuse_epi) return;
   __threadfence();
   __syncthreads();
@@ -513,7 +791,7 @@ static int ilog2_exact(int v) {
 }
 
 struct GemvPlan {
-  int C, g, warps, G, rows_per_cta_max, accs, tab_bytes;
+  int C, g, warps, accs, tab_bytes;
   int64_t row_bytes;
 };
 
@@ -535,19 +813,10 @@ static int gemv_plan(int codebook, int N, int K, GemvPlan* p) {
   if (wmax > GEMV_MAX_WARPS) wmax = GEMV_MAX_WARPS;
   if (p->C >= wmax) { p->g = 1; p->warps = wmax; }
   else { p->g = wmax / p->C; p->warps = p->g * p->C; }
-  const int sms = quipb200_sm_count();
-  if (sms < 1) return (int)cudaErrorNoDevice;
-  int G = sms * (g_opt_gemv_ctas_per_sm > 0 ? g_opt_gemv_ctas_per_sm : 1);
-  // keep at least ~2 rows per warp-slot so tiny layers do not launch idle CTAs
-  const int min_rows = p->g * 2;
-  if ((int64_t)G * min_rows > N) G = (N + min_rows - 1) / min_rows;
-  if (G < 1) G = 1;
-  p->G = G;
-  p->rows_per_cta_max = (N + G - 1) / G + 1;
   return 0;
 }
 
-// workspace carve: [xq: M*nseg*16][xscale: M*4 -> 256 aligned][acc: M*N*4][acc2: M*N*4]
+// per-linear workspace carve: [xq: M*nseg*16][xscale: M*4 -> 256 aligned][acc: M*N*4][acc2: M*N*4]
 struct Workspace {
   uint4* xq;
   float* xscale;
@@ -584,63 +853,108 @@ static float f16_round_host(float v) { return __half2float(__float2half_rn(v)); 
 
 constexpr size_t SMEM_LIMIT = 220 * 1024;
 
-// Enqueue the whole chain.  `pa`/`ea` describe the two rotations; gemv fields are filled here.
-static int run_chain(int codebook, const void* qidxs, const void* grid, int N, int K, int M, PrologueArgs pa,
-                     EpilogueArgs ea, void* workspace, size_t ws_bytes, cudaStream_t st) {
-  GemvPlan plan;
-  int rc = gemv_plan(codebook, N, K, &plan);
-  if (rc) return rc;
-  const bool two = plan.accs == 2;
-  Workspace ws = carve_ws(workspace, M, N, K, two);
-  if (!workspace || ws_bytes < ws.bytes) return QUIPB200_EWORKSPACE;
-  pa.xq = ws.xq; pa.xscale = ws.xscale;
-  ea.acc = ws.acc; ea.acc2 = ws.acc2; ea.xscale = ws.xscale;
+struct Member {
+  int codebook, N, K;
+  const void* qidxs;
+  const void* grid;
+  PrologueArgs pa;
+  EpilogueArgs ea;
+};
 
-  const size_t pro_smem = rot_smem_bytes(pa.q_in, pa.K);
-  const size_t epi_smem = rot_smem_bytes(ea.q_out, ea.K);
-  if (pro_smem > SMEM_LIMIT || epi_smem > SMEM_LIMIT) return QUIPB200_EUNSUPPORTED;
+// Enqueue a group of 1..3 linears of the same codebook in one GEMV launch (+ prologue / epilogue
+// kernels where they cannot be fused).
+static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  if (n < 1 || n > QUIPB200_MAX_GROUP) return QUIPB200_EINVAL;
+  const int sms = quipb200_sm_count();
+  if (sms < 1) return (int)cudaErrorNoDevice;
+  GemvPlan plan[QUIPB200_MAX_GROUP];
+  GroupArgs ga{};
+  ga.n = n;
+  int rc;
+  size_t ws_off = 0;
+  long long total_rows_w = 0;
+  for (int j = 0; j < n; j++) {
+    if (mem[j].codebook != mem[0].codebook) return QUIPB200_EUNSUPPORTED;
+    if ((rc = gemv_plan(mem[j].codebook, mem[j].N, mem[j].K, &plan[j]))) return rc;
+    if (plan[j].warps != plan[0].warps) return QUIPB200_EUNSUPPORTED;
+    total_rows_w += (long long)mem[j].N * mem[j].K;
+  }
+  // CTAs: one per SM in total, split between the members in proportion to their code bytes
+  int Gtot = sms * (g_opt_gemv_ctas_per_sm > 0 ? g_opt_gemv_ctas_per_sm : 1);
+  int cta = 0;
+  size_t smem = 0;
+  bool any_unfused_pro = false, any_unfused_epi = false;
+  for (int j = 0; j < n; j++) {
+    Member& mj = mem[j];
+    const bool two = plan[j].accs == 2;
+    Workspace ws = carve_ws(workspace ? (unsigned char*)workspace + ws_off : nullptr, M, mj.N, mj.K, two);
+    ws_off += ws.bytes;
+    if (!workspace || ws_bytes < ws_off) return QUIPB200_EWORKSPACE;
+    mj.pa.xq = ws.xq; mj.pa.xscale = ws.xscale;
+    mj.ea.acc = ws.acc; mj.ea.acc2 = ws.acc2; mj.ea.xscale = ws.xscale;
 
-  // fused prologue only for pure-FWHT (or identity) input sides: the hadK mix is too much work to
-  // repeat in every CTA
-  const size_t red_bytes = ((size_t)plan.rows_per_cta_max * plan.C * plan.accs * sizeof(int) + 15) / 16 * 16;
-  const size_t xq_bytes = (size_t)(K / 8) * 16;
-  bool fuse_pro = (g_opt_fuse & 1) && pa.K == 1;
-  bool fuse_epi = (g_opt_fuse & 2) != 0;
-  size_t smem;
-  for (;;) {
-    size_t rot = 0;
-    if (fuse_pro) rot = pro_smem;
-    if (fuse_epi && epi_smem > rot) rot = epi_smem;
-    smem = plan.tab_bytes + red_bytes + (fuse_pro ? xq_bytes : 0) + rot;
-    if (smem <= SMEM_LIMIT) break;
-    if (fuse_epi) fuse_epi = false;          // drop the larger consumer first
-    else if (fuse_pro) fuse_pro = false;
-    else return QUIPB200_EUNSUPPORTED;
+    int G = (int)((long long)Gtot * mj.N * mj.K / total_rows_w);
+    const int min_rows = plan[j].g * 2;   // keep ~2 rows per warp slot so tiny layers do not launch idle CTAs
+    if ((long long)G * min_rows > mj.N) G = (mj.N + min_rows - 1) / min_rows;
+    if (G < 1) G = 1;
+    ga.cta_begin[j] = cta;
+    cta += G;
+    ga.cta_begin[j + 1] = cta;
+    const int rows_per_cta = (mj.N + G - 1) / G + 1;
+
+    const size_t pro_smem = rot_smem_bytes(mj.pa.q_in, mj.pa.K);
+    const size_t epi_smem = rot_smem_bytes(mj.ea.q_out, mj.ea.K);
+    if (pro_smem > SMEM_LIMIT || epi_smem > SMEM_LIMIT) return QUIPB200_EUNSUPPORTED;
+    const size_t red_bytes = ((size_t)rows_per_cta * plan[j].C * plan[j].accs * sizeof(int) + 15) / 16 * 16;
+    const size_t xq_bytes = (size_t)(mj.K / 8) * 16;
+    // fused prologue only for pure-FWHT (or identity) input sides: the orthogonal-block mix is too
+    // much work to repeat in every CTA
+    bool fuse_pro = (g_opt_fuse & 1) && mj.pa.K == 1;
+    bool fuse_epi = (g_opt_fuse & 2) != 0;
+    size_t need;
+    for (;;) {
+      size_t rot = 0;
+      if (fuse_pro) rot = pro_smem;
+      if (fuse_epi && epi_smem > rot) rot = epi_smem;
+      need = plan[j].tab_bytes + red_bytes + (fuse_pro ? xq_bytes : 0) + rot;
+      if (need <= SMEM_LIMIT) break;
+      if (fuse_epi) fuse_epi = false;
+      else if (fuse_pro) fuse_pro = false;
+      else return QUIPB200_EUNSUPPORTED;
+    }
+    if (need > smem) smem = need;
+    any_unfused_pro |= !fuse_pro;
+    any_unfused_epi |= !fuse_epi;
+
+    GemvArgs& g = ga.a[j];
+    g.qidxs = (const unsigned char*)mj.qidxs; g.row_bytes = plan[j].row_bytes; g.table = mj.grid;
+    g.N = mj.N; g.nseg = mj.K / 8; g.C = plan[j].C; g.g = plan[j].g;
+    g.fuse_pro = fuse_pro ? 1 : 0; g.fuse_epi = fuse_epi ? 1 : 0;
+    g.pro = mj.pa; g.epi = mj.ea;
+    g.xq_off = (uint32_t)(plan[j].tab_bytes + red_bytes);
+    g.rot_off = (uint32_t)(plan[j].tab_bytes + red_bytes + (fuse_pro ? xq_bytes : 0));
+    g.counters = nullptr;
+    if (fuse_epi) {
+      unsigned int* counters = nullptr;
+      cudaError_t e = cudaGetSymbolAddress((void**)&counters, g_counters);
+      if (e != cudaSuccess) return (int)e;
+      g.counters = counters + (size_t)(__atomic_fetch_add(&g_next_slot, 1u, __ATOMIC_RELAXED) % COUNTER_SLOTS) *
+                                  QUIPB200_MM_MAX_M;
+    }
   }
 
-  if (!fuse_pro && (g_opt_stage_mask & 1)) {
-    if ((rc = set_smem_attr((const void*)ql_prologue_kernel, pro_smem))) return rc;
-    ql_prologue_kernel<<<M, PRO_THREADS, pro_smem, st>>>(pa);
-    QB_LAUNCH_CHECK();
+  if (any_unfused_pro && (g_opt_stage_mask & 1)) {
+    for (int j = 0; j < n; j++) {
+      if (ga.a[j].fuse_pro) continue;
+      const size_t pro_smem = rot_smem_bytes(mem[j].pa.q_in, mem[j].pa.K);
+      if ((rc = set_smem_attr((const void*)ql_prologue_kernel, pro_smem))) return rc;
+      ql_prologue_kernel<<<M, PRO_THREADS, pro_smem, st>>>(ga.a[j].pro);
+      QB_LAUNCH_CHECK();
+    }
   }
-
-  GemvArgs ga{};
-  ga.qidxs = (const unsigned char*)qidxs; ga.row_bytes = plan.row_bytes; ga.table = grid;
-  ga.N = N; ga.nseg = K / 8; ga.C = plan.C; ga.g = plan.g; ga.rows_per_cta_max = plan.rows_per_cta_max;
-  ga.fuse_pro = fuse_pro ? 1 : 0; ga.fuse_epi = fuse_epi ? 1 : 0;
-  ga.pro = pa; ga.epi = ea;
-  ga.xq_off = (uint32_t)(plan.tab_bytes + red_bytes);
-  ga.rot_off = (uint32_t)(plan.tab_bytes + red_bytes + (fuse_pro ? xq_bytes : 0));
-  unsigned int* counters = nullptr;
-  if (fuse_epi) {
-    cudaError_t e = cudaGetSymbolAddress((void**)&counters, g_counters);
-    if (e != cudaSuccess) return (int)e;
-    counters += (size_t)(__atomic_fetch_add(&g_next_slot, 1u, __ATOMIC_RELAXED) % COUNTER_SLOTS) * QUIPB200_MM_MAX_M;
-  }
-  ga.counters = counters;
   if (g_opt_stage_mask & 2) {
     const void* fn = nullptr;
-    switch (codebook) {
+    switch (mem[0].codebook) {
       case QUIPB200_CB_E8P12: fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12>; break;
       case QUIPB200_CB_E8P12RVQ4B: fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12RVQ4B>; break;
       case QUIPB200_CB_D4: fn = (const void*)ql_gemv_kernel<QUIPB200_CB_D4>; break;
@@ -648,15 +962,49 @@ static int run_chain(int codebook, const void* qidxs, const void* grid, int N, i
     }
     if ((rc = set_smem_attr(fn, smem))) return rc;
     void* args[] = {&ga};
-    cudaError_t e = cudaLaunchKernel(fn, dim3(plan.G, M), dim3(plan.warps * 32), args, smem, st);
+    cudaError_t e = cudaLaunchKernel(fn, dim3(cta, M), dim3(plan[0].warps * 32), args, smem, st);
     if (e != cudaSuccess) return (int)e;
     QB_LAUNCH_CHECK();
   }
-  if (!fuse_epi && (g_opt_stage_mask & 4)) {
-    if ((rc = set_smem_attr((const void*)ql_epilogue_kernel, epi_smem))) return rc;
-    ql_epilogue_kernel<<<M, PRO_THREADS, epi_smem, st>>>(ea);
-    QB_LAUNCH_CHECK();
+  if (any_unfused_epi && (g_opt_stage_mask & 4)) {
+    for (int j = 0; j < n; j++) {
+      if (ga.a[j].fuse_epi) continue;
+      const size_t epi_smem = rot_smem_bytes(mem[j].ea.q_out, mem[j].ea.K);
+      if ((rc = set_smem_attr((const void*)ql_epilogue_kernel, epi_smem))) return rc;
+      ql_epilogue_kernel<<<M, PRO_THREADS, epi_smem, st>>>(ga.a[j].epi);
+      QB_LAUNCH_CHECK();
+    }
   }
+  return 0;
+}
+
+static int member_from_layer(const quipb200_linear_t* L, const quipb200_fusion_t* fu, const void* x, int64_t ldx,
+                             void* y, int64_t ldy, Member* m) {
+  if (!L->qidxs || !L->grid || !x || !y) return QUIPB200_EINVAL;
+  if (L->K_left < 1 || L->K_right < 1 || L->q_in % L->K_left || L->q_out % L->K_right) return QUIPB200_EINVAL;
+  if (L->in_features > L->q_in || L->out_features > L->q_out) return QUIPB200_EINVAL;
+  if ((L->K_left > 1 && !L->had_left) || (L->K_right > 1 && !L->had_right)) return QUIPB200_EINVAL;
+  const int log2Lin = ilog2_exact(L->q_in / L->K_left), log2Lout = ilog2_exact(L->q_out / L->K_right);
+  if (log2Lin < 0 || log2Lout < 0) return QUIPB200_EINVAL;
+  if (!aligned16(L->qidxs) || !aligned16(L->grid)) return QUIPB200_EALIGN;
+  m->codebook = L->codebook; m->N = L->q_out; m->K = L->q_in; m->qidxs = L->qidxs; m->grid = L->grid;
+  PrologueArgs pa{};
+  pa.x = (const __half*)x; pa.ldx = ldx; pa.SU = (const __half*)L->SU; pa.hadK = (const __half*)L->had_left;
+  pa.K = L->K_left; pa.in_features = L->in_features; pa.q_in = L->q_in; pa.log2L = log2Lin; pa.transform = 1;
+  pa.scale = L->wscale_float / sqrtf((float)(L->q_in / L->K_left));   // quant.py:75
+  if (fu) {
+    pa.gate = (const __half*)fu->gate; pa.ldgate = fu->ldgate;
+    pa.norm_w = (const __half*)fu->pre_norm_weight; pa.norm_eps = fu->pre_norm_eps;
+  }
+  EpilogueArgs ea{};
+  ea.unit = (L->codebook == QUIPB200_CB_D4) ? 0.5f : 0.25f;
+  ea.resid_scale = f16_round_host(L->resid_scale);
+  ea.wscale_pc = (const __half*)L->wscale_pc; ea.hadK = (const __half*)L->had_right; ea.K = L->K_right;
+  ea.q_out = L->q_out; ea.out_features = L->out_features; ea.log2L = log2Lout; ea.transform = 1;
+  ea.scale = 1.0f / sqrtf((float)(L->q_out / L->K_right));
+  ea.SV = (const __half*)L->SV; ea.bias = (const __half*)L->bias; ea.y = (__half*)y; ea.ldy = ldy;
+  if (fu) { ea.residual = (const __half*)fu->residual; ea.ldres = fu->ldres; }
+  m->pa = pa; m->ea = ea;
   return 0;
 }
 
@@ -676,15 +1024,18 @@ extern "C" int quipb200_mm(int codebook, const void* x, const void* qidxs, const
   if (!x || !qidxs || !grid || !out) return QUIPB200_EINVAL;
   if (M > QUIPB200_MM_MAX_M) return QUIPB200_EUNSUPPORTED;
   if (!aligned16(x) || !aligned16(qidxs) || !aligned16(grid) || !aligned16(workspace)) return QUIPB200_EALIGN;
+  Member mem{};
+  mem.codebook = codebook; mem.N = N; mem.K = K; mem.qidxs = qidxs; mem.grid = grid;
   PrologueArgs pa{};
-  pa.x = (const __half*)x; pa.ldx = K; pa.SU = nullptr; pa.hadK = nullptr; pa.K = 1;
+  pa.x = (const __half*)x; pa.ldx = K; pa.K = 1;
   pa.in_features = K; pa.q_in = K; pa.log2L = 0; pa.transform = 0; pa.scale = 1.f;
   EpilogueArgs ea{};
   ea.unit = (codebook == QUIPB200_CB_D4) ? 0.5f : 0.25f;
   ea.resid_scale = f16_round_host(resid_scale);
-  ea.wscale_pc = nullptr; ea.hadK = nullptr; ea.K = 1; ea.q_out = N; ea.out_features = N; ea.log2L = 0;
-  ea.transform = 0; ea.scale = 1.f; ea.SV = nullptr; ea.bias = nullptr; ea.y = (__half*)out; ea.ldy = N;
-  return run_chain(codebook, qidxs, grid, N, K, M, pa, ea, workspace, ws_bytes, (cudaStream_t)stream);
+  ea.K = 1; ea.q_out = N; ea.out_features = N; ea.log2L = 0;
+  ea.transform = 0; ea.scale = 1.f; ea.y = (__half*)out; ea.ldy = N;
+  mem.pa = pa; mem.ea = ea;
+  return run_group(&mem, 1, M, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" size_t quipb200_linear_workspace_bytes(const quipb200_linear_t* L, int M) {
@@ -692,30 +1043,32 @@ extern "C" size_t quipb200_linear_workspace_bytes(const quipb200_linear_t* L, in
   return carve_ws(nullptr, M, L->q_out, L->q_in, true).bytes;
 }
 
+extern "C" size_t quipb200_linear_group_workspace_bytes(const quipb200_linear_t* layers, int n, int M) {
+  if (!layers || n < 1 || M < 1) return 0;
+  size_t b = 0;
+  for (int j = 0; j < n; j++) b += carve_ws(nullptr, M, layers[j].q_out, layers[j].q_in, true).bytes;
+  return b;
+}
+
+extern "C" int quipb200_linear_group_forward(const quipb200_linear_t* layers, int n, const quipb200_fusion_t* fusion,
+                                             const void* x, int64_t ldx, void* const* y, const int64_t* ldy, int M,
+                                             void* workspace, size_t ws_bytes, void* stream) {
+  if (!layers || !y || !ldy || n < 1 || n > QUIPB200_MAX_GROUP || M < 0) return QUIPB200_EINVAL;
+  if (M == 0) return 0;
+  if (M > QUIPB200_MM_MAX_M) return QUIPB200_EUNSUPPORTED;
+  if (!aligned16(workspace)) return QUIPB200_EALIGN;
+  Member mem[QUIPB200_MAX_GROUP];
+  for (int j = 0; j < n; j++) {
+    int rc = member_from_layer(&layers[j], fusion, x, ldx, y[j], ldy[j], &mem[j]);
+    if (rc) return rc;
+  }
+  return run_group(mem, n, M, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int quipb200_linear_forward(const quipb200_linear_t* L, const void* x, int64_t ldx, void* y,
                                        int64_t ldy, int M, void* workspace, size_t ws_bytes, void* stream) {
-  if (!L || M < 0) return QUIPB200_EINVAL;
-  if (M == 0) return 0;
-  if (!x || !y || !L->qidxs || !L->grid) return QUIPB200_EINVAL;
-  if (M > QUIPB200_MM_MAX_M) return QUIPB200_EUNSUPPORTED;
-  if (L->K_left < 1 || L->K_right < 1 || L->q_in % L->K_left || L->q_out % L->K_right) return QUIPB200_EINVAL;
-  if (L->in_features > L->q_in || L->out_features > L->q_out) return QUIPB200_EINVAL;
-  if ((L->K_left > 1 && !L->had_left) || (L->K_right > 1 && !L->had_right)) return QUIPB200_EINVAL;
-  const int log2Lin = ilog2_exact(L->q_in / L->K_left), log2Lout = ilog2_exact(L->q_out / L->K_right);
-  if (log2Lin < 0 || log2Lout < 0) return QUIPB200_EINVAL;
-  if (!aligned16(L->qidxs) || !aligned16(L->grid) || !aligned16(workspace)) return QUIPB200_EALIGN;
-
-  PrologueArgs pa{};
-  pa.x = (const __half*)x; pa.ldx = ldx; pa.SU = (const __half*)L->SU; pa.hadK = (const __half*)L->had_left;
-  pa.K = L->K_left; pa.in_features = L->in_features; pa.q_in = L->q_in; pa.log2L = log2Lin; pa.transform = 1;
-  pa.scale = L->wscale_float / sqrtf((float)(L->q_in / L->K_left));   // quant.py:75
-  EpilogueArgs ea{};
-  ea.unit = (L->codebook == QUIPB200_CB_D4) ? 0.5f : 0.25f;
-  ea.resid_scale = f16_round_host(L->resid_scale);
-  ea.wscale_pc = (const __half*)L->wscale_pc; ea.hadK = (const __half*)L->had_right; ea.K = L->K_right;
-  ea.q_out = L->q_out; ea.out_features = L->out_features; ea.log2L = log2Lout; ea.transform = 1;
-  ea.scale = 1.0f / sqrtf((float)(L->q_out / L->K_right));
-  ea.SV = (const __half*)L->SV; ea.bias = (const __half*)L->bias; ea.y = (__half*)y; ea.ldy = ldy;
-  return run_chain(L->codebook, L->qidxs, L->grid, L->q_out, L->q_in, M, pa, ea, workspace, ws_bytes,
-                   (cudaStream_t)stream);
+  if (!L) return QUIPB200_EINVAL;
+  void* ys[1] = {y};
+  int64_t lds[1] = {ldy};
+  return quipb200_linear_group_forward(L, 1, nullptr, x, ldx, ys, lds, M, workspace, ws_bytes, stream);
 }

@@ -29,6 +29,9 @@ LLAMA2_SHAPES = {
                        num_attention_heads=64, num_key_value_heads=8),
     "tiny": dict(hidden_size=256, intermediate_size=704, num_hidden_layers=2,
                  num_attention_heads=4, num_key_value_heads=4),
+    # head_dim 128 (fused attention path), GQA, non power-of-two intermediate (11 * 128)
+    "tiny128": dict(hidden_size=512, intermediate_size=1408, num_hidden_layers=2,
+                    num_attention_heads=4, num_key_value_heads=2),
 }
 
 
@@ -124,7 +127,7 @@ class LlamaDecodeEngine:
     """
 
     def __init__(self, model, max_cache_len: int = 512, first_stage: bool = True, last_stage: bool = True,
-                 use_cuda_graph: bool = True):
+                 use_cuda_graph: bool = True, fused: bool = True):
         self.model = model
         self.cfg = model.config
         self.layers = list(model.model.layers)
@@ -154,6 +157,40 @@ class LlamaDecodeEngine:
         self.hidden_out = torch.zeros(1, 1, cfg.hidden_size, dtype=dt, device=self.dev)
         self.use_graph = use_cuda_graph
         self.graph = None
+        self.fused = None
+        if fused:
+            self._build_fused()
+
+    def _build_fused(self):
+        """Per-layer launch groups for the fused decode step (5 launches of ours per layer + 1 prologue):
+        [norm+q,k,v] -> [rope+append+attention] -> [o + residual] -> [norm+gate,up] -> [silu*up+down + residual]."""
+        from .fused import LinearGroup
+        try:
+            groups = []
+            for lyr in self.layers:
+                at, mlp = lyr.self_attn, lyr.mlp
+                if not all(isinstance(m, QuantLinear) for m in
+                           (at.q_proj, at.k_proj, at.v_proj, at.o_proj, mlp.gate_proj, mlp.up_proj, mlp.down_proj)):
+                    raise ValueError("not all block linears are QuantLinear")
+                groups.append(dict(qkv=LinearGroup([at.q_proj, at.k_proj, at.v_proj]), o=LinearGroup([at.o_proj]),
+                                   gu=LinearGroup([mlp.gate_proj, mlp.up_proj]), down=LinearGroup([mlp.down_proj])))
+            if self.hd != 128:
+                raise ValueError("attention kernel needs head_dim 128")
+            self.fused = groups
+            self.attn_out = torch.empty(1, self.nh * self.hd, dtype=torch.float16, device=self.dev)
+        except ValueError:
+            self.fused = None
+
+    def _layer_fused(self, li, h):
+        """h: fp16 [1, hidden]; one decode position (self.pos)."""
+        from .fused import attn_decode
+        lyr, g = self.layers[li], self.fused[li]
+        q, k, v = g["qkv"](h, norm_w=lyr.input_layernorm.weight, eps=self.eps)
+        attn_decode(q, k, v, self.k_cache[li], self.v_cache[li], self.cos, self.sin, self.pos, self.attn_out,
+                    self.nh, self.nkv, self.hd)
+        h = g["o"](self.attn_out, residual=h)[0]
+        gate, up = g["gu"](h, norm_w=lyr.post_attention_layernorm.weight, eps=self.eps)
+        return g["down"](up, gate=gate, residual=h)[0]
 
     # ---- building blocks --------------------------------------------------------------------
     def _rms(self, x, w):
@@ -190,6 +227,15 @@ class LlamaDecodeEngine:
     def _forward(self, tok_or_hidden, pos):
         """pos: long [T] absolute positions. Returns next-token ids [1,1] (last stage) or hidden."""
         h = self.model.model.embed_tokens(tok_or_hidden) if self.first else tok_or_hidden
+        if self.fused is not None and h.shape[1] == 1 and pos is self.pos:
+            h2 = h.view(1, -1)
+            for li in range(len(self.layers)):
+                h2 = self._layer_fused(li, h2)
+            h = h2.view(1, 1, -1)
+            if not self.last:
+                return h
+            h = self._rms(h, self.model.model.norm.weight)
+            return self.model.lm_head(h).argmax(-1)
         cos = self.cos.index_select(0, pos)[None, None]
         sin = self.sin.index_select(0, pos)[None, None]
         mask = (self.arange[None, :] <= pos[:, None])[None, None]     # [1,1,T,max_len]

@@ -440,3 +440,97 @@ def test_decode_engine_matches_hf_greedy():
     hf = torch.cat(hf, 1)
     # identical up to fp16 noise flipping a near-tie: require the first tokens to agree
     assert torch.equal(out[:, :2], hf[:, :2])
+
+
+# ------------------------------------------------------------------------------------------------
+# grouped / hooked launches and the fused decode step
+# ------------------------------------------------------------------------------------------------
+def test_linear_group_matches_individual_layers():
+    from quip_for_all_b200.fused import LinearGroup
+    layers = [make_layer(512, n, "E8P12", bias=(i == 1), seed=30 + i, device=DEV) for i, n in enumerate((512, 256, 768))]
+    x = torch.randn(1, 512, generator=torch.Generator().manual_seed(9)).half().to(DEV)
+    with torch.no_grad():
+        outs = [o.clone() for o in LinearGroup(layers)(x)]
+        for o, l in zip(outs, layers):
+            assert torch.equal(o, l(x))                      # same kernels, same integer sums: bit-identical
+
+
+def test_fusion_hooks_norm_gate_residual():
+    from quip_for_all_b200.fused import LinearGroup
+    g = torch.Generator().manual_seed(4)
+    lay = make_layer(1408, 512, "E8P12", bias=True, seed=77, device=DEV)       # K_left = 11
+    lay2 = make_layer(512, 1408, "E8P12", seed=78, device=DEV)                 # K_right = 11
+    x = torch.randn(1, 1408, generator=g).half().to(DEV)
+    gate = torch.randn(1, 1408, generator=g).half().to(DEV)
+    res = torch.randn(1, 512, generator=g).half().to(DEV)
+    w = (1 + 0.1 * torch.randn(512, generator=g)).half().to(DEV)
+    with torch.no_grad():
+        y = LinearGroup([lay])(x, gate=gate, residual=res)[0].clone()
+        ref = lay(torch.nn.functional.silu(gate) * x) + res
+        assert (y - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item()
+        h = torch.randn(1, 512, generator=g).half().to(DEV)
+        y2 = LinearGroup([lay2])(h, norm_w=w, eps=1e-5)[0].clone()
+        hn = h.float()
+        hn = (hn * torch.rsqrt(hn.pow(2).mean(-1, keepdim=True) + 1e-5)).half()
+        ref2 = lay2(w * hn)
+        assert (y2 - ref2).abs().max().item() <= 2.0 ** -8 * ref2.abs().max().item()
+
+
+def test_attn_decode_kernel_matches_sdpa():
+    from quip_for_all_b200.fused import attn_decode
+    nh, nkv, hd, L, pos = 8, 2, 128, 96, 37
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(1, nh * hd, generator=g).half().to(DEV)
+    k = torch.randn(1, nkv * hd, generator=g).half().to(DEV)
+    v = torch.randn(1, nkv * hd, generator=g).half().to(DEV)
+    kc = torch.randn(1, nkv, L, hd, generator=g).half().to(DEV)
+    vc = torch.randn(1, nkv, L, hd, generator=g).half().to(DEV)
+    inv = 1.0 / (10000 ** (torch.arange(0, hd, 2).float() / hd))
+    fr = torch.outer(torch.arange(L).float(), inv)
+    emb = torch.cat((fr, fr), -1)
+    cos, sin = emb.cos().half().to(DEV), emb.sin().half().to(DEV)
+    p = torch.tensor([pos], device=DEV)
+    out = torch.empty(1, nh * hd, dtype=torch.float16, device=DEV)
+    kc2, vc2 = kc.clone(), vc.clone()
+    attn_decode(q, k, v, kc2, vc2, cos, sin, p, out, nh, nkv, hd)
+    rot = lambda x: torch.cat((-x[..., hd // 2:], x[..., :hd // 2]), -1)
+    qh = q.view(1, nh, 1, hd).float()
+    kh = k.view(1, nkv, 1, hd).float()
+    c, s = cos[pos].float(), sin[pos].float()
+    qr = (qh * c + rot(qh) * s).half().float()
+    kr = (kh * c + rot(kh) * s).half()
+    kref, vref = kc.clone(), vc.clone()
+    kref[:, :, pos] = kr[:, :, 0]
+    vref[:, :, pos] = v.view(1, nkv, hd)
+    assert torch.equal(kc2[:, :, :pos + 1], kref[:, :, :pos + 1]) and torch.equal(vc2[:, :, :pos + 1], vref[:, :, :pos + 1])
+    ref = torch.nn.functional.scaled_dot_product_attention(
+        qr, kref[:, :, :pos + 1].float(), vref[:, :, :pos + 1].float(), enable_gqa=True)
+    assert (out.float() - ref.reshape(1, -1)).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+
+
+def test_fused_decode_step_matches_unfused_engine():
+    from quip_for_all_b200.modeling import LlamaDecodeEngine, make_random_quantized_llama
+    model = make_random_quantized_llama("tiny128", "E8P12", seed=3, device=DEV)
+    ids = torch.randint(0, 32000, (1, 10), generator=torch.Generator().manual_seed(2)).to(DEV)
+    e1 = LlamaDecodeEngine(model, max_cache_len=64, fused=True)
+    assert e1.fused is not None
+    e2 = LlamaDecodeEngine(model, max_cache_len=64, fused=False, use_cuda_graph=False)
+    e1.prefill(ids)
+    e2.prefill(ids)
+    assert torch.equal(e1.tok, e2.tok)
+    # one step from identical state: hidden states agree to fp16 noise
+    with torch.no_grad():
+        h1 = e1.model.model.embed_tokens(e1.tok).view(1, -1)
+        h2 = h1.clone()
+        for li in range(len(e1.layers)):
+            h1 = e1._layer_fused(li, h1)
+        cos = e2.cos.index_select(0, e2.pos)[None, None]
+        sin = e2.sin.index_select(0, e2.pos)[None, None]
+        mask = (e2.arange[None, :] <= e2.pos[:, None])[None, None]
+        h2 = h2.view(1, 1, -1)
+        for li in range(len(e2.layers)):
+            h2 = e2._layer(li, h2, e2.pos, cos, sin, mask)
+    d = (h1.float() - h2.view(1, -1).float()).abs().max().item()
+    assert d <= 2.0 ** -6 * h2.float().abs().max().item(), d
+    out = e1.generate(ids, 6)          # graph-captured fused path runs end to end
+    assert out.shape == (1, 6)

@@ -96,6 +96,38 @@ def main():
             out.append(rec)
         del layers
         torch.cuda.empty_cache()
+    # grouped launches of a Llama-2-7B decoder layer (the engine's fused decode step)
+    if cb_name == "E8P12" and len(sys.argv) <= 3:
+        from quip_for_all_b200.fused import LinearGroup, attn_decode
+        NL = 16
+
+        def mk(fin, fout):
+            L = QuantLinear(fin, fout, codebook_id[cb_name](inference=True), bias=False).to(dev)
+            randomize_quantlinear(L, gen)
+            return L.eval()
+        qkv, og, gu, dn = [], [], [], []
+        for i in range(NL):
+            ls = [mk(4096, 4096) for _ in range(4)] + [mk(4096, 11008) for _ in range(2)] + [mk(11008, 4096)]
+            apply_load_time_tricks(torch.nn.ModuleList(ls))
+            qkv.append(LinearGroup(ls[0:3])); og.append(LinearGroup(ls[3:4])); gu.append(LinearGroup(ls[4:6]))
+            dn.append(LinearGroup(ls[6:7]))
+        h = torch.randn(1, 4096, device=dev, dtype=torch.float16)
+        w = torch.ones(4096, device=dev, dtype=torch.float16)
+        u = torch.randn(1, 11008, device=dev, dtype=torch.float16)
+        kc = torch.zeros(1, 32, 512, 128, device=dev, dtype=torch.float16)
+        vc = torch.zeros_like(kc)
+        cs = torch.ones(512, 128, device=dev, dtype=torch.float16)
+        pos = torch.tensor([384], device=dev)
+        ao = torch.empty(1, 4096, device=dev, dtype=torch.float16)
+        rec = {"shape": "llama2-7b decoder layer, grouped", "layers": NL}
+        rec["qkv_group_us"] = round(1000 * graph_time(lambda: [g(h, norm_w=w, eps=1e-5) for g in qkv]) / NL, 3)
+        rec["o_resid_us"] = round(1000 * graph_time(lambda: [g(h, residual=h) for g in og]) / NL, 3)
+        rec["gate_up_group_us"] = round(1000 * graph_time(lambda: [g(h, norm_w=w, eps=1e-5) for g in gu]) / NL, 3)
+        rec["down_silu_resid_us"] = round(1000 * graph_time(lambda: [g(u, gate=u, residual=h) for g in dn]) / NL, 3)
+        rec["attn_ctx384_us"] = round(1000 * graph_time(lambda: [attn_decode(h, h, h, kc, vc, cs, cs, pos, ao, 32, 32, 128) for _ in range(NL)]) / NL, 3)
+        rec["layer_total_us"] = round(sum(v for k, v in rec.items() if k.endswith("_us")), 3)
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"layer_bench_{cb_name}.json"), "w") as f:
         json.dump(out, f, indent=1)
