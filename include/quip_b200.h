@@ -163,6 +163,9 @@ int quipb200_attn_decode(const void* q, const void* k, const void* v, void* k_ca
 /* Tuning / introspection hooks used by bench.py and the tests (not part of the reference surface). */
 int quipb200_set_option(const char* name, int value);   /* e.g. "gemv_table_repl" = 1|16 */
 int quipb200_get_option(const char* name);
+/* profiling hook: when non-NULL, every CTA of the GEMV kernel writes 16 int64 clock64() stamps of its
+ * phases into buffer[cta*16 ..] (tools/timeline.py); pass NULL to switch it off. */
+int quipb200_debug_timeline(void* device_int64_buffer);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches evidence) */
 int64_t quipb200_launch_count(void);
 

@@ -23,7 +23,7 @@ EXPORTS = [
     "quipb200_mm_workspace_bytes", "quipb200_mm",
     "quipb200_linear_workspace_bytes", "quipb200_linear_forward",
     "quipb200_linear_group_workspace_bytes", "quipb200_linear_group_forward", "quipb200_attn_decode",
-    "quipb200_set_option", "quipb200_get_option", "quipb200_launch_count",
+    "quipb200_set_option", "quipb200_get_option", "quipb200_launch_count", "quipb200_debug_timeline",
 ]
 
 
@@ -82,6 +82,8 @@ def lib():
     L.quipb200_linear_group_forward.argtypes = [POINTER(LinearDesc), c_int, POINTER(Fusion), vp, c_int64,
                                                 POINTER(c_void_p), POINTER(c_int64), c_int, vp, c_size_t, vp]
     L.quipb200_attn_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp]
+    L.quipb200_debug_timeline.argtypes = [vp]
+    L.quipb200_debug_timeline.restype = c_int
     L.quipb200_set_option.argtypes = [c_char_p, c_int]
     L.quipb200_get_option.argtypes = [c_char_p]
     L.quipb200_launch_count.restype = c_int64

@@ -5,11 +5,13 @@
 
 namespace qb {
 int64_t g_launch_count = 0;
+int g_opt_pdl = 1;   // programmatic dependent launch between our kernels
 extern int g_opt_table_repl;
 extern int g_opt_gemv_warps;
 extern int g_opt_gemv_ctas_per_sm;
 extern int g_opt_stage_mask;
 extern int g_opt_fuse;
+extern int g_opt_phase0;
 }  // namespace qb
 
 extern "C" int quipb200_abi_version(void) { return QUIPB200_ABI_VERSION; }
@@ -60,6 +62,14 @@ extern "C" int quipb200_set_option(const char* name, int value) {
     qb::g_opt_stage_mask = value;
     return 0;
   }
+  if (!strcmp(name, "phase0")) {
+    qb::g_opt_phase0 = value ? 1 : 0;
+    return 0;
+  }
+  if (!strcmp(name, "pdl")) {
+    qb::g_opt_pdl = value ? 1 : 0;
+    return 0;
+  }
   if (!strcmp(name, "fuse")) {
     if (value < 0 || value > 3) return QUIPB200_EINVAL;
     qb::g_opt_fuse = value;
@@ -75,6 +85,7 @@ extern "C" int quipb200_get_option(const char* name) {
   if (!strcmp(name, "gemv_ctas_per_sm")) return qb::g_opt_gemv_ctas_per_sm;
   if (!strcmp(name, "stage_mask")) return qb::g_opt_stage_mask;
   if (!strcmp(name, "fuse")) return qb::g_opt_fuse;
+  if (!strcmp(name, "pdl")) return qb::g_opt_pdl;
   return QUIPB200_EINVAL;
 }
 

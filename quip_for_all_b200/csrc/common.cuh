@@ -19,6 +19,28 @@ extern int64_t g_launch_count;
     if (e__ != cudaSuccess) return (int)e__;           \
   } while (0)
 
+extern int g_opt_pdl;
+
+// Programmatic dependent launch: the kernel may start while its predecessor drains; it must call
+// pdl_wait() before touching anything a predecessor wrote (and before its own first global write).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+static inline cudaError_t launch_kernel(const void* fn, dim3 grid, dim3 block, void** args, size_t smem,
+                                        cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_opt_pdl ? 1 : 0;
+  return cudaLaunchKernelExC(&cfg, fn, args);
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---------------------------------------------------------------------------------------------
@@ -30,6 +52,20 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
+  return r;
+}
+// L2 evict-first policy for the weight stream: 1.6 GB of codes pass through the 126 MB L2 every token;
+// without the hint they evict everything else (kernel code, per-layer scale vectors, KV cache).
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ldg_stream_v4(const void* p, uint64_t pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
   return r;
 }
 __device__ __forceinline__ void stg_stream_v4(void* p, const uint4& v) {
@@ -189,6 +225,59 @@ __device__ __forceinline__ uint4 pack_h8(const float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
   return v;
+}
+
+// Butterfly passes with compile-time bit position: all shared-memory offsets become immediates.
+template <int R, int B>
+__device__ __forceinline__ void fwht_pass_c(float* s, int total, int tid, int nthreads) {
+  const int ngroups = total >> R;
+  for (int g = tid; g < ngroups; g += nthreads) {
+    const int lo = g & ((1 << B) - 1), hi = g >> B;
+    float* p = s + spad((hi << (B + R)) | lo);
+    float v[1 << R];
+#pragma unroll
+    for (int j = 0; j < (1 << R); j++) v[j] = p[(j << B) + (B >= 6 ? ((j << (B - 6)) << 3) : 0)];
+    butterfly_regs<R>(v);
+#pragma unroll
+    for (int j = 0; j < (1 << R); j++) p[(j << B) + (B >= 6 ? ((j << (B - 6)) << 3) : 0)] = v[j];
+  }
+}
+template <int R>
+__device__ __forceinline__ void fwht_pass_b(float* s, int total, int B, int tid, int nt) {
+  switch (B) {
+    case 3: fwht_pass_c<R, 3>(s, total, tid, nt); break;
+    case 6: fwht_pass_c<R, 6>(s, total, tid, nt); break;
+    case 9: fwht_pass_c<R, 9>(s, total, tid, nt); break;
+    default: fwht_pass_c<R, 12>(s, total, tid, nt); break;
+  }
+}
+// Butterfly stages for bits [3, log2L), highest bits first, each pass followed by a barrier.
+// Bits 0..2 are left to the caller, which finishes them in registers on contiguous octets.
+static __device__ __noinline__ void fwht_hi(float* s, int total, int log2L, int tid, int nt) {
+  const int nb = log2L - 3;
+  if (nb <= 0) return;
+  const int r0 = nb % 3;
+  int B = log2L - r0;
+  if (r0 == 1) { fwht_pass_b<1>(s, total, B, tid, nt); __syncthreads(); }
+  else if (r0 == 2) { fwht_pass_b<2>(s, total, B, tid, nt); __syncthreads(); }
+  for (B -= 3; B >= 3; B -= 3) {
+    fwht_pass_b<3>(s, total, B, tid, nt);
+    __syncthreads();
+  }
+}
+// last stages (bits 0..nbits-1) on 8 contiguous values held in registers
+__device__ __forceinline__ void butterfly_low(float (&v)[8], int nbits) {
+  if (nbits >= 3) butterfly_regs<3>(v);
+  else if (nbits == 2) {
+#pragma unroll
+    for (int h = 1; h < 4; h <<= 1)
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (!(j & h)) { const float a = v[j], c = v[j | h]; v[j] = a + c; v[j | h] = a - c; }
+  } else if (nbits == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) { const float a = v[j], c = v[j + 1]; v[j] = a + c; v[j + 1] = a - c; }
+  }
 }
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(
   __shared__ float sk[HD];
   __shared__ float sred[ATT_THREADS / 32];
   __shared__ float sout[4][HD];
+  pdl_launch_dependents();
+  pdl_wait();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = blockIdx.x;
   const int group = nh / nkv;
@@ -55,20 +57,40 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(
   static_assert(HD == 128, "lane mapping assumes head_dim 128");
   const float q0 = sq[lane * 4], q1 = sq[lane * 4 + 1], q2 = sq[lane * 4 + 2], q3 = sq[lane * 4 + 3];
   float lmax = -INFINITY;
-  for (int t = warp; t <= pos; t += ATT_THREADS / 32) {
-    float d;
-    if (t < pos) {
-      const uint2 raw = *reinterpret_cast<const uint2*>(kc + (size_t)t * HD + lane * 4);
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-      d = q0 * a.x + q1 * a.y + q2 * b.x + q3 * b.y;
-    } else {
-      d = q0 * sk[lane * 4] + q1 * sk[lane * 4 + 1] + q2 * sk[lane * 4 + 2] + q3 * sk[lane * 4 + 3];
+  constexpr int NW = ATT_THREADS / 32, UN = 8;   // 8 K rows in flight per warp
+  for (int t0 = warp; t0 <= pos; t0 += NW * UN) {
+    uint2 raw[UN];
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      const int t = t0 + u * NW;
+      raw[u] = make_uint2(0, 0);
+      if (t < pos) raw[u] = *reinterpret_cast<const uint2*>(kc + (size_t)t * HD + lane * 4);
+    }
+    float d[UN];
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      const int t = t0 + u * NW;
+      if (t == pos) {
+        d[u] = q0 * sk[lane * 4] + q1 * sk[lane * 4 + 1] + q2 * sk[lane * 4 + 2] + q3 * sk[lane * 4 + 3];
+      } else {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw[u].x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw[u].y));
+        d[u] = q0 * a.x + q1 * a.y + q2 * b.x + q3 * b.y;
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    if (lane == 0) sc[t] = d;
-    lmax = fmaxf(lmax, d);
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < UN; u++) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      const int t = t0 + u * NW;
+      if (t <= pos) {
+        if (lane == 0) sc[t] = d[u];
+        lmax = fmaxf(lmax, d[u]);
+      }
+    }
   }
   if (lane == 0) sred[warp] = lmax;
   __syncthreads();
@@ -94,13 +116,26 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(
   // ---- out = P . V : 4 groups of 64 threads split the positions, each thread owns 2 dims ----
   const int d2 = tid & 63, tg = tid >> 6;
   float o0 = 0.f, o1 = 0.f;
-  for (int t = tg; t <= pos; t += 4) {
-    float2 vv;
-    if (t < pos) vv = __half22float2(*reinterpret_cast<const __half2*>(vc + (size_t)t * HD + d2 * 2));
-    else vv = __half22float2(*reinterpret_cast<const __half2*>(v + kvh * HD + d2 * 2));
-    const float p = sc[t];
-    o0 = fmaf(p, vv.x, o0);
-    o1 = fmaf(p, vv.y, o1);
+  constexpr int UV = 8;
+  for (int t0 = tg; t0 <= pos; t0 += 4 * UV) {
+    __half2 vr[UV];
+#pragma unroll
+    for (int u = 0; u < UV; u++) {
+      const int t = t0 + u * 4;
+      vr[u] = __float2half2_rn(0.f);
+      if (t < pos) vr[u] = *reinterpret_cast<const __half2*>(vc + (size_t)t * HD + d2 * 2);
+      else if (t == pos) vr[u] = *reinterpret_cast<const __half2*>(v + kvh * HD + d2 * 2);
+    }
+#pragma unroll
+    for (int u = 0; u < UV; u++) {
+      const int t = t0 + u * 4;
+      if (t <= pos) {
+        const float2 vv = __half22float2(vr[u]);
+        const float p = sc[t];
+        o0 = fmaf(p, vv.x, o0);
+        o1 = fmaf(p, vv.y, o1);
+      }
+    }
   }
   sout[tg][d2 * 2] = o0;
   sout[tg][d2 * 2 + 1] = o1;
@@ -128,10 +163,11 @@ extern "C" int quipb200_attn_decode(const void* q, const void* k, const void* v,
                                          (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  attn_decode_kernel<128><<<n_heads, ATT_THREADS, smem, (cudaStream_t)stream>>>(
-      (const __half*)q, (const __half*)k, (const __half*)v, (__half*)k_cache, (__half*)v_cache,
-      (const __half*)cos_t, (const __half*)sin_t, (const long long*)pos, (__half*)out, n_heads, n_kv_heads,
-      max_len, 1.0f / sqrtf((float)head_dim));
+  float scale = 1.0f / sqrtf((float)head_dim);
+  void* args[] = {&q, &k, &v, &k_cache, &v_cache, &cos_t, &sin_t, &pos, &out, &n_heads, &n_kv_heads, &max_len, &scale};
+  cudaError_t e = launch_kernel((const void*)attn_decode_kernel<128>, dim3(n_heads), dim3(ATT_THREADS), args, smem,
+                                (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
   QB_LAUNCH_CHECK();
   return 0;
 }

@@ -33,6 +33,8 @@ int g_opt_gemv_warps = 0;    // 0: auto (16)
 int g_opt_gemv_ctas_per_sm = 1;
 int g_opt_stage_mask = 7;    // bench only: bit0 prologue, bit1 gemv, bit2 epilogue
 int g_opt_fuse = 3;          // bit0: fuse prologue into the GEMV kernel, bit1: last-CTA epilogue
+int g_opt_phase0 = 1;        // experiment: 0 = no early code prefetch
+long long* g_dbg_timeline = nullptr;   // profiling hook: per-CTA clock64 stamps of the GEMV kernel phases
 
 constexpr int PRO_THREADS = 512;
 constexpr int GEMV_MAX_WARPS = 16;
@@ -148,26 +150,12 @@ __device__ __forceinline__ void mix_mma_tiles(const RotSmem& sm, int K, int warp
   }
 }
 
-// Rotation: in: s[spad(i)] (fp32) with butterfly stages [0, b0) already applied;
-// out: t (fp16) = round( (M (x) H_L) s * scale ).  Rounding points follow the reference: fp16 after
-// the FWHT*scale (register_lib.py:20), fp16 after hadK@ (quant.py:83).  transform == 0: t = round(s).
-__device__ __forceinline__ void rotate_smem(const RotSmem& sm, int q, int K, float scale, int transform, int b0,
-                                            int tid, int nt) {
-  if (!transform) {
-    for (int i = tid; i < q; i += nt) sm.t[i] = __float2half_rn(sm.s[spad(i)]);
-    __syncthreads();
-    return;
-  }
-  fwht_smem(sm.s, q, sm.log2L, b0, tid, nt);
-  if (K == 1) {
-    for (int i = tid; i < q; i += nt) sm.t[i] = __float2half_rn(sm.s[spad(i)] * scale);
-    __syncthreads();
-    return;
-  }
+// Orthogonal-block mix (K > 1) of the fp16 rows already in t: cold path, kept out of line so the common
+// power-of-two path stays compact in the instruction cache.
+__device__ __noinline__ void rotate_mix(RotSmem sm, int q, int K, int tid, int nt) {
   const int L = 1 << sm.log2L;
   const int Kp = (K + 15) / 16 * 16;
   if (L >= 8 && Kp <= 64) {
-    for (int i = tid; i < q; i += nt) sm.t[t_index(sm, K, i)] = __float2half_rn(sm.s[spad(i)] * scale);
     for (int i = tid; i < sm.Ls; i += nt) sm.t[(size_t)K * sm.Ls + i] = __float2half_rn(0.f);
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
@@ -180,8 +168,9 @@ __device__ __forceinline__ void rotate_smem(const RotSmem& sm, int q, int K, flo
     __syncthreads();
     return;
   }
-  // generic CUDA-core mix (tiny blocks / very large K): out-of-place from s into t
-  for (int i = tid; i < q; i += nt) sm.s[spad(i)] = f16_round(sm.s[spad(i)] * scale);
+  // generic CUDA-core mix (tiny blocks / very large K): t -> s (fp32 copy) -> t
+  __syncthreads();
+  for (int i = tid; i < q; i += nt) sm.s[spad(i)] = __half2float(sm.t[t_index(sm, K, i)]);
   __syncthreads();
   for (int i = tid; i < q; i += nt) {
     const int ko = i >> sm.log2L, c = i & (L - 1);
@@ -193,7 +182,38 @@ __device__ __forceinline__ void rotate_smem(const RotSmem& sm, int q, int K, flo
   __syncthreads();
 }
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+// Rotation: in: s[spad(i)] (fp32, untransformed); out: t (fp16) = round( (M (x) H_L) s * scale ).
+// Butterfly order: bits [3, log2L) in shared memory (highest first), bits 0..2 last in registers on
+// the contiguous octet each thread then rounds and stores.  Rounding points follow the reference: fp16
+// after the FWHT*scale (register_lib.py:20), fp16 after hadK@ (quant.py:83).  transform == 0: t = round(s).
+__device__ __noinline__ void rotate_smem(RotSmem sm, int q, int K, float scale, int transform, int tid, int nt) {
+  if (transform) fwht_hi(sm.s, q, sm.log2L, tid, nt);
+  const int nbits = transform ? (sm.log2L < 3 ? sm.log2L : 3) : 0;
+  const float sc = transform ? scale : 1.0f;
+  const int L = 1 << sm.log2L;
+  const bool rowvec = (K == 1) || (L >= 8);
+  for (int o = tid; o < (q >> 3); o += nt) {
+    const float4* sp = reinterpret_cast<const float4*>(sm.s + spad(o * 8));
+    const float4 a = sp[0], b = sp[1];
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    butterfly_low(f, nbits);
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] *= sc;
+    if (rowvec) {
+      *reinterpret_cast<uint4*>(sm.t + t_index(sm, K, o * 8)) = pack_h8(f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) sm.t[t_index(sm, K, o * 8 + j)] = __float2half_rn(f[j]);
+    }
+  }
+  if (K == 1 || !transform) {
+    __syncthreads();
+    return;
+  }
+  rotate_mix(sm, q, K, tid, nt);
+}
+
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 // ---------------------------------------------------------------------------------------------
 // input side: [rmsnorm] [silu(gate)*x] x*SU -> rotation -> 16-bit fixed point records
@@ -215,22 +235,42 @@ struct PrologueArgs {
 
 __device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// element-wise pre-ops on 8 consecutive inputs (rounding points = the fp16 tensor ops HF / the reference issue)
-__device__ __forceinline__ void pre_ops(float (&f)[8], const float (&g)[8], bool has_gate, const float (&w)[8],
-                                        bool has_norm, float rstd, const float (&su)[8], bool has_su) {
+// element-wise pre-ops on 8 consecutive inputs (rounding points = the fp16 tensor ops HF / the reference issue).
+// Flags are tested once per octet, not per element, so the executed instruction stream stays dense.
+__device__ __forceinline__ void pre_ops(float (&f)[8], const uint4& gv, bool has_gate, const uint4& wv, bool has_norm,
+                                        float rstd, const uint4& sv, bool has_su) {
+  if (has_gate) {   // LlamaMLP: act_fn(gate) * up
+    float g[8];
+    unpack_h8(gv, g);
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    float v = f[j];
-    if (has_gate) v = f16_round(f16_round(silu_f(g[j])) * v);   // LlamaMLP: act_fn(gate) * up
-    if (has_norm) v = f16_round(__half2float(__float2half_rn(v * rstd)) * w[j]);   // LlamaRMSNorm
-    if (has_su) v = f16_round(v * su[j]);                        // qlinear.py:91
-    f[j] = v;
+    for (int j = 0; j < 8; j++) f[j] = f16_round(f16_round(silu_f(g[j])) * f[j]);
+  }
+  if (has_norm) {   // LlamaRMSNorm: weight * (x * rstd).to(fp16)
+    float w[8];
+    unpack_h8(wv, w);
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] = f16_round(f16_round(f[j] * rstd) * w[j]);
+  }
+  if (has_su) {     // qlinear.py:91
+    float su[8];
+    unpack_h8(sv, su);
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] * su[j]);
   }
 }
 
-// Computes the records into `dst` (shared or global) and returns the fixed-point scale.
+struct PrologueArgs;
+__device__ __noinline__ void prologue_scalar_fill(const PrologueArgs& a, RotSmem sm, const __half* xr, const __half* gr,
+                                                  int tid, int nt);
+
+// 16-byte records in shared memory are XOR-swizzled so that the GEMV lanes (which each read 8
+// consecutive records, i.e. a 128-byte stride between lanes) hit distinct banks
+__device__ __forceinline__ int swz(int seg) { return seg ^ ((seg >> 3) & 7); }
+
+// Computes the records into `dst` (shared: swizzled; global: linear) and returns the fixed-point scale.
+#define QB_DSTAMP(i) do { if (dbg && tid == 0) dbg[i] = clock64(); } while (0)
 __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned char* rot_base, uint4* dst, int m,
-                                               int tid, int nt) {
+                                               int tid, int nt, bool swizzle, long long* dbg = nullptr) {
   const RotSmem sm = rot_carve(rot_base, a.q_in, a.K, a.log2L);
   const __half* xr = a.x + (size_t)m * a.ldx;
   const __half* gr = a.gate ? a.gate + (size_t)m * a.ldgate : nullptr;
@@ -239,9 +279,7 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
   const int noct_in = a.in_features >> 3;
   const bool vec = (a.in_features & 7) == 0 && al16(xr) && (!gr || al16(gr)) && (!a.SU || al16(a.SU)) &&
                    (!a.norm_w || al16(a.norm_w));
-  const bool reg_pass = a.transform && a.log2L >= 3;   // first radix-8 butterfly in registers
   float rstd = 1.f;
-  const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (vec) {
     const bool single = noct <= nt * CH;    // everything fits one round: no re-read for the norm
     uint4 xv[CH];
@@ -260,12 +298,8 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
           unpack_h8(xv[c], f);
           if (gr) {   // the norm never follows a gate in Llama; keep the generic order anyway
             const int idx = base + c * nt + tid;
-            float g[8];
-            if (idx < noct_in) {
-              unpack_h8(*reinterpret_cast<const uint4*>(gr + (size_t)idx * 8), g);
-#pragma unroll
-              for (int j = 0; j < 8; j++) f[j] = f16_round(f16_round(silu_f(g[j])) * f[j]);
-            }
+            if (idx < noct_in)
+              pre_ops(f, *reinterpret_cast<const uint4*>(gr + (size_t)idx * 8), true, xv[c], false, 1.f, xv[c], false);
           }
 #pragma unroll
           for (int j = 0; j < 8; j++) ss = fmaf(f[j], f[j], ss);
@@ -293,13 +327,9 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
       for (int c = 0; c < CH; c++) {
         const int idx = base + c * nt + tid;
         if (idx < noct) {
-          float f[8], g[8], w[8], su[8];
+          float f[8];
           unpack_h8(xv[c], f);
-          unpack_h8(gv[c], g);
-          unpack_h8(wv[c], w);
-          unpack_h8(sv[c], su);
-          if (idx < noct_in) pre_ops(f, g, gr != nullptr, w, a.norm_w != nullptr, rstd, su, a.SU != nullptr);
-          if (reg_pass) butterfly_regs<3>(f);
+          if (idx < noct_in) pre_ops(f, gv[c], gr != nullptr, wv[c], a.norm_w != nullptr, rstd, sv[c], a.SU != nullptr);
           float4* d = reinterpret_cast<float4*>(sm.s + spad(idx * 8));
           d[0] = make_float4(f[0], f[1], f[2], f[3]);
           d[1] = make_float4(f[4], f[5], f[6], f[7]);
@@ -307,30 +337,12 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
       }
     }
   } else {
-    if (a.norm_w) {
-      float ss = 0.f;
-      for (int i = tid; i < a.in_features; i += nt) {
-        float v = __half2float(xr[i]);
-        if (gr) v = f16_round(f16_round(silu_f(__half2float(gr[i]))) * v);
-        ss = fmaf(v, v, ss);
-      }
-      ss = block_sum(ss, sm.red, tid, nt);
-      rstd = rsqrtf(ss / (float)a.in_features + a.norm_eps);
-    }
-    for (int i = tid; i < a.q_in; i += nt) {
-      float v = 0.f;
-      if (i < a.in_features) {
-        v = __half2float(xr[i]);
-        if (gr) v = f16_round(f16_round(silu_f(__half2float(gr[i]))) * v);
-        if (a.norm_w) v = f16_round(__half2float(__float2half_rn(v * rstd)) * __half2float(a.norm_w[i]));
-        if (a.SU) v = f16_round(v * __half2float(a.SU[i]));
-      }
-      sm.s[spad(i)] = v;
-    }
+    prologue_scalar_fill(a, sm, xr, gr, tid, nt);
   }
-  (void)zero8;
+  QB_DSTAMP(9);
   __syncthreads();
-  rotate_smem(sm, a.q_in, a.K, a.scale, a.transform, (vec && reg_pass) ? 3 : 0, tid, nt);
+  rotate_smem(sm, a.q_in, a.K, a.scale, a.transform, tid, nt);
+  QB_DSTAMP(10);
 
   // abs-max -> 16-bit fixed-point scale, then the records
   const int L = 1 << a.log2L;
@@ -347,6 +359,7 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
     for (int i = tid; i < a.q_in; i += nt) mx = fmaxf(mx, fabsf(__half2float(sm.t[t_index(sm, a.K, i)])));
   }
   mx = block_max(mx, sm.red, tid, nt);
+  QB_DSTAMP(11);
   const float inv = (mx > 0.f) ? 32767.0f / mx : 0.f;
   for (int sgi = tid; sgi < noct; sgi += nt) {
     float f[8];
@@ -369,15 +382,43 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
     r.y = hi[4] | (hi[5] << 8) | (hi[6] << 16) | (hi[7] << 24);
     r.z = lo[0] | (lo[1] << 8) | (lo[2] << 16) | (lo[3] << 24);
     r.w = lo[4] | (lo[5] << 8) | (lo[6] << 16) | (lo[7] << 24);
-    dst[sgi] = r;
+    dst[swizzle ? swz(sgi) : sgi] = r;
   }
   return (mx > 0.f) ? mx / 32767.0f : 0.f;
 }
 
+// cold path: unaligned rows or in_features % 8 != 0
+__device__ __noinline__ void prologue_scalar_fill(const PrologueArgs& a, RotSmem sm, const __half* xr, const __half* gr,
+                                                  int tid, int nt) {
+  float rstd = 1.f;
+  if (a.norm_w) {
+    float ss = 0.f;
+    for (int i = tid; i < a.in_features; i += nt) {
+      float v = __half2float(xr[i]);
+      if (gr) v = f16_round(f16_round(silu_f(__half2float(gr[i]))) * v);
+      ss = fmaf(v, v, ss);
+    }
+    ss = block_sum(ss, sm.red, tid, nt);
+    rstd = rsqrtf(ss / (float)a.in_features + a.norm_eps);
+  }
+  for (int i = tid; i < a.q_in; i += nt) {
+    float v = 0.f;
+    if (i < a.in_features) {
+      v = __half2float(xr[i]);
+      if (gr) v = f16_round(f16_round(silu_f(__half2float(gr[i]))) * v);
+      if (a.norm_w) v = f16_round(f16_round(v * rstd) * __half2float(a.norm_w[i]));
+      if (a.SU) v = f16_round(v * __half2float(a.SU[i]));
+    }
+    sm.s[spad(i)] = v;
+  }
+}
+
 __global__ void __launch_bounds__(PRO_THREADS) ql_prologue_kernel(PrologueArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.x;
-  const float xs = prologue_body(a, smem_raw, a.xq + (size_t)m * (a.q_in >> 3), m, threadIdx.x, PRO_THREADS);
+  const float xs = prologue_body(a, smem_raw, a.xq + (size_t)m * (a.q_in >> 3), m, threadIdx.x, PRO_THREADS, false);
   if (threadIdx.x == 0) a.xscale[m] = xs;
 }
 
@@ -403,15 +444,34 @@ struct EpilogueArgs {
 };
 
 __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned char* rot_base, int m, float xscale,
-                                              int tid, int nt) {
+                                              int tid, int nt, long long* dbg = nullptr) {
   const RotSmem sm = rot_carve(rot_base, a.q_out, a.K, a.log2L);
   load_hadK(sm, a.hadK, a.K, /*transpose=*/0, tid, nt);
   const float xs = xscale * a.unit;
   const float* ar = a.acc + (size_t)m * a.q_out;
   const float* ar2 = a.acc2 ? a.acc2 + (size_t)m * a.q_out : nullptr;
   const int noct = a.q_out >> 3;
-  const bool reg_pass = a.transform && a.log2L >= 3;
   const bool vec_in = (a.q_out & 7) == 0 && al16(ar) && (!ar2 || al16(ar2));
+  __half* yr = a.y + (size_t)m * a.ldy;
+  const __half* rr = a.residual ? a.residual + (size_t)m * a.ldres : nullptr;
+  const int L = 1 << a.log2L;
+  const bool vec_out = (a.out_features & 7) == 0 && al16(yr) && (!a.SV || al16(a.SV)) && (!a.bias || al16(a.bias)) &&
+                       (!rr || al16(rr)) && ((a.K == 1) || L >= 8);
+  const int noct_out = a.out_features >> 3;
+  const bool pre_out = vec_out && noct_out <= nt * CH;   // prefetch: these loads do not depend on the rotation
+  uint4 psv[CH], pbv[CH], prv[CH];
+  if (pre_out) {
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+      const int idx = c * nt + tid;
+      psv[c] = pbv[c] = prv[c] = make_uint4(0, 0, 0, 0);
+      if (idx < noct_out) {
+        if (a.SV) psv[c] = *reinterpret_cast<const uint4*>(a.SV + (size_t)idx * 8);
+        if (a.bias) pbv[c] = *reinterpret_cast<const uint4*>(a.bias + (size_t)idx * 8);
+        if (rr) prv[c] = *reinterpret_cast<const uint4*>(rr + (size_t)idx * 8);
+      }
+    }
+  }
   if (vec_in) {
     for (int base = 0; base < noct; base += nt * CH) {
       float4 v0[CH], v1[CH], w0[CH], w1[CH];
@@ -433,16 +493,17 @@ __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned ch
         const int idx = base + c * nt + tid;
         if (idx < noct) {
           float f[8] = {v0[c].x, v0[c].y, v0[c].z, v0[c].w, v1[c].x, v1[c].y, v1[c].z, v1[c].w};
-          const float r[8] = {w0[c].x, w0[c].y, w0[c].z, w0[c].w, w1[c].x, w1[c].y, w1[c].z, w1[c].w};
+          if (ar2) {
+            const float r[8] = {w0[c].x, w0[c].y, w0[c].z, w0[c].w, w1[c].x, w1[c].y, w1[c].z, w1[c].w};
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            float v = f[j];
-            if (ar2) v = fmaf(a.resid_scale, r[j], v);
-            v = f16_round(v * xs);                                                          // origin_order.cu:129
-            if (a.wscale_pc) v = f16_round(v * __half2float(a.wscale_pc[idx * 8 + j]));   // qlinear.py:107
-            f[j] = v;
+            for (int j = 0; j < 8; j++) f[j] = fmaf(a.resid_scale, r[j], f[j]);
           }
-          if (reg_pass) butterfly_regs<3>(f);
+#pragma unroll
+          for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] * xs);                      // origin_order.cu:129
+          if (a.wscale_pc) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] * __half2float(a.wscale_pc[idx * 8 + j]));   // qlinear.py:107
+          }
           float4* d = reinterpret_cast<float4*>(sm.s + spad(idx * 8));
           d[0] = make_float4(f[0], f[1], f[2], f[3]);
           d[1] = make_float4(f[4], f[5], f[6], f[7]);
@@ -458,23 +519,21 @@ __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned ch
       sm.s[spad(i)] = v;
     }
   }
+  QB_DSTAMP(13);
   __syncthreads();
-  rotate_smem(sm, a.q_out, a.K, a.scale, a.transform, (vec_in && reg_pass) ? 3 : 0, tid, nt);
+  rotate_smem(sm, a.q_out, a.K, a.scale, a.transform, tid, nt);
+  QB_DSTAMP(14);
 
-  __half* yr = a.y + (size_t)m * a.ldy;
-  const __half* rr = a.residual ? a.residual + (size_t)m * a.ldres : nullptr;
-  const int L = 1 << a.log2L;
-  const bool vec_out = (a.out_features & 7) == 0 && al16(yr) && (!a.SV || al16(a.SV)) && (!a.bias || al16(a.bias)) &&
-                       (!rr || al16(rr)) && ((a.K == 1) || L >= 8);
   if (vec_out) {
-    const int noct_out = a.out_features >> 3;
     for (int base = 0; base < noct_out; base += nt * CH) {
       uint4 sv[CH], bv[CH], rv[CH];
 #pragma unroll
       for (int c = 0; c < CH; c++) {
         const int idx = base + c * nt + tid;
         sv[c] = bv[c] = rv[c] = make_uint4(0, 0, 0, 0);
-        if (idx < noct_out) {
+        if (pre_out) {
+          sv[c] = psv[c]; bv[c] = pbv[c]; rv[c] = prv[c];
+        } else if (idx < noct_out) {
           if (a.SV) sv[c] = *reinterpret_cast<const uint4*>(a.SV + (size_t)idx * 8);
           if (a.bias) bv[c] = *reinterpret_cast<const uint4*>(a.bias + (size_t)idx * 8);
           if (rr) rv[c] = *reinterpret_cast<const uint4*>(rr + (size_t)idx * 8);
@@ -484,18 +543,22 @@ __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned ch
       for (int c = 0; c < CH; c++) {
         const int idx = base + c * nt + tid;
         if (idx < noct_out) {
-          float f[8], s8[8], b8[8], r8[8];
+          float f[8], o8[8];
           unpack_h8(*reinterpret_cast<const uint4*>(sm.t + t_index(sm, a.K, idx * 8)), f);
-          unpack_h8(sv[c], s8);
-          unpack_h8(bv[c], b8);
-          unpack_h8(rv[c], r8);
+          if (a.SV) {      // qlinear.py:112
+            unpack_h8(sv[c], o8);
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            float v = f[j];
-            if (a.SV) v = f16_round(v * s8[j]);      // qlinear.py:112
-            if (a.bias) v = f16_round(v + b8[j]);    // qlinear.py:114
-            if (rr) v = v + r8[j];                   // decoder-layer residual (fusion hook)
-            f[j] = v;
+            for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] * o8[j]);
+          }
+          if (a.bias) {    // qlinear.py:114
+            unpack_h8(bv[c], o8);
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] + o8[j]);
+          }
+          if (rr) {        // decoder-layer residual (fusion hook)
+            unpack_h8(rv[c], o8);
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[j] += o8[j];
           }
           *reinterpret_cast<uint4*>(yr + (size_t)idx * 8) = pack_h8(f);
         }
@@ -514,6 +577,8 @@ __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned ch
 
 __global__ void __launch_bounds__(PRO_THREADS) ql_epilogue_kernel(EpilogueArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait();
   epilogue_body(a, smem_raw, blockIdx.x, a.xscale[blockIdx.x], threadIdx.x, PRO_THREADS);
 }
 
@@ -525,6 +590,7 @@ struct GemvArgs {
   int64_t row_bytes;
   const void* table;           // E8P: uint2[256]; D4: fp16 [256][4]
   int N, nseg, C, g;           // rows, 8-element segments per row, chunks per row, warps per chunk
+  int rows_base, rows_rem;     // CTA b owns rows [b*base + min(b,rem), ...): N = G*base + rem
   int fuse_pro, fuse_epi;
   PrologueArgs pro;            // fuse_pro: computed in-kernel; else pro.xq / pro.xscale are read
   EpilogueArgs epi;            // epi.acc / epi.acc2 are this kernel's outputs
@@ -533,6 +599,8 @@ struct GemvArgs {
 };
 
 struct GroupArgs {
+  long long* dbg;   // optional [ctas][16] clock stamps (tools/timeline.py)
+  int phase0;
   int n;
   int cta_begin[QUIPB200_MAX_GROUP + 1];
   GemvArgs a[QUIPB200_MAX_GROUP];
@@ -598,6 +666,11 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   const int m = blockIdx.y;
 
+  pdl_launch_dependents();   // the next kernel may start prefetching its own weights while we run
+  long long* dbg = ga.dbg ? ga.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+#define QB_STAMP(i) do { if (dbg && threadIdx.x == 0) dbg[i] = clock64(); } while (0)
+  QB_STAMP(0);
+
   // ---- which member of the group, which rows ----
   int j = 0;
   if (ga.n > 1 && (int)blockIdx.x >= ga.cta_begin[1]) j = 1;
@@ -605,15 +678,76 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
   const GemvArgs& a = ga.a[j];
   const int G = ga.cta_begin[j + 1] - ga.cta_begin[j];
   const int bx = blockIdx.x - ga.cta_begin[j];
-  const int row_begin = (int)(((int64_t)bx * a.N) / G);
-  const int row_end = (int)(((int64_t)(bx + 1) * a.N) / G);
-  const int nrows = row_end - row_begin;
+  const int row_begin = bx * a.rows_base + min(bx, a.rows_rem);
+  const int nrows = a.rows_base + (bx < a.rows_rem ? 1 : 0);
   const int units = a.C * a.g;
 
+  // ---- warm L2 with the small per-layer vectors this CTA will need after the dependency wait ----
+  {
+    const char* pf = nullptr;
+    int lines = 0;
+    if (tid < 128) { pf = reinterpret_cast<const char*>(a.pro.SU); lines = (a.pro.in_features * 2 + 127) >> 7; }
+    else if (tid < 256) { pf = reinterpret_cast<const char*>(a.pro.norm_w); lines = (a.pro.in_features * 2 + 127) >> 7; }
+    else if (tid < 448) { pf = reinterpret_cast<const char*>(a.epi.SV); lines = (a.epi.out_features * 2 + 127) >> 7; }
+    const int li = tid < 128 ? tid : (tid < 256 ? tid - 128 : tid - 256);
+    if (pf != nullptr && li < lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t)li * 128));
+  }
+
   // ---- phase 0: first batch of code loads for this warp's first unit ----
+  const uint64_t pol = l2_evict_first_policy();
   uint4 cw[UNROLL];
   int unit = warp;
   {
+    const int chunk = unit / a.g, sub = unit - chunk * a.g;
+    const bool lv = unit < units && (chunk * 32 + lane) * T::SEGS < a.nseg;
+    const unsigned char* colp = a.qidxs + (size_t)(chunk * 32 + lane) * 16 + (size_t)row_begin * a.row_bytes;
+    if (ga.phase0) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        const int r = sub + u * a.g;
+        cw[u] = make_uint4(0, 0, 0, 0);
+        if (lv && r < nrows) cw[u] = ldg_stream_v4(colp + (size_t)r * a.row_bytes, pol);
+      }
+    }
+  }
+
+  // ---- table entry for this thread: issue the load now, park it in shared memory after phase 1 ----
+  uint2 tabv = make_uint2(0, 0);
+  if (tid < 256) tabv = reinterpret_cast<const uint2*>(a.table)[tid];   // E8P: int8x8 entry; D4: 4 x fp16
+
+  QB_STAMP(1);
+  // everything above read only weights; from here on we consume what earlier kernels produced
+  pdl_wait();
+  QB_STAMP(2);
+
+  // ---- phase 1: activation records ----
+  const uint4* xq;
+  float xscale;
+  if (a.fuse_pro) {
+    uint4* xq_s = reinterpret_cast<uint4*>(smem_raw + a.xq_off);
+    xscale = prologue_body(a.pro, smem_raw + a.rot_off, xq_s, m, tid, nt, true, dbg);
+    xq = xq_s;
+    if (!a.fuse_epi && bx == 0 && tid == 0) a.pro.xscale[m] = xscale;   // for the epilogue kernel
+  } else {
+    xq = a.pro.xq + (size_t)m * a.nseg;
+    xscale = a.pro.xscale[m];
+  }
+  if (tid < 256) {
+    if (CB == QUIPB200_CB_D4) {
+      // fp16 [4] -> int8 (units of 1/2), byte order (0,2,1,3) to match perm_0213'd activations
+      const __half2 h01 = *reinterpret_cast<const __half2*>(&tabv.x), h23 = *reinterpret_cast<const __half2*>(&tabv.y);
+      const int v0 = __float2int_rn(__low2float(h01) * 2.0f) & 0xff, v1 = __float2int_rn(__high2float(h01) * 2.0f) & 0xff;
+      const int v2 = __float2int_rn(__low2float(h23) * 2.0f) & 0xff, v3 = __float2int_rn(__high2float(h23) * 2.0f) & 0xff;
+      reinterpret_cast<uint32_t*>(tab)[tid] = (uint32_t)v0 | ((uint32_t)v2 << 8) | ((uint32_t)v1 << 16) | ((uint32_t)v3 << 24);
+    } else {
+      tabv.x |= 0x01010101u;
+      tabv.y |= 0x01010101u;
+      reinterpret_cast<uint2*>(tab)[tid] = tabv;
+    }
+  }
+  __syncthreads();
+  QB_STAMP(3);
+  if (!ga.phase0) {
     const int chunk = unit / a.g, sub = unit - chunk * a.g;
     const bool lv = unit < units && (chunk * 32 + lane) * T::SEGS < a.nseg;
     const unsigned char* colp = a.qidxs + (size_t)(chunk * 32 + lane) * 16 + (size_t)row_begin * a.row_bytes;
@@ -621,46 +755,12 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
     for (int u = 0; u < UNROLL; u++) {
       const int r = sub + u * a.g;
       cw[u] = make_uint4(0, 0, 0, 0);
-      if (lv && r < nrows) cw[u] = ldg_stream_v4(colp + (size_t)r * a.row_bytes);
+      if (lv && r < nrows) cw[u] = ldg_stream_v4(colp + (size_t)r * a.row_bytes, pol);
     }
   }
-
-  // ---- table ----
-  if (CB == QUIPB200_CB_D4) {
-    // fp16 [256][4] -> int8 (units of 1/2), byte order (0,2,1,3) to match perm_0213'd activations
-    const __half* g = reinterpret_cast<const __half*>(a.table);
-    for (int i = tid; i < 256; i += nt) {
-      int v[4];
-#pragma unroll
-      for (int jj = 0; jj < 4; jj++) v[jj] = __float2int_rn(__half2float(g[i * 4 + jj]) * 2.0f) & 0xff;
-      reinterpret_cast<uint32_t*>(tab)[i] = (uint32_t)v[0] | ((uint32_t)v[2] << 8) | ((uint32_t)v[1] << 16) |
-                                            ((uint32_t)v[3] << 24);
-    }
-  } else {
-    const uint2* g = reinterpret_cast<const uint2*>(a.table);
-    for (int i = tid; i < 256; i += nt) {
-      uint2 t = g[i];
-      t.x |= 0x01010101u;
-      t.y |= 0x01010101u;
-      reinterpret_cast<uint2*>(tab)[i] = t;
-    }
-  }
-
-  // ---- phase 1: activation records ----
-  const uint4* xq;
-  float xscale;
-  if (a.fuse_pro) {
-    uint4* xq_s = reinterpret_cast<uint4*>(smem_raw + a.xq_off);
-    xscale = prologue_body(a.pro, smem_raw + a.rot_off, xq_s, m, tid, nt);
-    xq = xq_s;
-    if (!a.fuse_epi && bx == 0 && tid == 0) a.pro.xscale[m] = xscale;   // for the epilogue kernel
-  } else {
-    xq = a.pro.xq + (size_t)m * a.nseg;
-    xscale = a.pro.xscale[m];
-  }
-  __syncthreads();
 
   // ---- phase 2: GEMV ----
+  bool first_unit = true;
   while (unit < units) {
     const int chunk = unit / a.g;
     const int sub = unit - chunk * a.g;
@@ -671,7 +771,7 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
 #pragma unroll
     for (int sgi = 0; sgi < T::SEGS; sgi++) {
       uint4 r = make_uint4(0, 0, 0, 0);
-      if (lane_valid) r = xq[seg0 + sgi];
+      if (lane_valid) r = xq[a.fuse_pro ? swz(seg0 + sgi) : seg0 + sgi];
       xs[sgi][0] = perm_0213(r.x);
       xs[sgi][1] = perm_0213(r.y);
       xs[sgi][2] = perm_0213(r.z);
@@ -681,6 +781,7 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
       xsum[sgi] = sh * 256 + sl;
     }
     const unsigned char* colp = a.qidxs + (size_t)(chunk * 32 + lane) * 16 + (size_t)row_begin * a.row_bytes;
+    if (first_unit) { QB_STAMP(4); first_unit = false; }
 
     for (int r0 = sub; r0 < nrows; r0 += a.g * UNROLL) {
       // software pipeline: fetch the next batch before decoding the current one
@@ -690,7 +791,7 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
       for (int u = 0; u < UNROLL; u++) {
         const int r = rn + u * a.g;
         nx[u] = make_uint4(0, 0, 0, 0);
-        if (lane_valid && r < nrows) nx[u] = ldg_stream_v4(colp + (size_t)r * a.row_bytes);
+        if (lane_valid && r < nrows) nx[u] = ldg_stream_v4(colp + (size_t)r * a.row_bytes, pol);
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; u++) {
@@ -699,9 +800,14 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
           int aH = 0, aL = 0, aP = 0, bH = 0, bL = 0, bP = 0;
           const uint32_t w[4] = {cw[u].x, cw[u].y, cw[u].z, cw[u].w};
           if (CB == QUIPB200_CB_E8P12) {
+            // four independent accumulation chains (two per word half) keep the dp4a pipe fed
+            int cH = 0, cL = 0, cP = 0;
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-              e8p_dot2(w[i], tab, xs[2 * i], xsum[2 * i], xs[2 * i + 1], xsum[2 * i + 1], aH, aL, aP);
+            for (int i = 0; i < 4; i++) {
+              e8p_dot((w[i] >> 5) & 0x7f8u, w[i] & 0xffu, tab, xs[2 * i], xsum[2 * i], aH, aL, aP);
+              e8p_dot((w[i] >> 21) & 0x7f8u, __byte_perm(w[i], 0, 0x4442), tab, xs[2 * i + 1], xsum[2 * i + 1], cH, cL, cP);
+            }
+            aH += cH; aL += cL; aP += cP;
           } else if (CB == QUIPB200_CB_E8P12RVQ4B) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -747,10 +853,11 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
       for (int u = 0; u < UNROLL; u++) {
         const int r = sub2 + u * a.g;
         cw[u] = make_uint4(0, 0, 0, 0);
-        if (lv && r < nrows) cw[u] = ldg_stream_v4(colp2 + (size_t)r * a.row_bytes);
+        if (lv && r < nrows) cw[u] = ldg_stream_v4(colp2 + (size_t)r * a.row_bytes, pol);
       }
     }
   }
+  QB_STAMP(5);
   __syncthreads();
   // ---- combine the C chunk partials of every row, coalesced store ----
   float* acc = const_cast<float*>(a.epi.acc);
@@ -765,20 +872,24 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
     if (T::ACCS == 2) __stcg(acc2 + (size_t)m * a.N + row_begin + r, (float)s2);
   }
 
+  QB_STAMP(6);
   // ---- phase 3: the last CTA of this member runs the output side ----
   if (!a.fuse_epi) return;
-  __threadfence();
-  __syncthreads();
+  __syncthreads();   // every thread's acc stores are ordered before thread 0's fence (fences are cumulative)
   if (tid == 0) {
+    __threadfence();
     const unsigned int prev = atomicAdd(a.counters + m, 1u);
     s_last = (prev == (unsigned int)(G - 1));
     if (a.fuse_pro) s_xscale = xscale;
   }
   __syncthreads();
+  QB_STAMP(7);
   if (!s_last) return;
-  __threadfence();
   if (tid == 0) a.counters[m] = 0;   // ready for the next launch that draws this slot
-  epilogue_body(a.epi, smem_raw + a.rot_off, m, a.fuse_pro ? s_xscale : a.pro.xscale[m], tid, nt);
+  epilogue_body(a.epi, smem_raw + a.rot_off, m, a.fuse_pro ? s_xscale : a.pro.xscale[m], tid, nt, dbg);
+  __syncthreads();
+  QB_STAMP(8);
+#undef QB_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -869,6 +980,8 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
   if (sms < 1) return (int)cudaErrorNoDevice;
   GemvPlan plan[QUIPB200_MAX_GROUP];
   GroupArgs ga{};
+  ga.dbg = g_dbg_timeline;
+  ga.phase0 = g_opt_phase0;
   ga.n = n;
   int rc;
   size_t ws_off = 0;
@@ -906,7 +1019,7 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
     const size_t epi_smem = rot_smem_bytes(mj.ea.q_out, mj.ea.K);
     if (pro_smem > SMEM_LIMIT || epi_smem > SMEM_LIMIT) return QUIPB200_EUNSUPPORTED;
     const size_t red_bytes = ((size_t)rows_per_cta * plan[j].C * plan[j].accs * sizeof(int) + 15) / 16 * 16;
-    const size_t xq_bytes = (size_t)(mj.K / 8) * 16;
+    const size_t xq_bytes = (size_t)((mj.K / 8 + 7) / 8 * 8) * 16;   // swizzle stays inside 8-record blocks
     // fused prologue only for pure-FWHT (or identity) input sides: the orthogonal-block mix is too
     // much work to repeat in every CTA
     bool fuse_pro = (g_opt_fuse & 1) && mj.pa.K == 1;
@@ -929,6 +1042,7 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
     GemvArgs& g = ga.a[j];
     g.qidxs = (const unsigned char*)mj.qidxs; g.row_bytes = plan[j].row_bytes; g.table = mj.grid;
     g.N = mj.N; g.nseg = mj.K / 8; g.C = plan[j].C; g.g = plan[j].g;
+    g.rows_base = mj.N / G; g.rows_rem = mj.N % G;
     g.fuse_pro = fuse_pro ? 1 : 0; g.fuse_epi = fuse_epi ? 1 : 0;
     g.pro = mj.pa; g.epi = mj.ea;
     g.xq_off = (uint32_t)(plan[j].tab_bytes + red_bytes);
@@ -948,7 +1062,9 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
       if (ga.a[j].fuse_pro) continue;
       const size_t pro_smem = rot_smem_bytes(mem[j].pa.q_in, mem[j].pa.K);
       if ((rc = set_smem_attr((const void*)ql_prologue_kernel, pro_smem))) return rc;
-      ql_prologue_kernel<<<M, PRO_THREADS, pro_smem, st>>>(ga.a[j].pro);
+      void* pargs[] = {&ga.a[j].pro};
+      cudaError_t pe = launch_kernel((const void*)ql_prologue_kernel, dim3(M), dim3(PRO_THREADS), pargs, pro_smem, st);
+      if (pe != cudaSuccess) return (int)pe;
       QB_LAUNCH_CHECK();
     }
   }
@@ -962,7 +1078,7 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
     }
     if ((rc = set_smem_attr(fn, smem))) return rc;
     void* args[] = {&ga};
-    cudaError_t e = cudaLaunchKernel(fn, dim3(cta, M), dim3(plan[0].warps * 32), args, smem, st);
+    cudaError_t e = launch_kernel(fn, dim3(cta, M), dim3(plan[0].warps * 32), args, smem, st);
     if (e != cudaSuccess) return (int)e;
     QB_LAUNCH_CHECK();
   }
@@ -971,7 +1087,9 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
       if (ga.a[j].fuse_epi) continue;
       const size_t epi_smem = rot_smem_bytes(mem[j].ea.q_out, mem[j].ea.K);
       if ((rc = set_smem_attr((const void*)ql_epilogue_kernel, epi_smem))) return rc;
-      ql_epilogue_kernel<<<M, PRO_THREADS, epi_smem, st>>>(ga.a[j].epi);
+      void* eargs[] = {&ga.a[j].epi};
+      cudaError_t ee = launch_kernel((const void*)ql_epilogue_kernel, dim3(M), dim3(PRO_THREADS), eargs, epi_smem, st);
+      if (ee != cudaSuccess) return (int)ee;
       QB_LAUNCH_CHECK();
     }
   }
@@ -1011,6 +1129,11 @@ static int member_from_layer(const quipb200_linear_t* L, const quipb200_fusion_t
 }  // namespace qb
 
 using namespace qb;
+
+extern "C" int quipb200_debug_timeline(void* device_int64_buffer) {
+  g_dbg_timeline = (long long*)device_int64_buffer;
+  return 0;
+}
 
 extern "C" size_t quipb200_mm_workspace_bytes(int M, int N, int K) {
   if (M < 1 || N < 1 || K < 8) return 0;

@@ -71,15 +71,17 @@ def main():
             def sweep():
                 for L in layers:
                     L(x)
-            for name, fuse, mask in (("fused", 3, 7), ("fuse_pro_only", 1, 7), ("unfused_all", 0, 7),
-                                     ("gemv_only", 0, 2), ("prologue_only", 0, 1), ("epilogue_only", 0, 4)):
+            for name, fuse, mask, pdl in (("fused", 3, 7, 1), ("fused_nopdl", 3, 7, 0), ("unfused_all", 0, 7, 1),
+                                          ("gemv_only", 0, 2, 0), ("prologue_only", 0, 1, 0), ("epilogue_only", 0, 4, 0)):
                 _native.set_option("fuse", fuse)
                 _native.set_option("stage_mask", mask)
+                _native.set_option("pdl", pdl)
                 try:
                     ms = graph_time(sweep)
                 finally:
                     _native.set_option("fuse", 3)
                     _native.set_option("stage_mask", 7)
+                    _native.set_option("pdl", 1)
                 rec[name + "_us"] = round(1000 * ms / NL, 3)
             rec["fused_gbs"] = round(code_bytes / (rec["fused_us"] * 1e-6) / 1e9, 1)
             rec["gemv_only_gbs"] = round(code_bytes / (rec["gemv_only_us"] * 1e-6) / 1e9, 1)
@@ -126,6 +128,18 @@ def main():
         rec["down_silu_resid_us"] = round(1000 * graph_time(lambda: [g(u, gate=u, residual=h) for g in dn]) / NL, 3)
         rec["attn_ctx384_us"] = round(1000 * graph_time(lambda: [attn_decode(h, h, h, kc, vc, cs, cs, pos, ao, 32, 32, 128) for _ in range(NL)]) / NL, 3)
         rec["layer_total_us"] = round(sum(v for k, v in rec.items() if k.endswith("_us")), 3)
+
+        def whole_layer():
+            for i in range(NL):
+                q, k, v = qkv[i](h, norm_w=w, eps=1e-5)
+                attn_decode(q, k, v, kc, vc, cs, cs, pos, ao, 32, 32, 128)
+                h2 = og[i](ao, residual=h)[0]
+                g_, u_ = gu[i](h2, norm_w=w, eps=1e-5)
+                dn[i](u_, gate=g_, residual=h2)
+        rec["layer_chained_us"] = round(1000 * graph_time(whole_layer) / NL, 3)
+        _native.set_option("pdl", 0)
+        rec["layer_chained_nopdl_us"] = round(1000 * graph_time(whole_layer) / NL, 3)
+        _native.set_option("pdl", 1)
         print(json.dumps(rec), flush=True)
         out.append(rec)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
