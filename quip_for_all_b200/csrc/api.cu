@@ -12,6 +12,7 @@ extern int g_opt_gemv_ctas_per_sm;
 extern int g_opt_stage_mask;
 extern int g_opt_fuse;
 extern int g_opt_phase0;
+extern int g_opt_lean;
 }  // namespace qb
 
 extern "C" int quipb200_abi_version(void) { return QUIPB200_ABI_VERSION; }
@@ -48,7 +49,7 @@ extern "C" int quipb200_set_option(const char* name, int value) {
     return 0;
   }
   if (!strcmp(name, "gemv_warps")) {
-    if (value < 0 || value > 24) return QUIPB200_EINVAL;
+    if (value < 0 || value > 32) return QUIPB200_EINVAL;
     qb::g_opt_gemv_warps = value;
     return 0;
   }
@@ -60,6 +61,10 @@ extern "C" int quipb200_set_option(const char* name, int value) {
   if (!strcmp(name, "stage_mask")) {
     if (value < 0 || value > 7) return QUIPB200_EINVAL;
     qb::g_opt_stage_mask = value;
+    return 0;
+  }
+  if (!strcmp(name, "lean")) {
+    qb::g_opt_lean = value ? 1 : 0;
     return 0;
   }
   if (!strcmp(name, "phase0")) {

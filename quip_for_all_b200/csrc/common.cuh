@@ -68,6 +68,13 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const void* p, uint64_t pol) {
                : "l"(p), "l"(pol));
   return r;
 }
+__device__ __forceinline__ uint2 ldg_stream_v2(const void* p, uint64_t pol) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+               : "=r"(r.x), "=r"(r.y)
+               : "l"(p), "l"(pol));
+  return r;
+}
 __device__ __forceinline__ void stg_stream_v4(void* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
                "r"(v.z), "r"(v.w)
@@ -265,6 +272,77 @@ static __device__ __noinline__ void fwht_hi(float* s, int total, int log2L, int 
     __syncthreads();
   }
 }
+// ---------------------------------------------------------------------------------------------
+// Stockham-style (autosort) block Walsh-Hadamard passes between two UNPADDED fp32 buffers.
+// A pass of radix 2^R on blocks of L = 2^p reads 2^R values at stride L/2^R (consecutive threads ->
+// consecutive words: conflict free) and writes its 2^R results CONTIGUOUSLY (one or two 128-bit
+// stores).  That matters on Blackwell: a CTA barrier drains every pending shared-memory store, and its
+// cost grows with the number of STS instructions in flight per warp -- 2 wide stores instead of 8
+// narrow ones per pass.  After all passes the data are back in natural order; the last radix-8 pass
+// is left to the caller, which keeps the finished octet in registers.
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void stockham_pass(const float* __restrict__ src, float* __restrict__ dst, int total,
+                                              int p, int tid, int nt) {
+  const int sh = p - R;                      // log2 of the read stride
+  for (int g = tid; g < (total >> R); g += nt) {
+    const int k = g >> sh, rest = g & ((1 << sh) - 1);
+    const float* in = src + (k << p) + rest;
+    float v[1 << R];
+#pragma unroll
+    for (int j = 0; j < (1 << R); j++) v[j] = in[j << sh];
+    butterfly_regs<R>(v);
+    float* out = dst + (k << p) + (rest << R);
+    if (R == 3) {
+      reinterpret_cast<float4*>(out)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(out)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else if (R == 2) {
+      reinterpret_cast<float4*>(out)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      reinterpret_cast<float2*>(out)[0] = make_float2(v[0], v[1]);
+    }
+  }
+}
+// All passes except the final radix-8 one (requires p >= 3).  Returns the buffer holding the result.
+static __device__ __noinline__ const float* stockham_hi(float* a, float* b, int total, int p, int tid, int nt) {
+  float* cur = a;
+  float* nxt = b;
+  const int r0 = p % 3;
+  if (r0 == 1) { stockham_pass<1>(cur, nxt, total, p, tid, nt); __syncthreads(); float* t = cur; cur = nxt; nxt = t; }
+  else if (r0 == 2) { stockham_pass<2>(cur, nxt, total, p, tid, nt); __syncthreads(); float* t = cur; cur = nxt; nxt = t; }
+  for (int i = 0; i < p / 3 - 1; i++) {
+    stockham_pass<3>(cur, nxt, total, p, tid, nt);
+    __syncthreads();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  return cur;
+}
+// final radix-8 pass of octet o (natural order result for elements 8o..8o+7)
+__device__ __forceinline__ void stockham_last(const float* __restrict__ src, int p, int o, float (&v)[8]) {
+  const int sh = p - 3;
+  const int k = o >> sh, rest = o & ((1 << sh) - 1);
+  const float* in = src + (k << p) + rest;
+#pragma unroll
+  for (int j = 0; j < 8; j++) v[j] = in[j << sh];
+  butterfly_regs<3>(v);
+}
+
+// 256-point WHT of one block held by ONE WARP (lane l owns elements 8l..8l+7): bits 0..2 in registers,
+// bits 3..7 across lanes with shuffles.  No shared memory, no barrier -- used for the 43 x 256 / 172 x 64-style
+// block rotations where blocks are independent.
+__device__ __forceinline__ void warp_fwht256(float (&v)[8], int lane) {
+  butterfly_regs<3>(v);
+#pragma unroll
+  for (int b = 0; b < 5; b++) {
+    const float sg = ((lane >> b) & 1) ? -1.f : 1.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float p = __shfl_xor_sync(0xffffffffu, v[j], 1 << b);
+      v[j] = fmaf(sg, v[j], p);
+    }
+  }
+}
+
 // last stages (bits 0..nbits-1) on 8 contiguous values held in registers
 __device__ __forceinline__ void butterfly_low(float (&v)[8], int nbits) {
   if (nbits >= 3) butterfly_regs<3>(v);
@@ -301,6 +379,14 @@ __device__ __forceinline__ float block_max(float v, float* red, int tid, int nt)
   float r = red[0];
   for (int w = 1; w < (nt >> 5); w++) r = fmaxf(r, red[w]);
   return r;
+}
+// single-barrier variant: `red` must not be in use by a reduction that other warps may still be reading
+__device__ __forceinline__ float block_max1(float v, float* red, int tid, int nt) {
+  v = warp_max(v);
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  float r = ((tid & 31) < (nt >> 5)) ? red[tid & 31] : 0.f;   // callers reduce |x| >= 0
+  return warp_max(r);
 }
 __device__ __forceinline__ float block_sum(float v, float* red, int tid, int nt) {
   v = warp_sum(v);

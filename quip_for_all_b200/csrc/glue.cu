@@ -10,7 +10,8 @@
 
 namespace qb {
 
-constexpr int ATT_THREADS = 256;
+constexpr int ATT_THREADS = 1024;   // latency bound: positions are spread over 32 warps / 16 PV groups
+constexpr int ATT_GROUPS = ATT_THREADS / 64;
 
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(
@@ -22,7 +23,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(
   __shared__ float sq[HD];
   __shared__ float sk[HD];
   __shared__ float sred[ATT_THREADS / 32];
-  __shared__ float sout[4][HD];
+  __shared__ float sout[ATT_GROUPS][HD];
   pdl_launch_dependents();
   pdl_wait();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -113,22 +114,22 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(
   for (int w = 0; w < ATT_THREADS / 32; w++) tot += sred[w];
   const float inv = 1.0f / tot;
 
-  // ---- out = P . V : 4 groups of 64 threads split the positions, each thread owns 2 dims ----
+  // ---- out = P . V : groups of 64 threads split the positions, each thread owns 2 dims ----
   const int d2 = tid & 63, tg = tid >> 6;
   float o0 = 0.f, o1 = 0.f;
   constexpr int UV = 8;
-  for (int t0 = tg; t0 <= pos; t0 += 4 * UV) {
+  for (int t0 = tg; t0 <= pos; t0 += ATT_GROUPS * UV) {
     __half2 vr[UV];
 #pragma unroll
     for (int u = 0; u < UV; u++) {
-      const int t = t0 + u * 4;
+      const int t = t0 + u * ATT_GROUPS;
       vr[u] = __float2half2_rn(0.f);
       if (t < pos) vr[u] = *reinterpret_cast<const __half2*>(vc + (size_t)t * HD + d2 * 2);
       else if (t == pos) vr[u] = *reinterpret_cast<const __half2*>(v + kvh * HD + d2 * 2);
     }
 #pragma unroll
     for (int u = 0; u < UV; u++) {
-      const int t = t0 + u * 4;
+      const int t = t0 + u * ATT_GROUPS;
       if (t <= pos) {
         const float2 vv = __half22float2(vr[u]);
         const float p = sc[t];
@@ -141,8 +142,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(
   sout[tg][d2 * 2 + 1] = o1;
   __syncthreads();
   if (tid < HD) {
-    const float r = (sout[0][tid] + sout[1][tid] + sout[2][tid] + sout[3][tid]) * inv;
-    out[h * HD + tid] = __float2half_rn(r);
+    float r = 0.f;
+#pragma unroll
+    for (int g2 = 0; g2 < ATT_GROUPS; g2++) r += sout[g2][tid];
+    out[h * HD + tid] = __float2half_rn(r * inv);
   }
 }
 

@@ -33,14 +33,17 @@ int g_opt_gemv_warps = 0;    // 0: auto (16)
 int g_opt_gemv_ctas_per_sm = 1;
 int g_opt_stage_mask = 7;    // bench only: bit0 prologue, bit1 gemv, bit2 epilogue
 int g_opt_fuse = 3;          // bit0: fuse prologue into the GEMV kernel, bit1: last-CTA epilogue
+int g_opt_lean = 1;          // use the instruction-cache-lean kernel instantiation when eligible
 int g_opt_phase0 = 1;        // experiment: 0 = no early code prefetch
 long long* g_dbg_timeline = nullptr;   // profiling hook: per-CTA clock64 stamps of the GEMV kernel phases
 
-constexpr int PRO_THREADS = 512;
-constexpr int GEMV_MAX_WARPS = 16;
+constexpr int PRO_THREADS = 512;    // (1024 threads / 64 registers measured slower for the rotation kernels too)
+constexpr int GEMV_MAX_WARPS = 16;   // 512 threads x <=128 registers (a 1024-thread / 64-register variant measured 40 % slower: spills)
 constexpr int GEMV_UNROLL = 4;
 constexpr int COUNTER_SLOTS = 4096;
-constexpr int CH = 2;        // octets (8 elements) a thread keeps in flight per round in the rotations
+// octets (8 elements) a thread keeps in flight per round in the rotations: 1 in the lean instantiations (code
+// size), 3 in the general ones (11008 / 512 threads = 2.7 octets per thread: one load round instead of three)
+template <bool LEAN> struct Rounds { static constexpr int CH = LEAN ? 1 : 3; };
 
 // tickets for the last-CTA-done epilogue: zero at module load, reset by the CTA that consumes them.
 // One slot per launched linear, handed out round-robin by the host; launches that share a slot must
@@ -56,7 +59,9 @@ static unsigned int g_next_slot = 0;
 //   hk : fp16 [Kp][Kp] coefficient matrix M[k_out][k_in], zero padded to Kp = roundup16(K)
 // ---------------------------------------------------------------------------------------------
 struct RotSmem {
-  float* s;
+  float* s;     // pp == 0: padded (spad) in-place butterfly array;  pp == 1: unpadded ping buffer
+  float* s2;    // pp == 1: pong buffer
+  int pp;
   __half* t;
   __half* hk;
   float* red;
@@ -66,18 +71,26 @@ struct RotSmem {
 
 static inline int kpad(int K) { return (K + 15) / 16 * 16; }
 static inline size_t rot_t_halfs(int q, int K) { return K > 1 ? (size_t)(K + 1) * (q / K + 8) : (size_t)q; }
+// ping-pong (Stockham) layout whenever two fp32 copies fit comfortably; else the in-place padded layout
+static inline bool rot_pingpong(int q, int K) {
+  int L = q / (K > 0 ? K : 1);
+  return L >= 8 && (size_t)q * 8 <= 96 * 1024;
+}
 static inline size_t rot_smem_bytes(int q, int K) {
-  size_t b = (spad_host((size_t)q) * sizeof(float) + 15) / 16 * 16;
+  size_t b = rot_pingpong(q, K) ? (size_t)q * 8 : (spad_host((size_t)q) * sizeof(float) + 15) / 16 * 16;
   b += (rot_t_halfs(q, K) * sizeof(__half) + 15) / 16 * 16;
   if (K > 1) b += (size_t)kpad(K) * kpad(K) * sizeof(__half);
-  b += 32 * sizeof(float);
+  b += 64 * sizeof(float);
   return (b + 15) / 16 * 16;
 }
 
 __device__ __forceinline__ RotSmem rot_carve(unsigned char* base, int q, int K, int log2L) {
   RotSmem r;
   r.s = reinterpret_cast<float*>(base);
-  size_t off = (((size_t)(q + ((q >> 6) << 3) + 8)) * sizeof(float) + 15) / 16 * 16;
+  const int Lb = q / (K > 0 ? K : 1);
+  r.pp = (Lb >= 8 && (size_t)q * 8 <= 96 * 1024) ? 1 : 0;
+  r.s2 = r.s + q;
+  size_t off = r.pp ? (size_t)q * 8 : (((size_t)(q + ((q >> 6) << 3) + 8)) * sizeof(float) + 15) / 16 * 16;
   r.t = reinterpret_cast<__half*>(base + off);
   const size_t th = K > 1 ? (size_t)(K + 1) * ((q / K) + 8) : (size_t)q;
   off += (th * sizeof(__half) + 15) / 16 * 16;
@@ -91,6 +104,8 @@ __device__ __forceinline__ RotSmem rot_carve(unsigned char* base, int q, int K, 
   r.log2L = log2L;
   return r;
 }
+
+__device__ __forceinline__ int s_index(const RotSmem& sm, int i) { return sm.pp ? i : spad(i); }
 
 __device__ __forceinline__ int t_index(const RotSmem& sm, int K, int i) {
   return K > 1 ? (i >> sm.log2L) * sm.Ls + (i & ((1 << sm.log2L) - 1)) : i;
@@ -170,13 +185,13 @@ __device__ __noinline__ void rotate_mix(RotSmem sm, int q, int K, int tid, int n
   }
   // generic CUDA-core mix (tiny blocks / very large K): t -> s (fp32 copy) -> t
   __syncthreads();
-  for (int i = tid; i < q; i += nt) sm.s[spad(i)] = __half2float(sm.t[t_index(sm, K, i)]);
+  for (int i = tid; i < q; i += nt) sm.s[s_index(sm, i)] = __half2float(sm.t[t_index(sm, K, i)]);
   __syncthreads();
   for (int i = tid; i < q; i += nt) {
     const int ko = i >> sm.log2L, c = i & (L - 1);
     float acc = 0.f;
     for (int kp = 0; kp < K; kp++)
-      acc = fmaf(__half2float(sm.hk[ko * Kp + kp]), sm.s[spad((kp << sm.log2L) + c)], acc);
+      acc = fmaf(__half2float(sm.hk[ko * Kp + kp]), sm.s[s_index(sm, (kp << sm.log2L) + c)], acc);
     sm.t[t_index(sm, K, i)] = __float2half_rn(acc);
   }
   __syncthreads();
@@ -187,16 +202,23 @@ __device__ __noinline__ void rotate_mix(RotSmem sm, int q, int K, int tid, int n
 // the contiguous octet each thread then rounds and stores.  Rounding points follow the reference: fp16
 // after the FWHT*scale (register_lib.py:20), fp16 after hadK@ (quant.py:83).  transform == 0: t = round(s).
 __device__ __noinline__ void rotate_smem(RotSmem sm, int q, int K, float scale, int transform, int tid, int nt) {
-  if (transform) fwht_hi(sm.s, q, sm.log2L, tid, nt);
-  const int nbits = transform ? (sm.log2L < 3 ? sm.log2L : 3) : 0;
   const float sc = transform ? scale : 1.0f;
   const int L = 1 << sm.log2L;
   const bool rowvec = (K == 1) || (L >= 8);
+  const float* fin = sm.s;
+  if (transform && sm.pp) fin = stockham_hi(sm.s, sm.s2, q, sm.log2L, tid, nt);
+  else if (transform) fwht_hi(sm.s, q, sm.log2L, tid, nt);
+  const int nbits = transform ? (sm.log2L < 3 ? sm.log2L : 3) : 0;
   for (int o = tid; o < (q >> 3); o += nt) {
-    const float4* sp = reinterpret_cast<const float4*>(sm.s + spad(o * 8));
-    const float4 a = sp[0], b = sp[1];
-    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    butterfly_low(f, nbits);
+    float f[8];
+    if (transform && sm.pp) {
+      stockham_last(fin, sm.log2L, o, f);
+    } else {
+      const float4* sp = reinterpret_cast<const float4*>(sm.s + s_index(sm, o * 8));
+      const float4 a = sp[0], b = sp[1];
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+      butterfly_low(f, nbits);
+    }
 #pragma unroll
     for (int j = 0; j < 8; j++) f[j] *= sc;
     if (rowvec) {
@@ -211,6 +233,34 @@ __device__ __noinline__ void rotate_smem(RotSmem sm, int q, int K, float scale, 
     return;
   }
   rotate_mix(sm, q, K, tid, nt);
+}
+
+// finished (fully transformed, unscaled) octet o of a K == 1 rotation whose high passes are done
+__device__ __forceinline__ void final_octet(const RotSmem& sm, const float* fin, int transform, int o, float (&f)[8]) {
+  if (transform && sm.pp) {
+    stockham_last(fin, sm.log2L, o, f);
+  } else {
+    const float4* sp = reinterpret_cast<const float4*>(sm.s + s_index(sm, o * 8));
+    const float4 a = sp[0], b = sp[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    if (transform) butterfly_low(f, sm.log2L < 3 ? sm.log2L : 3);
+  }
+}
+
+__device__ __forceinline__ void pack_record(const float (&f)[8], float inv, uint4& r) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    int v = __float2int_rn(f[j] * inv);
+    v = max(-32767, min(32767, v));
+    hi[j] = (uint32_t)(v >> 8) & 0xffu;
+    lo[j] = (uint32_t)v & 0xffu;
+  }
+  // byte order (0,2,1,3 | 4,6,5,7) = the packed-byte order of the decoded E8P word (D4 table follows suit)
+  r.x = hi[0] | (hi[2] << 8) | (hi[1] << 16) | (hi[3] << 24);
+  r.y = hi[4] | (hi[6] << 8) | (hi[5] << 16) | (hi[7] << 24);
+  r.z = lo[0] | (lo[2] << 8) | (lo[1] << 16) | (lo[3] << 24);
+  r.w = lo[4] | (lo[6] << 8) | (lo[5] << 16) | (lo[7] << 24);
 }
 
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
@@ -229,7 +279,7 @@ struct PrologueArgs {
   const __half* hadK;
   int K, in_features, q_in, log2L, transform;
   float scale;
-  uint4* xq;       // [M][q_in/8] records {H(0..3), H(4..7), L(0..3), L(4..7)}  (global)
+  uint4* xq;       // [M][q_in/8] records {H(0,2,1,3), H(4,6,5,7), L(0,2,1,3), L(4,6,5,7)}  (global)
   float* xscale;   // [M]
 };
 
@@ -269,17 +319,23 @@ __device__ __forceinline__ int swz(int seg) { return seg ^ ((seg >> 3) & 7); }
 
 // Computes the records into `dst` (shared: swizzled; global: linear) and returns the fixed-point scale.
 #define QB_DSTAMP(i) do { if (dbg && tid == 0) dbg[i] = clock64(); } while (0)
+// LEAN: the host has verified alignment, in_features % 8 == 0, K == 1, q_in / 8 <= threads and L >= 8, so only
+// the vectorised, register-resident path is compiled in (instruction-cache footprint of the hot kernel).
+template <bool LEAN>
 __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned char* rot_base, uint4* dst, int m,
                                                int tid, int nt, bool swizzle, long long* dbg = nullptr) {
+  constexpr int CH = Rounds<LEAN>::CH;
   const RotSmem sm = rot_carve(rot_base, a.q_in, a.K, a.log2L);
   const __half* xr = a.x + (size_t)m * a.ldx;
   const __half* gr = a.gate ? a.gate + (size_t)m * a.ldgate : nullptr;
   load_hadK(sm, a.hadK, a.K, /*transpose=*/1, tid, nt);
   const int noct = a.q_in >> 3;
   const int noct_in = a.in_features >> 3;
-  const bool vec = (a.in_features & 7) == 0 && al16(xr) && (!gr || al16(gr)) && (!a.SU || al16(a.SU)) &&
-                   (!a.norm_w || al16(a.norm_w));
+  const bool vec = LEAN || ((a.in_features & 7) == 0 && al16(xr) && (!gr || al16(gr)) && (!a.SU || al16(a.SU)) &&
+                           (!a.norm_w || al16(a.norm_w)));
   float rstd = 1.f;
+  // 256-wide blocks (11008 = 43 x 256): each warp transforms whole blocks in registers + shuffles
+  const bool wf = !LEAN && vec && a.transform && a.K > 1 && a.log2L == 8 && (nt & 31) == 0;
   if (vec) {
     const bool single = noct <= nt * CH;    // everything fits one round: no re-read for the norm
     uint4 xv[CH];
@@ -330,9 +386,16 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
           float f[8];
           unpack_h8(xv[c], f);
           if (idx < noct_in) pre_ops(f, gv[c], gr != nullptr, wv[c], a.norm_w != nullptr, rstd, sv[c], a.SU != nullptr);
-          float4* d = reinterpret_cast<float4*>(sm.s + spad(idx * 8));
-          d[0] = make_float4(f[0], f[1], f[2], f[3]);
-          d[1] = make_float4(f[4], f[5], f[6], f[7]);
+          if (wf) {   // idx / 32 is warp-uniform: the warp owns block idx >> 5
+            warp_fwht256(f, tid & 31);
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[j] *= a.scale;
+            *reinterpret_cast<uint4*>(sm.t + t_index(sm, a.K, idx * 8)) = pack_h8(f);
+          } else {
+            float4* d = reinterpret_cast<float4*>(sm.s + s_index(sm, idx * 8));
+            d[0] = make_float4(f[0], f[1], f[2], f[3]);
+            d[1] = make_float4(f[4], f[5], f[6], f[7]);
+          }
         }
       }
     }
@@ -341,7 +404,46 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
   }
   QB_DSTAMP(9);
   __syncthreads();
-  rotate_smem(sm, a.q_in, a.K, a.scale, a.transform, tid, nt);
+  if (LEAN || (a.K == 1 && noct <= nt * CH && (!a.transform || a.log2L >= 3))) {
+    // register-resident tail: last butterflies, abs-max and quantisation without another smem round trip
+    const float* fin = sm.s;
+    if (a.transform) {
+      if (LEAN || sm.pp) fin = stockham_hi(sm.s, sm.s2, a.q_in, a.log2L, tid, nt);
+      else fwht_hi(sm.s, a.q_in, a.log2L, tid, nt);
+    }
+    const float sc = a.transform ? a.scale : 1.0f;
+    float f[CH][8];
+    float mx = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+      const int o = c * nt + tid;
+      if (o < noct) {
+        final_octet(sm, fin, a.transform, o, f[c]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          f[c][j] = f16_round(f[c][j] * sc);   // the rotated vector is an fp16 tensor in the reference
+          mx = fmaxf(mx, fabsf(f[c][j]));
+        }
+      }
+    }
+    QB_DSTAMP(10);
+    mx = block_max1(mx, sm.red + 32, tid, nt);
+    QB_DSTAMP(11);
+    const float inv = (mx > 0.f) ? 32767.0f / mx : 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+      const int o = c * nt + tid;
+      if (o < noct) {
+        uint4 r;
+        pack_record(f[c], inv, r);
+        dst[swizzle ? swz(o) : o] = r;
+      }
+    }
+    return (mx > 0.f) ? mx / 32767.0f : 0.f;
+  }
+  if (LEAN) return 0.f;   // unreachable
+  if (wf) rotate_mix(sm, a.q_in, a.K, tid, nt);
+  else rotate_smem(sm, a.q_in, a.K, a.scale, a.transform, tid, nt);
   QB_DSTAMP(10);
 
   // abs-max -> 16-bit fixed-point scale, then the records
@@ -369,19 +471,8 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
 #pragma unroll
       for (int j = 0; j < 8; j++) f[j] = __half2float(sm.t[t_index(sm, a.K, sgi * 8 + j)]);
     }
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      int v = __float2int_rn(f[j] * inv);
-      v = max(-32767, min(32767, v));
-      hi[j] = (uint32_t)(v >> 8) & 0xffu;
-      lo[j] = (uint32_t)v & 0xffu;
-    }
     uint4 r;
-    r.x = hi[0] | (hi[1] << 8) | (hi[2] << 16) | (hi[3] << 24);
-    r.y = hi[4] | (hi[5] << 8) | (hi[6] << 16) | (hi[7] << 24);
-    r.z = lo[0] | (lo[1] << 8) | (lo[2] << 16) | (lo[3] << 24);
-    r.w = lo[4] | (lo[5] << 8) | (lo[6] << 16) | (lo[7] << 24);
+    pack_record(f, inv, r);
     dst[swizzle ? swz(sgi) : sgi] = r;
   }
   return (mx > 0.f) ? mx / 32767.0f : 0.f;
@@ -409,7 +500,7 @@ __device__ __noinline__ void prologue_scalar_fill(const PrologueArgs& a, RotSmem
       if (a.norm_w) v = f16_round(f16_round(v * rstd) * __half2float(a.norm_w[i]));
       if (a.SU) v = f16_round(v * __half2float(a.SU[i]));
     }
-    sm.s[spad(i)] = v;
+    sm.s[s_index(sm, i)] = v;
   }
 }
 
@@ -418,7 +509,7 @@ __global__ void __launch_bounds__(PRO_THREADS) ql_prologue_kernel(PrologueArgs a
   pdl_launch_dependents();
   pdl_wait();
   const int m = blockIdx.x;
-  const float xs = prologue_body(a, smem_raw, a.xq + (size_t)m * (a.q_in >> 3), m, threadIdx.x, PRO_THREADS, false);
+  const float xs = prologue_body<false>(a, smem_raw, a.xq + (size_t)m * (a.q_in >> 3), m, threadIdx.x, PRO_THREADS, false);
   if (threadIdx.x == 0) a.xscale[m] = xs;
 }
 
@@ -443,22 +534,24 @@ struct EpilogueArgs {
   int64_t ldy;
 };
 
+template <bool LEAN>
 __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned char* rot_base, int m, float xscale,
                                               int tid, int nt, long long* dbg = nullptr) {
+  constexpr int CH = Rounds<LEAN>::CH;
   const RotSmem sm = rot_carve(rot_base, a.q_out, a.K, a.log2L);
   load_hadK(sm, a.hadK, a.K, /*transpose=*/0, tid, nt);
   const float xs = xscale * a.unit;
   const float* ar = a.acc + (size_t)m * a.q_out;
   const float* ar2 = a.acc2 ? a.acc2 + (size_t)m * a.q_out : nullptr;
   const int noct = a.q_out >> 3;
-  const bool vec_in = (a.q_out & 7) == 0 && al16(ar) && (!ar2 || al16(ar2));
+  const bool vec_in = LEAN || ((a.q_out & 7) == 0 && al16(ar) && (!ar2 || al16(ar2)));
   __half* yr = a.y + (size_t)m * a.ldy;
   const __half* rr = a.residual ? a.residual + (size_t)m * a.ldres : nullptr;
   const int L = 1 << a.log2L;
-  const bool vec_out = (a.out_features & 7) == 0 && al16(yr) && (!a.SV || al16(a.SV)) && (!a.bias || al16(a.bias)) &&
-                       (!rr || al16(rr)) && ((a.K == 1) || L >= 8);
+  const bool vec_out = LEAN || ((a.out_features & 7) == 0 && al16(yr) && (!a.SV || al16(a.SV)) &&
+                               (!a.bias || al16(a.bias)) && (!rr || al16(rr)) && ((a.K == 1) || L >= 8));
   const int noct_out = a.out_features >> 3;
-  const bool pre_out = vec_out && noct_out <= nt * CH;   // prefetch: these loads do not depend on the rotation
+  const bool pre_out = LEAN || (vec_out && noct_out <= nt * CH);   // prefetch: loads independent of the rotation
   uint4 psv[CH], pbv[CH], prv[CH];
   if (pre_out) {
 #pragma unroll
@@ -472,6 +565,7 @@ __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned ch
       }
     }
   }
+  const bool wf = !LEAN && vec_in && a.transform && a.K > 1 && a.log2L == 8 && (nt & 31) == 0;
   if (vec_in) {
     for (int base = 0; base < noct; base += nt * CH) {
       float4 v0[CH], v1[CH], w0[CH], w1[CH];
@@ -504,9 +598,16 @@ __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned ch
 #pragma unroll
             for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] * __half2float(a.wscale_pc[idx * 8 + j]));   // qlinear.py:107
           }
-          float4* d = reinterpret_cast<float4*>(sm.s + spad(idx * 8));
-          d[0] = make_float4(f[0], f[1], f[2], f[3]);
-          d[1] = make_float4(f[4], f[5], f[6], f[7]);
+          if (wf) {
+            warp_fwht256(f, tid & 31);
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[j] *= a.scale;
+            *reinterpret_cast<uint4*>(sm.t + t_index(sm, a.K, idx * 8)) = pack_h8(f);
+          } else {
+            float4* d = reinterpret_cast<float4*>(sm.s + s_index(sm, idx * 8));
+            d[0] = make_float4(f[0], f[1], f[2], f[3]);
+            d[1] = make_float4(f[4], f[5], f[6], f[7]);
+          }
         }
       }
     }
@@ -516,12 +617,50 @@ __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned ch
       if (ar2) v = fmaf(a.resid_scale, __ldcg(ar2 + i), v);
       v = f16_round(v * xs);
       if (a.wscale_pc) v = f16_round(v * __half2float(a.wscale_pc[i]));
-      sm.s[spad(i)] = v;
+      sm.s[s_index(sm, i)] = v;
     }
   }
   QB_DSTAMP(13);
   __syncthreads();
-  rotate_smem(sm, a.q_out, a.K, a.scale, a.transform, tid, nt);
+  if (LEAN || (a.K == 1 && pre_out && noct <= nt * CH && (!a.transform || a.log2L >= 3))) {
+    const float* fin = sm.s;
+    if (a.transform) {
+      if (LEAN || sm.pp) fin = stockham_hi(sm.s, sm.s2, a.q_out, a.log2L, tid, nt);
+      else fwht_hi(sm.s, a.q_out, a.log2L, tid, nt);
+    }
+    QB_DSTAMP(14);
+    const float sc = a.transform ? a.scale : 1.0f;
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+      const int o = c * nt + tid;
+      if (o < noct_out) {
+        float f[8], o8[8];
+        final_octet(sm, fin, a.transform, o, f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] * sc);
+        if (a.SV) {
+          unpack_h8(psv[c], o8);
+#pragma unroll
+          for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] * o8[j]);
+        }
+        if (a.bias) {
+          unpack_h8(pbv[c], o8);
+#pragma unroll
+          for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] + o8[j]);
+        }
+        if (rr) {
+          unpack_h8(prv[c], o8);
+#pragma unroll
+          for (int j = 0; j < 8; j++) f[j] += o8[j];
+        }
+        *reinterpret_cast<uint4*>(yr + (size_t)o * 8) = pack_h8(f);
+      }
+    }
+    return;
+  }
+  if (LEAN) return;   // unreachable
+  if (wf) rotate_mix(sm, a.q_out, a.K, tid, nt);
+  else rotate_smem(sm, a.q_out, a.K, a.scale, a.transform, tid, nt);
   QB_DSTAMP(14);
 
   if (vec_out) {
@@ -579,7 +718,7 @@ __global__ void __launch_bounds__(PRO_THREADS) ql_epilogue_kernel(EpilogueArgs a
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_launch_dependents();
   pdl_wait();
-  epilogue_body(a, smem_raw, blockIdx.x, a.xscale[blockIdx.x], threadIdx.x, PRO_THREADS);
+  epilogue_body<false>(a, smem_raw, blockIdx.x, a.xscale[blockIdx.x], threadIdx.x, PRO_THREADS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -652,7 +791,7 @@ __device__ __forceinline__ void e8p_dot2(uint32_t w, const unsigned char* tab, c
   e8p_dot((w >> 21) & 0x7f8u, __byte_perm(w, 0, 0x4442), tab, x1, s1, aH, aL, aP);
 }
 
-template <int CB>
+template <int CB, bool LEAN, bool LEAN_EPI>
 __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const __grid_constant__ GroupArgs ga) {
   using T = CbTraits<CB>;
   constexpr int UNROLL = GEMV_UNROLL;
@@ -723,9 +862,9 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
   // ---- phase 1: activation records ----
   const uint4* xq;
   float xscale;
-  if (a.fuse_pro) {
+  if (LEAN || a.fuse_pro) {
     uint4* xq_s = reinterpret_cast<uint4*>(smem_raw + a.xq_off);
-    xscale = prologue_body(a.pro, smem_raw + a.rot_off, xq_s, m, tid, nt, true, dbg);
+    xscale = prologue_body<LEAN>(a.pro, smem_raw + a.rot_off, xq_s, m, tid, nt, true, dbg);
     xq = xq_s;
     if (!a.fuse_epi && bx == 0 && tid == 0) a.pro.xscale[m] = xscale;   // for the epilogue kernel
   } else {
@@ -771,11 +910,11 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
 #pragma unroll
     for (int sgi = 0; sgi < T::SEGS; sgi++) {
       uint4 r = make_uint4(0, 0, 0, 0);
-      if (lane_valid) r = xq[a.fuse_pro ? swz(seg0 + sgi) : seg0 + sgi];
-      xs[sgi][0] = perm_0213(r.x);
-      xs[sgi][1] = perm_0213(r.y);
-      xs[sgi][2] = perm_0213(r.z);
-      xs[sgi][3] = perm_0213(r.w);
+      if (lane_valid) r = xq[(LEAN || a.fuse_pro) ? swz(seg0 + sgi) : seg0 + sgi];
+      xs[sgi][0] = r.x;
+      xs[sgi][1] = r.y;
+      xs[sgi][2] = r.z;
+      xs[sgi][3] = r.w;
       const int sh = dp4a_ss(r.x, 0x01010101u, dp4a_ss(r.y, 0x01010101u, 0));
       const int sl = dp4a_su(0x01010101u, r.z, dp4a_su(0x01010101u, r.w, 0));
       xsum[sgi] = sh * 256 + sl;
@@ -793,12 +932,15 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
         nx[u] = make_uint4(0, 0, 0, 0);
         if (lane_valid && r < nrows) nx[u] = ldg_stream_v4(colp + (size_t)r * a.row_bytes, pol);
       }
-#pragma unroll
+      // one copy of the 8-code decode in the instruction stream (the kernel's hot code must stay well
+      // inside the 32 KB instruction cache: every launch runs it only a handful of times); the
+      // register queue is rotated instead of indexed
+#pragma unroll 1
       for (int u = 0; u < UNROLL; u++) {
         const int r = r0 + u * a.g;
         if (r < nrows) {   // warp-uniform
           int aH = 0, aL = 0, aP = 0, bH = 0, bL = 0, bP = 0;
-          const uint32_t w[4] = {cw[u].x, cw[u].y, cw[u].z, cw[u].w};
+          const uint32_t w[4] = {cw[0].x, cw[0].y, cw[0].z, cw[0].w};
           if (CB == QUIPB200_CB_E8P12) {
             // four independent accumulation chains (two per word half) keep the dp4a pipe fed
             int cH = 0, cL = 0, cP = 0;
@@ -840,6 +982,8 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
             if (T::ACCS == 2) red[(r * a.C + chunk) * T::ACCS + 1] = tot2;
           }
         }
+#pragma unroll
+        for (int v = 0; v + 1 < UNROLL; v++) cw[v] = cw[v + 1];
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; u++) cw[u] = nx[u];
@@ -874,19 +1018,19 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
 
   QB_STAMP(6);
   // ---- phase 3: the last CTA of this member runs the output side ----
-  if (!a.fuse_epi) return;
+  if (!LEAN_EPI && !a.fuse_epi) return;
   __syncthreads();   // every thread's acc stores are ordered before thread 0's fence (fences are cumulative)
   if (tid == 0) {
     __threadfence();
     const unsigned int prev = atomicAdd(a.counters + m, 1u);
     s_last = (prev == (unsigned int)(G - 1));
-    if (a.fuse_pro) s_xscale = xscale;
+    if (LEAN || a.fuse_pro) s_xscale = xscale;
   }
   __syncthreads();
   QB_STAMP(7);
   if (!s_last) return;
   if (tid == 0) a.counters[m] = 0;   // ready for the next launch that draws this slot
-  epilogue_body(a.epi, smem_raw + a.rot_off, m, a.fuse_pro ? s_xscale : a.pro.xscale[m], tid, nt, dbg);
+  epilogue_body<LEAN_EPI>(a.epi, smem_raw + a.rot_off, m, (LEAN || a.fuse_pro) ? s_xscale : a.pro.xscale[m], tid, nt, dbg);
   __syncthreads();
   QB_STAMP(8);
 #undef QB_STAMP
@@ -920,7 +1064,7 @@ static int gemv_plan(int codebook, int N, int K, GemvPlan* p) {
   p->accs = accs;
   p->tab_bytes = tab;
   p->row_bytes = row_bytes;
-  int wmax = g_opt_gemv_warps > 0 ? g_opt_gemv_warps : 16;
+  int wmax = g_opt_gemv_warps > 0 ? g_opt_gemv_warps : GEMV_MAX_WARPS;
   if (wmax > GEMV_MAX_WARPS) wmax = GEMV_MAX_WARPS;
   if (p->C >= wmax) { p->g = 1; p->warps = wmax; }
   else { p->g = wmax / p->C; p->warps = p->g * p->C; }
@@ -1057,6 +1201,23 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
     }
   }
 
+  // lean instantiations (instruction-cache footprint): fused, pure power-of-two rotation, every vector 16-byte
+  // aligned, one octet per thread.  Input and output side qualify independently (gate/up: lean in, 43-block out).
+  bool lean_pro = g_opt_lean && mem[0].codebook == QUIPB200_CB_E8P12;
+  bool lean_epi = lean_pro;
+  for (int j = 0; j < n; j++) {
+    const PrologueArgs& pa = ga.a[j].pro;
+    const EpilogueArgs& ea = ga.a[j].epi;
+    const int nt = plan[j].warps * 32;
+    lean_pro = lean_pro && ga.a[j].fuse_pro && pa.K == 1 && (pa.in_features & 7) == 0 && (pa.q_in >> 3) <= nt &&
+               (!pa.transform || pa.log2L >= 3) && rot_pingpong(pa.q_in, 1) && aligned16(pa.x) && aligned16(pa.gate) &&
+               aligned16(pa.SU) && aligned16(pa.norm_w) && (M == 1 || ((pa.ldx & 7) == 0 && (pa.ldgate & 7) == 0));
+    lean_epi = lean_epi && ga.a[j].fuse_epi && ea.K == 1 && (ea.q_out >> 3) <= nt && (ea.out_features & 7) == 0 &&
+               (!ea.transform || ea.log2L >= 3) && rot_pingpong(ea.q_out, 1) && aligned16(ea.SV) && aligned16(ea.bias) &&
+               aligned16(ea.residual) && aligned16(ea.y) && aligned16(ea.acc) &&
+               (M == 1 || ((ea.ldres & 7) == 0 && (ea.ldy & 7) == 0));
+  }
+
   if (any_unfused_pro && (g_opt_stage_mask & 1)) {
     for (int j = 0; j < n; j++) {
       if (ga.a[j].fuse_pro) continue;
@@ -1071,9 +1232,14 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
   if (g_opt_stage_mask & 2) {
     const void* fn = nullptr;
     switch (mem[0].codebook) {
-      case QUIPB200_CB_E8P12: fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12>; break;
-      case QUIPB200_CB_E8P12RVQ4B: fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12RVQ4B>; break;
-      case QUIPB200_CB_D4: fn = (const void*)ql_gemv_kernel<QUIPB200_CB_D4>; break;
+      case QUIPB200_CB_E8P12:
+        if (lean_pro && lean_epi) fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, true, true>;
+        else if (lean_pro) fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, true, false>;
+        else if (lean_epi) fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, false, true>;
+        else fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, false, false>;
+        break;
+      case QUIPB200_CB_E8P12RVQ4B: fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12RVQ4B, false, false>; break;
+      case QUIPB200_CB_D4: fn = (const void*)ql_gemv_kernel<QUIPB200_CB_D4, false, false>; break;
       default: return QUIPB200_EUNSUPPORTED;
     }
     if ((rc = set_smem_attr(fn, smem))) return rc;

@@ -241,7 +241,7 @@ FUSED_CODEBOOKS = ("E8P12", "E8P12RVQ4B", "D4")
 def fused_supported(codebook_id: str, q_in: int, M: int) -> bool:
     if codebook_id not in FUSED_CODEBOOKS or M > _native.MM_MAX_M:
         return False
-    return q_in % (32 if codebook_id == "E8P12RVQ4B" else 64) == 0
+    return q_in % (32 if codebook_id == "E8P12RVQ4B" else 64) == 0   # packed row pitch multiple of 16 bytes
 
 
 def _quantlinear_fwd(x: Tensor, Qidxs: Tensor, grid: Tensor, SU, SV, bias, had_left, had_right, wscale_pc,
