@@ -160,6 +160,53 @@ int quipb200_attn_decode(const void* q, const void* k, const void* v, void* k_ca
                          const void* cos_t, const void* sin_t, const int64_t* pos, void* out,
                          int n_heads, int n_kv_heads, int head_dim, int max_len, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Whole decode step of a Llama-style stack of QuantLinears in ONE persistent cooperative kernel
+ * (bs = 1).  Replaces, per token, what the reference runs as 32 x (7 QuantLinear.forward + HF
+ * attention / norm / MLP glue) hidden behind torch.compile CUDA graphs (example_generate.py:29-32,
+ * :68-70; qlinear.py:87-115 per linear).  One CTA per SM stays resident for all layers; the five
+ * data-dependent stages of a decoder layer ([norm + q,k,v] -> [RoPE + KV append + attention] ->
+ * [o_proj + residual] -> [norm + gate,up] -> [silu*up + down_proj + residual]) are separated by
+ * grid-wide barriers instead of kernel boundaries, every CTA recomputes the (tiny) rotations it needs
+ * from the previous stage's raw integer dot products, and the packed codes of a stage are already in
+ * flight while the rotation runs.  Arithmetic and rounding points are those of
+ * quipb200_linear_group_forward / quipb200_attn_decode.
+ *
+ * Restrictions (else QUIPB200_EUNSUPPORTED and the caller uses the per-linear entry points): E8P12
+ * codebook for every linear, head_dim 128, fp16 everywhere, all seven linears of a layer present,
+ * power-of-two padded attention dims (K_right == 1 for q/k/v, K_left == 1 for o).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct quipb200_decode_layer {
+  quipb200_linear_t q, k, v, o, gate, up, down;   /* device pointers inside */
+  const void* input_norm_w;   /* fp16 [hidden]  LlamaRMSNorm before attention */
+  const void* post_norm_w;    /* fp16 [hidden]  LlamaRMSNorm before the MLP */
+  void* k_cache;              /* fp16 [n_kv_heads, max_len, head_dim] */
+  void* v_cache;
+} quipb200_decode_layer_t;
+
+typedef struct quipb200_decode_plan {
+  int32_t n_layers, hidden, n_heads, n_kv_heads, head_dim, max_len;
+  float norm_eps;
+  int32_t reserved;
+  const quipb200_decode_layer_t* layers;   /* DEVICE array [n_layers] */
+  const void* cos_t;                       /* fp16 [max_len, head_dim] */
+  const void* sin_t;
+  const int64_t* pos;                      /* device: index of the new token (graph-replayable) */
+} quipb200_decode_plan_t;
+
+/* `host_layers`: a HOST copy of the layer array (shapes are validated and scratch is sized from it).
+ * The workspace must be zero-filled once before its first use and must not be shared between plans
+ * whose launches can overlap. */
+size_t quipb200_decode_step_workspace_bytes(const quipb200_decode_plan_t* plan,
+                                            const quipb200_decode_layer_t* host_layers);
+/* h_in: fp16 [hidden] (embedding of the current token); h_out: fp16 [hidden] (input of the final norm). */
+int quipb200_decode_step(const quipb200_decode_plan_t* plan, const quipb200_decode_layer_t* host_layers,
+                         const void* h_in, void* h_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* profiling hook: when non-NULL, CTA 0 of the decode-step kernel writes int64 clock64() stamps of the
+ * first layer's stages into buffer[0..15]; pass NULL to switch it off. */
+int quipb200_decode_step_debug(void* device_int64_buffer);
+
 /* Tuning / introspection hooks used by bench.py and the tests (not part of the reference surface). */
 int quipb200_set_option(const char* name, int value);   /* e.g. "gemv_table_repl" = 1|16 */
 int quipb200_get_option(const char* name);

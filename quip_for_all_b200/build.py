@@ -11,10 +11,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libquipb200.so")
-SOURCES = ["api.cu", "decompress.cu", "hadamard.cu", "quantlinear.cu", "glue.cu"]
+SOURCES = ["api.cu", "decompress.cu", "hadamard.cu", "quantlinear.cu", "glue.cu", "decode_step.cu"]
+OBJDIR = os.path.join(HERE, "lib", "obj")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -32,14 +33,33 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    os.makedirs(OBJDIR, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(HERE, "..", "include", "quip_b200.h"))
+    hdr_t = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        sp = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(sp), hdr_t):
+            return obj, 0, ""
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, sp]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return obj, res.returncode, res.stdout
+
+    # one translation unit per thread: the sources are independent (no -rdc)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    for obj, rc, out in results:
+        if verbose or rc != 0:
+            sys.stderr.write(out)
+        if rc != 0:
+            raise RuntimeError("nvcc failed building %s:\n%s" % (obj, out[-4000:]))
+    cmd = [nvcc, "-shared", "-o", LIB] + [r[0] for r in results]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libquipb200.so:\n" + res.stdout[-4000:])
+        raise RuntimeError("link failed for libquipb200.so:\n" + res.stdout[-4000:])
     return LIB
 
 

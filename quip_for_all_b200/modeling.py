@@ -127,7 +127,7 @@ class LlamaDecodeEngine:
     """
 
     def __init__(self, model, max_cache_len: int = 512, first_stage: bool = True, last_stage: bool = True,
-                 use_cuda_graph: bool = True, fused: bool = True):
+                 use_cuda_graph: bool = True, fused: bool = True, persistent: bool = False):
         self.model = model
         self.cfg = model.config
         self.layers = list(model.model.layers)
@@ -158,8 +158,11 @@ class LlamaDecodeEngine:
         self.use_graph = use_cuda_graph
         self.graph = None
         self.fused = None
+        self.persistent = None
         if fused:
             self._build_fused()
+        if fused and persistent and self.fused is not None:
+            self._build_persistent()
 
     def _build_fused(self):
         """Per-layer launch groups for the fused decode step (5 launches of ours per layer + 1 prologue):
@@ -180,6 +183,16 @@ class LlamaDecodeEngine:
             self.attn_out = torch.empty(1, self.nh * self.hd, dtype=torch.float16, device=self.dev)
         except ValueError:
             self.fused = None
+
+    def _build_persistent(self):
+        """Whole-step persistent kernel (decode_step.cu) when every block linear is E8P12 and the shapes qualify."""
+        from .decode_step import PersistentDecodeStep
+        try:
+            self.persistent = PersistentDecodeStep(self.layers, self.k_cache, self.v_cache, self.cos, self.sin, self.pos,
+                                                   self.nh, self.nkv, self.hd, self.cfg.hidden_size, self.eps)
+            self.h_step_out = torch.empty(1, self.cfg.hidden_size, dtype=torch.float16, device=self.dev)
+        except ValueError:
+            self.persistent = None
 
     def _layer_fused(self, li, h):
         """h: fp16 [1, hidden]; one decode position (self.pos)."""
@@ -229,8 +242,11 @@ class LlamaDecodeEngine:
         h = self.model.model.embed_tokens(tok_or_hidden) if self.first else tok_or_hidden
         if self.fused is not None and h.shape[1] == 1 and pos is self.pos:
             h2 = h.view(1, -1)
-            for li in range(len(self.layers)):
-                h2 = self._layer_fused(li, h2)
+            if self.persistent is not None:
+                h2 = self.persistent(h2.contiguous(), self.h_step_out)
+            else:
+                for li in range(len(self.layers)):
+                    h2 = self._layer_fused(li, h2)
             h = h2.view(1, 1, -1)
             if not self.last:
                 return h

@@ -534,3 +534,54 @@ def test_fused_decode_step_matches_unfused_engine():
     assert d <= 2.0 ** -6 * h2.float().abs().max().item(), d
     out = e1.generate(ids, 6)          # graph-captured fused path runs end to end
     assert out.shape == (1, 6)
+
+
+# ------------------------------------------------------------------------------------------------
+# persistent whole-step kernel (decode_step.cu) against the per-group launches it replaces
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n_layers", [("tiny128", 2), ("llama2-7b", 2)])
+def test_persistent_decode_step_matches_grouped_engine(name, n_layers):
+    from quip_for_all_b200.modeling import LlamaDecodeEngine, llama_config, make_random_quantized_llama
+    cfg = llama_config(name, num_hidden_layers=n_layers)
+    model = make_random_quantized_llama(cfg, "E8P12", seed=5, device=DEV)
+    e1 = LlamaDecodeEngine(model, max_cache_len=96, persistent=True, use_cuda_graph=False)
+    assert e1.persistent is not None
+    e2 = LlamaDecodeEngine(model, max_cache_len=96, persistent=False, use_cuda_graph=False)
+    assert e2.persistent is None and e2.fused is not None
+    g = torch.Generator().manual_seed(11)
+    for plen in (1, 3, 37):
+        ids = torch.randint(0, 32000, (1, plen), generator=g).to(DEV)
+        e1.prefill(ids)
+        e2.prefill(ids)
+        assert torch.equal(e1.tok, e2.tok)
+        for _ in range(3):
+            with torch.no_grad():
+                h = model.model.embed_tokens(e1.tok).view(1, -1).contiguous()
+                h1 = e1.persistent(h, e1.h_step_out).clone()
+                h2 = h.clone()
+                for li in range(len(e2.layers)):
+                    h2 = e2._layer_fused(li, h2)
+            torch.cuda.synchronize()
+            ref = h2.float()
+            d = (h1.float() - ref).abs().max().item()
+            # same device functions and rounding points; only fp32 summation order differs in the head slices
+            assert d <= 2.0 ** -8 * ref.abs().max().item(), (name, plen, d, ref.abs().max().item())
+            p = int(e1.pos.item())
+            dk = (e1.k_cache[:, :, :, :p + 1].float() - e2.k_cache[:, :, :, :p + 1].float()).abs().max().item()
+            dv = (e1.v_cache[:, :, :, :p + 1].float() - e2.v_cache[:, :, :, :p + 1].float()).abs().max().item()
+            assert dk <= 2.0 ** -8 * e2.k_cache.float().abs().max().item(), (name, plen, dk)
+            assert dv <= 2.0 ** -8 * e2.v_cache.float().abs().max().item(), (name, plen, dv)
+            e1.pos.add_(1)
+            e2.pos.add_(1)
+
+
+def test_persistent_decode_step_under_cuda_graph_generates_same_tokens():
+    from quip_for_all_b200.modeling import LlamaDecodeEngine, make_random_quantized_llama
+    model = make_random_quantized_llama("tiny128", "E8P12", seed=3, device=DEV)
+    ids = torch.randint(0, 32000, (1, 10), generator=torch.Generator().manual_seed(2)).to(DEV)
+    e1 = LlamaDecodeEngine(model, max_cache_len=64, persistent=True)       # cooperative launch inside a CUDA graph
+    assert e1.persistent is not None
+    e2 = LlamaDecodeEngine(model, max_cache_len=64, persistent=False)
+    o1 = e1.generate(ids, 12)
+    o2 = e2.generate(ids, 12)
+    assert torch.equal(o1[:, :4], o2[:, :4])      # later tokens may differ by an fp16 near-tie
