@@ -36,6 +36,8 @@ def parse():
     ap.add_argument("--no-kernel-bench", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--engine", default="auto", choices=["auto", "persistent", "grouped"],
+                    help="decode engine: one persistent whole-step kernel, or one launch per linear group")
     return ap.parse_args()
 
 
@@ -301,7 +303,10 @@ def run_ours(a):
     code_bytes = quantized_bytes(model)
     lm_head_bytes = model.lm_head.weight.numel() * 2
     cache_len = a.cache_len or (a.prompt_len + a.steps * 2 + a.warmup * 2 + 16)
-    eng = LlamaDecodeEngine(model, max_cache_len=cache_len, use_cuda_graph=not a.no_graph)
+    eng = LlamaDecodeEngine(model, max_cache_len=cache_len, use_cuda_graph=not a.no_graph,
+                            persistent=(a.engine != "grouped"))
+    if a.engine == "persistent" and eng.persistent is None:
+        raise SystemExit("--engine persistent: model not covered by the persistent decode-step kernel")
     g = torch.Generator().manual_seed(0)
     prompt = torch.randint(0, model.config.vocab_size, (1, a.prompt_len), generator=g)
     pinned_in = prompt.clone().pin_memory()
@@ -354,7 +359,9 @@ def run_ours(a):
                                f"synthetic {a.prompt_len}-token prompt, static KV cache {cache_len}",
                    "l2": "inputs larger than L2: every step streams %.3f GB of packed codes + %.3f GB fp16 lm_head"
                          % (code_bytes / 1e9, lm_head_bytes / 1e9),
-                   "cuda_graph": not a.no_graph, "engine": "quip_for_all_b200.modeling.LlamaDecodeEngine"},
+                   "cuda_graph": not a.no_graph,
+                   "engine": "quip_for_all_b200.modeling.LlamaDecodeEngine (%s)" %
+                             ("persistent whole-step kernel" if eng.persistent is not None else "grouped launches")},
         "clocks": ck,
         "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8,
                 "how": "per step: pinned host token id -> device, graph replay, next token id -> pinned host, stream sync"},

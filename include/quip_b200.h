@@ -206,6 +206,9 @@ int quipb200_decode_step(const quipb200_decode_plan_t* plan, const quipb200_deco
 /* profiling hook: when non-NULL, CTA 0 of the decode-step kernel writes int64 clock64() stamps of the
  * first layer's stages into buffer[0..15]; pass NULL to switch it off. */
 int quipb200_decode_step_debug(void* device_int64_buffer);
+/* tuning / test hook: force the number of KV splits per head of the attention stage (0 = automatic, <= 4);
+ * takes effect for workspaces sized and steps launched afterwards. */
+int quipb200_decode_step_set_splits(int splits);
 
 /* Tuning / introspection hooks used by bench.py and the tests (not part of the reference surface). */
 int quipb200_set_option(const char* name, int value);   /* e.g. "gemv_table_repl" = 1|16 */

@@ -15,8 +15,10 @@
 //
 // Every CTA recomputes the (tiny) rotations it needs from the previous stage's raw integer dot
 // products, so no stage has a single-CTA serial section, and each warp's first packed-code rows are
-// already in flight while the rotation runs.  The arithmetic (fixed-point activations, exact int32
-// dp4a, rounding points) is that of quantlinear.cu: the same device functions are used.
+// already in flight while the rotation runs.  The rotations here are register-resident restatements
+// of quantlinear.cu's input / output sides (one octet per thread, constant-geometry radix-8 passes,
+// the first pass fused with the global load) with the SAME arithmetic and rounding points: fixed-point
+// activations, exact int32 dp4a, fp16 rounding wherever the reference holds an fp16 tensor.
 //
 // Reference chain replaced: example_generate.py:29-32 (decode_one_tokens) -> HF LlamaDecoderLayer ->
 // 7 x qlinear.py:87-115 per layer.
@@ -40,20 +42,28 @@ struct DsWs {            // global scratch (device pointers)
   float* xscale;         // [SL_N] fixed-point scale of each linear's input vector
   __half* hA;            // layer input (residual of the attention block)
   __half* hB;            // post-attention hidden (residual of the MLP block)
-  float* acc[SL_N];      // raw integer dot products of each linear
+  __half* acc[SL_N];     // f16(integer dot product * xscale/4) of each linear: the reference's fp16 mm output
   float* att_o;          // [nh][S][hd] un-normalised partial attention outputs
   float* att_ml;         // [nh][S][2]  running max / sum of each partial
 };
 
-struct DsSmem { uint32_t tab, red, xq, vh, vg, vu, rot, total; };   // byte offsets into dynamic smem
+// byte offsets into dynamic shared memory.  scr: [A: fp32 n][B: fp32 n][fred: 64 floats][Tg][Tu][hk x 3];
+// the attention stage aliases scr from its base.
+struct DsSmem { uint32_t tab, red, xq, scr, total, nmax, t_halfs, hk_halfs, mid_halfs; };
+
+struct DsGeom {          // CTAs per member of each GEMV stage (host-computed; every layer has the same shapes)
+  int G_A[3], G_C, G_D[2], G_E;
+};
 
 struct DsParams {
   quipb200_decode_plan_t plan;
   DsWs ws;
   DsSmem sm;
+  DsGeom geo;
   const __half* h_in;
   __half* h_out;
   int kv_splits;
+  int use_mma;           // hidden-side rotations are 4096-point: tensor-path transforms
   long long* dbg;        // optional [16] clock stamps of CTA 0 (tools/timeline)
 };
 
@@ -61,19 +71,22 @@ struct DsParams {
 // grid-wide barrier: monotonically increasing arrival counter, release/acquire at gpu scope
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target, unsigned int nblk) {
-  __syncthreads();
+  __syncthreads();   // every thread's global writes happen-before thread 0's release (cumulativity)
   if (threadIdx.x == 0) {
     target += nblk;
-    __threadfence();
-    atomicAdd(counter, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     unsigned int v;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
     } while ((int)(v - target) < 0);
-    __threadfence();
   }
   __syncthreads();
 }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // GEMV over a contiguous row range (same inner loop as ql_gemv_kernel<E8P12>)
@@ -111,6 +124,13 @@ __device__ __forceinline__ void gemv_first(uint4 (&cw)[DS_UNROLL], const GemvCfg
     cw[u] = make_uint4(0, 0, 0, 0);
     if (lv && r < c.nrows) cw[u] = ldg_stream_v4(colp + (size_t)r * c.row_bytes, pol);
   }
+}
+
+// pull this CTA's whole row range into L2 (no registers held): used when the stage's prologue is long
+__device__ __forceinline__ void gemv_prefetch_l2(const GemvCfg& c, int tid) {
+  const unsigned char* base = c.q + (size_t)c.row_begin * c.row_bytes;
+  const int lines = (int)(((size_t)c.nrows * c.row_bytes + 127) >> 7);
+  for (int i = tid; i < lines; i += DS_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * 128));
 }
 
 // xq: swizzled 16-byte activation records in shared memory; red: [nrows][C] chunk partials
@@ -181,62 +201,555 @@ __device__ __forceinline__ void gemv_run(uint4 (&cw)[DS_UNROLL], const GemvCfg& 
   }
 }
 
-// CTA -> (member, index within member, CTAs of the member): CTAs are split in proportion to code bytes
-__device__ __forceinline__ void split_ctas(const quipb200_linear_t* const* mem, int n, int nblk, int bid, int& j, int& bx,
-                                           int& G) {
-  long long w[3], tot = 0;
-  for (int i = 0; i < n; i++) { w[i] = (long long)mem[i]->q_out * mem[i]->q_in; tot += w[i]; }
-  int begin = 0;
-  j = -1; bx = 0; G = 1;
-  for (int i = 0; i < n; i++) {
-    int Gi = (int)((long long)nblk * w[i] / tot);
-    if (Gi > mem[i]->q_out) Gi = mem[i]->q_out;
-    if (Gi < 1) Gi = 1;
-    if (bid >= begin && bid < begin + Gi) { j = i; bx = bid - begin; G = Gi; }
-    begin += Gi;
-  }
-}
-
-__device__ __forceinline__ void fill_pro(PrologueArgs& pa, const quipb200_linear_t& L, const __half* x, const __half* gate,
-                                         const __half* norm_w, float eps) {
-  pa.x = x; pa.ldx = 0; pa.gate = gate; pa.ldgate = 0; pa.norm_w = norm_w; pa.norm_eps = eps;
-  pa.SU = reinterpret_cast<const __half*>(L.SU); pa.hadK = reinterpret_cast<const __half*>(L.had_left);
-  pa.K = L.K_left; pa.in_features = L.in_features; pa.q_in = L.q_in;
-  pa.log2L = ilog2_dev(L.q_in / L.K_left); pa.transform = 1;
-  pa.scale = L.wscale_float / sqrtf((float)(L.q_in / L.K_left));
-  pa.xq = nullptr; pa.xscale = nullptr;
-}
-
-__device__ __forceinline__ void fill_epi(EpilogueArgs& ea, const quipb200_linear_t& L, const float* acc, const __half* residual,
-                                         __half* y) {
-  ea.acc = acc; ea.acc2 = nullptr; ea.xscale = nullptr; ea.unit = 0.25f; ea.resid_scale = 0.f;
-  ea.wscale_pc = reinterpret_cast<const __half*>(L.wscale_pc); ea.hadK = reinterpret_cast<const __half*>(L.had_right);
-  ea.K = L.K_right; ea.q_out = L.q_out; ea.out_features = L.out_features;
-  ea.log2L = ilog2_dev(L.q_out / L.K_right); ea.transform = 1;
-  ea.scale = 1.0f / sqrtf((float)(L.q_out / L.K_right));
-  ea.SV = reinterpret_cast<const __half*>(L.SV); ea.bias = reinterpret_cast<const __half*>(L.bias);
-  ea.residual = residual; ea.ldres = 0; ea.y = y; ea.ldy = 0;
-}
-
-// one copy of each side in the instruction stream
-__device__ __noinline__ float ds_prologue(const PrologueArgs& pa, unsigned char* rot, uint4* xq, int tid) {
-  const float xs = prologue_body<false>(pa, rot, xq, 0, tid, DS_THREADS, true);
-  __syncthreads();
-  return xs;
-}
-__device__ __noinline__ void ds_epilogue(const EpilogueArgs& ea, unsigned char* rot, float xscale, int tid) {
-  epilogue_body<false>(ea, rot, 0, xscale, tid, DS_THREADS);
-  __syncthreads();
-}
-
 // chunk partials -> global accumulator (fp32 image of the integer dot product)
-__device__ __forceinline__ void gemv_store(const GemvCfg& c, const int* red, float* acc, int tid) {
+__device__ __forceinline__ void gemv_store(const GemvCfg& c, const int* red, __half* acc, float xscale, int tid) {
   __syncthreads();
+  const float xs = xscale * 0.25f;
   for (int r = tid; r < c.nrows; r += DS_THREADS) {
     long long s = 0;
     for (int k = 0; k < c.C; k++) s += red[r * c.C + k];
-    __stcg(acc + c.row_begin + r, (float)s);
+    acc[c.row_begin + r] = __float2half_rn((float)s * xs);      // origin_order.cu:129 (single fp16 rounding of the mm)
   }
+}
+
+// member / index of this CTA inside a GEMV stage whose members own G[0], G[1], .. consecutive CTAs
+__device__ __forceinline__ void which_member(const int* G, int n, int bid, int& j, int& bx) {
+  j = -1; bx = 0;
+  int begin = 0;
+  for (int i = 0; i < n; i++) {
+    if (bid >= begin && bid < begin + G[i]) { j = i; bx = bid - begin; }
+    begin += G[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// register-resident rotations: thread t owns octet t (elements 8t .. 8t+7) of a vector of n <= 8*512
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void round_h8(float (&f)[8]) {   // f <- fp32(fp16(f)): an fp16 tensor in the reference
+  const uint4 v = pack_h8(f);
+  unpack_h8(v, f);
+}
+__device__ __forceinline__ void mul_round_h8(float (&f)[8], const uint4& hv) {
+  float o[8];
+  unpack_h8(hv, o);
+#pragma unroll
+  for (int j = 0; j < 8; j++) f[j] *= o[j];
+  round_h8(f);
+}
+__device__ __forceinline__ void add_round_h8(float (&f)[8], const uint4& hv) {
+  float o[8];
+  unpack_h8(hv, o);
+#pragma unroll
+  for (int j = 0; j < 8; j++) f[j] += o[j];
+  round_h8(f);
+}
+__device__ __forceinline__ uint4 ldg_u4(const __half* p, int oct) { return __ldg(reinterpret_cast<const uint4*>(p) + oct); }
+
+struct RotBuf { float* A; float* B; float* fred; };
+
+// (H_n v)[octet tid] with v[i] = f16(acc[i] * xs) [* wscale_pc]: the output-side rotation of a linear whose
+// raw dot products are in global memory (qlinear.py:106-109, origin_order.cu:129).  n = 2^p.
+__device__ __forceinline__ void rot_out_k1(const __half* acc, const __half* wpc, int n, int p, const RotBuf& rb,
+                                           int tid, float (&f)[8]) {
+  const int noct = n >> 3;
+  const float* fin;
+  if (p % 3 == 0 && p >= 6) {
+    // first constant-geometry radix-8 pass fused with the (coalesced, strided) global load
+    const int sh = p - 3;
+    if (tid < noct) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = __half2float(__ldcg(acc + tid + (j << sh)));
+      if (wpc) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = f16_round(v[j] * __half2float(wpc[tid + (j << sh)]));
+      }
+      butterfly_regs<3>(v);
+      float4* d = reinterpret_cast<float4*>(rb.A + tid * 8);
+      d[0] = make_float4(v[0], v[1], v[2], v[3]);
+      d[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    __syncthreads();
+    float* cur = rb.A;
+    float* nxt = rb.B;
+    for (int i = 0; i < p / 3 - 2; i++) {
+      stockham_pass<3>(cur, nxt, n, p, tid, DS_THREADS);
+      __syncthreads();
+      float* t = cur; cur = nxt; nxt = t;
+    }
+    fin = cur;
+  } else {
+    if (tid < noct) {
+      float v[8];
+      unpack_h8(__ldcg(reinterpret_cast<const uint4*>(acc) + tid), v);
+      if (wpc) mul_round_h8(v, ldg_u4(wpc, tid));
+      float4* d = reinterpret_cast<float4*>(rb.A + tid * 8);
+      d[0] = make_float4(v[0], v[1], v[2], v[3]);
+      d[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    __syncthreads();
+    fin = stockham_hi(rb.A, rb.B, n, p, tid, DS_THREADS);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) f[j] = 0.f;
+  if (tid < noct) stockham_last(fin, p, tid, f);
+}
+
+// in-register octet -> rotated octet (input side, quant.py:72-84 with K == 1)
+__device__ __forceinline__ void rot_in_k1(float (&f)[8], int n, int p, const RotBuf& rb, int tid) {
+  const int noct = n >> 3;
+  __syncthreads();   // earlier readers of A / B are done
+  if (tid < noct) {
+    float4* d = reinterpret_cast<float4*>(rb.A + tid * 8);
+    d[0] = make_float4(f[0], f[1], f[2], f[3]);
+    d[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  __syncthreads();
+  const float* fin = stockham_hi(rb.A, rb.B, n, p, tid, DS_THREADS);
+  if (tid < noct) stockham_last(fin, p, tid, f);
+}
+
+// Output side of linear Lp (K_right == 1): rotation, 1/sqrt(n), SV, bias, residual (qlinear.py:108-114 plus the
+// decoder-layer skip connection).  f = octet tid of the fp32 result BEFORE the final fp16 rounding (zeros beyond
+// out_features).
+__device__ __forceinline__ void out_side_k1(const quipb200_linear_t& Lp, const __half* acc, const __half* resid,
+                                            const RotBuf& rb, int tid, float (&f)[8]) {
+  const bool vout = tid < (Lp.out_features >> 3);
+  const __half* SV = reinterpret_cast<const __half*>(Lp.SV);
+  const __half* bias = reinterpret_cast<const __half*>(Lp.bias);
+  uint4 svv = make_uint4(0, 0, 0, 0), bv = svv, rv = svv;
+  if (vout) {
+    if (SV) svv = ldg_u4(SV, tid);
+    if (bias) bv = ldg_u4(bias, tid);
+    if (resid) rv = __ldcg(reinterpret_cast<const uint4*>(resid) + tid);
+  }
+  const int p = ilog2_dev(Lp.q_out);
+  rot_out_k1(acc, reinterpret_cast<const __half*>(Lp.wscale_pc), Lp.q_out, p, rb, tid, f);
+  const float sc = 1.0f / sqrtf((float)Lp.q_out);
+#pragma unroll
+  for (int j = 0; j < 8; j++) f[j] *= sc;
+  round_h8(f);
+  if (SV) mul_round_h8(f, svv);
+  if (bias) add_round_h8(f, bv);
+  if (resid) {
+    float o[8];
+    unpack_h8(rv, o);
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] += o[j];
+  }
+  if (!vout) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] = 0.f;
+  }
+}
+
+// Input side of linear L (K_left == 1) from an fp16-valued octet held in registers: [RMSNorm] -> SU -> rotation ->
+// * wscale/sqrt(n) -> 16-bit fixed point record in xq (qlinear.py:90-102).  Returns the fixed-point scale.
+__device__ __forceinline__ float in_side_k1(float (&f)[8], const __half* norm_w, float eps, const quipb200_linear_t& L,
+                                            const RotBuf& rb, uint4* xq, int tid) {
+  const bool vin = tid < (L.in_features >> 3);
+  const int noct = L.q_in >> 3;
+  const __half* SU = reinterpret_cast<const __half*>(L.SU);
+  uint4 wv = make_uint4(0, 0, 0, 0), sv = wv;
+  if (vin && norm_w) wv = ldg_u4(norm_w, tid);
+  if (vin && SU) sv = ldg_u4(SU, tid);
+  if (norm_w) {   // LlamaRMSNorm: weight * (x * rstd).to(fp16)
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) ss = fmaf(f[j], f[j], ss);
+    ss = block_sum(ss, rb.fred, tid, DS_THREADS);
+    const float rstd = rsqrtf(ss / (float)L.in_features + eps);
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] *= rstd;
+    round_h8(f);
+    mul_round_h8(f, wv);
+  }
+  if (SU) mul_round_h8(f, sv);
+  rot_in_k1(f, L.q_in, ilog2_dev(L.q_in), rb, tid);
+  const float scale = L.wscale_float / sqrtf((float)L.q_in);
+  float mx = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; j++) f[j] *= scale;
+  round_h8(f);
+  if (tid < noct) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) mx = fmaxf(mx, fabsf(f[j]));
+  }
+  mx = block_max1(mx, rb.fred + 32, tid, DS_THREADS);
+  const float inv = (mx > 0.f) ? 32767.0f / mx : 0.f;
+  if (tid < noct) {
+    uint4 r;
+    pack_record(f, inv, r);
+    xq[swz(tid)] = r;
+  }
+  __syncthreads();
+  return (mx > 0.f) ? mx / 32767.0f : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Walsh-Hadamard transforms on the (legacy) tensor path, register resident.
+//   H_256 = H_16 (x) H_16 and H_4096 = H_16 (x) H_16 (x) H_16; one factor = one mma.sync.m16n8k16 with A = H_16 / 4
+//   (+-0.25: exact in fp16, and three factors give exactly the 1/sqrt(4096) of quant.py:75, two the 1/sqrt(256)).
+//   A 16x16 tile M[x][y] lives in a warp in "F(x,y)" layout = the C fragments of its two 8-column halves:
+//       r0,r1 = M[g][2t,2t+1]   r2,r3 = M[g+8][2t,2t+1]   r4,r5 = M[g][2t+8,2t+9]   r6,r7 = M[g+8][2t+8,2t+9]
+//   (g = lane/4, t = lane%4).  Re-packed pairwise these registers ARE the B fragments of M^T, so
+//       hT:  F(x,y) -> F(y',x)   transforms the y index with no data movement at all;
+//   applying it twice transforms both indices and restores the layout.  fp32 intermediates are fed back as
+//   hi + lo fp16 pairs (two mma), so every factor is exact to ~22 bits: the arithmetic is at least as
+//   accurate as the fp32 butterflies it replaces.
+// ---------------------------------------------------------------------------------------------
+struct HFrag { uint32_t a[4]; };
+__device__ __forceinline__ HFrag make_hfrag(int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  auto h = [](int r, int c) -> uint32_t { return (__popc(r & c) & 1) ? 0xB400u : 0x3400u; };   // -+0.25
+  HFrag f;
+  f.a[0] = h(g, 2 * t) | (h(g, 2 * t + 1) << 16);
+  f.a[1] = h(g + 8, 2 * t) | (h(g + 8, 2 * t + 1) << 16);
+  f.a[2] = h(g, 2 * t + 8) | (h(g, 2 * t + 9) << 16);
+  f.a[3] = h(g + 8, 2 * t + 8) | (h(g + 8, 2 * t + 9) << 16);
+  return f;
+}
+__device__ __forceinline__ uint32_t pk_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// packed fp16 pairs (p[0] = r0r1, p[1] = r2r3, p[2] = r4r5, p[3] = r6r7) -> transformed tile (fp32)
+__device__ __forceinline__ void hT_packed(const uint32_t (&p)[4], const HFrag& A, float (&r)[8]) {
+  float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t b0[2] = {p[0], p[2]}, b1[2] = {p[1], p[3]};
+  mma_16816(d0, A.a, b0);
+  mma_16816(d1, A.a, b1);
+#pragma unroll
+  for (int j = 0; j < 4; j++) { r[j] = d0[j]; r[4 + j] = d1[j]; }
+}
+// fp32 tile -> transformed tile, inputs split into hi + lo fp16 parts
+__device__ __forceinline__ void hT_split(float (&r)[8], const HFrag& A) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const __half2 h = __floats2half2_rn(r[2 * q], r[2 * q + 1]);
+    const float2 hf = __half22float2(h);
+    hi[q] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[q] = pk_h2(r[2 * q] - hf.x, r[2 * q + 1] - hf.y);
+  }
+  float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t b0h[2] = {hi[0], hi[2]}, b1h[2] = {hi[1], hi[3]};
+  const uint32_t b0l[2] = {lo[0], lo[2]}, b1l[2] = {lo[1], lo[3]};
+  mma_16816(d0, A.a, b0h);
+  mma_16816(d1, A.a, b1h);
+  mma_16816(d0, A.a, b0l);
+  mma_16816(d1, A.a, b1l);
+#pragma unroll
+  for (int j = 0; j < 4; j++) { r[j] = d0[j]; r[4 + j] = d1[j]; }
+}
+// 256-point transform (x 1/16) of a block whose fp16 pairs are given in F(n, k) layout, element = 16 n + k
+__device__ __forceinline__ void fwht256_frag(const uint32_t (&p)[4], const HFrag& A, float (&r)[8]) {
+  hT_packed(p, A, r);
+  hT_split(r, A);
+}
+// position of register pair q (q = 0..3 <-> r[2q], r[2q+1]) inside a 16x16 tile in F layout: x*16 + y
+__device__ __forceinline__ int frag_x(int lane, int q) { return (lane >> 2) + 8 * (q & 1); }
+__device__ __forceinline__ int frag_y(int lane, int q) { return 2 * (lane & 3) + 8 * (q >> 1); }
+
+// 4096-point transform (x 1/64) across the 16 warps of the CTA.  In: fp16 pairs of tile F(x, y) of warp w.
+// The two tile indices are transformed in registers, the warp index after one exchange through shared memory
+// (S: 16 rows of DS_XROW floats; bank-conflict free both ways).  Out: r = F(w', x') of warp x'' ... precisely: the
+// value at (row index = warp-index group, x, y) ends up as r of the lane holding (x' = g(+8): old warp group,
+// y' = pairs: old x group) in warp = old y group.  Callers use idx_out / idx_in below.
+constexpr int DS_XROW = 388;
+__device__ __forceinline__ void fwht4096_frag(const uint32_t (&p)[4], const HFrag& A, float* S, int warp, int lane,
+                                              float (&r)[8]) {
+  hT_packed(p, A, r);
+  hT_split(r, A);
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+    *reinterpret_cast<float2*>(S + warp * DS_XROW + frag_x(lane, q) * 24 + frag_y(lane, q)) = make_float2(r[2 * q], r[2 * q + 1]);
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    r[2 * q] = S[frag_y(lane, q) * DS_XROW + warp * 24 + frag_x(lane, q)];
+    r[2 * q + 1] = S[(frag_y(lane, q) + 1) * DS_XROW + warp * 24 + frag_x(lane, q)];
+  }
+  hT_split(r, A);
+}
+// element index of register pair q (first element; the second is +1):
+//   block layout   : warp = top 4 bits, x = middle, y = low      (input of the output-side rotation, output of the input side)
+//   spread layout  : x = top 4 bits, warp = middle, y = low      (output of the output-side rotation, input of the input side)
+__device__ __forceinline__ int idx_block(int warp, int lane, int q) { return warp * 256 + frag_x(lane, q) * 16 + frag_y(lane, q); }
+__device__ __forceinline__ int idx_spread(int warp, int lane, int q) { return frag_x(lane, q) * 256 + warp * 16 + frag_y(lane, q); }
+
+// ---------------------------------------------------------------------------------------------
+// output / input side of a linear with a 4096-point rotation, tensor-path version (same rounding points
+// as out_side_k1 / in_side_k1; values live as register pairs at idx_spread / idx_block positions)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ldg_h2(const __half* p, int i) { return __ldg(reinterpret_cast<const unsigned int*>(p + i)); }
+__device__ __forceinline__ __half2 as_h2(uint32_t v) { return *reinterpret_cast<const __half2*>(&v); }
+__device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
+
+// f[2q], f[2q+1]: fp32 result at elements idx_spread(warp, lane, q) (+1) BEFORE the final fp16 rounding
+__device__ __forceinline__ void out_side_m(const quipb200_linear_t& Lp, const __half* acc, const __half* resid,
+                                           const HFrag& A, float* S, int warp, int lane, float (&f)[8]) {
+  const __half* SV = reinterpret_cast<const __half*>(Lp.SV);
+  const __half* bias = reinterpret_cast<const __half*>(Lp.bias);
+  const __half* wpc = reinterpret_cast<const __half*>(Lp.wscale_pc);
+  uint32_t svv[4], bv[4], rv[4], p[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int i = idx_spread(warp, lane, q);
+    const bool ok = i < Lp.out_features;
+    svv[q] = (ok && SV) ? ldg_h2(SV, i) : 0u;
+    bv[q] = (ok && bias) ? ldg_h2(bias, i) : 0u;
+    rv[q] = (ok && resid) ? __ldcg(reinterpret_cast<const unsigned int*>(resid + i)) : 0u;
+    p[q] = __ldcg(reinterpret_cast<const unsigned int*>(acc + idx_block(warp, lane, q)));
+  }
+  if (wpc) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) p[q] = as_u32(__hmul2(as_h2(p[q]), as_h2(ldg_h2(wpc, idx_block(warp, lane, q)))));   // qlinear.py:107
+  }
+  fwht4096_frag(p, A, S, warp, lane, f);                                             // includes 1/sqrt(4096)
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const bool ok = idx_spread(warp, lane, q) < Lp.out_features;
+    __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
+    if (SV) h = __hmul2(h, as_h2(svv[q]));                                           // qlinear.py:112
+    if (bias) h = __hadd2(h, as_h2(bv[q]));                                          // qlinear.py:114
+    float2 v = __half22float2(h);
+    if (resid) {
+      const float2 r = __half22float2(as_h2(rv[q]));
+      v.x += r.x;
+      v.y += r.y;
+    }
+    f[2 * q] = ok ? v.x : 0.f;
+    f[2 * q + 1] = ok ? v.y : 0.f;
+  }
+}
+
+// f: fp16-valued pairs at idx_spread positions (zeros beyond in_features): [RMSNorm] -> SU -> rotation -> * wscale/64 ->
+// 16-bit fixed point records (via the fp16 vector V, 4096 halfs).  Returns the fixed-point scale.
+__device__ __forceinline__ float in_side_m(const float (&f)[8], const __half* norm_w, float eps, const quipb200_linear_t& L,
+                                           const HFrag& A, float* S, __half* V, float* fred, uint4* xq, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const __half* SU = reinterpret_cast<const __half*>(L.SU);
+  uint32_t wv[4], sv[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int i = idx_spread(warp, lane, q);
+    const bool ok = i < L.in_features;
+    wv[q] = (ok && norm_w) ? ldg_h2(norm_w, i) : 0u;
+    sv[q] = (ok && SU) ? ldg_h2(SU, i) : 0u;
+  }
+  float rstd = 1.f;
+  if (norm_w) {   // LlamaRMSNorm: weight * (x * rstd).to(fp16)
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) ss = fmaf(f[j], f[j], ss);
+    ss = block_sum(ss, fred, tid, DS_THREADS);
+    rstd = rsqrtf(ss / (float)L.in_features + eps);
+  }
+  uint32_t p[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    __half2 h = __floats2half2_rn(f[2 * q] * rstd, f[2 * q + 1] * rstd);
+    if (norm_w) h = __hmul2(as_h2(wv[q]), h);
+    if (SU) h = __hmul2(h, as_h2(sv[q]));                                            // qlinear.py:91
+    p[q] = as_u32(h);
+  }
+  float r[8];
+  fwht4096_frag(p, A, S, warp, lane, r);                                             // block layout, 1/64 included
+  const float ws = L.wscale_float;
+  float mx = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const __half2 h = __floats2half2_rn(r[2 * q] * ws, r[2 * q + 1] * ws);           // register_lib.py:20 (fp16 out)
+    const float2 v = __half22float2(h);
+    mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
+    *reinterpret_cast<__half2*>(V + idx_block(warp, lane, q)) = h;
+  }
+  mx = block_max1(mx, fred + 32, tid, DS_THREADS);                                   // its barrier also publishes V
+  const float inv = (mx > 0.f) ? 32767.0f / mx : 0.f;
+  {
+    float o8[8];
+    unpack_h8(*reinterpret_cast<const uint4*>(V + tid * 8), o8);
+    uint4 rec;
+    pack_record(o8, inv, rec);
+    xq[swz(tid)] = rec;
+  }
+  __syncthreads();
+  return (mx > 0.f) ? mx / 32767.0f : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block rotations (K blocks of 256, K x K orthogonal mix): gate / up output side, down input side
+// ---------------------------------------------------------------------------------------------
+struct BlkBuf { __half* Tg; __half* Tu; __half* hkg; __half* hku; __half* hkd; __half* vSVg; __half* vSVu; __half* vSUd; int LS; };
+
+// coefficient matrix M[k_out][k_in] (zero padded to Kp <= 64): hadK (output side) or hadK^T (input side)
+__device__ __forceinline__ void load_hk(__half* dst, const __half* src, int K, int Kp, int transpose, int tid) {
+  const int ki = tid & 63;
+  for (int ko = tid >> 6; ko < Kp; ko += DS_THREADS / 64) {
+    if (ki < Kp) {
+      __half v = __float2half_rn(0.f);
+      if (ko < K && ki < K) v = transpose ? src[ki * K + ko] : src[ko * K + ki];
+      dst[ko * Kp + ki] = v;
+    }
+  }
+}
+
+__device__ __forceinline__ void mix_blocks(__half* T, __half* hk, int K, int LS, float* dummy, int tid) {
+  RotSmem r;
+  r.s = dummy; r.s2 = dummy; r.pp = 1; r.t = T; r.hk = hk; r.red = dummy; r.Ls = LS; r.log2L = 8;
+  rotate_mix(r, K * 256, K, tid, DS_THREADS);   // zero row + barrier + mma.sync tiles + barrier
+}
+
+// Stage-E input construction for K > 1:  x = rot_in_down( SU_d . silu(out(gate)) * out(up) ), records -> xq.
+// Everything the stage reads from global memory is requested up front (one L2 round trip): the raw dot
+// products of this warp's blocks into registers, SV_gate / SV_up / SU_down into shared memory with cp.async,
+// the three K x K coefficient matrices with batched 2-byte loads.
+constexpr int DS_EB = 3;   // blocks per warp in flight (K <= 48 in one round)
+__device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, const quipb200_linear_t& Lu,
+                                                const quipb200_linear_t& Ld, const __half* acc_g, const __half* acc_u,
+                                                const BlkBuf& bb, const HFrag& A,
+                                                float* fred, uint4* xq, int tid, long long* dbg) {
+#define DS_E(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+  const int lane = tid & 31, warp = tid >> 5;
+  const int K = Lg.K_right, Kp = (K + 15) / 16 * 16, LS = bb.LS;
+  const int noct_mid = Lg.out_features >> 3;
+  const __half* SVg = reinterpret_cast<const __half*>(Lg.SV);
+  const __half* SVu = reinterpret_cast<const __half*>(Lu.SV);
+  const __half* SUd = reinterpret_cast<const __half*>(Ld.SU);
+  const __half* bg = reinterpret_cast<const __half*>(Lg.bias);
+  const __half* bu = reinterpret_cast<const __half*>(Lu.bias);
+  const __half* wg = reinterpret_cast<const __half*>(Lg.wscale_pc);
+  const __half* wu = reinterpret_cast<const __half*>(Lu.wscale_pc);
+  for (int o = tid; o < noct_mid; o += DS_THREADS) {
+    if (SVg) cp_async16(bb.vSVg + o * 8, SVg + o * 8);
+    if (SVu) cp_async16(bb.vSVu + o * 8, SVu + o * 8);
+    if (SUd) cp_async16(bb.vSUd + o * 8, SUd + o * 8);
+  }
+  // coefficient matrices M[k_out][k_in], zero padded to Kp <= 64 (input side of down: hadK^T)
+  {
+    const __half* src[3] = {reinterpret_cast<const __half*>(Lg.had_right), reinterpret_cast<const __half*>(Lu.had_right),
+                            reinterpret_cast<const __half*>(Ld.had_left)};
+    __half* dst[3] = {bb.hkg, bb.hku, bb.hkd};
+    const int ki = tid & 63;
+    __half hv[3][8];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int ko = (tid >> 6) + 8 * i;
+        hv[m][i] = __float2half_rn(0.f);
+        if (ko < K && ki < K) hv[m][i] = (m == 2) ? src[m][ki * K + ko] : src[m][ko * K + ki];
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int ko = (tid >> 6) + 8 * i;
+        if (ko < Kp && ki < Kp) dst[m][ko * Kp + ki] = hv[m][i];
+      }
+    }
+  }
+  DS_E(30);
+  // block transforms of the raw dot products (256-point WHT per warp on the tensor path, x 1/16), fp16
+  for (int b0 = warp; b0 < K; b0 += DS_WARPS * DS_EB) {
+    uint32_t ga[DS_EB][4], ua[DS_EB][4];
+#pragma unroll
+    for (int r = 0; r < DS_EB; r++) {
+      const int b = b0 + r * DS_WARPS;
+      if (b < K) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int e = b * 256 + frag_x(lane, q) * 16 + frag_y(lane, q);
+          ga[r][q] = __ldcg(reinterpret_cast<const unsigned int*>(acc_g + e));
+          ua[r][q] = __ldcg(reinterpret_cast<const unsigned int*>(acc_u + e));
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < DS_EB; r++) {
+      const int b = b0 + r * DS_WARPS;
+      if (b < K) {
+        uint32_t pg[4], pu[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int e = b * 256 + frag_x(lane, q) * 16 + frag_y(lane, q);
+          __half2 hg = as_h2(ga[r][q]);
+          __half2 hu = as_h2(ua[r][q]);
+          if (wg) hg = __hmul2(hg, as_h2(ldg_h2(wg, e)));
+          if (wu) hu = __hmul2(hu, as_h2(ldg_h2(wu, e)));
+          pg[q] = as_u32(hg);
+          pu[q] = as_u32(hu);
+        }
+        float g[8], u[8];
+        fwht256_frag(pg, A, g);
+        fwht256_frag(pu, A, u);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int e = frag_x(lane, q) * 16 + frag_y(lane, q);
+          *reinterpret_cast<__half2*>(bb.Tg + b * LS + e) = __floats2half2_rn(g[2 * q], g[2 * q + 1]);
+          *reinterpret_cast<__half2*>(bb.Tu + b * LS + e) = __floats2half2_rn(u[2 * q], u[2 * q + 1]);
+        }
+      }
+    }
+  }
+  cp_async_wait_all();
+  DS_E(31);
+  mix_blocks(bb.Tg, bb.hkg, K, LS, fred, tid);
+  mix_blocks(bb.Tu, bb.hku, K, LS, fred, tid);
+  DS_E(32);
+  // SV / bias of gate and up, silu(gate) * up, SU of down, block transform of down's input (x wscale/16)
+  const float ws_d = Ld.wscale_float;
+  for (int b = warp; b < K; b += DS_WARPS) {
+    uint32_t pa[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int e = frag_x(lane, q) * 16 + frag_y(lane, q);
+      const int i = b * 256 + e;
+      __half2 g = *reinterpret_cast<const __half2*>(bb.Tg + b * LS + e);
+      __half2 u = *reinterpret_cast<const __half2*>(bb.Tu + b * LS + e);
+      if (SVg) g = __hmul2(g, *reinterpret_cast<const __half2*>(bb.vSVg + i));
+      if (bg) g = __hadd2(g, as_h2(ldg_h2(bg, i)));
+      if (SVu) u = __hmul2(u, *reinterpret_cast<const __half2*>(bb.vSVu + i));
+      if (bu) u = __hadd2(u, as_h2(ldg_h2(bu, i)));
+      const float2 gf = __half22float2(g);
+      const __half2 sg = __floats2half2_rn(silu_f(gf.x), silu_f(gf.y));
+      __half2 a = __hmul2(sg, u);                                    // LlamaMLP: act_fn(gate) * up
+      if (SUd) a = __hmul2(a, *reinterpret_cast<const __half2*>(bb.vSUd + i));
+      pa[q] = (i < (noct_mid << 3)) ? as_u32(a) : 0u;
+    }
+    float u[8];
+    fwht256_frag(pa, A, u);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int e = frag_x(lane, q) * 16 + frag_y(lane, q);
+      *reinterpret_cast<__half2*>(bb.Tu + b * LS + e) = __floats2half2_rn(u[2 * q] * ws_d, u[2 * q + 1] * ws_d);   // in place
+    }
+  }
+  DS_E(33);
+  mix_blocks(bb.Tu, bb.hkd, K, LS, fred, tid);
+  DS_E(34);
+  float mx = 0.f;
+  for (int b = warp; b < K; b += DS_WARPS) {
+    float u[8];
+    unpack_h8(*reinterpret_cast<const uint4*>(bb.Tu + b * LS + lane * 8), u);
+#pragma unroll
+    for (int j = 0; j < 8; j++) mx = fmaxf(mx, fabsf(u[j]));
+  }
+  mx = block_max(mx, fred, tid, DS_THREADS);
+  const float inv = (mx > 0.f) ? 32767.0f / mx : 0.f;
+  for (int b = warp; b < K; b += DS_WARPS) {
+    float u[8];
+    unpack_h8(*reinterpret_cast<const uint4*>(bb.Tu + b * LS + lane * 8), u);
+    uint4 r;
+    pack_record(u, inv, r);
+    xq[swz(b * 32 + lane)] = r;
+  }
+  __syncthreads();
+  DS_E(35);
+#undef DS_E
+  return (mx > 0.f) ? mx / 32767.0f : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -244,16 +757,28 @@ __device__ __forceinline__ void gemv_store(const GemvCfg& c, const int* red, flo
 // ---------------------------------------------------------------------------------------------
 // 128 outputs [128*j, 128*j+128) of H_n f (n = 128*nb, Sylvester order): first the nb blocks are combined
 // with the signs of row j of H_nb, then one 128-point transform.  part: [4][128] floats.
-__device__ __forceinline__ void slice_partial(const quipb200_linear_t& L, const float* acc, float xs, int j, float* part,
-                                              int tid) {
+// (n <= 4096: at most 8 blocks per thread, all loads issued before any is used)
+__device__ __forceinline__ void slice_load(int nb, const __half* acc, int tid, float (&a)[8]) {
   const int lo = tid & 127, prt = tid >> 7;
-  const int nb = L.q_out >> 7;
+#pragma unroll
+  for (int u = 0; u < 8; u++) {
+    const int ih = prt + 4 * u;
+    a[u] = (ih < nb) ? __half2float(__ldcg(acc + ih * 128 + lo)) : 0.f;
+  }
+}
+__device__ __forceinline__ void slice_sum(const quipb200_linear_t& L, int nb, const float (&a)[8], int j,
+                                          float* part, int tid) {
+  const int lo = tid & 127, prt = tid >> 7;
   const __half* wpc = reinterpret_cast<const __half*>(L.wscale_pc);
   float s = 0.f;
-  for (int ih = prt; ih < nb; ih += 4) {
-    float f = f16_round(__ldcg(acc + ih * 128 + lo) * xs);
-    if (wpc) f = f16_round(f * __half2float(wpc[ih * 128 + lo]));
-    s += (__popc(j & ih) & 1) ? -f : f;
+#pragma unroll
+  for (int u = 0; u < 8; u++) {
+    const int ih = prt + 4 * u;
+    if (ih < nb) {
+      float f = a[u];
+      if (wpc) f = f16_round(f * __half2float(wpc[ih * 128 + lo]));
+      s += (__popc(j & ih) & 1) ? -f : f;
+    }
   }
   part[prt * 128 + lo] = s;
 }
@@ -299,14 +824,34 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
   unsigned char* tab = smem + p.sm.tab;
   int* red = reinterpret_cast<int*>(smem + p.sm.red);
   uint4* xq = reinterpret_cast<uint4*>(smem + p.sm.xq);
-  __half* vh = reinterpret_cast<__half*>(smem + p.sm.vh);
-  __half* vg = reinterpret_cast<__half*>(smem + p.sm.vg);
-  __half* vu = reinterpret_cast<__half*>(smem + p.sm.vu);
-  unsigned char* rot = smem + p.sm.rot;
+  unsigned char* scr = smem + p.sm.scr;
+  RotBuf rb;
+  rb.A = reinterpret_cast<float*>(scr);
+  rb.B = rb.A + p.sm.nmax;
+  rb.fred = rb.B + p.sm.nmax;
+  BlkBuf bb;
+  bb.Tg = reinterpret_cast<__half*>(rb.fred + 64);
+  bb.Tu = bb.Tg + p.sm.t_halfs;
+  bb.hkg = bb.Tu + p.sm.t_halfs;
+  bb.hku = bb.hkg + p.sm.hk_halfs;
+  bb.hkd = bb.hku + p.sm.hk_halfs;
+  bb.vSVg = bb.hkd + p.sm.hk_halfs;
+  bb.vSVu = bb.vSVg + p.sm.mid_halfs;
+  bb.vSUd = bb.vSVu + p.sm.mid_halfs;
+  bb.LS = 256 + 8;
+  const HFrag hfrag = make_hfrag(lane);
+  float* const XS = rb.A;                                   // exchange buffer of fwht4096_frag (16 x DS_XROW floats)
+  __half* const V = reinterpret_cast<__half*>(rb.fred + 64);   // fp16 [4096] (aliases the block buffers, unused in A / C / D)
   long long* dbg = (p.dbg && bid == 0 && tid == 0) ? p.dbg : nullptr;
 #define DS_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
 #define DS_ST(i) do { if (dbg && l == 1) dbg[i] = clock64(); } while (0)
   DS_STAMP(0);
+
+  // layer descriptors: two slots in shared memory, layer l+1 is fetched (cp.async) while layer l runs
+  __shared__ __align__(16) quipb200_decode_layer_t s_desc[2];
+  constexpr int DESC_U2 = (int)(sizeof(quipb200_decode_layer_t) / 8);
+  static_assert(sizeof(quipb200_decode_layer_t) % 8 == 0, "descriptor copy granularity");
+  if (tid < DESC_U2) reinterpret_cast<uint2*>(&s_desc[0])[tid] = reinterpret_cast<const uint2*>(&P.layers[0])[tid];
 
   unsigned int bar_target = 0;
   if (tid == 0) bar_target = *reinterpret_cast<volatile unsigned int*>(p.ws.bar + 32);
@@ -320,9 +865,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     reinterpret_cast<uint2*>(tab)[tid] = t;
   }
   const int hid8 = P.hidden >> 3;
-  if (bid == 0)
-    for (int i = tid; i < hid8; i += DS_THREADS)
-      reinterpret_cast<uint4*>(p.ws.hA)[i] = reinterpret_cast<const uint4*>(p.h_in)[i];
+  if (bid == 0 && tid < hid8) reinterpret_cast<uint4*>(p.ws.hA)[tid] = reinterpret_cast<const uint4*>(p.h_in)[tid];
   __syncthreads();
 
   int pos = (int)(*P.pos);
@@ -332,39 +875,62 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
   const float attn_scale = 1.0f / sqrtf((float)DS_HD);
 
   for (int l = 0; l < P.n_layers; l++) {
-    const quipb200_decode_layer_t& Ly = P.layers[l];
+    const quipb200_decode_layer_t& Ly = s_desc[l & 1];
     uint4 cw[DS_UNROLL];
     // ======================= stage A: q, k, v =======================
     {
-      const quipb200_linear_t* mem[3] = {&Ly.q, &Ly.k, &Ly.v};
-      int j, bx, G;
-      split_ctas(mem, 3, nblk, bid, j, bx, G);
+      int j, bx;
+      which_member(p.geo.G_A, 3, bid, j, bx);
       if (j >= 0) {
-        const quipb200_linear_t& L = *mem[j];
-        const GemvCfg c = make_cfg(L, bx, G);
+        const quipb200_linear_t L = (j == 0) ? Ly.q : (j == 1 ? Ly.k : Ly.v);
+        const GemvCfg c = make_cfg(L, bx, p.geo.G_A[j]);
         DS_ST(1);
-        gemv_first(cw, c, warp, lane, pol);
-        if (l == 0) {
-          for (int i = tid; i < hid8; i += DS_THREADS)
-            reinterpret_cast<uint4*>(vh)[i] = reinterpret_cast<const uint4*>(p.h_in)[i];
-          __syncthreads();
+        gemv_prefetch_l2(c, tid);
+        float f[8];
+        float xs;
+        if (p.use_mma) {
+          if (l == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const float2 v = __half22float2(as_h2(ldg_h2(p.h_in, idx_spread(warp, lane, q))));
+              f[2 * q] = v.x;
+              f[2 * q + 1] = v.y;
+            }
+          } else {
+            const quipb200_linear_t Lp = s_desc[(l - 1) & 1].down;
+            out_side_m(Lp, p.ws.acc[SL_D], p.ws.hB, hfrag, XS, warp, lane, f);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
+              if (bid == 0) *reinterpret_cast<__half2*>(p.ws.hA + idx_spread(warp, lane, q)) = h;
+              const float2 v = __half22float2(h);
+              f[2 * q] = v.x;
+              f[2 * q + 1] = v.y;
+            }
+          }
+          DS_ST(2);
+          xs = in_side_m(f, reinterpret_cast<const __half*>(Ly.input_norm_w), P.norm_eps, L, hfrag, XS, V, rb.fred, xq, tid);
         } else {
-          EpilogueArgs ea;
-          fill_epi(ea, P.layers[l - 1].down, p.ws.acc[SL_D], p.ws.hB, vh);
-          ds_epilogue(ea, rot, __ldcg(p.ws.xscale + SL_D), tid);
-          if (bid == 0)
-            for (int i = tid; i < hid8; i += DS_THREADS)
-              reinterpret_cast<uint4*>(p.ws.hA)[i] = reinterpret_cast<const uint4*>(vh)[i];
+          if (l == 0) {
+            uint4 hv = make_uint4(0, 0, 0, 0);
+            if (tid < hid8) hv = reinterpret_cast<const uint4*>(p.h_in)[tid];
+            unpack_h8(hv, f);
+          } else {
+            const quipb200_linear_t Lp = s_desc[(l - 1) & 1].down;
+            out_side_k1(Lp, p.ws.acc[SL_D], p.ws.hB, rb, tid, f);
+            const uint4 hv = pack_h8(f);
+            if (bid == 0 && tid < hid8) reinterpret_cast<uint4*>(p.ws.hA)[tid] = hv;
+            unpack_h8(hv, f);
+          }
+          DS_ST(2);
+          xs = in_side_k1(f, reinterpret_cast<const __half*>(Ly.input_norm_w), P.norm_eps, L, rb, xq, tid);
         }
-        DS_ST(2);
-        PrologueArgs pa;
-        fill_pro(pa, L, vh, nullptr, reinterpret_cast<const __half*>(Ly.input_norm_w), P.norm_eps);
-        const float xs = ds_prologue(pa, rot, xq, tid);
         if (bx == 0 && tid == 0) p.ws.xscale[SL_Q + j] = xs;
         DS_ST(3);
+        gemv_first(cw, c, warp, lane, pol);
         gemv_run(cw, c, xq, tab, red, warp, lane, pol);
         DS_ST(4);
-        gemv_store(c, red, p.ws.acc[SL_Q + j], tid);
+        gemv_store(c, red, p.ws.acc[SL_Q + j], xs, tid);
         DS_ST(5);
       }
       grid_barrier(p.ws.bar, bar_target, nblk);
@@ -373,12 +939,15 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     // ======================= stage B: attention =======================
     {
       const int nh = P.n_heads, nkv = P.n_kv_heads, group = nh / nkv;
+      if (l + 1 < P.n_layers && tid < DESC_U2)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(reinterpret_cast<uint2*>(&s_desc[(l + 1) & 1]) + tid)),
+                     "l"(reinterpret_cast<const uint2*>(&P.layers[l + 1]) + tid) : "memory");
       if (bid < nh * S) {
         const int h = bid / S, s = bid - h * S, kvh = h / group;
         const int T = pos + 1, chunk = (T + S - 1) / S;
         const int t_begin = s * chunk, t_end = min(T, t_begin + chunk);
         const bool has_new = (t_begin <= pos) && (pos < t_end);
-        float* part = reinterpret_cast<float*>(rot);          // [3][4][128]
+        float* part = reinterpret_cast<float*>(scr);          // [3][4][128]
         float* sq = part + 3 * 512;                           // [128] rotated, scaled query
         float* sk = sq + 128;                                 // [128] new key (post RoPE)
         float* sv = sk + 128;                                 // [128] new value
@@ -387,10 +956,19 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         float* sc = sout + DS_PV_GROUPS * 128;                // [chunk] scores
         __half* kc = reinterpret_cast<__half*>(Ly.k_cache) + (size_t)kvh * P.max_len * DS_HD;
         __half* vc = reinterpret_cast<__half*>(Ly.v_cache) + (size_t)kvh * P.max_len * DS_HD;
-        slice_partial(Ly.q, p.ws.acc[SL_Q], __ldcg(p.ws.xscale + SL_Q) * 0.25f, h, part, tid);
-        if (has_new) {
-          slice_partial(Ly.k, p.ws.acc[SL_K], __ldcg(p.ws.xscale + SL_K) * 0.25f, kvh, part + 512, tid);
-          slice_partial(Ly.v, p.ws.acc[SL_V], __ldcg(p.ws.xscale + SL_V) * 0.25f, kvh, part + 1024, tid);
+        {
+          const int nbq = Ly.q.q_out >> 7, nbk = Ly.k.q_out >> 7, nbv = Ly.v.q_out >> 7;
+          float aq[8], ak[8], av[8];
+          slice_load(nbq, p.ws.acc[SL_Q], tid, aq);
+          if (has_new) {
+            slice_load(nbk, p.ws.acc[SL_K], tid, ak);
+            slice_load(nbv, p.ws.acc[SL_V], tid, av);
+          }
+          slice_sum(Ly.q, nbq, aq, h, part, tid);
+          if (has_new) {
+            slice_sum(Ly.k, nbk, ak, kvh, part + 512, tid);
+            slice_sum(Ly.v, nbv, av, kvh, part + 1024, tid);
+          }
         }
         __syncthreads();
         DS_ST(7);
@@ -524,107 +1102,182 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         }
         DS_ST(10);
       }
+      cp_async_wait_all();
       grid_barrier(p.ws.bar, bar_target, nblk);
       DS_ST(11);
     }
     // ======================= stage C: o_proj =======================
     {
-      const quipb200_linear_t* mem[1] = {&Ly.o};
-      int j, bx, G;
-      split_ctas(mem, 1, nblk, bid, j, bx, G);
+      int j, bx;
+      which_member(&p.geo.G_C, 1, bid, j, bx);
       if (j >= 0) {
-        const quipb200_linear_t& L = Ly.o;
-        const GemvCfg c = make_cfg(L, bx, G);
-        gemv_first(cw, c, warp, lane, pol);
-        // combine the split-KV partials into the fp16 attention output
-        const int nh = P.n_heads;
-        for (int o = tid; o < (nh * DS_HD) >> 3; o += DS_THREADS) {
-          const int h = (o * 8) / DS_HD, d = (o * 8) % DS_HD;
-          float m[DS_MAX_SPLITS], M = -INFINITY, den = 0.f;
-          for (int s = 0; s < S; s++) {
-            m[s] = __ldcg(p.ws.att_ml + (size_t)(h * S + s) * 2);
+        const quipb200_linear_t L = Ly.o;
+        const GemvCfg c = make_cfg(L, bx, p.geo.G_C);
+        gemv_prefetch_l2(c, tid);
+        // combine the split-KV partials into the fp16 attention output.  Split weights exp(m_s - M) / sum go through
+        // shared memory: [head][split] floats, computed once per CTA
+        float* wsm = rb.fred + 64;   // aliases the block buffers (unused in this stage); n_heads * S <= 512 floats
+        if (tid < P.n_heads) {
+          float m[DS_MAX_SPLITS], lsum[DS_MAX_SPLITS], M = -INFINITY, den = 0.f;
+#pragma unroll
+          for (int s = 0; s < DS_MAX_SPLITS; s++) {
+            m[s] = (s < S) ? __ldcg(p.ws.att_ml + (size_t)(tid * S + s) * 2) : -INFINITY;
+            lsum[s] = (s < S) ? __ldcg(p.ws.att_ml + (size_t)(tid * S + s) * 2 + 1) : 0.f;
             M = fmaxf(M, m[s]);
           }
-          float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          for (int s = 0; s < S; s++) {
-            const float w = (m[s] == -INFINITY) ? 0.f : __expf(m[s] - M);
-            den = fmaf(w, __ldcg(p.ws.att_ml + (size_t)(h * S + s) * 2 + 1), den);
-            const float4 a = __ldcg(reinterpret_cast<const float4*>(p.ws.att_o + (size_t)(h * S + s) * DS_HD + d));
-            const float4 b = __ldcg(reinterpret_cast<const float4*>(p.ws.att_o + (size_t)(h * S + s) * DS_HD + d) + 1);
-            f[0] = fmaf(w, a.x, f[0]); f[1] = fmaf(w, a.y, f[1]); f[2] = fmaf(w, a.z, f[2]); f[3] = fmaf(w, a.w, f[3]);
-            f[4] = fmaf(w, b.x, f[4]); f[5] = fmaf(w, b.y, f[5]); f[6] = fmaf(w, b.z, f[6]); f[7] = fmaf(w, b.w, f[7]);
+#pragma unroll
+          for (int s = 0; s < DS_MAX_SPLITS; s++) {
+            m[s] = (m[s] == -INFINITY) ? 0.f : __expf(m[s] - M);
+            den = fmaf(m[s], lsum[s], den);
           }
           const float inv = 1.0f / den;
 #pragma unroll
-          for (int e = 0; e < 8; e++) f[e] *= inv;
-          reinterpret_cast<uint4*>(vh)[o] = pack_h8(f);
+          for (int s = 0; s < DS_MAX_SPLITS; s++)
+            if (s < S) wsm[tid * S + s] = m[s] * inv;
         }
         __syncthreads();
-        DS_ST(12);
-        PrologueArgs pa;
-        fill_pro(pa, L, vh, nullptr, nullptr, 0.f);
-        const float xs = ds_prologue(pa, rot, xq, tid);
+        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float xs;
+        if (p.use_mma) {
+          // register pairs at idx_spread positions: pairs q and q+2 share a head
+#pragma unroll
+          for (int xh = 0; xh < 2; xh++) {
+            const int i0 = idx_spread(warp, lane, xh);
+            if (i0 < P.n_heads * DS_HD) {
+              const int h = i0 >> 7;
+              float w[DS_MAX_SPLITS];
+#pragma unroll
+              for (int s = 0; s < DS_MAX_SPLITS; s++) w[s] = (s < S) ? wsm[h * S + s] : 0.f;
+#pragma unroll
+              for (int yh = 0; yh < 2; yh++) {
+                const int q = xh + 2 * yh;
+                const int d = idx_spread(warp, lane, q) & (DS_HD - 1);
+                float ax = 0.f, ay = 0.f;
+#pragma unroll
+                for (int s = 0; s < DS_MAX_SPLITS; s++) {
+                  if (s < S) {
+                    const float2 a = __ldcg(reinterpret_cast<const float2*>(p.ws.att_o + (size_t)(h * S + s) * DS_HD + d));
+                    ax = fmaf(w[s], a.x, ax);
+                    ay = fmaf(w[s], a.y, ay);
+                  }
+                }
+                const float2 v = __half22float2(__floats2half2_rn(ax, ay));
+                f[2 * q] = v.x;
+                f[2 * q + 1] = v.y;
+              }
+            }
+          }
+          DS_ST(12);
+          xs = in_side_m(f, nullptr, 0.f, L, hfrag, XS, V, rb.fred, xq, tid);
+        } else {
+          if (tid < ((P.n_heads * DS_HD) >> 3)) {
+            const int h = (tid * 8) / DS_HD, d = (tid * 8) % DS_HD;
+#pragma unroll
+            for (int s = 0; s < DS_MAX_SPLITS; s++) {
+              if (s < S) {
+                const float w = wsm[h * S + s];
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(p.ws.att_o + (size_t)(h * S + s) * DS_HD + d));
+                const float4 b = __ldcg(reinterpret_cast<const float4*>(p.ws.att_o + (size_t)(h * S + s) * DS_HD + d) + 1);
+                f[0] = fmaf(w, a.x, f[0]); f[1] = fmaf(w, a.y, f[1]); f[2] = fmaf(w, a.z, f[2]); f[3] = fmaf(w, a.w, f[3]);
+                f[4] = fmaf(w, b.x, f[4]); f[5] = fmaf(w, b.y, f[5]); f[6] = fmaf(w, b.z, f[6]); f[7] = fmaf(w, b.w, f[7]);
+              }
+            }
+            round_h8(f);
+          }
+          DS_ST(12);
+          xs = in_side_k1(f, nullptr, 0.f, L, rb, xq, tid);
+        }
         if (bx == 0 && tid == 0) p.ws.xscale[SL_O] = xs;
         DS_ST(13);
+        gemv_first(cw, c, warp, lane, pol);
         gemv_run(cw, c, xq, tab, red, warp, lane, pol);
         DS_ST(14);
-        gemv_store(c, red, p.ws.acc[SL_O], tid);
+        gemv_store(c, red, p.ws.acc[SL_O], xs, tid);
       }
       grid_barrier(p.ws.bar, bar_target, nblk);
       DS_ST(15);
     }
     // ======================= stage D: gate, up =======================
     {
-      const quipb200_linear_t* mem[2] = {&Ly.gate, &Ly.up};
-      int j, bx, G;
-      split_ctas(mem, 2, nblk, bid, j, bx, G);
+      int j, bx;
+      which_member(p.geo.G_D, 2, bid, j, bx);
       if (j >= 0) {
-        const quipb200_linear_t& L = *mem[j];
-        const GemvCfg c = make_cfg(L, bx, G);
-        gemv_first(cw, c, warp, lane, pol);
-        EpilogueArgs ea;
-        fill_epi(ea, Ly.o, p.ws.acc[SL_O], p.ws.hA, vh);
-        ds_epilogue(ea, rot, __ldcg(p.ws.xscale + SL_O), tid);
-        if (bid == 0)
-          for (int i = tid; i < hid8; i += DS_THREADS)
-            reinterpret_cast<uint4*>(p.ws.hB)[i] = reinterpret_cast<const uint4*>(vh)[i];
-        DS_ST(16);
-        PrologueArgs pa;
-        fill_pro(pa, L, vh, nullptr, reinterpret_cast<const __half*>(Ly.post_norm_w), P.norm_eps);
-        const float xs = ds_prologue(pa, rot, xq, tid);
+        const quipb200_linear_t L = (j == 0) ? Ly.gate : Ly.up;
+        const GemvCfg c = make_cfg(L, bx, p.geo.G_D[j]);
+        gemv_prefetch_l2(c, tid);
+        float f[8];
+        float xs;
+        const quipb200_linear_t Lp = Ly.o;
+        if (p.use_mma) {
+          out_side_m(Lp, p.ws.acc[SL_O], p.ws.hA, hfrag, XS, warp, lane, f);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
+            if (bid == 0) *reinterpret_cast<__half2*>(p.ws.hB + idx_spread(warp, lane, q)) = h;
+            const float2 v = __half22float2(h);
+            f[2 * q] = v.x;
+            f[2 * q + 1] = v.y;
+          }
+          DS_ST(16);
+          xs = in_side_m(f, reinterpret_cast<const __half*>(Ly.post_norm_w), P.norm_eps, L, hfrag, XS, V, rb.fred, xq, tid);
+        } else {
+          out_side_k1(Lp, p.ws.acc[SL_O], p.ws.hA, rb, tid, f);
+          const uint4 hv = pack_h8(f);
+          if (bid == 0 && tid < hid8) reinterpret_cast<uint4*>(p.ws.hB)[tid] = hv;
+          unpack_h8(hv, f);
+          DS_ST(16);
+          xs = in_side_k1(f, reinterpret_cast<const __half*>(Ly.post_norm_w), P.norm_eps, L, rb, xq, tid);
+        }
         if (bx == 0 && tid == 0) p.ws.xscale[SL_G + j] = xs;
         DS_ST(17);
+        gemv_first(cw, c, warp, lane, pol);
         gemv_run(cw, c, xq, tab, red, warp, lane, pol);
         DS_ST(18);
-        gemv_store(c, red, p.ws.acc[SL_G + j], tid);
+        gemv_store(c, red, p.ws.acc[SL_G + j], xs, tid);
       }
       grid_barrier(p.ws.bar, bar_target, nblk);
       DS_ST(19);
     }
     // ======================= stage E: down =======================
     {
-      const quipb200_linear_t* mem[1] = {&Ly.down};
-      int j, bx, G;
-      split_ctas(mem, 1, nblk, bid, j, bx, G);
+      int j, bx;
+      which_member(&p.geo.G_E, 1, bid, j, bx);
       if (j >= 0) {
-        const quipb200_linear_t& L = Ly.down;
-        const GemvCfg c = make_cfg(L, bx, G);
-        gemv_first(cw, c, warp, lane, pol);
-        EpilogueArgs ea;
-        fill_epi(ea, Ly.gate, p.ws.acc[SL_G], nullptr, vg);
-        ds_epilogue(ea, rot, __ldcg(p.ws.xscale + SL_G), tid);
-        DS_ST(20);
-        fill_epi(ea, Ly.up, p.ws.acc[SL_U], nullptr, vu);
-        ds_epilogue(ea, rot, __ldcg(p.ws.xscale + SL_U), tid);
-        DS_ST(21);
-        PrologueArgs pa;
-        fill_pro(pa, L, vu, vg, nullptr, 0.f);
-        const float xs = ds_prologue(pa, rot, xq, tid);
-        if (bx == 0 && tid == 0) p.ws.xscale[SL_D] = xs;
+        const quipb200_linear_t L = Ly.down;
+        const GemvCfg c = make_cfg(L, bx, p.geo.G_E);
+        float xs;
+        if (L.K_left > 1) {
+          gemv_prefetch_l2(c, tid);   // (stage E)
+          xs = stage_e_blocks(Ly.gate, Ly.up, L, p.ws.acc[SL_G], p.ws.acc[SL_U], bb,
+                              hfrag, rb.fred, xq, tid, (dbg && l == 1) ? dbg : nullptr);
+        } else {
+          gemv_prefetch_l2(c, tid);
+          float g[8], u[8];
+          {
+            const quipb200_linear_t Lg = Ly.gate;
+            out_side_k1(Lg, p.ws.acc[SL_G], nullptr, rb, tid, g);
+            round_h8(g);
+          }
+          __syncthreads();
+          {
+            const quipb200_linear_t Lu = Ly.up;
+            out_side_k1(Lu, p.ws.acc[SL_U], nullptr, rb, tid, u);
+            round_h8(u);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; e++) g[e] = silu_f(g[e]);
+          round_h8(g);
+#pragma unroll
+          for (int e = 0; e < 8; e++) u[e] *= g[e];
+          round_h8(u);
+          xs = in_side_k1(u, nullptr, 0.f, L, rb, xq, tid);
+        }
         DS_ST(22);
+        if (bx == 0 && tid == 0) p.ws.xscale[SL_D] = xs;
+        gemv_first(cw, c, warp, lane, pol);
         gemv_run(cw, c, xq, tab, red, warp, lane, pol);
         DS_ST(23);
-        gemv_store(c, red, p.ws.acc[SL_D], tid);
+        gemv_store(c, red, p.ws.acc[SL_D], xs, tid);
       }
       grid_barrier(p.ws.bar, bar_target, nblk);
       DS_ST(24);
@@ -632,9 +1285,19 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
   }
   // ---- output of the last layer: rot_out(down) + residual -> h_out ----
   if (bid == 0) {
-    EpilogueArgs ea;
-    fill_epi(ea, P.layers[P.n_layers - 1].down, p.ws.acc[SL_D], p.ws.hB, p.h_out);
-    ds_epilogue(ea, rot, __ldcg(p.ws.xscale + SL_D), tid);
+    float f[8];
+    const quipb200_linear_t Lp = s_desc[(P.n_layers - 1) & 1].down;
+    if (p.use_mma) {
+      out_side_m(Lp, p.ws.acc[SL_D], p.ws.hB, hfrag, XS, warp, lane, f);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int i = idx_spread(warp, lane, q);
+        if (i < P.hidden) *reinterpret_cast<__half2*>(p.h_out + i) = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
+      }
+    } else {
+      out_side_k1(Lp, p.ws.acc[SL_D], p.ws.hB, rb, tid, f);
+      if (tid < hid8) reinterpret_cast<uint4*>(p.h_out)[tid] = pack_h8(f);
+    }
     if (tid == 0) *reinterpret_cast<volatile unsigned int*>(p.ws.bar + 32) = bar_target;
   }
   DS_STAMP(63);
@@ -677,76 +1340,126 @@ static int group_ctas(const quipb200_linear_t* const* mem, int n, int nblk, int*
   return 0;
 }
 
+int g_ds_splits = 0;   // test / tuning hook: force the number of KV splits (0 = automatic)
+
 struct DsLayout {
   DsSmem sm;
+  DsGeom geo;
   size_t ws_bytes;
   size_t off_bar, off_xscale, off_hA, off_hB, off_acc[SL_N], off_att_o, off_att_ml;
   int splits;
+  int use_mma;
 };
+
+static bool same_shape(const quipb200_linear_t& a, const quipb200_linear_t& b) {
+  return a.in_features == b.in_features && a.out_features == b.out_features && a.q_in == b.q_in && a.q_out == b.q_out &&
+         a.K_left == b.K_left && a.K_right == b.K_right;
+}
 
 static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_layer_t* hl, int nblk, DsLayout* out) {
   if (!P || !hl || P->n_layers < 1 || P->head_dim != DS_HD || P->n_heads < 1 || P->n_kv_heads < 1 ||
       P->n_heads % P->n_kv_heads || P->max_len < 1 || (P->hidden & 7))
     return QUIPB200_EUNSUPPORTED;
-  size_t red = 0, xq = 0, rotb = 0, vh = 0, vmid = 0, accb[SL_N] = {0, 0, 0, 0, 0, 0, 0};
+  const quipb200_decode_layer_t& Y = hl[0];
   for (int l = 0; l < P->n_layers; l++) {
-    const quipb200_decode_layer_t& Y = hl[l];
-    const quipb200_linear_t* all[SL_N] = {&Y.q, &Y.k, &Y.v, &Y.o, &Y.gate, &Y.up, &Y.down};
+    const quipb200_decode_layer_t& Z = hl[l];
+    const quipb200_linear_t* all[SL_N] = {&Z.q, &Z.k, &Z.v, &Z.o, &Z.gate, &Z.up, &Z.down};
+    const quipb200_linear_t* ref[SL_N] = {&Y.q, &Y.k, &Y.v, &Y.o, &Y.gate, &Y.up, &Y.down};
     for (int i = 0; i < SL_N; i++)
-      if (!linear_ok(*all[i])) return QUIPB200_EUNSUPPORTED;
-    if (!Y.input_norm_w || !Y.post_norm_w || !Y.k_cache || !Y.v_cache) return QUIPB200_EINVAL;
-    // shape chain of a Llama decoder layer
-    if (Y.q.in_features != P->hidden || Y.k.in_features != P->hidden || Y.v.in_features != P->hidden) return QUIPB200_EUNSUPPORTED;
-    if (Y.q.out_features != P->n_heads * DS_HD || Y.k.out_features != P->n_kv_heads * DS_HD ||
-        Y.v.out_features != P->n_kv_heads * DS_HD)
-      return QUIPB200_EUNSUPPORTED;
-    if (Y.q.K_right != 1 || Y.k.K_right != 1 || Y.v.K_right != 1) return QUIPB200_EUNSUPPORTED;
-    if (Y.q.q_out < 128 || Y.k.q_out < 128 || Y.v.q_out < 128) return QUIPB200_EUNSUPPORTED;
-    if (Y.o.in_features != P->n_heads * DS_HD || Y.o.out_features != P->hidden) return QUIPB200_EUNSUPPORTED;
-    if (Y.gate.in_features != P->hidden || Y.up.in_features != P->hidden) return QUIPB200_EUNSUPPORTED;
-    if (Y.gate.out_features != Y.up.out_features || Y.down.in_features != Y.gate.out_features ||
-        Y.down.out_features != P->hidden)
-      return QUIPB200_EUNSUPPORTED;
-    const quipb200_linear_t* gA[3] = {&Y.q, &Y.k, &Y.v};
-    const quipb200_linear_t* gC[1] = {&Y.o};
-    const quipb200_linear_t* gD[2] = {&Y.gate, &Y.up};
-    const quipb200_linear_t* gE[1] = {&Y.down};
-    struct { const quipb200_linear_t* const* m; int n; } groups[4] = {{gA, 3}, {gC, 1}, {gD, 2}, {gE, 1}};
-    for (auto& g : groups) {
-      int G[3];
-      group_ctas(g.m, g.n, nblk, G);
-      for (int i = 0; i < g.n; i++) {
-        const quipb200_linear_t& L = *g.m[i];
-        const int nseg = L.q_in / 8, lanes = (nseg + 7) / 8, C = (lanes + 31) / 32;
-        const size_t rows = (size_t)L.q_out / G[i] + 1;
-        red = std::max(red, rows * C * sizeof(int));
-        xq = std::max(xq, (size_t)((nseg + 7) / 8 * 8) * 16);
-        rotb = std::max(rotb, rot_smem_bytes(L.q_in, L.K_left));
-        rotb = std::max(rotb, rot_smem_bytes(L.q_out, L.K_right));
-      }
-    }
-    for (int i = 0; i < SL_N; i++) accb[i] = std::max(accb[i], (size_t)all[i]->q_out * sizeof(float));
-    vh = std::max(vh, (size_t)std::max(P->hidden, P->n_heads * DS_HD) * 2);
-    vmid = std::max(vmid, (size_t)Y.gate.out_features * 2);
+      if (!linear_ok(*all[i]) || !same_shape(*all[i], *ref[i])) return QUIPB200_EUNSUPPORTED;
+    if (!Z.input_norm_w || !Z.post_norm_w || !Z.k_cache || !Z.v_cache) return QUIPB200_EINVAL;
   }
+  // shape chain of a Llama decoder layer
+  if (Y.q.in_features != P->hidden || Y.k.in_features != P->hidden || Y.v.in_features != P->hidden) return QUIPB200_EUNSUPPORTED;
+  if (Y.q.out_features != P->n_heads * DS_HD || Y.k.out_features != P->n_kv_heads * DS_HD ||
+      Y.v.out_features != P->n_kv_heads * DS_HD)
+    return QUIPB200_EUNSUPPORTED;
+  if (Y.o.in_features != P->n_heads * DS_HD || Y.o.out_features != P->hidden) return QUIPB200_EUNSUPPORTED;
+  if (Y.gate.in_features != P->hidden || Y.up.in_features != P->hidden) return QUIPB200_EUNSUPPORTED;
+  if (Y.gate.out_features != Y.up.out_features || Y.gate.q_out != Y.up.q_out || Y.down.in_features != Y.gate.out_features ||
+      Y.down.q_in != Y.gate.q_out || Y.down.out_features != P->hidden)
+    return QUIPB200_EUNSUPPORTED;
+  // rotations covered by the register-resident code: pure power-of-two (<= 4096 points) everywhere except the MLP
+  // intermediate, which may be K blocks of 256 with a K x K mix (K <= 64)
+  const quipb200_linear_t* k1[4] = {&Y.q, &Y.k, &Y.v, &Y.o};
+  size_t nmax = 64;
+  for (const quipb200_linear_t* L : k1) {
+    if (L->K_left != 1 || L->K_right != 1) return QUIPB200_EUNSUPPORTED;
+    nmax = std::max(nmax, (size_t)std::max(L->q_in, L->q_out));
+  }
+  if (Y.q.q_out < 128 || Y.k.q_out < 128 || Y.v.q_out < 128) return QUIPB200_EUNSUPPORTED;
+  if (Y.gate.K_left != 1 || Y.up.K_left != 1 || Y.down.K_right != 1) return QUIPB200_EUNSUPPORTED;
+  nmax = std::max(nmax, (size_t)std::max(Y.gate.q_in, Y.down.q_out));
+  const int K = Y.gate.K_right;
+  if (Y.up.K_right != K || Y.down.K_left != K) return QUIPB200_EUNSUPPORTED;
+  size_t t_halfs = 0, hk_halfs = 0, mid_halfs = 0;
+  if (K == 1) {
+    nmax = std::max(nmax, (size_t)Y.gate.q_out);
+  } else {
+    if (Y.gate.q_out / K != 256 || K > 64) return QUIPB200_EUNSUPPORTED;
+    t_halfs = (size_t)(K + 1) * (256 + 8);
+    const size_t Kp = (K + 15) / 16 * 16;
+    hk_halfs = Kp * Kp;
+    mid_halfs = ((size_t)Y.gate.out_features + 7) / 8 * 8;
+  }
+  if (nmax > 8 * DS_THREADS) return QUIPB200_EUNSUPPORTED;
+
+  const quipb200_linear_t* gA[3] = {&Y.q, &Y.k, &Y.v};
+  const quipb200_linear_t* gC[1] = {&Y.o};
+  const quipb200_linear_t* gD[2] = {&Y.gate, &Y.up};
+  const quipb200_linear_t* gE[1] = {&Y.down};
+  DsGeom geo;
+  group_ctas(gA, 3, nblk, geo.G_A);
+  group_ctas(gC, 1, nblk, &geo.G_C);
+  group_ctas(gD, 2, nblk, geo.G_D);
+  group_ctas(gE, 1, nblk, &geo.G_E);
+  out->geo = geo;
+  struct { const quipb200_linear_t* const* m; int n; const int* G; } groups[4] = {
+      {gA, 3, geo.G_A}, {gC, 1, &geo.G_C}, {gD, 2, geo.G_D}, {gE, 1, &geo.G_E}};
+  size_t red = 0, xq = 0, accb[SL_N];
+  for (auto& g : groups) {
+    for (int i = 0; i < g.n; i++) {
+      const quipb200_linear_t& L = *g.m[i];
+      const int nseg = L.q_in / 8, lanes = (nseg + 7) / 8, C = (lanes + 31) / 32;
+      const size_t rows = (size_t)L.q_out / g.G[i] + 1;
+      red = std::max(red, rows * C * sizeof(int));
+      xq = std::max(xq, (size_t)((nseg + 7) / 8 * 8) * 16);
+    }
+  }
+  const quipb200_linear_t* all[SL_N] = {&Y.q, &Y.k, &Y.v, &Y.o, &Y.gate, &Y.up, &Y.down};
+  for (int i = 0; i < SL_N; i++) accb[i] = (size_t)all[i]->q_out * sizeof(__half);
+
+  // KV splits per head: one per ~128 cached positions, at most 4 (measured: 4 splits beat 1 at 384 positions)
   int S = nblk / P->n_heads;
   if (S > DS_MAX_SPLITS) S = DS_MAX_SPLITS;
   if (S < 1) return QUIPB200_EUNSUPPORTED;        // fewer CTAs than heads
+  if (g_ds_splits > 0) S = std::min(S, g_ds_splits);
+  else S = std::min(S, std::max(1, (P->max_len + 127) / 128));
+  if (P->n_heads * S > 512) return QUIPB200_EUNSUPPORTED;
   out->splits = S;
   const size_t chunk = ((size_t)P->max_len + S - 1) / S;
   const size_t attn = (3 * 512 + 3 * 128 + 32 + DS_PV_GROUPS * 128 + chunk) * sizeof(float);
-  rotb = std::max(rotb, attn);
+  // tensor-path rotations when every hidden-side rotation has exactly 4096 points
+  const bool use_mma = Y.q.q_in == 4096 && Y.k.q_in == 4096 && Y.v.q_in == 4096 && Y.o.q_in == 4096 && Y.o.q_out == 4096 &&
+                       Y.gate.q_in == 4096 && Y.up.q_in == 4096 && Y.down.q_out == 4096 && P->hidden <= 4096;
+  out->use_mma = use_mma ? 1 : 0;
+  if (use_mma) nmax = std::max(nmax, (size_t)4096);   // the exchange buffer (16 x 388 floats) lives in A | B
+  size_t blk = 2 * t_halfs * 2 + 3 * hk_halfs * 2 + 3 * mid_halfs * 2;
+  if (use_mma) blk = std::max(blk, (size_t)8192);     // fp16 [4096] staging vector of the input side
+  size_t scr = 2 * nmax * sizeof(float) + 64 * sizeof(float) + blk;
+  scr = std::max(scr, attn);
   auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
   DsSmem sm;
   size_t off = 0;
   sm.tab = 0; off += 2048;
   sm.red = (uint32_t)off; off += up16(red);
   sm.xq = (uint32_t)off; off += up16(xq);
-  sm.vh = (uint32_t)off; off += up16(vh);
-  sm.vg = (uint32_t)off; off += up16(vmid);
-  sm.vu = (uint32_t)off; off += up16(vmid);
-  sm.rot = (uint32_t)off; off += up16(rotb);
+  sm.scr = (uint32_t)off; off += up16(scr);
   sm.total = (uint32_t)off;
+  sm.nmax = (uint32_t)nmax;
+  sm.t_halfs = (uint32_t)t_halfs;
+  sm.hk_halfs = (uint32_t)hk_halfs;
+  sm.mid_halfs = (uint32_t)mid_halfs;
   if (off > 227 * 1024) return QUIPB200_EUNSUPPORTED;
   out->sm = sm;
   size_t w = 0;
@@ -767,6 +1480,12 @@ long long* g_ds_dbg = nullptr;
 }  // namespace qb
 
 using namespace qb;
+
+extern "C" int quipb200_decode_step_set_splits(int splits) {
+  if (splits < 0 || splits > DS_MAX_SPLITS) return QUIPB200_EINVAL;
+  g_ds_splits = splits;
+  return 0;
+}
 
 extern "C" int quipb200_decode_step_debug(void* device_int64_buffer) {
   g_ds_dbg = (long long*)device_int64_buffer;
@@ -813,13 +1532,15 @@ extern "C" int quipb200_decode_step(const quipb200_decode_plan_t* plan, const qu
   p.ws.xscale = reinterpret_cast<float*>(w + lay.off_xscale);
   p.ws.hA = reinterpret_cast<__half*>(w + lay.off_hA);
   p.ws.hB = reinterpret_cast<__half*>(w + lay.off_hB);
-  for (int i = 0; i < SL_N; i++) p.ws.acc[i] = reinterpret_cast<float*>(w + lay.off_acc[i]);
+  for (int i = 0; i < SL_N; i++) p.ws.acc[i] = reinterpret_cast<__half*>(w + lay.off_acc[i]);
   p.ws.att_o = reinterpret_cast<float*>(w + lay.off_att_o);
   p.ws.att_ml = reinterpret_cast<float*>(w + lay.off_att_ml);
   p.sm = lay.sm;
+  p.geo = lay.geo;
   p.h_in = reinterpret_cast<const __half*>(h_in);
   p.h_out = reinterpret_cast<__half*>(h_out);
   p.kv_splits = lay.splits;
+  p.use_mma = lay.use_mma;
   p.dbg = g_ds_dbg;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(sms);

@@ -37,6 +37,8 @@ def _bind():
         L.quipb200_decode_step.restype = ctypes.c_int
         L.quipb200_decode_step.argtypes = [POINTER(DecodePlan), POINTER(DecodeLayer), c_void_p, c_void_p, c_void_p,
                                            c_size_t, c_void_p]
+        L.quipb200_decode_step_set_splits.restype = ctypes.c_int
+        L.quipb200_decode_step_set_splits.argtypes = [ctypes.c_int]
         L.quipb200_decode_step_debug.restype = ctypes.c_int
         L.quipb200_decode_step_debug.argtypes = [c_void_p]
         _bound = True

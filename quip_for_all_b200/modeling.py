@@ -32,6 +32,11 @@ LLAMA2_SHAPES = {
     # head_dim 128 (fused attention path), GQA, non power-of-two intermediate (11 * 128)
     "tiny128": dict(hidden_size=512, intermediate_size=1408, num_hidden_layers=2,
                     num_attention_heads=4, num_key_value_heads=2),
+    # shapes the persistent decode-step kernel covers: intermediate = 11 blocks of 256 / a pure power of two
+    "tiny256": dict(hidden_size=512, intermediate_size=2816, num_hidden_layers=2,
+                    num_attention_heads=4, num_key_value_heads=2),
+    "tinypow2": dict(hidden_size=256, intermediate_size=1024, num_hidden_layers=2,
+                     num_attention_heads=2, num_key_value_heads=1),
 }
 
 
@@ -127,7 +132,7 @@ class LlamaDecodeEngine:
     """
 
     def __init__(self, model, max_cache_len: int = 512, first_stage: bool = True, last_stage: bool = True,
-                 use_cuda_graph: bool = True, fused: bool = True, persistent: bool = False):
+                 use_cuda_graph: bool = True, fused: bool = True, persistent: bool = True):
         self.model = model
         self.cfg = model.config
         self.layers = list(model.model.layers)

@@ -512,7 +512,7 @@ def test_fused_decode_step_matches_unfused_engine():
     from quip_for_all_b200.modeling import LlamaDecodeEngine, make_random_quantized_llama
     model = make_random_quantized_llama("tiny128", "E8P12", seed=3, device=DEV)
     ids = torch.randint(0, 32000, (1, 10), generator=torch.Generator().manual_seed(2)).to(DEV)
-    e1 = LlamaDecodeEngine(model, max_cache_len=64, fused=True)
+    e1 = LlamaDecodeEngine(model, max_cache_len=64, fused=True, persistent=False)
     assert e1.fused is not None
     e2 = LlamaDecodeEngine(model, max_cache_len=64, fused=False, use_cuda_graph=False)
     e1.prefill(ids)
@@ -539,8 +539,18 @@ def test_fused_decode_step_matches_unfused_engine():
 # ------------------------------------------------------------------------------------------------
 # persistent whole-step kernel (decode_step.cu) against the per-group launches it replaces
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name,n_layers", [("tiny128", 2), ("llama2-7b", 2)])
-def test_persistent_decode_step_matches_grouped_engine(name, n_layers):
+@pytest.fixture
+def kv_splits(request):
+    from quip_for_all_b200.decode_step import _bind
+    L = _bind()
+    assert L.quipb200_decode_step_set_splits(request.param) == 0
+    yield request.param
+    L.quipb200_decode_step_set_splits(0)
+
+
+@pytest.mark.parametrize("kv_splits", [0, 4], indirect=True)
+@pytest.mark.parametrize("name,n_layers", [("tiny256", 2), ("tinypow2", 3), ("llama2-7b", 2)])
+def test_persistent_decode_step_matches_grouped_engine(name, n_layers, kv_splits):
     from quip_for_all_b200.modeling import LlamaDecodeEngine, llama_config, make_random_quantized_llama
     cfg = llama_config(name, num_hidden_layers=n_layers)
     model = make_random_quantized_llama(cfg, "E8P12", seed=5, device=DEV)
@@ -577,7 +587,7 @@ def test_persistent_decode_step_matches_grouped_engine(name, n_layers):
 
 def test_persistent_decode_step_under_cuda_graph_generates_same_tokens():
     from quip_for_all_b200.modeling import LlamaDecodeEngine, make_random_quantized_llama
-    model = make_random_quantized_llama("tiny128", "E8P12", seed=3, device=DEV)
+    model = make_random_quantized_llama("tiny256", "E8P12", seed=3, device=DEV)
     ids = torch.randint(0, 32000, (1, 10), generator=torch.Generator().manual_seed(2)).to(DEV)
     e1 = LlamaDecodeEngine(model, max_cache_len=64, persistent=True)       # cooperative launch inside a CUDA graph
     assert e1.persistent is not None
