@@ -94,6 +94,19 @@ int quipb200_mm(int codebook, const void* x_f16, const void* qidxs, const void* 
                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Batched decode + GEMM on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulators), 1 <= M <= 256:
+ *   same contract as quipb200_mm for E8P12, replacing the reference's M >= 32 route
+ *   "decompress_e8p_origorder + input @ W.T" (codebook/e8p12.py:153-155, origin_order.cu:837-885) without
+ *   ever materialising the dense weight: packed codes are decoded straight into the UMMA shared-memory
+ *   layout.  Requires N % 128 == 0 and K % 64 == 0 (else QUIPB200_EUNSUPPORTED -> caller uses the dense path).
+ *   workspace: >= quipb200_e8p_mm_umma_workspace_bytes(M_max, N, K) bytes, 256-byte aligned, zero-filled ONCE
+ *   by the caller; the kernel returns it zeroed (split-K partial sums are cleared by the CTA that converts them).
+ * ------------------------------------------------------------------------------------------- */
+size_t quipb200_e8p_mm_umma_workspace_bytes(int M, int N, int K);
+int quipb200_e8p_mm_umma(const void* x_f16, const void* qidxs, const void* grid_packed_abs, void* out_f16,
+                         int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused QuantLinear.forward (eval branch)                          qlinear.py:87-115
  *   y = [(hadK_R (x) H) ( decode(Qidxs) . ((hadK_L^T (x) H) (SU . x)) * wscale ) * Wscale_pc][:out] . SV + bias
  *   i.e. the whole chain  x*SU -> matmul_hadUt_cuda -> codebook(x, Qidxs) -> [*Wscale] ->

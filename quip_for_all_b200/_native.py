@@ -24,6 +24,7 @@ EXPORTS = [
     "quipb200_linear_workspace_bytes", "quipb200_linear_forward",
     "quipb200_linear_group_workspace_bytes", "quipb200_linear_group_forward", "quipb200_attn_decode",
     "quipb200_decode_step_workspace_bytes", "quipb200_decode_step", "quipb200_decode_step_debug", "quipb200_decode_step_set_splits",
+    "quipb200_e8p_mm_umma_workspace_bytes", "quipb200_e8p_mm_umma",
     "quipb200_set_option", "quipb200_get_option", "quipb200_launch_count", "quipb200_debug_timeline",
 ]
 
@@ -83,6 +84,10 @@ def lib():
     L.quipb200_linear_group_forward.argtypes = [POINTER(LinearDesc), c_int, POINTER(Fusion), vp, c_int64,
                                                 POINTER(c_void_p), POINTER(c_int64), c_int, vp, c_size_t, vp]
     L.quipb200_attn_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp]
+    L.quipb200_e8p_mm_umma_workspace_bytes.restype = c_size_t
+    L.quipb200_e8p_mm_umma_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    L.quipb200_e8p_mm_umma.restype = c_int
+    L.quipb200_e8p_mm_umma.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, vp, c_size_t, vp]
     L.quipb200_debug_timeline.argtypes = [vp]
     L.quipb200_debug_timeline.restype = c_int
     L.quipb200_set_option.argtypes = [c_char_p, c_int]
@@ -109,6 +114,10 @@ def check(rc, what=""):
 
 def set_option(name, value):
     check(lib().quipb200_set_option(name.encode(), int(value)), f"set_option({name})")
+
+
+def get_option(name):
+    return int(lib().quipb200_get_option(name.encode()))
 
 
 def launch_count():

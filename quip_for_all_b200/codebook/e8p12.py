@@ -113,7 +113,9 @@ class E8P12_codebook(nn.Module):
         return torch.ops.quip_lib.decompress_e8p_origorder(Qidxs, self.grid_packed_abs)
 
     def forward(self, input, Qidxs):
-        # same dispatch rule as the reference (codebook/e8p12.py:147-155)
-        if input.size(0) < 32:
+        # the reference's dispatch rule is M < 32 -> custom kernel, else decompress + GEMM (codebook/e8p12.py:147-155);
+        # here the mm op also covers 17 <= M <= 256 with an in-kernel-decode tcgen05 GEMM (and falls back to the
+        # dense path by itself for shapes it does not cover), so only large M re-materialises the dense weight
+        if input.size(0) <= 256:
             return torch.ops.quip_lib.e8p_mm_origorder(input, Qidxs, self.grid_packed_abs)
         return input @ self.decompress_weight(Qidxs).T

@@ -13,6 +13,7 @@ extern int g_opt_stage_mask;
 extern int g_opt_fuse;
 extern int g_opt_phase0;
 extern int g_opt_lean;
+int g_opt_umma = 1;     // 17 <= M <= 256: in-kernel decode + tcgen05 GEMM instead of decompress + dense GEMM
 }  // namespace qb
 
 extern "C" int quipb200_abi_version(void) { return QUIPB200_ABI_VERSION; }
@@ -75,6 +76,10 @@ extern "C" int quipb200_set_option(const char* name, int value) {
     qb::g_opt_pdl = value ? 1 : 0;
     return 0;
   }
+  if (!strcmp(name, "umma")) {
+    qb::g_opt_umma = value ? 1 : 0;
+    return 0;
+  }
   if (!strcmp(name, "fuse")) {
     if (value < 0 || value > 3) return QUIPB200_EINVAL;
     qb::g_opt_fuse = value;
@@ -91,6 +96,7 @@ extern "C" int quipb200_get_option(const char* name) {
   if (!strcmp(name, "stage_mask")) return qb::g_opt_stage_mask;
   if (!strcmp(name, "fuse")) return qb::g_opt_fuse;
   if (!strcmp(name, "pdl")) return qb::g_opt_pdl;
+  if (!strcmp(name, "umma")) return qb::g_opt_umma;
   return QUIPB200_EINVAL;
 }
 

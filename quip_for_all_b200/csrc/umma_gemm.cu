@@ -1,0 +1,284 @@
+// Batched (prefill-side) E8P12 decode + GEMM on the 5th-generation tensor cores:
+//
+//     out[M, N] (fp16) = x[M, K] (fp16) . decode(Qidxs[N, K/8])^T         17 <= M <= 256
+//
+// Replaces, for moderate M, the reference's "decompress to a dense fp16 matrix, then cuBLAS" path
+// (codebook/e8p12.py:153-155 -> origin_order.cu:837-885 + input @ W.T), which writes and re-reads
+// 2*N*K bytes of dense weights per call (32 MiB for 4096 x 4096) to do a few GFLOP of math.  Here the
+// packed codes (N*K/4 bytes) are the only weight traffic: every CTA decodes its 128 x 64 weight tile
+// straight into the UMMA-canonical shared-memory layout (K-major, 128-byte swizzle) and one elected
+// thread feeds it to tcgen05.mma (kind::f16, fp32 accumulators in TMEM).
+//
+//   MMA shape : D[128 weight rows x NTOK tokens] += A[128 x 16] . B[NTOK x 16]^T   (cta_group::1, M = 128)
+//   grid      : (N / 128 row tiles) x (split-K so that ~all SMs have a CTA)
+//   pipeline  : STAGES shared-memory slots; all 8 warps are producers (weights: table lookup + sign decode
+//               + int8 -> fp16 with the reference's exact 0x5c80 trick, one 16-byte swizzled store per code;
+//               activations: cp.async one stage ahead); slot reuse is gated by an mbarrier that
+//               tcgen05.commit arrives on when the MMAs that read the slot have retired.
+//   epilogue  : tcgen05.ld (32 lanes x 32 bit x 16 columns) -> fp16 store, or fp32 atomics into a
+//               self-cleaning split-K workspace whose last CTA (ticket) converts the tile.
+//
+// Numerics: fp16 x fp16 products accumulated in fp32 (hardware order), one fp16 rounding -- the same
+// class as the reference's mma.sync kernel and cuBLAS path; decoded weights are bit-exact.
+#include "common.cuh"
+
+namespace qb {
+
+constexpr int UG_THREADS = 256;
+constexpr int UG_BM = 128;   // weight rows per CTA = UMMA M
+constexpr int UG_BK = 64;    // k per stage = one 128-byte swizzle row of fp16 = 8 codes
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3fffu);
+  d |= (uint64_t)1 << 16;     // leading byte offset (unused for swizzled K-major): 1
+  d |= (uint64_t)64 << 32;    // stride byte offset: 1024 >> 4
+  d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;     // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t sdst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+struct UmmaArgs {
+  const unsigned char* codes;   // [N][K/8] int16
+  const __half* x;              // [M][K]
+  const uint2* table;           // int64[256] abs table
+  __half* out;                  // [M][N]
+  float* ws;                    // [M][N] fp32 split-K partials (zero on entry, zero on exit)
+  unsigned int* tickets;        // [N/128]
+  int M, N, K, ksplit, kb_per_split;
+};
+
+template <int NTOK, int STAGES>
+__global__ void __launch_bounds__(UG_THREADS, 1) e8p_umma_kernel(const __grid_constant__ UmmaArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  constexpr uint32_t A_BYTES = UG_BM * 128, B_BYTES = NTOK * 128;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle atoms need 1024-byte alignment
+  unsigned char* gbase = smem_raw + (base - raw);
+  const uint32_t sA = base, sB = base + STAGES * A_BYTES;
+  unsigned char* tab = gbase + STAGES * (A_BYTES + B_BYTES);    // 2 KB table
+  const uint32_t sbar = base + STAGES * (A_BYTES + B_BYTES) + 2048;   // empty[STAGES], done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + STAGES * (A_BYTES + B_BYTES) + 2048 + 8 * (STAGES + 1));
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * UG_BM;
+  const int kb_begin = blockIdx.y * a.kb_per_split;
+  const int nit = min(a.kb_per_split, a.K / UG_BK - kb_begin);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s <= STAGES; s++) mbar_init(sbar + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), NTOK);
+  {
+    uint2 t = a.table[tid];
+    t.x |= 0x01010101u;
+    t.y |= 0x01010101u;
+    reinterpret_cast<uint2*>(tab)[tid] = t;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // instruction descriptor: D = F32, A = B = F16, both K-major, N = NTOK, M = 128 (cute::UMMA::InstrDescriptor)
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NTOK >> 3) << 17) | ((uint32_t)(UG_BM >> 4) << 24);
+
+  // producer roles: thread -> (weight row, 4 of its 8 codes); activations: 16-byte chunks round-robin
+  const int wrow = tid >> 1, whalf = tid & 1;
+  const unsigned char* wsrc = a.codes + (size_t)(n0 + wrow) * (a.K >> 2) + whalf * 8;
+  const uint64_t pol = l2_evict_first_policy();
+  auto load_codes_p = [&](int it) -> uint2 { return ldg_stream_v2(wsrc + (size_t)(kb_begin + it) * 16, pol); };
+  auto issue_acts = [&](int it) {
+    const int s = it % STAGES;
+    const __half* xs = a.x + (size_t)(kb_begin + it) * UG_BK;
+    for (int c = tid; c < NTOK * 8; c += UG_THREADS) {
+      const int tok = c >> 3, ch = c & 7;
+      const bool ok = tok < a.M;
+      const __half* src = xs + (size_t)(ok ? tok : 0) * a.K + ch * 8;
+      cp_async16_zfill(sB + s * B_BYTES + tok * 128 + ((ch ^ (tok & 7)) << 4), src, ok ? 16u : 0u);
+    }
+  };
+
+  uint2 cur = make_uint2(0, 0);
+  if (nit > 0) {
+    cur = load_codes_p(0);
+    issue_acts(0);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  for (int it = 0; it < nit; it++) {
+    const int s = it % STAGES;
+    uint2 nxt = make_uint2(0, 0);
+    if (it + 1 < nit) {
+      nxt = load_codes_p(it + 1);
+      if (it + 1 >= STAGES) mbar_wait(sbar + 8 * ((it + 1) % STAGES), (uint32_t)(((it + 1) / STAGES - 1) & 1));
+      issue_acts(it + 1);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // ---- weights of stage `it` -> slot s (free: its mbarrier was waited on one iteration ago, or it < STAGES)
+    {
+      const uint32_t w[2] = {cur.x, cur.y};
+      unsigned char* arow = gbase + (size_t)s * A_BYTES + wrow * 128;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t code = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+        const uint2 t1 = *reinterpret_cast<const uint2*>(tab + ((code >> 8) << 3));
+        const uint2 q = e8p_decode_q(t1, code);
+        __half2 e0, o0, e1, o1;
+        q4_to_half2(q.x, e0, o0);     // weights (0,1) = bytes (0,2); (2,3) = bytes (1,3)
+        q4_to_half2(q.y, e1, o1);
+        uint4 v;
+        v.x = *reinterpret_cast<const uint32_t*>(&e0);
+        v.y = *reinterpret_cast<const uint32_t*>(&o0);
+        v.z = *reinterpret_cast<const uint32_t*>(&e1);
+        v.w = *reinterpret_cast<const uint32_t*>(&o1);
+        const int ch = whalf * 4 + j;
+        *reinterpret_cast<uint4*>(arow + ((ch ^ (wrow & 7)) << 4)) = v;
+      }
+    }
+    asm volatile("cp.async.wait_group 1;" ::: "memory");        // activations of stage `it` have landed
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t ad = umma_smem_desc(sA + s * A_BYTES), bd = umma_smem_desc(sB + s * B_BYTES);
+#pragma unroll
+      for (int k = 0; k < UG_BK / 16; k++)    // +32 bytes along K inside the swizzled row = +2 in the address field
+        umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, (it > 0 || k > 0) ? 1u : 0u);
+      umma_commit(sbar + 8 * s);               // slot s is free again when these MMAs retire
+    }
+    cur = nxt;
+  }
+  if (tid == 0) umma_commit(sbar + 8 * STAGES);   // all MMAs of this CTA
+  mbar_wait(sbar + 8 * STAGES, 0);
+  tc_fence_after();
+
+  // ---- epilogue: TMEM lane = weight row, column = token.  Warp w reads lane quadrant w % 4, column half w / 4.
+  if (nit > 0) {
+    const int quad = warp & 3, chalf = warp >> 2;
+    const int n = n0 + quad * 32 + lane;
+    for (int c0 = chalf * (NTOK / 2); c0 < (chalf + 1) * (NTOK / 2); c0 += 16) {
+      if (c0 >= a.M) break;                        // warp-uniform: token columns beyond M hold zeros
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int tok = c0 + j;
+        if (tok < a.M) {
+          if (a.ksplit == 1) a.out[(size_t)tok * a.N + n] = __float2half_rn(v[j]);
+          else atomicAdd(a.ws + (size_t)tok * a.N + n, v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, NTOK);
+  if (a.ksplit == 1) return;
+  // ---- split-K: the last CTA of this row tile converts the fp32 partial sums and clears them
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(a.tickets + blockIdx.x, 1u);
+    s_last = (prev == (unsigned int)(a.ksplit - 1));
+    if (s_last) a.tickets[blockIdx.x] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = tid; i < a.M * UG_BM; i += UG_THREADS) {
+    const int tok = i >> 7, n = n0 + (i & 127);
+    float* p = a.ws + (size_t)tok * a.N + n;
+    a.out[(size_t)tok * a.N + n] = __float2half_rn(__ldcg(p));
+    __stcg(p, 0.f);
+  }
+}
+
+template <int NTOK, int STAGES>
+static int launch_umma(const UmmaArgs& a, dim3 grid, cudaStream_t st) {
+  const size_t smem = (size_t)STAGES * (UG_BM * 128 + NTOK * 128) + 2048 + 8 * (STAGES + 1) + 16 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(e8p_umma_kernel<NTOK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  e8p_umma_kernel<NTOK, STAGES><<<grid, UG_THREADS, smem, st>>>(a);
+  QB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" size_t quipb200_e8p_mm_umma_workspace_bytes(int M, int N, int K) {
+  if (M < 1 || N < 1 || K < 1) return 0;
+  return (size_t)M * N * sizeof(float) + (size_t)(N / UG_BM + 1) * sizeof(unsigned int) + 256;
+}
+
+extern "C" int quipb200_e8p_mm_umma(const void* x, const void* qidxs, const void* grid, void* out, int M, int N, int K,
+                                    void* workspace, size_t ws_bytes, void* stream) {
+  if (!x || !qidxs || !grid || !out) return QUIPB200_EINVAL;
+  if (M < 1 || M > 256 || N < UG_BM || N % UG_BM || K < UG_BK || K % UG_BK) return QUIPB200_EUNSUPPORTED;
+  if (!aligned16(x) || !aligned16(qidxs) || !aligned16(grid) || !aligned16(out)) return QUIPB200_EALIGN;
+  const int sms = quipb200_sm_count();
+  if (sms < 1) return (int)cudaErrorNoDevice;
+  const int tiles = N / UG_BM, nkb = K / UG_BK;
+  int ksplit = 1;
+  while (ksplit < 16 && tiles * ksplit * 2 <= sms && nkb / (ksplit * 2) >= 8) ksplit *= 2;
+  UmmaArgs a{};
+  a.codes = (const unsigned char*)qidxs; a.x = (const __half*)x; a.table = (const uint2*)grid; a.out = (__half*)out;
+  a.M = M; a.N = N; a.K = K;
+  a.ksplit = ksplit;
+  a.kb_per_split = (nkb + ksplit - 1) / ksplit;
+  if (ksplit > 1) {
+    if (!workspace || ((uintptr_t)workspace & 255) || ws_bytes < quipb200_e8p_mm_umma_workspace_bytes(M, N, K))
+      return QUIPB200_EWORKSPACE;
+    a.ws = (float*)workspace;
+    a.tickets = (unsigned int*)((unsigned char*)workspace + (((size_t)M * N * sizeof(float) + 255) / 256 * 256));
+  }
+  const dim3 grid_dim(tiles, ksplit);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M <= 32) return launch_umma<32, 4>(a, grid_dim, st);
+  if (M <= 64) return launch_umma<64, 4>(a, grid_dim, st);
+  if (M <= 128) return launch_umma<128, 4>(a, grid_dim, st);
+  return launch_umma<256, 4>(a, grid_dim, st);
+}

@@ -179,6 +179,32 @@ def _mm_fused(codebook, x, Qidxs, grid, scale, K):
     return out
 
 
+_UMMA_WS = {}
+
+
+def _mm_umma(x, Qidxs, grid, K):
+    """17 <= M <= 256, E8P12: in-kernel decode + tcgen05 GEMM (csrc/umma_gemm.cu); None if the shape is not covered."""
+    M, N = x.shape[0], Qidxs.shape[0]
+    if M < 1 or M > 256 or N % 128 or K % 64:
+        return None
+    L = lib()
+    key = (x.device.index, N)
+    ws = _UMMA_WS.get(key)
+    if ws is None:      # zero-filled once; the kernel leaves it zero (self-cleaning split-K partials)
+        nbytes = L.quipb200_e8p_mm_umma_workspace_bytes(256, N, K)
+        ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=x.device)
+        _UMMA_WS[key] = ws
+    off = (-ws.data_ptr()) % 256
+    out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.quipb200_e8p_mm_umma(_ptr(x), _ptr(Qidxs), _ptr(grid), _ptr(out), M, N, K,
+                                    ctypes.c_void_p(ws.data_ptr() + off), ws.numel() - 256, _stream())
+    if rc == _native.EUNSUPPORTED:
+        return None
+    check(rc, "e8p_mm_umma")
+    return out
+
+
 def _mm(codebook, name, x, Qidxs, grid, scale, K, dense):
     if x.dim() != 2 or Qidxs.dim() != 2:
         raise RuntimeError(f"quip_lib::{name}: x and Qidxs must be 2-D")
@@ -189,6 +215,8 @@ def _mm(codebook, name, x, Qidxs, grid, scale, K, dense):
     xh = _contig(x if x.dtype == torch.float16 else x.to(torch.float16))
     q = _contig(Qidxs)
     out = _mm_fused(codebook, xh, q, grid, scale, K) if codebook is not None else None
+    if out is None and codebook == _native.CB_E8P12 and _native.get_option("umma"):
+        out = _mm_umma(xh, q, grid, K)
     if out is None:
         # decompress + dense GEMM: what the reference itself does for M >= 32 (codebook/e8p12.py:153-155)
         out = xh @ dense(q).T

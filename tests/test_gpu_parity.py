@@ -595,3 +595,41 @@ def test_persistent_decode_step_under_cuda_graph_generates_same_tokens():
     o1 = e1.generate(ids, 12)
     o2 = e2.generate(ids, 12)
     assert torch.equal(o1[:, :4], o2[:, :4])      # later tokens may differ by an fp16 near-tie
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 decode + GEMM (umma_gemm.cu): 17 <= M <= 256
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M", [17, 32, 33, 64, 100, 128, 200, 256])
+@pytest.mark.parametrize("N,K", [(128, 64), (512, 4096), (4096, 4096), (1408, 1024 + 64)])
+def test_e8p_mm_umma_matches_oracle(M, N, K):
+    from quip_for_all_b200 import _native
+    assert _native.get_option("umma") == 1
+    g = torch.Generator().manual_seed(M * 11 + N + K)
+    q = torch.randint(-32768, 32768, (N, K // 8), generator=g).to(torch.int16)
+    x = torch.randn(M, K, generator=g).half()
+    lc0 = _native.launch_count()
+    qd, xd = q.to(DEV), x.to(DEV)
+    out = torch.ops.quip_lib.e8p_mm_origorder(xd, qd, _grid())
+    out2 = torch.ops.quip_lib.e8p_mm_origorder(xd, qd, _grid())      # split-K workspace is self-cleaning
+    assert _native.launch_count() - lc0 == 2                          # one launch of ours per call: no dense path
+    assert out.shape == (M, N) and out.dtype == torch.float16
+    W = qo.decompress_e8p(q.numpy())
+    _mm_check(out, x, W)
+    _mm_check(out2, x, W)
+    # against the dense route on the same device (decompress + cuBLAS): both fp32-accumulate, fp16 out
+    _native.set_option("umma", 0)
+    try:
+        dense = torch.ops.quip_lib.e8p_mm_origorder(xd, qd, _grid())
+    finally:
+        _native.set_option("umma", 1)
+    d = (out.float() - dense.float()).abs().max().item()
+    assert d <= 2.0 ** -9 * dense.float().abs().max().item() + 1e-6, d
+
+
+def test_e8p_mm_umma_unsupported_shapes_take_dense_path():
+    g = torch.Generator().manual_seed(5)
+    q = torch.randint(-32768, 32768, (96, 32), generator=g).to(torch.int16)      # N % 128 != 0
+    x = torch.randn(40, 256, generator=g).half()
+    out = torch.ops.quip_lib.e8p_mm_origorder(x.to(DEV), q.to(DEV), _grid())
+    _mm_check(out, x, qo.decompress_e8p(q.numpy()))
