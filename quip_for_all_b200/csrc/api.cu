@@ -13,7 +13,8 @@ extern int g_opt_stage_mask;
 extern int g_opt_fuse;
 extern int g_opt_phase0;
 extern int g_opt_lean;
-int g_opt_umma = 1;     // 17 <= M <= 256: in-kernel decode + tcgen05 GEMM instead of decompress + dense GEMM
+int g_opt_umma = 0;     // 17 <= M <= 256: in-kernel decode + tcgen05 GEMM instead of decompress + dense GEMM
+                        // (off by default: first version, slower than decompress + cuBLAS -- profiles/README.md)
 }  // namespace qb
 
 extern "C" int quipb200_abi_version(void) { return QUIPB200_ABI_VERSION; }

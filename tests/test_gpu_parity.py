@@ -604,14 +604,17 @@ def test_persistent_decode_step_under_cuda_graph_generates_same_tokens():
 @pytest.mark.parametrize("N,K", [(128, 64), (512, 4096), (4096, 4096), (1408, 1024 + 64)])
 def test_e8p_mm_umma_matches_oracle(M, N, K):
     from quip_for_all_b200 import _native
-    assert _native.get_option("umma") == 1
+    _native.set_option("umma", 1)
     g = torch.Generator().manual_seed(M * 11 + N + K)
     q = torch.randint(-32768, 32768, (N, K // 8), generator=g).to(torch.int16)
     x = torch.randn(M, K, generator=g).half()
     lc0 = _native.launch_count()
     qd, xd = q.to(DEV), x.to(DEV)
-    out = torch.ops.quip_lib.e8p_mm_origorder(xd, qd, _grid())
-    out2 = torch.ops.quip_lib.e8p_mm_origorder(xd, qd, _grid())      # split-K workspace is self-cleaning
+    try:
+        out = torch.ops.quip_lib.e8p_mm_origorder(xd, qd, _grid())
+        out2 = torch.ops.quip_lib.e8p_mm_origorder(xd, qd, _grid())      # split-K workspace is self-cleaning
+    finally:
+        _native.set_option("umma", 0)
     assert _native.launch_count() - lc0 == 2                          # one launch of ours per call: no dense path
     assert out.shape == (M, N) and out.dtype == torch.float16
     W = qo.decompress_e8p(q.numpy())
@@ -619,10 +622,7 @@ def test_e8p_mm_umma_matches_oracle(M, N, K):
     _mm_check(out2, x, W)
     # against the dense route on the same device (decompress + cuBLAS): both fp32-accumulate, fp16 out
     _native.set_option("umma", 0)
-    try:
-        dense = torch.ops.quip_lib.e8p_mm_origorder(xd, qd, _grid())
-    finally:
-        _native.set_option("umma", 1)
+    dense = torch.ops.quip_lib.e8p_mm_origorder(xd, qd, _grid())
     d = (out.float() - dense.float()).abs().max().item()
     assert d <= 2.0 ** -9 * dense.float().abs().max().item() + 1e-6, d
 

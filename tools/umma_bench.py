@@ -55,7 +55,7 @@ def main():
                 try:
                     ms = graph_time(lambda: [torch.ops.quip_lib.e8p_mm_origorder(x, q, grid) for q in qs])
                 finally:
-                    _native.set_option("umma", 1)
+                    _native.set_option("umma", 0)
                 us = 1000 * ms / NL
                 rec[name + "_us"] = round(us, 2)
                 rec[name + "_tflops"] = round(rec["gflop"] / us / 1e3, 1)
