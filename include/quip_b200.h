@@ -195,6 +195,9 @@ typedef struct quipb200_decode_layer {
   const void* post_norm_w;    /* fp16 [hidden]  LlamaRMSNorm before the MLP */
   void* k_cache;              /* fp16 [n_kv_heads, max_len, head_dim] */
   void* v_cache;
+  const void* mlp_hk;         /* optional (NULL ok): fp16 [3][Kp][Kp], Kp = roundup16(K_right of gate): gate.had_right,
+                                 up.had_right and down.had_left^T, each zero padded -- lets the kernel fetch the three
+                                 coefficient matrices with 16-byte requests */
 } quipb200_decode_layer_t;
 
 typedef struct quipb200_decode_plan {
@@ -219,6 +222,7 @@ int quipb200_decode_step(const quipb200_decode_plan_t* plan, const quipb200_deco
 /* profiling hook: when non-NULL, CTA 0 of the decode-step kernel writes int64 clock64() stamps of the
  * first layer's stages into buffer[0..15]; pass NULL to switch it off. */
 int quipb200_decode_step_debug(void* device_int64_buffer);
+int quipb200_decode_step_debug_cta(int cta);   /* which CTA writes the stamps (default 0) */
 /* tuning / test hook: force the number of KV splits per head of the attention stage (0 = automatic, <= 4);
  * takes effect for workspaces sized and steps launched afterwards. */
 int quipb200_decode_step_set_splits(int splits);

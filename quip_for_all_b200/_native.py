@@ -23,7 +23,7 @@ EXPORTS = [
     "quipb200_mm_workspace_bytes", "quipb200_mm",
     "quipb200_linear_workspace_bytes", "quipb200_linear_forward",
     "quipb200_linear_group_workspace_bytes", "quipb200_linear_group_forward", "quipb200_attn_decode",
-    "quipb200_decode_step_workspace_bytes", "quipb200_decode_step", "quipb200_decode_step_debug", "quipb200_decode_step_set_splits",
+    "quipb200_decode_step_workspace_bytes", "quipb200_decode_step", "quipb200_decode_step_debug", "quipb200_decode_step_debug_cta", "quipb200_decode_step_set_splits",
     "quipb200_e8p_mm_umma_workspace_bytes", "quipb200_e8p_mm_umma",
     "quipb200_set_option", "quipb200_get_option", "quipb200_launch_count", "quipb200_debug_timeline",
 ]
@@ -96,7 +96,7 @@ def lib():
     for fn in ("quipb200_hadamard", "quipb200_decompress_e8p", "quipb200_decompress_e8prvq4",
                "quipb200_decompress_d4", "quipb200_decompress_e8prvq3", "quipb200_decompress_hi",
                "quipb200_mm", "quipb200_linear_forward", "quipb200_linear_group_forward", "quipb200_attn_decode",
-               "quipb200_decode_step_workspace_bytes", "quipb200_decode_step", "quipb200_decode_step_debug", "quipb200_decode_step_set_splits",
+               "quipb200_decode_step_workspace_bytes", "quipb200_decode_step", "quipb200_decode_step_debug", "quipb200_decode_step_debug_cta", "quipb200_decode_step_set_splits",
     "quipb200_set_option", "quipb200_get_option"):
         getattr(L, fn).restype = c_int
     if L.quipb200_abi_version() != 1:

@@ -30,7 +30,7 @@ namespace qb {
 
 constexpr int DS_THREADS = 512;
 constexpr int DS_WARPS = DS_THREADS / 32;
-constexpr int DS_UNROLL = 4;
+constexpr int DS_UNROLL = 2;
 constexpr int DS_MAX_SPLITS = 4;
 constexpr int DS_HD = 128;
 constexpr int DS_PV_GROUPS = DS_THREADS / 64;
@@ -64,7 +64,8 @@ struct DsParams {
   __half* h_out;
   int kv_splits;
   int use_mma;           // hidden-side rotations are 4096-point: tensor-path transforms
-  long long* dbg;        // optional [16] clock stamps of CTA 0 (tools/timeline)
+  long long* dbg;        // optional [64] clock stamps of one CTA (tools/ds_timeline.py)
+  int dbg_cta;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -486,36 +487,58 @@ __device__ __forceinline__ uint32_t ldg_h2(const __half* p, int i) { return __ld
 __device__ __forceinline__ __half2 as_h2(uint32_t v) { return *reinterpret_cast<const __half2*>(&v); }
 __device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
 
-// f[2q], f[2q+1]: fp32 result at elements idx_spread(warp, lane, q) (+1) BEFORE the final fp16 rounding
-__device__ __forceinline__ void out_side_m(const quipb200_linear_t& Lp, const __half* acc, const __half* resid,
-                                           const HFrag& A, float* S, int warp, int lane, float (&f)[8]) {
-  const __half* SV = reinterpret_cast<const __half*>(Lp.SV);
-  const __half* bias = reinterpret_cast<const __half*>(Lp.bias);
-  const __half* wpc = reinterpret_cast<const __half*>(Lp.wscale_pc);
-  uint32_t svv[4], bv[4], rv[4], p[4];
+// Staging area for the small per-layer vectors of a hidden-side stage.  Everything a stage reads from global memory
+// is requested with 16-byte cp.async (one request per 8 elements) right after the grid barrier and consumed from shared
+// memory in whatever register layout the tensor-path rotations need: on B200 the number of (narrow, same-address)
+// requests that 148 CTAs throw at L2 at the same instant is what these stages were bound by.
+struct Stg {
+  __half* sv;      // [4096] SV of the producing linear
+  __half* bias;    // [4096]
+  __half* resid;   // [4096] skip connection
+  __half* nw;      // [4096] RMSNorm weight
+  __half* su;      // [4096] SU of the consuming linear
+  float* atto;     // [n_heads * S * 128] split-KV partial outputs (stage C; aliases sv .. nw)
+  __half* wscr;    // [16 warps][256] per-warp scratch (octet -> fragment layout)
+};
+__device__ __forceinline__ void stg_vec(__half* dst, const __half* src, int n, int tid) {
+  if (src != nullptr && tid * 8 < n) cp_async16(dst + tid * 8, src + tid * 8);
+}
+// fragment-layout pairs of one 256-element block held as octets by the lanes of a warp (lane l: elements 8l .. 8l+7)
+__device__ __forceinline__ void warp_octets_to_frag(const uint4& oct, __half* wscr_warp, int lane, uint32_t (&p)[4]) {
+  __syncwarp();
+  *reinterpret_cast<uint4*>(wscr_warp + lane * 8) = oct;
+  __syncwarp();
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const int i = idx_spread(warp, lane, q);
-    const bool ok = i < Lp.out_features;
-    svv[q] = (ok && SV) ? ldg_h2(SV, i) : 0u;
-    bv[q] = (ok && bias) ? ldg_h2(bias, i) : 0u;
-    rv[q] = (ok && resid) ? __ldcg(reinterpret_cast<const unsigned int*>(resid + i)) : 0u;
-    p[q] = __ldcg(reinterpret_cast<const unsigned int*>(acc + idx_block(warp, lane, q)));
-  }
+  for (int q = 0; q < 4; q++) p[q] = *reinterpret_cast<const uint32_t*>(wscr_warp + frag_x(lane, q) * 16 + frag_y(lane, q));
+}
+
+// f[2q], f[2q+1]: fp32 result at elements idx_spread(warp, lane, q) (+1) BEFORE the final fp16 rounding.
+// The caller has issued stg_vec() for sv / bias / resid of this linear (and whatever the input side needs).
+__device__ __forceinline__ uint4 out_side_load(const __half* acc, int warp, int lane) {   // block `warp`, octet `lane`
+  return __ldcg(reinterpret_cast<const uint4*>(acc) + warp * 32 + lane);
+}
+__device__ __forceinline__ void out_side_m(const quipb200_linear_t& Lp, const uint4& oct, bool has_resid, const Stg& st,
+                                           const HFrag& A, float* S, int warp, int lane, float (&f)[8]) {
+  const bool has_sv = Lp.SV != nullptr, has_bias = Lp.bias != nullptr;
+  const __half* wpc = reinterpret_cast<const __half*>(Lp.wscale_pc);
+  uint32_t p[4];
+  warp_octets_to_frag(oct, st.wscr + warp * 256, lane, p);
   if (wpc) {
 #pragma unroll
     for (int q = 0; q < 4; q++) p[q] = as_u32(__hmul2(as_h2(p[q]), as_h2(ldg_h2(wpc, idx_block(warp, lane, q)))));   // qlinear.py:107
   }
-  fwht4096_frag(p, A, S, warp, lane, f);                                             // includes 1/sqrt(4096)
+  cp_async_wait_all();                                                               // staged vectors: visible after the
+  fwht4096_frag(p, A, S, warp, lane, f);                                             // exchange barrier inside; x 1/64
 #pragma unroll
   for (int q = 0; q < 4; q++) {
-    const bool ok = idx_spread(warp, lane, q) < Lp.out_features;
+    const int i = idx_spread(warp, lane, q);
+    const bool ok = i < Lp.out_features;
     __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
-    if (SV) h = __hmul2(h, as_h2(svv[q]));                                           // qlinear.py:112
-    if (bias) h = __hadd2(h, as_h2(bv[q]));                                          // qlinear.py:114
+    if (has_sv) h = __hmul2(h, *reinterpret_cast<const __half2*>(st.sv + i));        // qlinear.py:112
+    if (has_bias) h = __hadd2(h, *reinterpret_cast<const __half2*>(st.bias + i));    // qlinear.py:114
     float2 v = __half22float2(h);
-    if (resid) {
-      const float2 r = __half22float2(as_h2(rv[q]));
+    if (has_resid) {
+      const float2 r = __half22float2(*reinterpret_cast<const __half2*>(st.resid + i));
       v.x += r.x;
       v.y += r.y;
     }
@@ -526,20 +549,19 @@ __device__ __forceinline__ void out_side_m(const quipb200_linear_t& Lp, const __
 
 // f: fp16-valued pairs at idx_spread positions (zeros beyond in_features): [RMSNorm] -> SU -> rotation -> * wscale/64 ->
 // 16-bit fixed point records (via the fp16 vector V, 4096 halfs).  Returns the fixed-point scale.
-__device__ __forceinline__ float in_side_m(const float (&f)[8], const __half* norm_w, float eps, const quipb200_linear_t& L,
-                                           const HFrag& A, float* S, __half* V, float* fred, uint4* xq, int tid) {
+// The caller has issued stg_vec() for nw / su and guarantees a CTA barrier after this thread's cp.async.wait_all
+// (staged == true), or passes staged == false and the function synchronises itself.
+__device__ __forceinline__ float in_side_m(const float (&f)[8], bool has_norm, float eps, const quipb200_linear_t& L,
+                                           const Stg& st, bool staged, const HFrag& A, float* S, __half* V, float* fred,
+                                           uint4* xq, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
-  const __half* SU = reinterpret_cast<const __half*>(L.SU);
-  uint32_t wv[4], sv[4];
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const int i = idx_spread(warp, lane, q);
-    const bool ok = i < L.in_features;
-    wv[q] = (ok && norm_w) ? ldg_h2(norm_w, i) : 0u;
-    sv[q] = (ok && SU) ? ldg_h2(SU, i) : 0u;
+  const bool has_su = L.SU != nullptr;
+  if (!staged) {
+    cp_async_wait_all();
+    __syncthreads();
   }
   float rstd = 1.f;
-  if (norm_w) {   // LlamaRMSNorm: weight * (x * rstd).to(fp16)
+  if (has_norm) {   // LlamaRMSNorm: weight * (x * rstd).to(fp16)
     float ss = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; j++) ss = fmaf(f[j], f[j], ss);
@@ -549,10 +571,12 @@ __device__ __forceinline__ float in_side_m(const float (&f)[8], const __half* no
   uint32_t p[4];
 #pragma unroll
   for (int q = 0; q < 4; q++) {
+    const int i = idx_spread(warp, lane, q);
+    const bool ok = i < L.in_features;
     __half2 h = __floats2half2_rn(f[2 * q] * rstd, f[2 * q + 1] * rstd);
-    if (norm_w) h = __hmul2(as_h2(wv[q]), h);
-    if (SU) h = __hmul2(h, as_h2(sv[q]));                                            // qlinear.py:91
-    p[q] = as_u32(h);
+    if (has_norm) h = __hmul2(*reinterpret_cast<const __half2*>(st.nw + i), h);
+    if (has_su) h = __hmul2(h, *reinterpret_cast<const __half2*>(st.su + i));        // qlinear.py:91
+    p[q] = ok ? as_u32(h) : 0u;
   }
   float r[8];
   fwht4096_frag(p, A, S, warp, lane, r);                                             // block layout, 1/64 included
@@ -608,8 +632,8 @@ __device__ __forceinline__ void mix_blocks(__half* T, __half* hk, int K, int LS,
 constexpr int DS_EB = 3;   // blocks per warp in flight (K <= 48 in one round)
 __device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, const quipb200_linear_t& Lu,
                                                 const quipb200_linear_t& Ld, const __half* acc_g, const __half* acc_u,
-                                                const BlkBuf& bb, const HFrag& A,
-                                                float* fred, uint4* xq, int tid, long long* dbg) {
+                                                const __half* hk_blob, const BlkBuf& bb, const HFrag& A, __half* wscr,
+                                                const GemvCfg& pf, float* fred, uint4* xq, int tid, long long* dbg) {
 #define DS_E(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   const int lane = tid & 31, warp = tid >> 5;
   const int K = Lg.K_right, Kp = (K + 15) / 16 * 16, LS = bb.LS;
@@ -626,8 +650,12 @@ __device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, con
     if (SVu) cp_async16(bb.vSVu + o * 8, SVu + o * 8);
     if (SUd) cp_async16(bb.vSUd + o * 8, SUd + o * 8);
   }
-  // coefficient matrices M[k_out][k_in], zero padded to Kp <= 64 (input side of down: hadK^T)
-  {
+  // coefficient matrices M[k_out][k_in], zero padded to Kp <= 64 (input side of down: hadK^T): one pre-padded blob per
+  // layer when the caller provides it (16-byte requests), else gathered from the raw K x K tensors
+  if (hk_blob != nullptr) {
+    const int n16 = (3 * Kp * Kp) >> 3;
+    for (int i = tid; i < n16; i += DS_THREADS) cp_async16(bb.hkg + i * 8, hk_blob + i * 8);
+  } else {
     const __half* src[3] = {reinterpret_cast<const __half*>(Lg.had_right), reinterpret_cast<const __half*>(Lu.had_right),
                             reinterpret_cast<const __half*>(Ld.had_left)};
     __half* dst[3] = {bb.hkg, bb.hku, bb.hkd};
@@ -654,33 +682,30 @@ __device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, con
   DS_E(30);
   // block transforms of the raw dot products (256-point WHT per warp on the tensor path, x 1/16), fp16
   for (int b0 = warp; b0 < K; b0 += DS_WARPS * DS_EB) {
-    uint32_t ga[DS_EB][4], ua[DS_EB][4];
+    uint4 ga[DS_EB], ua[DS_EB];      // one 16-byte octet per lane per block
 #pragma unroll
     for (int r = 0; r < DS_EB; r++) {
       const int b = b0 + r * DS_WARPS;
       if (b < K) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int e = b * 256 + frag_x(lane, q) * 16 + frag_y(lane, q);
-          ga[r][q] = __ldcg(reinterpret_cast<const unsigned int*>(acc_g + e));
-          ua[r][q] = __ldcg(reinterpret_cast<const unsigned int*>(acc_u + e));
-        }
+        ga[r] = __ldcg(reinterpret_cast<const uint4*>(acc_g) + b * 32 + lane);
+        ua[r] = __ldcg(reinterpret_cast<const uint4*>(acc_u) + b * 32 + lane);
       }
     }
+    if (b0 == warp) gemv_prefetch_l2(pf, tid);   // down_proj's packed codes -> L2, queued behind this stage's own requests
 #pragma unroll
     for (int r = 0; r < DS_EB; r++) {
       const int b = b0 + r * DS_WARPS;
       if (b < K) {
         uint32_t pg[4], pu[4];
+        warp_octets_to_frag(ga[r], wscr + warp * 512, lane, pg);
+        warp_octets_to_frag(ua[r], wscr + warp * 512 + 256, lane, pu);
+        if (wg || wu) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int e = b * 256 + frag_x(lane, q) * 16 + frag_y(lane, q);
-          __half2 hg = as_h2(ga[r][q]);
-          __half2 hu = as_h2(ua[r][q]);
-          if (wg) hg = __hmul2(hg, as_h2(ldg_h2(wg, e)));
-          if (wu) hu = __hmul2(hu, as_h2(ldg_h2(wu, e)));
-          pg[q] = as_u32(hg);
-          pu[q] = as_u32(hu);
+          for (int q = 0; q < 4; q++) {
+            const int e = b * 256 + frag_x(lane, q) * 16 + frag_y(lane, q);
+            if (wg) pg[q] = as_u32(__hmul2(as_h2(pg[q]), as_h2(ldg_h2(wg, e))));
+            if (wu) pu[q] = as_u32(__hmul2(as_h2(pu[q]), as_h2(ldg_h2(wu, e))));
+          }
         }
         float g[8], u[8];
         fwht256_frag(pg, A, g);
@@ -757,30 +782,31 @@ __device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, con
 // ---------------------------------------------------------------------------------------------
 // 128 outputs [128*j, 128*j+128) of H_n f (n = 128*nb, Sylvester order): first the nb blocks are combined
 // with the signs of row j of H_nb, then one 128-point transform.  part: [4][128] floats.
-// (n <= 4096: at most 8 blocks per thread, all loads issued before any is used)
-__device__ __forceinline__ void slice_load(int nb, const __half* acc, int tid, float (&a)[8]) {
-  const int lo = tid & 127, prt = tid >> 7;
-#pragma unroll
-  for (int u = 0; u < 8; u++) {
-    const int ih = prt + 4 * u;
-    a[u] = (ih < nb) ? __half2float(__ldcg(acc + ih * 128 + lo)) : 0.f;
-  }
+// Thread t loads one 16-byte octet: block ih = t / 16, elements 8*(t % 16) .. +7 (n <= 4096: one load per thread).
+// Blocks are combined with the signs of row j of H_nb: first the two blocks of a warp (shuffle), then the 16 warps
+// through shared memory (part: [16][128] floats, summed by slice_finish).
+__device__ __forceinline__ uint4 slice_load(int nb, const __half* acc, int tid) {
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if ((tid >> 4) < nb) v = __ldcg(reinterpret_cast<const uint4*>(acc) + tid);
+  return v;
 }
-__device__ __forceinline__ void slice_sum(const quipb200_linear_t& L, int nb, const float (&a)[8], int j,
-                                          float* part, int tid) {
-  const int lo = tid & 127, prt = tid >> 7;
+__device__ __forceinline__ void slice_sum(const quipb200_linear_t& L, int nb, const uint4& raw, int j, float* part, int tid) {
+  const int ih = tid >> 4, o = tid & 15, warp = tid >> 5;
   const __half* wpc = reinterpret_cast<const __half*>(L.wscale_pc);
-  float s = 0.f;
+  float f[8];
+  unpack_h8(raw, f);
+  if (wpc && ih < nb) mul_round_h8(f, ldg_u4(wpc, tid));
+  const float sg = (ih < nb) ? ((__popc(j & ih) & 1) ? -1.f : 1.f) : 0.f;
 #pragma unroll
-  for (int u = 0; u < 8; u++) {
-    const int ih = prt + 4 * u;
-    if (ih < nb) {
-      float f = a[u];
-      if (wpc) f = f16_round(f * __half2float(wpc[ih * 128 + lo]));
-      s += (__popc(j & ih) & 1) ? -f : f;
-    }
+  for (int e = 0; e < 8; e++) {
+    f[e] *= sg;
+    f[e] += __shfl_xor_sync(0xffffffffu, f[e], 16);     // the warp's other block
   }
-  part[prt * 128 + lo] = s;
+  if ((tid & 16) == 0) {
+    float4* d = reinterpret_cast<float4*>(part + warp * 128 + o * 8);
+    d[0] = make_float4(f[0], f[1], f[2], f[3]);
+    d[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
 }
 
 // warp-level 128-point WHT: lane holds elements 4*lane .. 4*lane+3
@@ -801,8 +827,12 @@ __device__ __forceinline__ void warp_fwht128(float (&v)[4], int lane) {
 // finish one head slice in a single warp: transform, output-side scalings of the linear (qlinear.py:108-114)
 __device__ __forceinline__ void slice_finish(const quipb200_linear_t& L, const float* part, int j, int lane, float (&v)[4]) {
 #pragma unroll
-  for (int e = 0; e < 4; e++)
-    v[e] = part[lane * 4 + e] + part[128 + lane * 4 + e] + part[256 + lane * 4 + e] + part[384 + lane * 4 + e];
+  for (int e = 0; e < 4; e++) v[e] = 0.f;
+#pragma unroll
+  for (int w = 0; w < DS_WARPS; w++) {
+    const float4 t4 = *reinterpret_cast<const float4*>(part + w * 128 + lane * 4);
+    v[0] += t4.x; v[1] += t4.y; v[2] += t4.z; v[3] += t4.w;
+  }
   warp_fwht128(v, lane);
   const float sc = 1.0f / sqrtf((float)L.q_out);
   const __half* SV = reinterpret_cast<const __half*>(L.SV);
@@ -842,7 +872,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
   const HFrag hfrag = make_hfrag(lane);
   float* const XS = rb.A;                                   // exchange buffer of fwht4096_frag (16 x DS_XROW floats)
   __half* const V = reinterpret_cast<__half*>(rb.fred + 64);   // fp16 [4096] (aliases the block buffers, unused in A / C / D)
-  long long* dbg = (p.dbg && bid == 0 && tid == 0) ? p.dbg : nullptr;
+  Stg stg;                                                   // staging vectors: behind V, same aliasing
+  stg.sv = V + 4096; stg.bias = stg.sv + 4096; stg.resid = stg.bias + 4096; stg.nw = stg.resid + 4096;
+  stg.atto = reinterpret_cast<float*>(stg.sv);               // 64 KB (n_heads * S * 128 floats <= 16384)
+  stg.su = stg.sv + 32768; stg.wscr = stg.su + 4096;
+  long long* dbg = (p.dbg && bid == p.dbg_cta && tid == 0) ? p.dbg : nullptr;
 #define DS_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
 #define DS_ST(i) do { if (dbg && l == 1) dbg[i] = clock64(); } while (0)
   DS_STAMP(0);
@@ -885,7 +919,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         const quipb200_linear_t L = (j == 0) ? Ly.q : (j == 1 ? Ly.k : Ly.v);
         const GemvCfg c = make_cfg(L, bx, p.geo.G_A[j]);
         DS_ST(1);
-        gemv_prefetch_l2(c, tid);
+        if (!p.use_mma || l == 0) gemv_prefetch_l2(c, tid);
         float f[8];
         float xs;
         if (p.use_mma) {
@@ -898,7 +932,14 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             }
           } else {
             const quipb200_linear_t Lp = s_desc[(l - 1) & 1].down;
-            out_side_m(Lp, p.ws.acc[SL_D], p.ws.hB, hfrag, XS, warp, lane, f);
+            stg_vec(stg.sv, reinterpret_cast<const __half*>(Lp.SV), Lp.out_features, tid);
+            stg_vec(stg.bias, reinterpret_cast<const __half*>(Lp.bias), Lp.out_features, tid);
+            stg_vec(stg.resid, p.ws.hB, Lp.out_features, tid);
+            stg_vec(stg.nw, reinterpret_cast<const __half*>(Ly.input_norm_w), L.in_features, tid);
+            stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
+            const uint4 oct = out_side_load(p.ws.acc[SL_D], warp, lane);
+            gemv_prefetch_l2(c, tid);      // after this stage's own (latency-critical) requests: the SM's load queue is FIFO
+            out_side_m(Lp, oct, true, stg, hfrag, XS, warp, lane, f);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
               const __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
@@ -909,7 +950,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             }
           }
           DS_ST(2);
-          xs = in_side_m(f, reinterpret_cast<const __half*>(Ly.input_norm_w), P.norm_eps, L, hfrag, XS, V, rb.fred, xq, tid);
+          if (l == 0) {
+            stg_vec(stg.nw, reinterpret_cast<const __half*>(Ly.input_norm_w), L.in_features, tid);
+            stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
+          }
+          xs = in_side_m(f, true, P.norm_eps, L, stg, l != 0, hfrag, XS, V, rb.fred, xq, tid);
         } else {
           if (l == 0) {
             uint4 hv = make_uint4(0, 0, 0, 0);
@@ -944,11 +989,19 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                      "l"(reinterpret_cast<const uint2*>(&P.layers[l + 1]) + tid) : "memory");
       if (bid < nh * S) {
         const int h = bid / S, s = bid - h * S, kvh = h / group;
-        const int T = pos + 1, chunk = (T + S - 1) / S;
-        const int t_begin = s * chunk, t_end = min(T, t_begin + chunk);
+        // cached positions [0, pos) are split evenly over the first S-1 CTAs of the head; the last one takes only the
+        // new token, whose k / v slices it has to rotate first (balances the stage: 3 slices ~ a third of the cache)
+        int t_begin, t_end;
+        if (S == 1) { t_begin = 0; t_end = pos + 1; }
+        else if (s == S - 1) { t_begin = pos; t_end = pos + 1; }
+        else {
+          const int chunk = (pos + S - 2) / (S - 1);
+          t_begin = s * chunk;
+          t_end = min(pos, t_begin + chunk);
+        }
         const bool has_new = (t_begin <= pos) && (pos < t_end);
-        float* part = reinterpret_cast<float*>(scr);          // [3][4][128]
-        float* sq = part + 3 * 512;                           // [128] rotated, scaled query
+        float* part = reinterpret_cast<float*>(scr);          // [3][16][128]
+        float* sq = part + 3 * DS_WARPS * 128;                           // [128] rotated, scaled query
         float* sk = sq + 128;                                 // [128] new key (post RoPE)
         float* sv = sk + 128;                                 // [128] new value
         float* sred = sv + 128;                               // [32]
@@ -958,16 +1011,16 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         __half* vc = reinterpret_cast<__half*>(Ly.v_cache) + (size_t)kvh * P.max_len * DS_HD;
         {
           const int nbq = Ly.q.q_out >> 7, nbk = Ly.k.q_out >> 7, nbv = Ly.v.q_out >> 7;
-          float aq[8], ak[8], av[8];
-          slice_load(nbq, p.ws.acc[SL_Q], tid, aq);
+          const uint4 aq = slice_load(nbq, p.ws.acc[SL_Q], tid);
+          uint4 ak = make_uint4(0, 0, 0, 0), av = ak;
           if (has_new) {
-            slice_load(nbk, p.ws.acc[SL_K], tid, ak);
-            slice_load(nbv, p.ws.acc[SL_V], tid, av);
+            ak = slice_load(nbk, p.ws.acc[SL_K], tid);
+            av = slice_load(nbv, p.ws.acc[SL_V], tid);
           }
           slice_sum(Ly.q, nbq, aq, h, part, tid);
           if (has_new) {
-            slice_sum(Ly.k, nbk, ak, kvh, part + 512, tid);
-            slice_sum(Ly.v, nbv, av, kvh, part + 1024, tid);
+            slice_sum(Ly.k, nbk, ak, kvh, part + DS_WARPS * 128, tid);
+            slice_sum(Ly.v, nbv, av, kvh, part + 2 * DS_WARPS * 128, tid);
           }
         }
         __syncthreads();
@@ -975,7 +1028,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         if (warp < (has_new ? 3 : 1)) {
           float v[4];
           const quipb200_linear_t& L = warp == 0 ? Ly.q : (warp == 1 ? Ly.k : Ly.v);
-          slice_finish(L, part + warp * 512, warp == 0 ? h : kvh, lane, v);
+          slice_finish(L, part + warp * DS_WARPS * 128, warp == 0 ? h : kvh, lane, v);
           if (warp < 2) {   // RoPE, HF rotate_half convention: x*cos + rotate_half(x)*sin
             const __half* ct = reinterpret_cast<const __half*>(P.cos_t) + (size_t)pos * DS_HD;
             const __half* st = reinterpret_cast<const __half*>(P.sin_t) + (size_t)pos * DS_HD;
@@ -1113,10 +1166,15 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
       if (j >= 0) {
         const quipb200_linear_t L = Ly.o;
         const GemvCfg c = make_cfg(L, bx, p.geo.G_C);
-        gemv_prefetch_l2(c, tid);
         // combine the split-KV partials into the fp16 attention output.  Split weights exp(m_s - M) / sum go through
         // shared memory: [head][split] floats, computed once per CTA
         float* wsm = rb.fred + 64;   // aliases the block buffers (unused in this stage); n_heads * S <= 512 floats
+        if (p.use_mma) {             // partial outputs and SU of o_proj -> shared memory, 16 bytes per request
+          const int n4 = (P.n_heads * S * DS_HD) >> 2;
+          for (int i = tid; i < n4; i += DS_THREADS) cp_async16(stg.atto + i * 4, p.ws.att_o + i * 4);
+          stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
+        }
+        gemv_prefetch_l2(c, tid);
         if (tid < P.n_heads) {
           float m[DS_MAX_SPLITS], lsum[DS_MAX_SPLITS], M = -INFINITY, den = 0.f;
 #pragma unroll
@@ -1135,6 +1193,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
           for (int s = 0; s < DS_MAX_SPLITS; s++)
             if (s < S) wsm[tid * S + s] = m[s] * inv;
         }
+        cp_async_wait_all();
         __syncthreads();
         float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float xs;
@@ -1156,7 +1215,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
 #pragma unroll
                 for (int s = 0; s < DS_MAX_SPLITS; s++) {
                   if (s < S) {
-                    const float2 a = __ldcg(reinterpret_cast<const float2*>(p.ws.att_o + (size_t)(h * S + s) * DS_HD + d));
+                    const float2 a = *reinterpret_cast<const float2*>(stg.atto + (h * S + s) * DS_HD + d);
                     ax = fmaf(w[s], a.x, ax);
                     ay = fmaf(w[s], a.y, ay);
                   }
@@ -1168,7 +1227,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             }
           }
           DS_ST(12);
-          xs = in_side_m(f, nullptr, 0.f, L, hfrag, XS, V, rb.fred, xq, tid);
+          xs = in_side_m(f, false, 0.f, L, stg, true, hfrag, XS, V, rb.fred, xq, tid);
         } else {
           if (tid < ((P.n_heads * DS_HD) >> 3)) {
             const int h = (tid * 8) / DS_HD, d = (tid * 8) % DS_HD;
@@ -1204,12 +1263,19 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
       if (j >= 0) {
         const quipb200_linear_t L = (j == 0) ? Ly.gate : Ly.up;
         const GemvCfg c = make_cfg(L, bx, p.geo.G_D[j]);
-        gemv_prefetch_l2(c, tid);
+        if (!p.use_mma) gemv_prefetch_l2(c, tid);
         float f[8];
         float xs;
         const quipb200_linear_t Lp = Ly.o;
         if (p.use_mma) {
-          out_side_m(Lp, p.ws.acc[SL_O], p.ws.hA, hfrag, XS, warp, lane, f);
+          stg_vec(stg.sv, reinterpret_cast<const __half*>(Lp.SV), Lp.out_features, tid);
+          stg_vec(stg.bias, reinterpret_cast<const __half*>(Lp.bias), Lp.out_features, tid);
+          stg_vec(stg.resid, p.ws.hA, Lp.out_features, tid);
+          stg_vec(stg.nw, reinterpret_cast<const __half*>(Ly.post_norm_w), L.in_features, tid);
+          stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
+          const uint4 oct = out_side_load(p.ws.acc[SL_O], warp, lane);
+          gemv_prefetch_l2(c, tid);
+          out_side_m(Lp, oct, true, stg, hfrag, XS, warp, lane, f);
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             const __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
@@ -1219,7 +1285,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             f[2 * q + 1] = v.y;
           }
           DS_ST(16);
-          xs = in_side_m(f, reinterpret_cast<const __half*>(Ly.post_norm_w), P.norm_eps, L, hfrag, XS, V, rb.fred, xq, tid);
+          xs = in_side_m(f, true, P.norm_eps, L, stg, true, hfrag, XS, V, rb.fred, xq, tid);
         } else {
           out_side_k1(Lp, p.ws.acc[SL_O], p.ws.hA, rb, tid, f);
           const uint4 hv = pack_h8(f);
@@ -1247,9 +1313,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         const GemvCfg c = make_cfg(L, bx, p.geo.G_E);
         float xs;
         if (L.K_left > 1) {
-          gemv_prefetch_l2(c, tid);   // (stage E)
-          xs = stage_e_blocks(Ly.gate, Ly.up, L, p.ws.acc[SL_G], p.ws.acc[SL_U], bb,
-                              hfrag, rb.fred, xq, tid, (dbg && l == 1) ? dbg : nullptr);
+          xs = stage_e_blocks(Ly.gate, Ly.up, L, p.ws.acc[SL_G], p.ws.acc[SL_U], reinterpret_cast<const __half*>(Ly.mlp_hk), bb,
+                              hfrag, reinterpret_cast<__half*>(rb.A), c, rb.fred, xq, tid, (dbg && l == 1) ? dbg : nullptr);
         } else {
           gemv_prefetch_l2(c, tid);
           float g[8], u[8];
@@ -1288,7 +1353,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     float f[8];
     const quipb200_linear_t Lp = s_desc[(P.n_layers - 1) & 1].down;
     if (p.use_mma) {
-      out_side_m(Lp, p.ws.acc[SL_D], p.ws.hB, hfrag, XS, warp, lane, f);
+      stg_vec(stg.sv, reinterpret_cast<const __half*>(Lp.SV), Lp.out_features, tid);
+      stg_vec(stg.bias, reinterpret_cast<const __half*>(Lp.bias), Lp.out_features, tid);
+      stg_vec(stg.resid, p.ws.hB, Lp.out_features, tid);
+      out_side_m(Lp, out_side_load(p.ws.acc[SL_D], warp, lane), true, stg, hfrag, XS, warp, lane, f);
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const int i = idx_spread(warp, lane, q);
@@ -1401,6 +1469,7 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
     const size_t Kp = (K + 15) / 16 * 16;
     hk_halfs = Kp * Kp;
     mid_halfs = ((size_t)Y.gate.out_features + 7) / 8 * 8;
+    nmax = std::max(nmax, (size_t)2048);   // A | B doubles as the per-warp octet -> fragment scratch (16 KB)
   }
   if (nmax > 8 * DS_THREADS) return QUIPB200_EUNSUPPORTED;
 
@@ -1435,17 +1504,17 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
   if (S < 1) return QUIPB200_EUNSUPPORTED;        // fewer CTAs than heads
   if (g_ds_splits > 0) S = std::min(S, g_ds_splits);
   else S = std::min(S, std::max(1, (P->max_len + 127) / 128));
-  if (P->n_heads * S > 512) return QUIPB200_EUNSUPPORTED;
+  if (P->n_heads * S > 512 || P->n_heads * S * DS_HD > 16384) return QUIPB200_EUNSUPPORTED;
   out->splits = S;
-  const size_t chunk = ((size_t)P->max_len + S - 1) / S;
-  const size_t attn = (3 * 512 + 3 * 128 + 32 + DS_PV_GROUPS * 128 + chunk) * sizeof(float);
+  const size_t chunk = S > 1 ? ((size_t)P->max_len + S - 2) / (S - 1) : (size_t)P->max_len;
+  const size_t attn = (3 * DS_WARPS * 128 + 3 * 128 + 32 + DS_PV_GROUPS * 128 + chunk) * sizeof(float);
   // tensor-path rotations when every hidden-side rotation has exactly 4096 points
   const bool use_mma = Y.q.q_in == 4096 && Y.k.q_in == 4096 && Y.v.q_in == 4096 && Y.o.q_in == 4096 && Y.o.q_out == 4096 &&
                        Y.gate.q_in == 4096 && Y.up.q_in == 4096 && Y.down.q_out == 4096 && P->hidden <= 4096;
   out->use_mma = use_mma ? 1 : 0;
   if (use_mma) nmax = std::max(nmax, (size_t)4096);   // the exchange buffer (16 x 388 floats) lives in A | B
   size_t blk = 2 * t_halfs * 2 + 3 * hk_halfs * 2 + 3 * mid_halfs * 2;
-  if (use_mma) blk = std::max(blk, (size_t)8192);     // fp16 [4096] staging vector of the input side
+  if (use_mma) blk = std::max(blk, (size_t)90112);    // V (8 KB) + staged vectors / attention partials (72 KB) + warp scratch (8 KB)
   size_t scr = 2 * nmax * sizeof(float) + 64 * sizeof(float) + blk;
   scr = std::max(scr, attn);
   auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
@@ -1476,6 +1545,7 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
 }
 
 long long* g_ds_dbg = nullptr;
+int g_ds_dbg_cta = 0;
 
 }  // namespace qb
 
@@ -1489,6 +1559,11 @@ extern "C" int quipb200_decode_step_set_splits(int splits) {
 
 extern "C" int quipb200_decode_step_debug(void* device_int64_buffer) {
   g_ds_dbg = (long long*)device_int64_buffer;
+  return 0;
+}
+
+extern "C" int quipb200_decode_step_debug_cta(int cta) {
+  g_ds_dbg_cta = cta < 0 ? 0 : cta;
   return 0;
 }
 
@@ -1542,6 +1617,7 @@ extern "C" int quipb200_decode_step(const quipb200_decode_plan_t* plan, const qu
   p.kv_splits = lay.splits;
   p.use_mma = lay.use_mma;
   p.dbg = g_ds_dbg;
+  p.dbg_cta = g_ds_dbg_cta;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(sms);
   cfg.blockDim = dim3(DS_THREADS);

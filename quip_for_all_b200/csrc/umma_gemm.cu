@@ -11,10 +11,11 @@
 //
 //   MMA shape : D[128 weight rows x NTOK tokens] += A[128 x 16] . B[NTOK x 16]^T   (cta_group::1, M = 128)
 //   grid      : (N / 128 row tiles) x (split-K so that ~all SMs have a CTA)
-//   pipeline  : STAGES shared-memory slots; all 8 warps are producers (weights: table lookup + sign decode
-//               + int8 -> fp16 with the reference's exact 0x5c80 trick, one 16-byte swizzled store per code;
-//               activations: cp.async one stage ahead); slot reuse is gated by an mbarrier that
-//               tcgen05.commit arrives on when the MMAs that read the slot have retired.
+//   pipeline  : STAGES shared-memory slots of 128 k; 16 producer warps (weights: table lookup + sign decode +
+//               int8 -> fp16 with the reference's exact 0x5c80 trick, one 16-byte swizzled store per code;
+//               activations: cp.async one stage ahead) arrive on full[s]; a 17th warp waits on it, issues the 8
+//               MMAs of the stage and tcgen05.commit's to empty[s], which gates the slot's reuse.  No CTA-wide
+//               barrier inside the main loop.
 //   epilogue  : tcgen05.ld (32 lanes x 32 bit x 16 columns) -> fp16 store, or fp32 atomics into a
 //               self-cleaning split-K workspace whose last CTA (ticket) converts the tile.
 //
@@ -83,36 +84,56 @@ struct UmmaArgs {
   const __half* x;              // [M][K]
   const uint2* table;           // int64[256] abs table
   __half* out;                  // [M][N]
-  float* ws;                    // [M][N] fp32 split-K partials (zero on entry, zero on exit)
+  float* ws;                    // [256][N] fp32 split-K partials (zero on entry, zero on exit)
   unsigned int* tickets;        // [N/128]
   int M, N, K, ksplit, kb_per_split;
 };
 
+constexpr int UG_PRODUCERS = 512;               // 16 producer warps
+constexpr int UG_THREADS2 = UG_PRODUCERS + 32;  // + 1 MMA-issue warp
+constexpr int UG_BK2 = 128;                     // k per stage: two 64-wide swizzle tiles
+constexpr int UG_WS_LD = 256;                   // token pitch of the split-K workspace
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Warp-specialised: 16 producer warps fill the stage slots (no CTA-wide barrier in the main loop), warp 16 waits on
+// full[s], issues the 8 MMAs of the stage and commits to empty[s].
 template <int NTOK, int STAGES>
-__global__ void __launch_bounds__(UG_THREADS, 1) e8p_umma_kernel(const __grid_constant__ UmmaArgs a) {
+__global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_constant__ UmmaArgs a) {
   extern __shared__ unsigned char smem_raw[];
-  constexpr uint32_t A_BYTES = UG_BM * 128, B_BYTES = NTOK * 128;
+  constexpr uint32_t A_SUB = UG_BM * 128, B_SUB = NTOK * 128;           // one 64-wide swizzle tile
+  constexpr uint32_t A_BYTES = 2 * A_SUB, B_BYTES = 2 * B_SUB;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle atoms need 1024-byte alignment
   unsigned char* gbase = smem_raw + (base - raw);
   const uint32_t sA = base, sB = base + STAGES * A_BYTES;
   unsigned char* tab = gbase + STAGES * (A_BYTES + B_BYTES);    // 2 KB table
-  const uint32_t sbar = base + STAGES * (A_BYTES + B_BYTES) + 2048;   // empty[STAGES], done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + STAGES * (A_BYTES + B_BYTES) + 2048 + 8 * (STAGES + 1));
+  const uint32_t sbar = base + STAGES * (A_BYTES + B_BYTES) + 2048;   // full[STAGES], empty[STAGES], done
+  const uint32_t bar_full = sbar, bar_empty = sbar + 8 * STAGES, bar_done = sbar + 16 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + STAGES * (A_BYTES + B_BYTES) + 2048 + 8 * (2 * STAGES + 1));
   __shared__ int s_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * UG_BM;
-  const int kb_begin = blockIdx.y * a.kb_per_split;
-  const int nit = min(a.kb_per_split, a.K / UG_BK - kb_begin);
+  const int kb_begin = blockIdx.y * a.kb_per_split;                       // in units of UG_BK2
+  const int nit = min(a.kb_per_split, a.K / UG_BK2 - kb_begin);
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s <= STAGES; s++) mbar_init(sbar + 8 * s, 1);
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(bar_full + 8 * s, UG_PRODUCERS / 32);    // one arrive per producer warp
+      mbar_init(bar_empty + 8 * s, 1);                   // tcgen05.commit
+    }
+    mbar_init(bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), NTOK);
-  {
+  if (tid < 256) {
     uint2 t = a.table[tid];
     t.x |= 0x01010101u;
     t.y |= 0x01010101u;
@@ -125,91 +146,104 @@ __global__ void __launch_bounds__(UG_THREADS, 1) e8p_umma_kernel(const __grid_co
   // instruction descriptor: D = F32, A = B = F16, both K-major, N = NTOK, M = 128 (cute::UMMA::InstrDescriptor)
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NTOK >> 3) << 17) | ((uint32_t)(UG_BM >> 4) << 24);
 
-  // producer roles: thread -> (weight row, 4 of its 8 codes); activations: 16-byte chunks round-robin
-  const int wrow = tid >> 1, whalf = tid & 1;
-  const unsigned char* wsrc = a.codes + (size_t)(n0 + wrow) * (a.K >> 2) + whalf * 8;
-  const uint64_t pol = l2_evict_first_policy();
-  auto load_codes_p = [&](int it) -> uint2 { return ldg_stream_v2(wsrc + (size_t)(kb_begin + it) * 16, pol); };
-  auto issue_acts = [&](int it) {
-    const int s = it % STAGES;
-    const __half* xs = a.x + (size_t)(kb_begin + it) * UG_BK;
-    for (int c = tid; c < NTOK * 8; c += UG_THREADS) {
-      const int tok = c >> 3, ch = c & 7;
-      const bool ok = tok < a.M;
-      const __half* src = xs + (size_t)(ok ? tok : 0) * a.K + ch * 8;
-      cp_async16_zfill(sB + s * B_BYTES + tok * 128 + ((ch ^ (tok & 7)) << 4), src, ok ? 16u : 0u);
+  if (warp == UG_PRODUCERS / 32) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      for (int it = 0; it < nit; it++) {
+        const int s = it % STAGES;
+        mbar_wait(bar_full + 8 * s, (uint32_t)((it / STAGES) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const uint64_t ad = umma_smem_desc(sA + s * A_BYTES + h * A_SUB), bd = umma_smem_desc(sB + s * B_BYTES + h * B_SUB);
+#pragma unroll
+          for (int k = 0; k < 4; k++)    // +32 bytes along K inside the swizzled row = +2 in the address field
+            umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, (it > 0 || h > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_empty + 8 * s);          // slot s is free again when these MMAs retire
+      }
+      umma_commit(bar_done);                     // all MMAs of this CTA
     }
-  };
-
-  uint2 cur = make_uint2(0, 0);
-  if (nit > 0) {
-    cur = load_codes_p(0);
-    issue_acts(0);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-
-  for (int it = 0; it < nit; it++) {
-    const int s = it % STAGES;
-    uint2 nxt = make_uint2(0, 0);
-    if (it + 1 < nit) {
-      nxt = load_codes_p(it + 1);
-      if (it + 1 >= STAGES) mbar_wait(sbar + 8 * ((it + 1) % STAGES), (uint32_t)(((it + 1) / STAGES - 1) & 1));
-      issue_acts(it + 1);
+    __syncwarp();
+  } else {
+    // ===== producers: thread -> (weight row, 4 of its 16 codes of the stage); activations: 16-byte chunks round-robin
+    const int wrow = tid >> 2, wq = tid & 3;
+    const unsigned char* wsrc = a.codes + (size_t)(n0 + wrow) * (a.K >> 2) + wq * 8;
+    const uint64_t pol = l2_evict_first_policy();
+    auto load_codes = [&](int it) -> uint2 { return ldg_stream_v2(wsrc + (size_t)(kb_begin + it) * 32, pol); };
+    auto issue_acts = [&](int it) {
+      const int s = it % STAGES;
+      const __half* xs = a.x + (size_t)(kb_begin + it) * UG_BK2;
+      for (int c = tid; c < NTOK * 16; c += UG_PRODUCERS) {
+        const int tok = c >> 4, h = (c >> 3) & 1, ch = c & 7;
+        const bool ok = tok < a.M;
+        const __half* src = xs + (size_t)(ok ? tok : 0) * a.K + h * 64 + ch * 8;
+        cp_async16_zfill(sB + s * B_BYTES + h * B_SUB + tok * 128 + ((ch ^ (tok & 7)) << 4), src, ok ? 16u : 0u);
+      }
+    };
+    uint2 cur = make_uint2(0, 0);
+    if (nit > 0) {
+      cur = load_codes(0);
+      issue_acts(0);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    // ---- weights of stage `it` -> slot s (free: its mbarrier was waited on one iteration ago, or it < STAGES)
-    {
-      const uint32_t w[2] = {cur.x, cur.y};
-      unsigned char* arow = gbase + (size_t)s * A_BYTES + wrow * 128;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t code = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
-        const uint2 t1 = *reinterpret_cast<const uint2*>(tab + ((code >> 8) << 3));
-        const uint2 q = e8p_decode_q(t1, code);
-        __half2 e0, o0, e1, o1;
-        q4_to_half2(q.x, e0, o0);     // weights (0,1) = bytes (0,2); (2,3) = bytes (1,3)
-        q4_to_half2(q.y, e1, o1);
-        uint4 v;
-        v.x = *reinterpret_cast<const uint32_t*>(&e0);
-        v.y = *reinterpret_cast<const uint32_t*>(&o0);
-        v.z = *reinterpret_cast<const uint32_t*>(&e1);
-        v.w = *reinterpret_cast<const uint32_t*>(&o1);
-        const int ch = whalf * 4 + j;
-        *reinterpret_cast<uint4*>(arow + ((ch ^ (wrow & 7)) << 4)) = v;
+    for (int it = 0; it < nit; it++) {
+      const int s = it % STAGES;
+      uint2 nxt = make_uint2(0, 0);
+      if (it + 1 < nit) {
+        nxt = load_codes(it + 1);
+        if (it + 1 >= STAGES) mbar_wait(bar_empty + 8 * ((it + 1) % STAGES), (uint32_t)(((it + 1) / STAGES - 1) & 1));
+        issue_acts(it + 1);
       }
-    }
-    asm volatile("cp.async.wait_group 1;" ::: "memory");        // activations of stage `it` have landed
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint64_t ad = umma_smem_desc(sA + s * A_BYTES), bd = umma_smem_desc(sB + s * B_BYTES);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      // weights of stage `it` -> slot s (free: empty[s] was waited on one iteration ago, or it < STAGES)
+      {
+        const uint32_t w[2] = {cur.x, cur.y};
+        unsigned char* arow = gbase + (size_t)s * A_BYTES + (wq >> 1) * A_SUB + wrow * 128;
 #pragma unroll
-      for (int k = 0; k < UG_BK / 16; k++)    // +32 bytes along K inside the swizzled row = +2 in the address field
-        umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, (it > 0 || k > 0) ? 1u : 0u);
-      umma_commit(sbar + 8 * s);               // slot s is free again when these MMAs retire
+        for (int j = 0; j < 4; j++) {
+          const uint32_t code = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+          const uint2 t1 = *reinterpret_cast<const uint2*>(tab + ((code >> 8) << 3));
+          const uint2 q = e8p_decode_q(t1, code);
+          __half2 e0, o0, e1, o1;
+          q4_to_half2(q.x, e0, o0);     // weights (0,1) = bytes (0,2); (2,3) = bytes (1,3)
+          q4_to_half2(q.y, e1, o1);
+          uint4 v;
+          v.x = *reinterpret_cast<const uint32_t*>(&e0);
+          v.y = *reinterpret_cast<const uint32_t*>(&o0);
+          v.z = *reinterpret_cast<const uint32_t*>(&e1);
+          v.w = *reinterpret_cast<const uint32_t*>(&o1);
+          const int ch = (wq & 1) * 4 + j;
+          *reinterpret_cast<uint4*>(arow + ((ch ^ (wrow & 7)) << 4)) = v;
+        }
+      }
+      asm volatile("cp.async.wait_group 1;" ::: "memory");           // this thread's activation chunks of stage `it`
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      cur = nxt;
     }
-    cur = nxt;
   }
-  if (tid == 0) umma_commit(sbar + 8 * STAGES);   // all MMAs of this CTA
-  mbar_wait(sbar + 8 * STAGES, 0);
+  mbar_wait(bar_done, 0);
   tc_fence_after();
 
-  // ---- epilogue: TMEM lane = weight row, column = token.  Warp w reads lane quadrant w % 4, column half w / 4.
-  if (nit > 0) {
-    const int quad = warp & 3, chalf = warp >> 2;
+  // ---- epilogue: TMEM lane = weight row, column = token.  Producer warp w: lane quadrant w % 4, column quarter w / 4.
+  if (warp < UG_PRODUCERS / 32 && nit > 0) {
+    const int quad = warp & 3, cq = warp >> 2;
     const int n = n0 + quad * 32 + lane;
-    for (int c0 = chalf * (NTOK / 2); c0 < (chalf + 1) * (NTOK / 2); c0 += 16) {
+    constexpr int CW = NTOK / 4 < 16 ? 16 : NTOK / 4;        // columns per warp (>= one 16-column load)
+    for (int c0 = cq * CW; c0 < (cq + 1) * CW && c0 < NTOK; c0 += 16) {
       if (c0 >= a.M) break;                        // warp-uniform: token columns beyond M hold zeros
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      if (a.ksplit == 1) {
 #pragma unroll
-      for (int j = 0; j < 16; j++) {
-        const int tok = c0 + j;
-        if (tok < a.M) {
-          if (a.ksplit == 1) a.out[(size_t)tok * a.N + n] = __float2half_rn(v[j]);
-          else atomicAdd(a.ws + (size_t)tok * a.N + n, v[j]);
-        }
+        for (int j = 0; j < 16; j++)
+          if (c0 + j < a.M) a.out[(size_t)(c0 + j) * a.N + n] = __float2half_rn(v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++)      // a warp adds 32 consecutive floats of one token row: one 128-byte L2 reduction
+          if (c0 + j < a.M) atomicAdd(a.ws + (size_t)(c0 + j) * a.N + n, v[j]);
       }
     }
   }
@@ -227,7 +261,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) e8p_umma_kernel(const __grid_co
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int i = tid; i < a.M * UG_BM; i += UG_THREADS) {
+  for (int i = tid; i < a.M * UG_BM; i += UG_THREADS2) {
     const int tok = i >> 7, n = n0 + (i & 127);
     float* p = a.ws + (size_t)tok * a.N + n;
     a.out[(size_t)tok * a.N + n] = __float2half_rn(__ldcg(p));
@@ -237,10 +271,10 @@ __global__ void __launch_bounds__(UG_THREADS, 1) e8p_umma_kernel(const __grid_co
 
 template <int NTOK, int STAGES>
 static int launch_umma(const UmmaArgs& a, dim3 grid, cudaStream_t st) {
-  const size_t smem = (size_t)STAGES * (UG_BM * 128 + NTOK * 128) + 2048 + 8 * (STAGES + 1) + 16 + 1024;
+  const size_t smem = (size_t)STAGES * 2 * (UG_BM * 128 + NTOK * 128) + 2048 + 8 * (2 * STAGES + 1) + 16 + 1024;
   cudaError_t e = cudaFuncSetAttribute(e8p_umma_kernel<NTOK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  e8p_umma_kernel<NTOK, STAGES><<<grid, UG_THREADS, smem, st>>>(a);
+  e8p_umma_kernel<NTOK, STAGES><<<grid, UG_THREADS2, smem, st>>>(a);
   QB_LAUNCH_CHECK();
   return 0;
 }
@@ -251,19 +285,19 @@ using namespace qb;
 
 extern "C" size_t quipb200_e8p_mm_umma_workspace_bytes(int M, int N, int K) {
   if (M < 1 || N < 1 || K < 1) return 0;
-  return (size_t)M * N * sizeof(float) + (size_t)(N / UG_BM + 1) * sizeof(unsigned int) + 256;
+  return (size_t)N * UG_WS_LD * sizeof(float) + (size_t)(N / UG_BM + 1) * sizeof(unsigned int) + 256;
 }
 
 extern "C" int quipb200_e8p_mm_umma(const void* x, const void* qidxs, const void* grid, void* out, int M, int N, int K,
                                     void* workspace, size_t ws_bytes, void* stream) {
   if (!x || !qidxs || !grid || !out) return QUIPB200_EINVAL;
-  if (M < 1 || M > 256 || N < UG_BM || N % UG_BM || K < UG_BK || K % UG_BK) return QUIPB200_EUNSUPPORTED;
+  if (M < 1 || M > 256 || N < UG_BM || N % UG_BM || K < UG_BK2 || K % UG_BK2) return QUIPB200_EUNSUPPORTED;
   if (!aligned16(x) || !aligned16(qidxs) || !aligned16(grid) || !aligned16(out)) return QUIPB200_EALIGN;
   const int sms = quipb200_sm_count();
   if (sms < 1) return (int)cudaErrorNoDevice;
-  const int tiles = N / UG_BM, nkb = K / UG_BK;
+  const int tiles = N / UG_BM, nkb = K / UG_BK2;
   int ksplit = 1;
-  while (ksplit < 16 && tiles * ksplit * 2 <= sms && nkb / (ksplit * 2) >= 8) ksplit *= 2;
+  while (ksplit < 16 && tiles * ksplit * 2 <= sms && nkb / (ksplit * 2) >= 4) ksplit *= 2;
   UmmaArgs a{};
   a.codes = (const unsigned char*)qidxs; a.x = (const __half*)x; a.table = (const uint2*)grid; a.out = (__half*)out;
   a.M = M; a.N = N; a.K = K;
@@ -273,12 +307,12 @@ extern "C" int quipb200_e8p_mm_umma(const void* x, const void* qidxs, const void
     if (!workspace || ((uintptr_t)workspace & 255) || ws_bytes < quipb200_e8p_mm_umma_workspace_bytes(M, N, K))
       return QUIPB200_EWORKSPACE;
     a.ws = (float*)workspace;
-    a.tickets = (unsigned int*)((unsigned char*)workspace + (((size_t)M * N * sizeof(float) + 255) / 256 * 256));
+    a.tickets = (unsigned int*)((unsigned char*)workspace + (size_t)N * UG_WS_LD * sizeof(float));
   }
   const dim3 grid_dim(tiles, ksplit);
   cudaStream_t st = (cudaStream_t)stream;
   if (M <= 32) return launch_umma<32, 4>(a, grid_dim, st);
   if (M <= 64) return launch_umma<64, 4>(a, grid_dim, st);
-  if (M <= 128) return launch_umma<128, 4>(a, grid_dim, st);
-  return launch_umma<256, 4>(a, grid_dim, st);
+  if (M <= 128) return launch_umma<128, 3>(a, grid_dim, st);
+  return launch_umma<256, 2>(a, grid_dim, st);
 }

@@ -15,7 +15,8 @@ class DecodeLayer(Structure):
     """struct quipb200_decode_layer."""
     _fields_ = [("q", LinearDesc), ("k", LinearDesc), ("v", LinearDesc), ("o", LinearDesc),
                 ("gate", LinearDesc), ("up", LinearDesc), ("down", LinearDesc),
-                ("input_norm_w", c_void_p), ("post_norm_w", c_void_p), ("k_cache", c_void_p), ("v_cache", c_void_p)]
+                ("input_norm_w", c_void_p), ("post_norm_w", c_void_p), ("k_cache", c_void_p), ("v_cache", c_void_p),
+                ("mlp_hk", c_void_p)]
 
 
 class DecodePlan(Structure):
@@ -74,7 +75,16 @@ class PersistentDecodeStep:
                 raise ValueError("persistent decode step needs fp16 norm weights")
             d.input_norm_w, d.post_norm_w = nw1.data_ptr(), nw2.data_ptr()
             d.k_cache, d.v_cache = k_cache[i].data_ptr(), v_cache[i].data_ptr()
-            self._keep.append((mods, nw1, nw2))
+            hk = None
+            K = mlp.gate_proj.K_right
+            if K > 1 and mlp.up_proj.K_right == K and mlp.down_proj.K_left == K and mlp.gate_proj.had_right is not None:
+                Kp = (K + 15) // 16 * 16
+                hk = torch.zeros(3, Kp, Kp, dtype=torch.float16, device=self.dev)
+                hk[0, :K, :K] = mlp.gate_proj.had_right
+                hk[1, :K, :K] = mlp.up_proj.had_right
+                hk[2, :K, :K] = mlp.down_proj.had_left.t()      # input side: M[k_out][k_in] = hadK^T (quant.py:79-80)
+            d.mlp_hk = hk.data_ptr() if hk is not None else None
+            self._keep.append((mods, nw1, nw2, hk))
         raw = bytes(self.host_layers)
         self.dev_layers = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.dev)
         self.plan = DecodePlan(n, hidden, n_heads, n_kv_heads, head_dim, k_cache.shape[-2], float(eps), 0,

@@ -185,7 +185,7 @@ _UMMA_WS = {}
 def _mm_umma(x, Qidxs, grid, K):
     """17 <= M <= 256, E8P12: in-kernel decode + tcgen05 GEMM (csrc/umma_gemm.cu); None if the shape is not covered."""
     M, N = x.shape[0], Qidxs.shape[0]
-    if M < 1 or M > 256 or N % 128 or K % 64:
+    if M < 1 or M > 256 or N % 128 or K % 128:
         return None
     L = lib()
     key = (x.device.index, N)

@@ -601,7 +601,7 @@ def test_persistent_decode_step_under_cuda_graph_generates_same_tokens():
 # tcgen05 decode + GEMM (umma_gemm.cu): 17 <= M <= 256
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M", [17, 32, 33, 64, 100, 128, 200, 256])
-@pytest.mark.parametrize("N,K", [(128, 64), (512, 4096), (4096, 4096), (1408, 1024 + 64)])
+@pytest.mark.parametrize("N,K", [(128, 128), (512, 4096), (4096, 4096), (1408, 1024 + 128)])
 def test_e8p_mm_umma_matches_oracle(M, N, K):
     from quip_for_all_b200 import _native
     _native.set_option("umma", 1)

@@ -13,6 +13,7 @@ from quip_for_all_b200.modeling import LlamaDecodeEngine, llama_config, make_ran
 
 nl = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 ctx = int(sys.argv[2]) if len(sys.argv) > 2 else 384
+cta = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 dev = torch.device("cuda:0")
 model = make_random_quantized_llama(llama_config("llama2-7b", num_hidden_layers=nl), "E8P12", seed=0, device=dev)
 eng = LlamaDecodeEngine(model, max_cache_len=ctx + 64, use_cuda_graph=False)
@@ -24,6 +25,7 @@ L = _bind()
 for _ in range(5):
     eng.step()
 torch.cuda.synchronize()
+L.quipb200_decode_step_debug_cta(cta)
 L.quipb200_decode_step_debug(buf.data_ptr())
 eng.step()
 torch.cuda.synchronize()
