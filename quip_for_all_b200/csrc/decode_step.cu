@@ -134,6 +134,21 @@ __device__ __forceinline__ void gemv_prefetch_l2(const GemvCfg& c, int tid) {
   for (int i = tid; i < lines; i += DS_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * 128));
 }
 
+// Packed codes of this CTA's share of a later stage -> L2.  Issued when the current stage's GEMV starts, so the HBM
+// fetch of stage X+1 runs under the (compute-bound) GEMV of stage X and never in front of a prologue's own requests.
+__device__ __forceinline__ void prefetch_stage(const quipb200_linear_t* const* mem, const int* G, int n, int bid, int tid) {
+  int j, bx = 0;
+  j = -1;
+  int begin = 0;
+  for (int i = 0; i < n; i++) {
+    if (bid >= begin && bid < begin + G[i]) { j = i; bx = bid - begin; }
+    begin += G[i];
+  }
+  if (j < 0) return;
+  const GemvCfg c = make_cfg(*mem[j], bx, G[j]);
+  gemv_prefetch_l2(c, tid);
+}
+
 // xq: swizzled 16-byte activation records in shared memory; red: [nrows][C] chunk partials
 __device__ __forceinline__ void gemv_run(uint4 (&cw)[DS_UNROLL], const GemvCfg& c, const uint4* xq,
                                          const unsigned char* tab, int* red, int warp, int lane, uint64_t pol) {
@@ -518,17 +533,21 @@ __device__ __forceinline__ uint4 out_side_load(const __half* acc, int warp, int 
   return __ldcg(reinterpret_cast<const uint4*>(acc) + warp * 32 + lane);
 }
 __device__ __forceinline__ void out_side_m(const quipb200_linear_t& Lp, const uint4& oct, bool has_resid, const Stg& st,
-                                           const HFrag& A, float* S, int warp, int lane, float (&f)[8]) {
+                                           const HFrag& A, float* S, int warp, int lane, float (&f)[8],
+                                           long long* dbg = nullptr) {
   const bool has_sv = Lp.SV != nullptr, has_bias = Lp.bias != nullptr;
   const __half* wpc = reinterpret_cast<const __half*>(Lp.wscale_pc);
   uint32_t p[4];
   warp_octets_to_frag(oct, st.wscr + warp * 256, lane, p);
+  if (dbg) dbg[40] = clock64() + (p[0] & 0);
   if (wpc) {
 #pragma unroll
     for (int q = 0; q < 4; q++) p[q] = as_u32(__hmul2(as_h2(p[q]), as_h2(ldg_h2(wpc, idx_block(warp, lane, q)))));   // qlinear.py:107
   }
   cp_async_wait_all();                                                               // staged vectors: visible after the
+  if (dbg) dbg[41] = clock64();
   fwht4096_frag(p, A, S, warp, lane, f);                                             // exchange barrier inside; x 1/64
+  if (dbg) dbg[42] = clock64() + (__float_as_int(f[0]) & 0);
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     const int i = idx_spread(warp, lane, q);
@@ -633,7 +652,7 @@ constexpr int DS_EB = 3;   // blocks per warp in flight (K <= 48 in one round)
 __device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, const quipb200_linear_t& Lu,
                                                 const quipb200_linear_t& Ld, const __half* acc_g, const __half* acc_u,
                                                 const __half* hk_blob, const BlkBuf& bb, const HFrag& A, __half* wscr,
-                                                const GemvCfg& pf, float* fred, uint4* xq, int tid, long long* dbg) {
+                                                float* fred, uint4* xq, int tid, long long* dbg) {
 #define DS_E(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   const int lane = tid & 31, warp = tid >> 5;
   const int K = Lg.K_right, Kp = (K + 15) / 16 * 16, LS = bb.LS;
@@ -691,7 +710,6 @@ __device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, con
         ua[r] = __ldcg(reinterpret_cast<const uint4*>(acc_u) + b * 32 + lane);
       }
     }
-    if (b0 == warp) gemv_prefetch_l2(pf, tid);   // down_proj's packed codes -> L2, queued behind this stage's own requests
 #pragma unroll
     for (int r = 0; r < DS_EB; r++) {
       const int b = b0 + r * DS_WARPS;
@@ -902,6 +920,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
   if (bid == 0 && tid < hid8) reinterpret_cast<uint4*>(p.ws.hA)[tid] = reinterpret_cast<const uint4*>(p.h_in)[tid];
   __syncthreads();
 
+  {
+    const quipb200_linear_t* nx[3] = {&s_desc[0].q, &s_desc[0].k, &s_desc[0].v};
+    prefetch_stage(nx, p.geo.G_A, 3, bid, tid);
+  }
   int pos = (int)(*P.pos);
   if (pos >= P.max_len) pos = P.max_len - 1;
   if (pos < 0) pos = 0;
@@ -919,7 +941,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         const quipb200_linear_t L = (j == 0) ? Ly.q : (j == 1 ? Ly.k : Ly.v);
         const GemvCfg c = make_cfg(L, bx, p.geo.G_A[j]);
         DS_ST(1);
-        if (!p.use_mma || l == 0) gemv_prefetch_l2(c, tid);
         float f[8];
         float xs;
         if (p.use_mma) {
@@ -938,7 +959,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             stg_vec(stg.nw, reinterpret_cast<const __half*>(Ly.input_norm_w), L.in_features, tid);
             stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
             const uint4 oct = out_side_load(p.ws.acc[SL_D], warp, lane);
-            gemv_prefetch_l2(c, tid);      // after this stage's own (latency-critical) requests: the SM's load queue is FIFO
             out_side_m(Lp, oct, true, stg, hfrag, XS, warp, lane, f);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
@@ -972,11 +992,18 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         }
         if (bx == 0 && tid == 0) p.ws.xscale[SL_Q + j] = xs;
         DS_ST(3);
+        {
+          const quipb200_linear_t* nx[1] = {&Ly.o};
+          prefetch_stage(nx, &p.geo.G_C, 1, bid, tid);
+        }
         gemv_first(cw, c, warp, lane, pol);
         gemv_run(cw, c, xq, tab, red, warp, lane, pol);
         DS_ST(4);
         gemv_store(c, red, p.ws.acc[SL_Q + j], xs, tid);
         DS_ST(5);
+      } else {   // idle in this stage, not in the next
+        const quipb200_linear_t* nx[1] = {&Ly.o};
+        prefetch_stage(nx, &p.geo.G_C, 1, bid, tid);
       }
       grid_barrier(p.ws.bar, bar_target, nblk);
       DS_ST(6);
@@ -1174,7 +1201,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
           for (int i = tid; i < n4; i += DS_THREADS) cp_async16(stg.atto + i * 4, p.ws.att_o + i * 4);
           stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
         }
-        gemv_prefetch_l2(c, tid);
         if (tid < P.n_heads) {
           float m[DS_MAX_SPLITS], lsum[DS_MAX_SPLITS], M = -INFINITY, den = 0.f;
 #pragma unroll
@@ -1248,10 +1274,17 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         }
         if (bx == 0 && tid == 0) p.ws.xscale[SL_O] = xs;
         DS_ST(13);
+        {
+          const quipb200_linear_t* nx[2] = {&Ly.gate, &Ly.up};
+          prefetch_stage(nx, p.geo.G_D, 2, bid, tid);
+        }
         gemv_first(cw, c, warp, lane, pol);
         gemv_run(cw, c, xq, tab, red, warp, lane, pol);
         DS_ST(14);
         gemv_store(c, red, p.ws.acc[SL_O], xs, tid);
+      } else {
+        const quipb200_linear_t* nx[2] = {&Ly.gate, &Ly.up};
+        prefetch_stage(nx, p.geo.G_D, 2, bid, tid);
       }
       grid_barrier(p.ws.bar, bar_target, nblk);
       DS_ST(15);
@@ -1263,7 +1296,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
       if (j >= 0) {
         const quipb200_linear_t L = (j == 0) ? Ly.gate : Ly.up;
         const GemvCfg c = make_cfg(L, bx, p.geo.G_D[j]);
-        if (!p.use_mma) gemv_prefetch_l2(c, tid);
         float f[8];
         float xs;
         const quipb200_linear_t Lp = Ly.o;
@@ -1274,8 +1306,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
           stg_vec(stg.nw, reinterpret_cast<const __half*>(Ly.post_norm_w), L.in_features, tid);
           stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
           const uint4 oct = out_side_load(p.ws.acc[SL_O], warp, lane);
-          gemv_prefetch_l2(c, tid);
-          out_side_m(Lp, oct, true, stg, hfrag, XS, warp, lane, f);
+          out_side_m(Lp, oct, true, stg, hfrag, XS, warp, lane, f, (dbg && l == 1) ? dbg : nullptr);
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             const __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
@@ -1296,10 +1327,17 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         }
         if (bx == 0 && tid == 0) p.ws.xscale[SL_G + j] = xs;
         DS_ST(17);
+        {
+          const quipb200_linear_t* nx[1] = {&Ly.down};
+          prefetch_stage(nx, &p.geo.G_E, 1, bid, tid);
+        }
         gemv_first(cw, c, warp, lane, pol);
         gemv_run(cw, c, xq, tab, red, warp, lane, pol);
         DS_ST(18);
         gemv_store(c, red, p.ws.acc[SL_G + j], xs, tid);
+      } else {
+        const quipb200_linear_t* nx[1] = {&Ly.down};
+        prefetch_stage(nx, &p.geo.G_E, 1, bid, tid);
       }
       grid_barrier(p.ws.bar, bar_target, nblk);
       DS_ST(19);
@@ -1314,9 +1352,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         float xs;
         if (L.K_left > 1) {
           xs = stage_e_blocks(Ly.gate, Ly.up, L, p.ws.acc[SL_G], p.ws.acc[SL_U], reinterpret_cast<const __half*>(Ly.mlp_hk), bb,
-                              hfrag, reinterpret_cast<__half*>(rb.A), c, rb.fred, xq, tid, (dbg && l == 1) ? dbg : nullptr);
+                              hfrag, reinterpret_cast<__half*>(rb.A), rb.fred, xq, tid, (dbg && l == 1) ? dbg : nullptr);
         } else {
-          gemv_prefetch_l2(c, tid);
           float g[8], u[8];
           {
             const quipb200_linear_t Lg = Ly.gate;
@@ -1339,10 +1376,19 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         }
         DS_ST(22);
         if (bx == 0 && tid == 0) p.ws.xscale[SL_D] = xs;
+        if (l + 1 < P.n_layers) {
+          const quipb200_decode_layer_t& Ln = s_desc[(l + 1) & 1];
+          const quipb200_linear_t* nx[3] = {&Ln.q, &Ln.k, &Ln.v};
+          prefetch_stage(nx, p.geo.G_A, 3, bid, tid);
+        }
         gemv_first(cw, c, warp, lane, pol);
         gemv_run(cw, c, xq, tab, red, warp, lane, pol);
         DS_ST(23);
         gemv_store(c, red, p.ws.acc[SL_D], xs, tid);
+      } else if (l + 1 < P.n_layers) {
+        const quipb200_decode_layer_t& Ln = s_desc[(l + 1) & 1];
+        const quipb200_linear_t* nx[3] = {&Ln.q, &Ln.k, &Ln.v};
+        prefetch_stage(nx, p.geo.G_A, 3, bid, tid);
       }
       grid_barrier(p.ws.bar, bar_target, nblk);
       DS_ST(24);
