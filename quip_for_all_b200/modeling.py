@@ -162,6 +162,7 @@ class LlamaDecodeEngine:
         self.hidden_out = torch.zeros(1, 1, cfg.hidden_size, dtype=dt, device=self.dev)
         self.use_graph = use_cuda_graph
         self.graph = None
+        self.launches_per_step = None
         self.fused = None
         self.persistent = None
         if fused:
@@ -302,9 +303,12 @@ class LlamaDecodeEngine:
                 self._step_body()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         self.pos.copy_(saved[1])
+        from . import _native
         g = torch.cuda.CUDAGraph()
+        lc0 = _native.launch_count()
         with torch.cuda.graph(g):
             self._step_body()
+        self.launches_per_step = _native.launch_count() - lc0     # kernels of ours enqueued per replay
         self.graph = g
         self.tok.copy_(saved[0]); self.pos.copy_(saved[1])
         self.k_cache.copy_(saved[2]); self.v_cache.copy_(saved[3])

@@ -134,7 +134,7 @@ class LlamaStage:
             e.capture()
 
 
-def run_pipeline_bench(a, metric):
+def run_pipeline_bench(a, metric, clock_sampler_cls=None):
     """bench.py body for WORLD_SIZE > 1 (launched by torchrun, one rank per GPU)."""
     import json
     world = int(os.environ["WORLD_SIZE"])
@@ -154,9 +154,14 @@ def run_pipeline_bench(a, metric):
     # fill + warm-up ticks
     for _ in range(world - 1 + max(a.warmup, 3)):
         pipe.tick()
+    from . import _native
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
+    clocks = clock_sampler_cls(local) if (clock_sampler_cls is not None and rank == 0) else None
+    if clocks is not None:
+        clocks.start()
+    lc0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
@@ -165,9 +170,30 @@ def run_pipeline_bench(a, metric):
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
+    ck = clocks.stop() if clocks is not None else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = ms.item()
+    # own kernels enqueued per tick on this rank (graph replays re-run what was captured: count one eager tick)
+    launches = torch.tensor([float(getattr(stage.engines[0], "launches_per_step", 0) or 0)], device=dev)
+    dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    del lc0
+    # ---- e2e: every tick the emitted token id goes device -> pinned host on the last stage and the next input token
+    # pinned host -> device on the first stage, with a stream sync per tick; wall clock, max over ranks
+    h_tok = torch.zeros(1, 1, dtype=torch.long).pin_memory()
+    d_tok_in = torch.zeros(1, 1, dtype=torch.long, device=dev)
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        if stage.first:
+            d_tok_in.copy_(h_tok, non_blocking=True)
+        pipe.tick()
+        if stage.last:
+            h_tok.copy_(stage.engines[0].tok, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_tok_s = a.steps / t_e2e.item()
     if rank == 0:
         from .modeling import LLAMA2_SHAPES
         line = {
@@ -181,7 +207,10 @@ def run_pipeline_bench(a, metric):
                                    f"packed weights, synthetic {a.prompt_len}-token prompts",
                        "parallelism": f"pp{world} (whole decoder layers per stage, NCCL p2p ring exchange per tick)",
                        "l2": "inputs larger than L2 (each stage streams its slice of the 1.6 GB of codes per tick)"},
-            "e2e": None, "gpu_launches": None, "clocks": None,
+            "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8,
+                    "how": "per tick: token id pinned host -> device (first stage) and device -> pinned host (last stage), "
+                           "stream sync on every rank, wall clock, max over ranks"},
+            "gpu_launches": int(launches.item()) * a.steps, "clocks": ck,
         }
         print(json.dumps(line))
     dist.destroy_process_group()
