@@ -94,6 +94,21 @@ int quipb200_mm(int codebook, const void* x_f16, const void* qidxs, const void* 
                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Batched fused rotation (M >= 17 path of QuantLinear.forward): one pass over [M, n] instead of the reference's
+ * x*SU -> F.pad -> hadamard -> hadK.T.contiguous() -> hadK @ .. (input side, qlinear.py:91,99-100, quant.py:72-88) or
+ * hadamard -> hadK @ .. -> [:out_features] -> *SV -> +bias (output side, qlinear.py:108-114):
+ *     y[M, out_features] = f16( f16( (M_K (x) H_{n/K}) f16(x * pre) * scale )[:out_features] * post ) + bias
+ *   pre / post / bias: fp16 vectors or NULL; hk_padded: fp16 [Kp][Kp] (Kp = roundup16(K)), zero padded, holding the
+ *   coefficient matrix M_K[k_out][k_in] (hadK for the output side, hadK^T for the input side) or NULL when K == 1;
+ *   scale as passed to quip_lib::hadamard (quant.py:75: scale / sqrt(n/K)).
+ *   Covered: n == 4096 with K == 1, and n == 256*K with K <= 64; else QUIPB200_EUNSUPPORTED (caller keeps the
+ *   reference's op sequence over quipb200_hadamard).  in/out_features % 8 == 0, row pitches % 8 == 0.
+ * ------------------------------------------------------------------------------------------- */
+int quipb200_rotate_batched(const void* x_f16, int64_t ldx, void* y_f16, int64_t ldy, const void* pre, const void* post,
+                            const void* bias, const void* hk_padded, int M, int in_features, int out_features,
+                            int n, int K, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Batched decode + GEMM on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulators), 1 <= M <= 256:
  *   same contract as quipb200_mm for E8P12, replacing the reference's M >= 32 route
  *   "decompress_e8p_origorder + input @ W.T" (codebook/e8p12.py:153-155, origin_order.cu:837-885) without

@@ -1,0 +1,179 @@
+// Batched fused rotation for the M >= 17 path of QuantLinear.forward (qlinear.py:90-114):
+//
+//   input side :  y = f16( (hadK^T (x) H_L) f16(x * SU) * scale )                       quant.py:72-88, qlinear.py:91,99
+//   output side:  y = f16( f16( (hadK (x) H_L) x * scale )[:out] * SV ) + bias          qlinear.py:108-114
+//
+// The reference runs these as 3-6 separate passes over the [M, n] activation tensor (x*SU, F.pad, the external
+// fast_hadamard_transform kernel, hadK.T.contiguous(), a batched K x K matmul, the slice, *SV, +bias): at prefill
+// sizes (M = 65 536) that is several GB of HBM traffic per linear and costs more than the GEMM itself
+// (profiles/README.md).  Here each row is read once and written once: one 512-thread CTA per row, the transform on
+// the legacy tensor path (fwht_mma.cuh: H_4096 = H_16^(x)3 with one shared-memory exchange, or K blocks of H_256 =
+// H_16^(x)2 held by one warp each), the K x K mix as mma.sync tiles in shared memory, SU / SV / bias applied in
+// registers with the reference's fp16 rounding points.  HBM-bound by construction: 2 * n * 2 bytes per row.
+//
+// Covered: n == 4096 with K == 1, and n == K * 256 with K <= 64 (Llama-2-7B: 4096 and 11008 = 43 * 256).  Anything
+// else returns QUIPB200_EUNSUPPORTED and the caller keeps the reference's op sequence (quipb200_hadamard + matmul).
+#include "fwht_mma.cuh"
+#include "ql_device.cuh"
+
+namespace qb {
+
+constexpr int RB_THREADS = 512;
+constexpr int RB_WARPS = RB_THREADS / 32;
+constexpr int RB_LS = 256 + 8;      // row stride (halfs) of the block buffer: ldmatrix friendly
+
+struct RotBArgs {
+  const __half* x; int64_t ldx;     // [M][in_feat]
+  __half* y; int64_t ldy;           // [M][out_feat]
+  const __half* pre;                // [in_feat]  or NULL  (SU)
+  const __half* post;               // [out_feat] or NULL  (SV)
+  const __half* bias;               // [out_feat] or NULL
+  const __half* hk;                 // [Kp][Kp] zero-padded coefficient matrix M[k_out][k_in], or NULL when K == 1
+  int M, in_feat, out_feat, n, K;
+  float post_scale;                 // scale * sqrt(n / K): what is left after the 1/sqrt(L) built into the H_16/4 factors
+};
+
+__device__ __forceinline__ uint4 hmul2x4(const uint4& a, const uint4& b) {
+  uint4 r;
+  r.x = as_u32(__hmul2(as_h2(a.x), as_h2(b.x)));
+  r.y = as_u32(__hmul2(as_h2(a.y), as_h2(b.y)));
+  r.z = as_u32(__hmul2(as_h2(a.z), as_h2(b.z)));
+  r.w = as_u32(__hmul2(as_h2(a.w), as_h2(b.w)));
+  return r;
+}
+__device__ __forceinline__ uint4 hadd2x4(const uint4& a, const uint4& b) {
+  uint4 r;
+  r.x = as_u32(__hadd2(as_h2(a.x), as_h2(b.x)));
+  r.y = as_u32(__hadd2(as_h2(a.y), as_h2(b.y)));
+  r.z = as_u32(__hadd2(as_h2(a.z), as_h2(b.z)));
+  r.w = as_u32(__hadd2(as_h2(a.w), as_h2(b.w)));
+  return r;
+}
+
+// ---- n == 4096, K == 1: thread t owns octet t of the row --------------------------------------------------
+__global__ void __launch_bounds__(RB_THREADS) rot4096_kernel(const __grid_constant__ RotBArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* S = reinterpret_cast<float*>(smem);                                   // 16 x DS_XROW floats
+  __half* wscr = reinterpret_cast<__half*>(smem + 16 * DS_XROW * sizeof(float));   // [16][256]
+  __half* V = wscr + RB_WARPS * 256;                                           // [4096]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const HFrag hf = make_hfrag(lane);
+  const bool vin = tid * 8 < a.in_feat, vout = tid * 8 < a.out_feat;
+  uint4 pre = make_uint4(0, 0, 0, 0), post = pre, bias = pre;
+  if (a.pre && vin) pre = __ldg(reinterpret_cast<const uint4*>(a.pre) + tid);
+  if (a.post && vout) post = __ldg(reinterpret_cast<const uint4*>(a.post) + tid);
+  if (a.bias && vout) bias = __ldg(reinterpret_cast<const uint4*>(a.bias) + tid);
+  const float sc = a.post_scale;
+  for (int row = blockIdx.x; row < a.M; row += gridDim.x) {
+    uint4 oct = make_uint4(0, 0, 0, 0);
+    if (vin) oct = ldg_stream_v4(a.x + (size_t)row * a.ldx + tid * 8);
+    if (a.pre) oct = hmul2x4(oct, pre);                                        // qlinear.py:91 (fp16 tensor)
+    uint32_t p[4];
+    warp_octets_to_frag(oct, wscr + warp * 256, lane, p);                      // block layout: warp = top 4 index bits
+    float r[8];
+    fwht4096_frag(p, hf, S, warp, lane, r);                                    // spread layout, x 1/64
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      *reinterpret_cast<__half2*>(V + idx_spread(warp, lane, q)) = __floats2half2_rn(r[2 * q] * sc, r[2 * q + 1] * sc);
+    __syncthreads();
+    if (vout) {
+      uint4 o = *reinterpret_cast<const uint4*>(V + tid * 8);
+      if (a.post) o = hmul2x4(o, post);                                        // qlinear.py:112
+      if (a.bias) o = hadd2x4(o, bias);                                        // qlinear.py:114
+      stg_stream_v4(a.y + (size_t)row * a.ldy + tid * 8, o);
+    }
+  }
+}
+
+// ---- n == K * 256: warp w owns blocks w, w + 16, ..; K x K mix on the tensor path in shared memory ----------
+__global__ void __launch_bounds__(RB_THREADS) rotblk_kernel(const __grid_constant__ RotBArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int K = a.K, Kp = (K + 15) / 16 * 16;
+  __half* T = reinterpret_cast<__half*>(smem);                                 // [(K + 1)][RB_LS]
+  __half* hk = T + (size_t)(K + 1) * RB_LS;                                    // [Kp][Kp]
+  __half* wscr = hk + (size_t)Kp * Kp;                                         // [16][256]
+  float* dummy = reinterpret_cast<float*>(wscr + RB_WARPS * 256);              // 64 floats (unused reduction scratch)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const HFrag hf = make_hfrag(lane);
+  if (K > 1)
+    for (int i = tid; i < (Kp * Kp) >> 3; i += RB_THREADS)
+      reinterpret_cast<uint4*>(hk)[i] = __ldg(reinterpret_cast<const uint4*>(a.hk) + i);
+  const int noct_in = a.in_feat >> 3, noct_out = a.out_feat >> 3;
+  const float sc = a.post_scale;
+  RotSmem rs;
+  rs.s = dummy; rs.s2 = dummy; rs.pp = 1; rs.t = T; rs.hk = hk; rs.red = dummy; rs.Ls = RB_LS; rs.log2L = 8;
+  for (int row = blockIdx.x; row < a.M; row += gridDim.x) {
+    const __half* xr = a.x + (size_t)row * a.ldx;
+    for (int b = warp; b < K; b += RB_WARPS) {
+      const int oi = b * 32 + lane;
+      uint4 oct = make_uint4(0, 0, 0, 0);
+      if (oi < noct_in) {
+        oct = ldg_stream_v4(xr + oi * 8);
+        if (a.pre) oct = hmul2x4(oct, __ldg(reinterpret_cast<const uint4*>(a.pre) + oi));
+      }
+      uint32_t p[4];
+      warp_octets_to_frag(oct, wscr + warp * 256, lane, p);
+      float r[8];
+      fwht256_frag(p, hf, r);                                                  // x 1/16
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        *reinterpret_cast<__half2*>(T + b * RB_LS + frag_x(lane, q) * 16 + frag_y(lane, q)) =
+            __floats2half2_rn(r[2 * q] * sc, r[2 * q + 1] * sc);              // register_lib.py:20 (fp16 out)
+    }
+    if (K > 1) rotate_mix(rs, K * 256, K, tid, RB_THREADS);                    // barrier, mma.sync tiles (quant.py:83), barrier
+    else __syncthreads();
+    __half* yr = a.y + (size_t)row * a.ldy;
+    for (int o = tid; o < noct_out; o += RB_THREADS) {
+      uint4 v = *reinterpret_cast<const uint4*>(T + (o >> 5) * RB_LS + (o & 31) * 8);
+      if (a.post) v = hmul2x4(v, __ldg(reinterpret_cast<const uint4*>(a.post) + o));
+      if (a.bias) v = hadd2x4(v, __ldg(reinterpret_cast<const uint4*>(a.bias) + o));
+      stg_stream_v4(yr + o * 8, v);
+    }
+    __syncthreads();      // T is rewritten by the next row
+  }
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" int quipb200_rotate_batched(const void* x, int64_t ldx, void* y, int64_t ldy, const void* pre, const void* post,
+                                       const void* bias, const void* hk_padded, int M, int in_features, int out_features,
+                                       int n, int K, float scale, void* stream) {
+  if (!x || !y || M < 0 || K < 1 || n < 1 || n % K) return QUIPB200_EINVAL;
+  if (M == 0) return 0;
+  if (in_features > n || out_features > n || (in_features & 7) || (out_features & 7) || (ldx & 7) || (ldy & 7))
+    return QUIPB200_EUNSUPPORTED;
+  if (!aligned16(x) || !aligned16(y) || !aligned16(pre) || !aligned16(post) || !aligned16(bias) || !aligned16(hk_padded))
+    return QUIPB200_EALIGN;
+  const int L = n / K;
+  RotBArgs a{};
+  a.x = (const __half*)x; a.ldx = ldx; a.y = (__half*)y; a.ldy = ldy;
+  a.pre = (const __half*)pre; a.post = (const __half*)post; a.bias = (const __half*)bias; a.hk = (const __half*)hk_padded;
+  a.M = M; a.in_feat = in_features; a.out_feat = out_features; a.n = n; a.K = K;
+  a.post_scale = scale * sqrtf((float)L);
+  const int sms = quipb200_sm_count();
+  if (sms < 1) return (int)cudaErrorNoDevice;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K == 1 && n == 4096) {
+    const size_t smem = 16 * DS_XROW * sizeof(float) + RB_WARPS * 256 * 2 + 4096 * 2;
+    cudaError_t e = cudaFuncSetAttribute(rot4096_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int grid = M < sms * 4 ? M : sms * 4;
+    rot4096_kernel<<<grid, RB_THREADS, smem, st>>>(a);
+  } else if (L == 256 && K <= 64 && (K == 1 || hk_padded)) {
+    const int Kp = (K + 15) / 16 * 16;
+    const size_t smem = (size_t)(K + 1) * RB_LS * 2 + (size_t)Kp * Kp * 2 + RB_WARPS * 256 * 2 + 64 * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(rotblk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = (int)((200 * 1024) / (smem + 1024));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    const int grid = M < sms * per_sm ? M : sms * per_sm;
+    rotblk_kernel<<<grid, RB_THREADS, smem, st>>>(a);
+  } else {
+    return QUIPB200_EUNSUPPORTED;
+  }
+  QB_LAUNCH_CHECK();
+  return 0;
+}

@@ -84,6 +84,35 @@ class QuantLinear(nn.Module):
             return g
         return cb.grid_packed_abs
 
+    def _batched_fused_ok(self, x):
+        from .register_lib import rotate_supported
+        if not x.is_cuda or x.dtype != torch.float16 or self.weight_dtype != torch.float16:
+            return False
+        if self.in_features % 8 or self.out_features % 8:
+            return False
+        for t in (self.SU, self.SV, self.bias, self.had_left, self.had_right):
+            if t is not None and t.dtype != torch.float16:
+                return False
+        return rotate_supported(self.q_in_features, self.K_left) and rotate_supported(self.q_out_features, self.K_right)
+
+    def _hk_padded(self, side):
+        """Zero-padded [Kp, Kp] coefficient matrix M[k_out][k_in] of the K x K block mix: hadK^T on the input side
+        (quant.py:79-80), hadK on the output side.  Cached; rebuilt when the buffer changes."""
+        had = self.had_left if side == "left" else self.had_right
+        K = self.K_left if side == "left" else self.K_right
+        if K == 1 or had is None:
+            return None
+        cache = self.__dict__.setdefault("_hk_cache", {})
+        key = (side, had.data_ptr(), had._version, had.device)
+        hit = cache.get(side)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        Kp = (K + 15) // 16 * 16
+        pad = torch.zeros(Kp, Kp, dtype=torch.float16, device=had.device)
+        pad[:K, :K] = had.t() if side == "left" else had
+        cache[side] = (key, pad)
+        return pad
+
     def forward(self, input):
         x = input.reshape(-1, input.shape[-1])
         x_dtype = x.dtype
@@ -108,6 +137,19 @@ class QuantLinear(nn.Module):
                 float(self.wscale_float), float(getattr(cb, "opt_resid_scale", 0.0) or 0.0))
             if x_dtype != torch.float16:
                 out = out.to(x_dtype)
+            return out.view(*input.shape[:-1], out.shape[-1])   # SV and bias already applied
+        elif self._batched_fused_ok(x):
+            # M >= 17: same chain, the two rotations (with SU / SV / bias and the slice folded in) as one pass each
+            import math
+            out = torch.ops.quip_lib.rotate_fused(
+                x, self.SU, self._hk_padded("left"), None, None, self.q_in_features, self.K_left, self.q_in_features,
+                float(self.wscale_float) / math.sqrt(self.q_in_features // self.K_left))
+            out = self.codebook(out, self.Qidxs)
+            if self.per_channel:
+                out = out * self.Wscale
+            out = torch.ops.quip_lib.rotate_fused(
+                out, None, self._hk_padded("right"), self.SV, self.bias, self.q_out_features, self.K_right,
+                self.out_features, 1.0 / math.sqrt(self.q_out_features // self.K_right))
             return out.view(*input.shape[:-1], out.shape[-1])   # SV and bias already applied
         else:
             # the reference's op sequence (qlinear.py:90-112)

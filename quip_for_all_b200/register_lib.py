@@ -261,6 +261,34 @@ _define("hi_mm_origorder(Tensor x, Tensor Qidxs) -> Tensor", _hi_mm, _fake_mm)
 
 
 # ------------------------------------------------------------------------------------------------
+# batched fused rotation (new)                          quant.py:72-88 + qlinear.py:91, :108-114
+# ------------------------------------------------------------------------------------------------
+def rotate_supported(n: int, K: int) -> bool:
+    return (K == 1 and n == 4096) or (n == 256 * K and K <= 64)
+
+
+def _rotate_fused(x: Tensor, pre, hk, post, bias, n: int, K: int, out_features: int, scale: float) -> Tensor:
+    if x.dim() != 2 or x.dtype != torch.float16:
+        raise RuntimeError("quip_lib::rotate_fused: x must be fp16 [M, in_features]")
+    M, fin = x.shape
+    y = torch.empty((M, out_features), dtype=torch.float16, device=x.device)
+    if M == 0:
+        return y
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    with torch.cuda.device(x.device):
+        check(lib().quipb200_rotate_batched(_ptr(x), x.stride(0), _ptr(y), y.stride(0), _ptr(pre), _ptr(post), _ptr(bias),
+                                            _ptr(hk), M, fin, out_features, n, K, float(scale), _stream()),
+              "rotate_fused")
+    return y
+
+
+_define("rotate_fused(Tensor x, Tensor? pre, Tensor? hk, Tensor? post, Tensor? bias, int n, int K, int out_features, "
+        "float scale) -> Tensor", _rotate_fused,
+        lambda x, pre, hk, post, bias, n, K, out_features, scale: x.new_empty((x.shape[0], out_features)))
+
+
+# ------------------------------------------------------------------------------------------------
 # fused QuantLinear.forward (new)                                            qlinear.py:87-115
 # ------------------------------------------------------------------------------------------------
 FUSED_CODEBOOKS = ("E8P12", "E8P12RVQ4B", "D4")

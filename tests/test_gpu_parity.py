@@ -633,3 +633,54 @@ def test_e8p_mm_umma_unsupported_shapes_take_dense_path():
     x = torch.randn(40, 256, generator=g).half()
     out = torch.ops.quip_lib.e8p_mm_origorder(x.to(DEV), q.to(DEV), _grid())
     _mm_check(out, x, qo.decompress_e8p(q.numpy()))
+
+
+# ------------------------------------------------------------------------------------------------
+# batched fused rotation (rotate_batched.cu) and the M >= 17 forward built on it
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,K,fin,fout", [(4096, 1, 4096, 4096), (4096, 1, 4000, 3968), (11008, 43, 11008, 11008),
+                                          (2816, 11, 2816, 2800), (256, 1, 256, 256)])
+@pytest.mark.parametrize("M", [1, 17, 300])
+def test_rotate_fused_matches_unfused_op_sequence(n, K, fin, fout, M):
+    """One-pass rotation == the reference's pass-per-op sequence (x*pre -> pad -> hadamard -> hadK @ -> slice -> *post
+    -> +bias) built from the individual quip_lib ops, to fp16 rounding of the last step."""
+    import math
+    from quip_for_all_b200.quant import matmul_hadU_cuda
+    g = torch.Generator().manual_seed(n + K + M)
+    x = torch.randn(M, fin, generator=g).half().to(DEV)
+    pre = (1 + 0.1 * torch.randn(fin, generator=g)).half().to(DEV)
+    post = (1 + 0.1 * torch.randn(fout, generator=g)).half().to(DEV)
+    bias = (0.1 * torch.randn(fout, generator=g)).half().to(DEV)
+    hadK = None
+    hk = None
+    if K > 1:
+        qm, _ = torch.linalg.qr(torch.randn(K, K, generator=g))
+        hadK = qm.half().to(DEV)
+        Kp = (K + 15) // 16 * 16
+        hk = torch.zeros(Kp, Kp, dtype=torch.float16, device=DEV)
+        hk[:K, :K] = hadK
+    scale = 0.37 / math.sqrt(n // K)
+    y = torch.ops.quip_lib.rotate_fused(x, pre, hk, post, bias, n, K, fout, scale)
+    ref = matmul_hadU_cuda(x * pre, hadK, K, n, scale=0.37)[..., :fout] * post + bias
+    assert y.shape == ref.shape
+    d = (y.float() - ref.float()).abs().max().item()
+    assert d <= 2.0 ** -9 * ref.float().abs().max().item(), (d, ref.float().abs().max().item())
+    # no pre / post / bias: plain rotation
+    y2 = torch.ops.quip_lib.rotate_fused(x, None, hk, None, None, n, K, n, scale)
+    ref2 = matmul_hadU_cuda(x, hadK, K, n, scale=0.37)
+    assert (y2.float() - ref2.float()).abs().max().item() <= 2.0 ** -9 * ref2.float().abs().max().item()
+
+
+@pytest.mark.parametrize("fin,fout,bias", [(4096, 11008, True), (11008, 4096, False), (4096, 4096, True)])
+@pytest.mark.parametrize("M", [17, 40, 300])
+def test_batched_forward_vs_oracle(fin, fout, bias, M):
+    layer = make_layer(fin, fout, "E8P12", bias=bias, seed=fin + M, device=DEV)
+    assert layer._batched_fused_ok(torch.empty(M, fin, dtype=torch.float16, device=DEV))
+    x = torch.randn(M, fin, generator=torch.Generator().manual_seed(M)).half()
+    with torch.no_grad():
+        y = layer(x.to(DEV))
+    ref = oracle_forward(layer, x, rounding="reference")
+    err = np.abs(y.float().cpu().numpy() - ref)
+    assert err.max() <= tol_of(ref), (err.max(), tol_of(ref))
+    ref64 = oracle_forward(layer, x, rounding="none")
+    assert np.abs(y.float().cpu().numpy() - ref64).max() <= tol_of(ref64)
