@@ -44,7 +44,7 @@ struct DsWs {            // global scratch (device pointers)
   __half* hA;            // layer input (residual of the attention block)
   __half* hB;            // post-attention hidden (residual of the MLP block)
   __half* acc[SL_N];     // f16(integer dot product * xscale/4) of each linear: the reference's fp16 mm output
-  float* att_o;          // [nh][S][hd] un-normalised partial attention outputs
+  __half* att_o;         // [nh][S][hd] normalised partial attention outputs (fp16: halves the combine stage's traffic)
   float* att_ml;         // [nh][S][2]  running max / sum of each partial
 };
 
@@ -418,7 +418,7 @@ struct Stg {
   __half* resid;   // [4096] skip connection
   __half* nw;      // [4096] RMSNorm weight
   __half* su;      // [4096] SU of the consuming linear
-  float* atto;     // [n_heads * S * 128] split-KV partial outputs (stage C; aliases sv .. nw)
+  __half* atto;    // [n_heads * S * 128] split-KV partial outputs (stage C; aliases sv .. nw)
   __half* wscr;    // [16 warps][256] per-warp scratch (octet -> fragment layout)
 };
 __device__ __forceinline__ void stg_vec(__half* dst, const __half* src, int n, int tid) {
@@ -536,10 +536,65 @@ __device__ __forceinline__ void load_hk(__half* dst, const __half* src, int K, i
   }
 }
 
-__device__ __forceinline__ void mix_blocks(__half* T, __half* hk, int K, int LS, float* dummy, int tid) {
-  RotSmem r;
-  r.s = dummy; r.s2 = dummy; r.pp = 1; r.t = T; r.hk = hk; r.red = dummy; r.Ls = LS; r.log2L = 8;
-  rotate_mix(r, K * 256, K, tid, DS_THREADS);   // zero row + barrier + mma.sync tiles + barrier
+// In-place K x K mix  T <- M T  of one or two block buffers (256 columns, row stride LS) on the tensor path.  The A
+// fragments of the coefficient matrix are loaded once per call and reused for every 8-column tile the warp owns; both
+// buffers share one barrier pair.  fp16 operands, fp32 accumulate, one fp16 rounding: the reference's `hadK @ y`
+// (quant.py:83).  MT = Kp / 16.
+template <int MT>
+__device__ __forceinline__ void mix_tiles_one(__half* T, const __half* hk, int K, int LS, int warp, int lane) {
+  constexpr int Kp = MT * 16;
+  uint32_t af[MT][MT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+    for (int kt = 0; kt < MT; kt++)
+      ldmatrix_x4(af[mt][kt], hk + (size_t)(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * Kp + kt * 16 + (lane >> 4) * 8);
+  const int g = lane >> 2, tq = lane & 3;
+  for (int nt_i = warp; nt_i < 32; nt_i += DS_WARPS) {
+    const int c0 = nt_i << 3;
+    uint32_t bf[MT][2];
+#pragma unroll
+    for (int kt = 0; kt < MT; kt++) {
+      int r = kt * 16 + (lane & 15);
+      if (r >= K) r = K;                                   // the zero row
+      ldmatrix_x2_trans(bf[kt], T + (size_t)r * LS + c0);
+    }
+    float acc[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[mt][j] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < MT; kt++) mma_16816(acc[mt], af[mt][kt], bf[kt]);
+    }
+    __syncwarp();                                          // every lane has read its B fragments of this tile
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      if (r0 < K) *reinterpret_cast<__half2*>(T + (size_t)r0 * LS + c0 + tq * 2) = __floats2half2_rn(acc[mt][0], acc[mt][1]);
+      if (r1 < K) *reinterpret_cast<__half2*>(T + (size_t)r1 * LS + c0 + tq * 2) = __floats2half2_rn(acc[mt][2], acc[mt][3]);
+    }
+  }
+}
+template <int MT>
+__device__ __forceinline__ void mix_tiles(__half* T0, const __half* hk0, __half* T1, const __half* hk1, int K, int LS, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < LS; i += DS_THREADS) {             // the zero row read in place of rows >= K
+    T0[(size_t)K * LS + i] = __float2half_rn(0.f);
+    if (T1) T1[(size_t)K * LS + i] = __float2half_rn(0.f);
+  }
+  __syncthreads();
+  mix_tiles_one<MT>(T0, hk0, K, LS, warp, lane);
+  if (T1) mix_tiles_one<MT>(T1, hk1, K, LS, warp, lane);
+  __syncthreads();
+}
+__device__ __forceinline__ void mix_blocks(__half* T0, const __half* hk0, __half* T1, const __half* hk1, int K, int LS, int tid) {
+  switch ((K + 15) >> 4) {
+    case 1: mix_tiles<1>(T0, hk0, T1, hk1, K, LS, tid); break;
+    case 2: mix_tiles<2>(T0, hk0, T1, hk1, K, LS, tid); break;
+    case 3: mix_tiles<3>(T0, hk0, T1, hk1, K, LS, tid); break;
+    default: mix_tiles<4>(T0, hk0, T1, hk1, K, LS, tid); break;
+  }
 }
 
 // Stage-E input construction for K > 1:  x = rot_in_down( SU_d . silu(out(gate)) * out(up) ), records -> xq.
@@ -637,8 +692,7 @@ __device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, con
   }
   cp_async_wait_all();
   DS_E(31);
-  mix_blocks(bb.Tg, bb.hkg, K, LS, fred, tid);
-  mix_blocks(bb.Tu, bb.hku, K, LS, fred, tid);
+  mix_blocks(bb.Tg, bb.hkg, bb.Tu, bb.hku, K, LS, tid);
   DS_E(32);
   // SV / bias of gate and up, silu(gate) * up, SU of down, block transform of down's input (x wscale/16)
   const float ws_d = Ld.wscale_float;
@@ -669,7 +723,7 @@ __device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, con
     }
   }
   DS_E(33);
-  mix_blocks(bb.Tu, bb.hkd, K, LS, fred, tid);
+  mix_blocks(bb.Tu, bb.hkd, nullptr, nullptr, K, LS, tid);
   DS_E(34);
   float mx = 0.f;
   for (int b = warp; b < K; b += DS_WARPS) {
@@ -790,7 +844,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
   __half* const V = reinterpret_cast<__half*>(rb.fred + 64);   // fp16 [4096] (aliases the block buffers, unused in A / C / D)
   Stg stg;                                                   // staging vectors: behind V, same aliasing
   stg.sv = V + 4096; stg.bias = stg.sv + 4096; stg.resid = stg.bias + 4096; stg.nw = stg.resid + 4096;
-  stg.atto = reinterpret_cast<float*>(stg.sv);               // 64 KB (n_heads * S * 128 floats <= 16384)
+  stg.atto = stg.sv;                                          // 32 KB (n_heads * S * 128 halfs <= 16384)
   stg.su = stg.sv + 32768; stg.wscr = stg.su + 4096;
   long long* dbg = (p.dbg && bid == p.dbg_cta && tid == 0) ? p.dbg : nullptr;
 #define DS_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
@@ -1072,7 +1126,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
           float r = 0.f;
 #pragma unroll
           for (int g2 = 0; g2 < DS_PV_GROUPS; g2++) r += sout[g2 * 128 + tid];
-          __stcg(p.ws.att_o + (size_t)(h * S + s) * DS_HD + tid, r);
+          p.ws.att_o[(size_t)(h * S + s) * DS_HD + tid] = __float2half_rn(tot > 0.f ? r / tot : 0.f);
         }
         if (tid == 0) {
           __stcg(p.ws.att_ml + (size_t)(h * S + s) * 2, mx);
@@ -1095,8 +1149,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         // shared memory: [head][split] floats, computed once per CTA
         float* wsm = rb.fred + 64;   // aliases the block buffers (unused in this stage); n_heads * S <= 512 floats
         if (p.use_mma) {             // partial outputs and SU of o_proj -> shared memory, 16 bytes per request
-          const int n4 = (P.n_heads * S * DS_HD) >> 2;
-          for (int i = tid; i < n4; i += DS_THREADS) cp_async16(stg.atto + i * 4, p.ws.att_o + i * 4);
+          const int n8 = (P.n_heads * S * DS_HD) >> 3;
+          for (int i = tid; i < n8; i += DS_THREADS) cp_async16(stg.atto + i * 8, p.ws.att_o + i * 8);
           stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
         }
         if (tid < P.n_heads) {
@@ -1115,7 +1169,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
           const float inv = 1.0f / den;
 #pragma unroll
           for (int s = 0; s < DS_MAX_SPLITS; s++)
-            if (s < S) wsm[tid * S + s] = m[s] * inv;
+            if (s < S) wsm[tid * S + s] = m[s] * lsum[s] * inv;      // partial outputs are normalised by their own sum
         }
         cp_async_wait_all();
         __syncthreads();
@@ -1139,7 +1193,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
 #pragma unroll
                 for (int s = 0; s < DS_MAX_SPLITS; s++) {
                   if (s < S) {
-                    const float2 a = *reinterpret_cast<const float2*>(stg.atto + (h * S + s) * DS_HD + d);
+                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(stg.atto + (h * S + s) * DS_HD + d));
                     ax = fmaf(w[s], a.x, ax);
                     ay = fmaf(w[s], a.y, ay);
                   }
@@ -1159,10 +1213,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             for (int s = 0; s < DS_MAX_SPLITS; s++) {
               if (s < S) {
                 const float w = wsm[h * S + s];
-                const float4 a = __ldcg(reinterpret_cast<const float4*>(p.ws.att_o + (size_t)(h * S + s) * DS_HD + d));
-                const float4 b = __ldcg(reinterpret_cast<const float4*>(p.ws.att_o + (size_t)(h * S + s) * DS_HD + d) + 1);
-                f[0] = fmaf(w, a.x, f[0]); f[1] = fmaf(w, a.y, f[1]); f[2] = fmaf(w, a.z, f[2]); f[3] = fmaf(w, a.w, f[3]);
-                f[4] = fmaf(w, b.x, f[4]); f[5] = fmaf(w, b.y, f[5]); f[6] = fmaf(w, b.z, f[6]); f[7] = fmaf(w, b.w, f[7]);
+                float a8[8];
+                unpack_h8(__ldcg(reinterpret_cast<const uint4*>(p.ws.att_o + (size_t)(h * S + s) * DS_HD + d)), a8);
+#pragma unroll
+                for (int e = 0; e < 8; e++) f[e] = fmaf(w, a8[e], f[e]);
               }
             }
             round_h8(f);
@@ -1482,7 +1536,7 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
   out->off_hA = take((size_t)P->hidden * 2);
   out->off_hB = take((size_t)P->hidden * 2);
   for (int i = 0; i < SL_N; i++) out->off_acc[i] = take(accb[i]);
-  out->off_att_o = take((size_t)P->n_heads * S * DS_HD * sizeof(float));
+  out->off_att_o = take((size_t)P->n_heads * S * DS_HD * sizeof(__half));
   out->off_att_ml = take((size_t)P->n_heads * S * 2 * sizeof(float));
   out->ws_bytes = w;
   return 0;
@@ -1552,7 +1606,7 @@ extern "C" int quipb200_decode_step(const quipb200_decode_plan_t* plan, const qu
   p.ws.hA = reinterpret_cast<__half*>(w + lay.off_hA);
   p.ws.hB = reinterpret_cast<__half*>(w + lay.off_hB);
   for (int i = 0; i < SL_N; i++) p.ws.acc[i] = reinterpret_cast<__half*>(w + lay.off_acc[i]);
-  p.ws.att_o = reinterpret_cast<float*>(w + lay.off_att_o);
+  p.ws.att_o = reinterpret_cast<__half*>(w + lay.off_att_o);
   p.ws.att_ml = reinterpret_cast<float*>(w + lay.off_att_ml);
   p.sm = lay.sm;
   p.geo = lay.geo;

@@ -64,9 +64,12 @@ __global__ void __launch_bounds__(RB_THREADS) rot4096_kernel(const __grid_consta
   if (a.post && vout) post = __ldg(reinterpret_cast<const uint4*>(a.post) + tid);
   if (a.bias && vout) bias = __ldg(reinterpret_cast<const uint4*>(a.bias) + tid);
   const float sc = a.post_scale;
+  uint4 nxt = make_uint4(0, 0, 0, 0);
+  if (vin && (int)blockIdx.x < a.M) nxt = ldg_stream_v4(a.x + (size_t)blockIdx.x * a.ldx + tid * 8);
   for (int row = blockIdx.x; row < a.M; row += gridDim.x) {
-    uint4 oct = make_uint4(0, 0, 0, 0);
-    if (vin) oct = ldg_stream_v4(a.x + (size_t)row * a.ldx + tid * 8);
+    uint4 oct = nxt;
+    const int rown = row + gridDim.x;      // the next row's octet is in flight while this one is transformed
+    if (vin && rown < a.M) nxt = ldg_stream_v4(a.x + (size_t)rown * a.ldx + tid * 8);
     if (a.pre) oct = hmul2x4(oct, pre);                                        // qlinear.py:91 (fp16 tensor)
     uint32_t p[4];
     warp_octets_to_frag(oct, wscr + warp * 256, lane, p);                      // block layout: warp = top 4 index bits
@@ -102,15 +105,32 @@ __global__ void __launch_bounds__(RB_THREADS) rotblk_kernel(const __grid_constan
   const float sc = a.post_scale;
   RotSmem rs;
   rs.s = dummy; rs.s2 = dummy; rs.pp = 1; rs.t = T; rs.hk = hk; rs.red = dummy; rs.Ls = RB_LS; rs.log2L = 8;
+  constexpr int NB = 4;                      // blocks per warp (K <= 64)
+  uint4 nxt[NB];
+#pragma unroll
+  for (int j = 0; j < NB; j++) {
+    const int oi = (warp + j * RB_WARPS) * 32 + lane;
+    nxt[j] = make_uint4(0, 0, 0, 0);
+    if (warp + j * RB_WARPS < K && oi < noct_in && (int)blockIdx.x < a.M)
+      nxt[j] = ldg_stream_v4(a.x + (size_t)blockIdx.x * a.ldx + oi * 8);
+  }
   for (int row = blockIdx.x; row < a.M; row += gridDim.x) {
-    const __half* xr = a.x + (size_t)row * a.ldx;
-    for (int b = warp; b < K; b += RB_WARPS) {
+    uint4 cur[NB];
+    const int rown = row + gridDim.x;        // the next row's octets are in flight while this row is transformed
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      cur[j] = nxt[j];
+      const int oi = (warp + j * RB_WARPS) * 32 + lane;
+      nxt[j] = make_uint4(0, 0, 0, 0);
+      if (warp + j * RB_WARPS < K && oi < noct_in && rown < a.M) nxt[j] = ldg_stream_v4(a.x + (size_t)rown * a.ldx + oi * 8);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      const int b = warp + j * RB_WARPS;
+      if (b >= K) break;
       const int oi = b * 32 + lane;
-      uint4 oct = make_uint4(0, 0, 0, 0);
-      if (oi < noct_in) {
-        oct = ldg_stream_v4(xr + oi * 8);
-        if (a.pre) oct = hmul2x4(oct, __ldg(reinterpret_cast<const uint4*>(a.pre) + oi));
-      }
+      uint4 oct = cur[j];
+      if (a.pre && oi < noct_in) oct = hmul2x4(oct, __ldg(reinterpret_cast<const uint4*>(a.pre) + oi));
       uint32_t p[4];
       warp_octets_to_frag(oct, wscr + warp * 256, lane, p);
       float r[8];
