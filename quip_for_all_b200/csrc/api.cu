@@ -13,8 +13,8 @@ extern int g_opt_stage_mask;
 extern int g_opt_fuse;
 extern int g_opt_phase0;
 extern int g_opt_lean;
-int g_opt_umma = 0;     // 17 <= M <= 256: in-kernel decode + tcgen05 GEMM instead of decompress + dense GEMM
-                        // (off by default: first version, slower than decompress + cuBLAS -- profiles/README.md)
+int g_opt_umma = 2;     // in-kernel decode + tcgen05 GEMM (umma_gemm.cu): 0 = never, 1 = whenever the shape is covered
+                        // (M <= 256), 2 = auto: where it measured faster than the alternatives (profiles/README.md)
 }  // namespace qb
 
 extern "C" int quipb200_abi_version(void) { return QUIPB200_ABI_VERSION; }
@@ -78,7 +78,8 @@ extern "C" int quipb200_set_option(const char* name, int value) {
     return 0;
   }
   if (!strcmp(name, "umma")) {
-    qb::g_opt_umma = value ? 1 : 0;
+    if (value < 0 || value > 2) return QUIPB200_EINVAL;
+    qb::g_opt_umma = value;
     return 0;
   }
   if (!strcmp(name, "fuse")) {

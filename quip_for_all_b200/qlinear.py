@@ -95,6 +95,13 @@ class QuantLinear(nn.Module):
                 return False
         return rotate_supported(self.q_in_features, self.K_left) and rotate_supported(self.q_out_features, self.K_right)
 
+    def _batched_umma_ok(self, x):
+        """4 <= M <= 16 rows: rotations as one pass each + the tcgen05 mm (codes decoded once for all rows) beats the
+        single fused launch, whose GEMV runs once per row."""
+        from .register_lib import umma_preferred
+        return (self.codebook.id == "E8P12" and not self.per_channel and self._batched_fused_ok(x)
+                and umma_preferred(x.shape[0], self.q_out_features, self.q_in_features))
+
     def _hk_padded(self, side):
         """Zero-padded [Kp, Kp] coefficient matrix M[k_out][k_in] of the K x K block mix: hadK^T on the input side
         (quant.py:79-80), hadK on the output side.  Cached; rebuilt when the buffer changes."""
@@ -125,7 +132,7 @@ class QuantLinear(nn.Module):
             out = (x @ W)[..., :self.out_features]
             if self.SV is not None:
                 out = out * self.SV
-        elif self._fused_ok(x):
+        elif self._fused_ok(x) and not (x.shape[0] >= 4 and self._batched_umma_ok(x)):
             xh = x if x_dtype == torch.float16 else x.to(torch.float16)
             cb = self.codebook
             out = torch.ops.quip_lib.quantlinear_fwd(

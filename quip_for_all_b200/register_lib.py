@@ -182,6 +182,18 @@ def _mm_fused(codebook, x, Qidxs, grid, scale, K):
 _UMMA_WS = {}
 
 
+def umma_preferred(M: int, N: int, K: int) -> bool:
+    """Dispatch policy of the E8P12 mm (measured on B200, profiles/README.md): the tcgen05 kernel decodes every code once
+    for all rows, the integer-dp4a GEMV once per row (1 row: 10 us, 4 rows: 37 us, 16 rows: 121 us at 4096 x 4096), and
+    decompress + cuBLAS catches up from ~64 rows on."""
+    opt = _native.get_option("umma")
+    if opt == 0 or N % 128 or K % 128 or M < 1 or M > 256:
+        return False
+    if opt == 1:
+        return M > 16
+    return 4 <= M <= 32 or (M <= 64 and N * K >= (32 << 20))
+
+
 def _mm_umma(x, Qidxs, grid, K):
     """17 <= M <= 256, E8P12: in-kernel decode + tcgen05 GEMM (csrc/umma_gemm.cu); None if the shape is not covered."""
     M, N = x.shape[0], Qidxs.shape[0]
@@ -214,8 +226,13 @@ def _mm(codebook, name, x, Qidxs, grid, scale, K, dense):
         raise RuntimeError(f"quip_lib::{name}: x and Qidxs on different devices")
     xh = _contig(x if x.dtype == torch.float16 else x.to(torch.float16))
     q = _contig(Qidxs)
-    out = _mm_fused(codebook, xh, q, grid, scale, K) if codebook is not None else None
-    if out is None and codebook == _native.CB_E8P12 and _native.get_option("umma"):
+    out = None
+    M = xh.shape[0]
+    if codebook == _native.CB_E8P12 and umma_preferred(M, q.shape[0], K):
+        out = _mm_umma(xh, q, grid, K)        # tcgen05: decode once, all rows (the dp4a path re-decodes per row)
+    if out is None and codebook is not None:
+        out = _mm_fused(codebook, xh, q, grid, scale, K)
+    if out is None and codebook == _native.CB_E8P12 and _native.get_option("umma") == 1:
         out = _mm_umma(xh, q, grid, K)
     if out is None:
         # decompress + dense GEMM: what the reference itself does for M >= 32 (codebook/e8p12.py:153-155)

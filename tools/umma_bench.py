@@ -50,12 +50,12 @@ def main():
         for M in Ms:
             x = torch.randn(M, K, device=dev, dtype=torch.float16)
             rec = {"N": N, "K": K, "M": M, "layers": NL, "code_bytes": per, "gflop": 2.0 * M * N * K / 1e9}
-            for name, flag in (("umma", 1), ("dense", 0)):
+            for name, flag in (("umma", 1 if M > 16 else 2), ("dense", 0)):
                 _native.set_option("umma", flag)
                 try:
                     ms = graph_time(lambda: [torch.ops.quip_lib.e8p_mm_origorder(x, q, grid) for q in qs])
                 finally:
-                    _native.set_option("umma", 0)
+                    _native.set_option("umma", 2)
                 us = 1000 * ms / NL
                 rec[name + "_us"] = round(us, 2)
                 rec[name + "_tflops"] = round(rec["gflop"] / us / 1e3, 1)
