@@ -76,20 +76,28 @@ __device__ __forceinline__ int frag_y(int lane, int q) { return 2 * (lane & 3) +
 // value at (row index = warp-index group, x, y) ends up as r of the lane holding (x' = g(+8): old warp group,
 // y' = pairs: old x group) in warp = old y group.  Callers use idx_out / idx_in below.
 constexpr int DS_XROW = 388;
+// `active` is warp-uniform: CTAs with more than 16 warps pass false for the extra warps, which only take part in the barrier.
 __device__ __forceinline__ void fwht4096_frag(const uint32_t (&p)[4], const HFrag& A, float* S, int warp, int lane,
-                                              float (&r)[8]) {
-  hT_packed(p, A, r);
-  hT_split(r, A);
+                                              float (&r)[8], bool active = true) {
+  if (active) {
+    hT_packed(p, A, r);
+    hT_split(r, A);
 #pragma unroll
-  for (int q = 0; q < 4; q++)
-    *reinterpret_cast<float2*>(S + warp * DS_XROW + frag_x(lane, q) * 24 + frag_y(lane, q)) = make_float2(r[2 * q], r[2 * q + 1]);
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    r[2 * q] = S[frag_y(lane, q) * DS_XROW + warp * 24 + frag_x(lane, q)];
-    r[2 * q + 1] = S[(frag_y(lane, q) + 1) * DS_XROW + warp * 24 + frag_x(lane, q)];
+    for (int q = 0; q < 4; q++)
+      *reinterpret_cast<float2*>(S + warp * DS_XROW + frag_x(lane, q) * 24 + frag_y(lane, q)) = make_float2(r[2 * q], r[2 * q + 1]);
   }
-  hT_split(r, A);
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      r[2 * q] = S[frag_y(lane, q) * DS_XROW + warp * 24 + frag_x(lane, q)];
+      r[2 * q + 1] = S[(frag_y(lane, q) + 1) * DS_XROW + warp * 24 + frag_x(lane, q)];
+    }
+    hT_split(r, A);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = 0.f;
+  }
 }
 // element index of register pair q (first element; the second is +1):
 //   block layout   : warp = top 4 bits, x = middle, y = low      (input of the output-side rotation, output of the input side)

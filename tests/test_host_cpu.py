@@ -271,3 +271,50 @@ def test_load_quantized_model_requires_cuda(tmp_path):
         pytest.skip("CUDA present")
     with pytest.raises(RuntimeError, match="No GPU found"):
         load_quantized_model(str(tmp_path))
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors used by the Python host side have the layout the C ABI declares (include/quip_b200.h):
+    compile a probe with gcc and compare sizeof / offsetof."""
+    import ctypes
+    import subprocess
+    from quip_for_all_b200._native import Fusion, LinearDesc
+    from quip_for_all_b200.decode_step import DecodeLayer, DecodePlan
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "probe.c"
+    src.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "quip_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu\\n", sizeof(quipb200_linear_t), sizeof(quipb200_fusion_t), sizeof(quipb200_decode_layer_t),
+         sizeof(quipb200_decode_plan_t));
+  printf("%zu %zu %zu %zu\\n", offsetof(quipb200_linear_t, qidxs), offsetof(quipb200_linear_t, wscale_pc),
+         offsetof(quipb200_decode_layer_t, input_norm_w), offsetof(quipb200_decode_layer_t, mlp_hk));
+  printf("%zu %zu\\n", offsetof(quipb200_decode_plan_t, layers), offsetof(quipb200_decode_plan_t, pos));
+  return 0;
+}
+''')
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    got = [int(v) for v in out]
+    want = [ctypes.sizeof(LinearDesc), ctypes.sizeof(Fusion), ctypes.sizeof(DecodeLayer), ctypes.sizeof(DecodePlan),
+            LinearDesc.qidxs.offset, LinearDesc.wscale_pc.offset, DecodeLayer.input_norm_w.offset, DecodeLayer.mlp_hk.offset,
+            DecodePlan.layers.offset, DecodePlan.pos.offset]
+    assert got == want, (got, want)
+
+
+def test_mm_dispatch_policy_and_rotation_coverage():
+    """Host-side dispatch rules of the batched path (register_lib): which (M, N, K) go to the tcgen05 kernel and which
+    rotation lengths the one-pass kernels cover (everything else keeps the reference's op sequence)."""
+    from quip_for_all_b200 import _native, register_lib as rl
+    lib_present = os.path.exists(_native.LIB_PATH)
+    assert rl.rotate_supported(4096, 1) and rl.rotate_supported(11008, 43) and rl.rotate_supported(256, 1)
+    assert not rl.rotate_supported(8192, 1) and not rl.rotate_supported(28672, 7) and not rl.rotate_supported(11008, 172)
+    if lib_present:
+        assert _native.get_option("umma") == 2
+        assert not rl.umma_preferred(1, 4096, 4096) and not rl.umma_preferred(3, 4096, 4096)
+        assert rl.umma_preferred(4, 4096, 4096) and rl.umma_preferred(32, 4096, 4096)
+        assert not rl.umma_preferred(33, 4096, 4096) and rl.umma_preferred(64, 4096, 11008)
+        assert not rl.umma_preferred(16, 4096 + 64, 4096) and not rl.umma_preferred(300, 4096, 4096)
