@@ -34,7 +34,7 @@ constexpr int DS_WARPS = DS_THREADS / 32;
 constexpr int DS_UNROLL = 2;
 constexpr int DS_MAX_SPLITS = 4;
 constexpr int DS_HD = 128;
-constexpr int DS_PV_GROUPS = DS_THREADS / 64;
+constexpr int DS_PV_GROUPS = DS_THREADS / 16;   // 16 threads (8 dims each) per cached position in the P.V pass
 
 enum { SL_Q = 0, SL_K, SL_V, SL_O, SL_G, SL_U, SL_D, SL_N };
 
@@ -1034,44 +1034,53 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         }
         __syncthreads();
         DS_ST(8);
-        // ---- scores over [t_begin, t_end) ----
-        const float q0 = sq[lane * 4], q1 = sq[lane * 4 + 1], q2 = sq[lane * 4 + 2], q3 = sq[lane * 4 + 3];
+        // ---- scores over [t_begin, t_end): a half-warp per cached position, 16-byte loads (8 dims per lane) ----
+        const int l16 = lane & 15, hw = lane >> 4;
+        float qv[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) qv[e] = sq[l16 * 8 + e];
         float lmax = -INFINITY;
-        constexpr int UN = 8;
-        for (int t0 = t_begin + warp; t0 < t_end; t0 += DS_WARPS * UN) {
-          uint2 raw[UN];
+        constexpr int UN = 4;
+        for (int tb = t_begin + warp * 2; tb < t_end; tb += DS_WARPS * 2 * UN) {   // warp-uniform trip count (full-mask shuffles inside)
+          const int t0 = tb + hw;
+          uint4 raw[UN];
 #pragma unroll
           for (int u = 0; u < UN; u++) {
-            const int t = t0 + u * DS_WARPS;
-            raw[u] = make_uint2(0, 0);
-            if (t < t_end && t != pos) raw[u] = __ldcg(reinterpret_cast<const uint2*>(kc + (size_t)t * DS_HD + lane * 4));
+            const int t = t0 + u * DS_WARPS * 2;
+            raw[u] = make_uint4(0, 0, 0, 0);
+            if (t < t_end && t != pos) raw[u] = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)t * DS_HD) + l16);
           }
           float d[UN];
 #pragma unroll
           for (int u = 0; u < UN; u++) {
-            const int t = t0 + u * DS_WARPS;
+            const int t = t0 + u * DS_WARPS * 2;
+            float kf[8];
             if (t == pos) {
-              d[u] = q0 * sk[lane * 4] + q1 * sk[lane * 4 + 1] + q2 * sk[lane * 4 + 2] + q3 * sk[lane * 4 + 3];
+#pragma unroll
+              for (int e = 0; e < 8; e++) kf[e] = sk[l16 * 8 + e];
             } else {
-              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw[u].x));
-              const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw[u].y));
-              d[u] = q0 * a.x + q1 * a.y + q2 * b.x + q3 * b.y;
+              unpack_h8(raw[u], kf);
             }
+            float acc = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; e++) acc = fmaf(qv[e], kf[e], acc);
+            d[u] = acc;
           }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
+          for (int o = 8; o > 0; o >>= 1) {
 #pragma unroll
             for (int u = 0; u < UN; u++) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
           }
 #pragma unroll
           for (int u = 0; u < UN; u++) {
-            const int t = t0 + u * DS_WARPS;
+            const int t = t0 + u * DS_WARPS * 2;
             if (t < t_end) {
-              if (lane == 0) sc[t - t_begin] = d[u];
+              if (l16 == 0) sc[t - t_begin] = d[u];
               lmax = fmaxf(lmax, d[u]);
             }
           }
         }
+        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, 16));
         if (lane == 0) sred[warp] = lmax;
         __syncthreads();
         float mx = -INFINITY;
@@ -1091,36 +1100,40 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
 #pragma unroll
         for (int w = 0; w < DS_WARPS; w++) tot += sred[w];
         DS_ST(9);
-        // ---- partial out = P . V ----
-        const int d2 = tid & 63, tg = tid >> 6;
-        float o0 = 0.f, o1 = 0.f;
-        constexpr int UV = 8;
-        for (int t0 = t_begin + tg; t0 < t_end; t0 += DS_PV_GROUPS * UV) {
-          __half2 vr[UV];
+        // ---- partial out = P . V: 16 threads per position (8 dims each, 16-byte loads), 32 positions per pass ----
+        {
+          const int pg = tid >> 4, t16 = tid & 15;
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          constexpr int UV = 4;
+          for (int t0 = t_begin + pg; t0 < t_end; t0 += DS_PV_GROUPS * UV) {
+            uint4 vr[UV];
 #pragma unroll
-          for (int u = 0; u < UV; u++) {
-            const int t = t0 + u * DS_PV_GROUPS;
-            vr[u] = __float2half2_rn(0.f);
-            if (t < t_end && t != pos) {
-              const unsigned int w32 = __ldcg(reinterpret_cast<const unsigned int*>(vc + (size_t)t * DS_HD + d2 * 2));
-              vr[u] = *reinterpret_cast<const __half2*>(&w32);
-            } else if (t == pos) {
-              vr[u] = __floats2half2_rn(sv[d2 * 2], sv[d2 * 2 + 1]);
+            for (int u = 0; u < UV; u++) {
+              const int t = t0 + u * DS_PV_GROUPS;
+              vr[u] = make_uint4(0, 0, 0, 0);
+              if (t < t_end && t != pos) vr[u] = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)t * DS_HD) + t16);
+            }
+#pragma unroll
+            for (int u = 0; u < UV; u++) {
+              const int t = t0 + u * DS_PV_GROUPS;
+              if (t < t_end) {
+                float vf[8];
+                if (t == pos) {
+#pragma unroll
+                  for (int e = 0; e < 8; e++) vf[e] = sv[t16 * 8 + e];
+                } else {
+                  unpack_h8(vr[u], vf);
+                }
+                const float pr = sc[t - t_begin];
+#pragma unroll
+                for (int e = 0; e < 8; e++) acc[e] = fmaf(pr, vf[e], acc[e]);
+              }
             }
           }
-#pragma unroll
-          for (int u = 0; u < UV; u++) {
-            const int t = t0 + u * DS_PV_GROUPS;
-            if (t < t_end) {
-              const float2 vv = __half22float2(vr[u]);
-              const float pr = sc[t - t_begin];
-              o0 = fmaf(pr, vv.x, o0);
-              o1 = fmaf(pr, vv.y, o1);
-            }
-          }
+          float4* so = reinterpret_cast<float4*>(sout + pg * 128 + t16 * 8);
+          so[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          so[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
-        sout[tg * 128 + d2 * 2] = o0;
-        sout[tg * 128 + d2 * 2 + 1] = o1;
         __syncthreads();
         if (tid < DS_HD) {
           float r = 0.f;
