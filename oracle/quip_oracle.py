@@ -510,3 +510,64 @@ def qidxs_shape(in_features: int, out_features: int, codebook: str, use_rand: bo
     _, q_in, _ = hadK_shape(in_features, use_rand)
     _, q_out, _ = hadK_shape(out_features, use_rand)
     return q_out, int(q_in // (codesz * packsz))
+
+
+# --------------------------------------------------------------------------------------------------
+# decode step of a Llama decoder layer built from QuantLinears (the loop body of the reference's generation example)
+# --------------------------------------------------------------------------------------------------
+def llama_decoder_layer_step(h, layer, k_cache, v_cache, pos, *, n_heads, n_kv_heads, head_dim, eps, theta=10000.0,
+                             rounding="reference"):
+    """One bs=1 decode position through one decoder layer whose seven projections are QuantLinears.
+
+    Follows what the reference's decode loop executes per layer (example_generate.py:29-32 ->
+    HF LlamaDecoderLayer.forward with the block linears swapped for QuantLinear, quantizer.py:193-248):
+        x = RMSNorm(h); q,k,v = QuantLinear(x); RoPE(q,k) (rotate_half); append k,v at `pos`;
+        o = softmax(q k^T / sqrt(d)) v over positions 0..pos (GQA: query head j uses kv head j // group);
+        h = h + o_proj(o); x = RMSNorm(h); h = h + down(silu(gate(x)) * up(x)).
+    h: [hidden] fp16-valued; layer: dict with 'input_norm', 'post_norm' (fp16 vectors) and 'q','k','v','o','gate','up',
+    'down' -> kwargs of quantlinear_forward (W_hat, dims, SU, SV, ...); k_cache / v_cache: float arrays
+    [n_kv_heads, max_len, head_dim] holding fp16 values, updated in place at `pos`.
+    rounding="reference" keeps fp16 tensors where HF holds fp16 tensors (norm output, q/k after RoPE, attention
+    output, residual sums, silu and its product); accumulations are float64.  Returns the new hidden state (float64).
+    """
+    rd = _r16 if rounding == "reference" else (lambda a: np.asarray(a, dtype=np.float64))
+    f64 = np.float64
+
+    def rms(x, w):
+        v = np.asarray(x, dtype=f64)
+        v = rd(v / np.sqrt((v * v).mean() + eps))
+        return rd(np.asarray(w, dtype=f64) * v)
+
+    def lin(name, x):
+        return quantlinear_forward(np.asarray(x, dtype=f64)[None, :], rounding=rounding, **layer[name])[0]
+
+    h = np.asarray(h, dtype=f64)
+    x = rms(h, layer["input_norm"])
+    q = lin("q", x).reshape(n_heads, head_dim)
+    k = lin("k", x).reshape(n_kv_heads, head_dim)
+    v = lin("v", x).reshape(n_kv_heads, head_dim)
+    inv = 1.0 / (theta ** (np.arange(0, head_dim, 2, dtype=f64) / head_dim))
+    ang = np.concatenate([pos * inv, pos * inv])
+    cos, sin = rd(np.cos(ang)), rd(np.sin(ang))                    # HF keeps the rotary tables in the model dtype
+
+    def rope(t):
+        half = head_dim // 2
+        rot = np.concatenate([-t[:, half:], t[:, :half]], axis=1)
+        return rd(t * cos + rot * sin)
+
+    q, k = rope(q), rope(k)
+    k_cache[:, pos] = k
+    v_cache[:, pos] = v
+    group = n_heads // n_kv_heads
+    o = np.zeros((n_heads, head_dim), dtype=f64)
+    for j in range(n_heads):
+        kk, vv = k_cache[j // group, :pos + 1].astype(f64), v_cache[j // group, :pos + 1].astype(f64)
+        s = kk @ q[j] / math.sqrt(head_dim)
+        p = np.exp(s - s.max())
+        o[j] = (p / p.sum()) @ vv
+    o = rd(o).reshape(-1)
+    h = rd(h + lin("o", o))
+    x = rms(h, layer["post_norm"])
+    g, u = lin("gate", x), lin("up", x)
+    act = rd(rd(g / (1.0 + np.exp(-g))) * u)
+    return rd(h + lin("down", act))

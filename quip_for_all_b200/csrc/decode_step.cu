@@ -524,18 +524,6 @@ __device__ __forceinline__ float in_side_m(const float (&f)[8], bool has_norm, f
 // ---------------------------------------------------------------------------------------------
 struct BlkBuf { __half* Tg; __half* Tu; __half* hkg; __half* hku; __half* hkd; __half* vSVg; __half* vSVu; __half* vSUd; int LS; };
 
-// coefficient matrix M[k_out][k_in] (zero padded to Kp <= 64): hadK (output side) or hadK^T (input side)
-__device__ __forceinline__ void load_hk(__half* dst, const __half* src, int K, int Kp, int transpose, int tid) {
-  const int ki = tid & 63;
-  for (int ko = tid >> 6; ko < Kp; ko += DS_THREADS / 64) {
-    if (ki < Kp) {
-      __half v = __float2half_rn(0.f);
-      if (ko < K && ki < K) v = transpose ? src[ki * K + ko] : src[ko * K + ki];
-      dst[ko * Kp + ki] = v;
-    }
-  }
-}
-
 // In-place K x K mix  T <- M T  of one or two block buffers (256 columns, row stride LS) on the tensor path.  The A
 // fragments of the coefficient matrix are loaded once per call and reused for every 8-column tile the warp owns; both
 // buffers share one barrier pair.  fp16 operands, fp32 accumulate, one fp16 rounding: the reference's `hadK @ y`

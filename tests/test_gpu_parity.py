@@ -692,3 +692,54 @@ def test_batched_forward_vs_oracle(fin, fout, bias, M):
     assert err.max() <= tol_of(ref), (err.max(), tol_of(ref))
     ref64 = oracle_forward(layer, x, rounding="none")
     assert np.abs(y.float().cpu().numpy() - ref64).max() <= tol_of(ref64)
+
+
+def _oracle_layer_params(lyr):
+    def lin(m):
+        return dict(W_hat=qo.decompress_e8p(m.Qidxs.cpu().numpy()), in_features=m.in_features, out_features=m.out_features,
+                    q_in=m.q_in_features, q_out=m.q_out_features,
+                    SU=None if m.SU is None else m.SU.detach().float().cpu().numpy(),
+                    SV=None if m.SV is None else m.SV.detach().float().cpu().numpy(),
+                    bias=None if m.bias is None else m.bias.float().cpu().numpy(), wscale_float=m.wscale_float,
+                    had_left=None if m.had_left is None else m.had_left.float().cpu().numpy(), K_left=m.K_left,
+                    had_right=None if m.had_right is None else m.had_right.float().cpu().numpy(), K_right=m.K_right)
+    at, mlp = lyr.self_attn, lyr.mlp
+    return dict(input_norm=lyr.input_layernorm.weight.float().cpu().numpy(),
+                post_norm=lyr.post_attention_layernorm.weight.float().cpu().numpy(),
+                q=lin(at.q_proj), k=lin(at.k_proj), v=lin(at.v_proj), o=lin(at.o_proj),
+                gate=lin(mlp.gate_proj), up=lin(mlp.up_proj), down=lin(mlp.down_proj))
+
+
+@pytest.mark.parametrize("name", ["tiny256", "tinypow2"])
+def test_persistent_decode_step_matches_cpu_oracle(name):
+    """The persistent whole-step kernel against the CPU oracle of the decode loop body (oracle/quip_oracle.py:
+    llama_decoder_layer_step): hidden state after every layer's worth of work and the appended K/V rows."""
+    from quip_for_all_b200.modeling import LlamaDecodeEngine, llama_config, make_random_quantized_llama
+    cfg = llama_config(name, num_hidden_layers=2)
+    model = make_random_quantized_llama(cfg, "E8P12", seed=9, device=DEV)
+    eng = LlamaDecodeEngine(model, max_cache_len=48, persistent=True, use_cuda_graph=False)
+    assert eng.persistent is not None
+    ids = torch.randint(0, 32000, (1, 5), generator=torch.Generator().manual_seed(4)).to(DEV)
+    eng.prefill(ids)
+    nh, nkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, eng.hd
+    params = [_oracle_layer_params(l) for l in model.model.layers]
+    for _ in range(2):
+        pos = int(eng.pos.item())
+        kc = [eng.k_cache[i, 0].float().cpu().numpy().astype(np.float64) for i in range(2)]
+        vc = [eng.v_cache[i, 0].float().cpu().numpy().astype(np.float64) for i in range(2)]
+        with torch.no_grad():
+            h = model.model.embed_tokens(eng.tok).view(1, -1).contiguous()
+            got = eng.persistent(h, eng.h_step_out).float().cpu().numpy()[0]
+        torch.cuda.synchronize()
+        ref = h.float().cpu().numpy()[0].astype(np.float64)
+        for i in range(2):
+            ref = qo.llama_decoder_layer_step(ref, params[i], kc[i], vc[i], pos, n_heads=nh, n_kv_heads=nkv, head_dim=hd,
+                                              eps=cfg.rms_norm_eps)
+        tol = 2.0 ** -6 * np.abs(ref).max()        # two layers of chained fp16 rounding points (cf. the unfused-engine test)
+        assert np.abs(got - ref).max() <= tol, (np.abs(got - ref).max(), tol)
+        for i in range(2):                          # the appended rows of the KV cache
+            gk = eng.k_cache[i, 0, :, pos].float().cpu().numpy()
+            gv = eng.v_cache[i, 0, :, pos].float().cpu().numpy()
+            assert np.abs(gk - kc[i][:, pos]).max() <= 2.0 ** -7 * np.abs(kc[i][:, pos]).max() + 1e-3
+            assert np.abs(gv - vc[i][:, pos]).max() <= 2.0 ** -7 * np.abs(vc[i][:, pos]).max() + 1e-3
+        eng.pos.add_(1)

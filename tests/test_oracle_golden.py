@@ -180,3 +180,46 @@ def test_qidxs_shapes():
     assert qo.qidxs_shape(4096, 4096, "E8P12RVQ3B") == (4096, 384)
     assert qo.qidxs_shape(66, 50, "E8P12", use_rand=False) == (64, 16)   # exp<2: padded to 128 / 64
     assert qo.qidxs_shape(88, 40, "E8P12", use_rand=False) == (40, 11)   # tables 44 and 20 exist
+
+
+def test_decoder_layer_step_oracle_matches_hf_llama_layer():
+    """Pin the decode-loop-body oracle (llama_decoder_layer_step: RMSNorm, rotate_half RoPE, GQA attention over the
+    KV cache, residuals, SiLU MLP) on HuggingFace's own LlamaModel: one layer, dense nn.Linear weights equal to the
+    QuantLinears' effective matrices, a 6-token causal forward vs 6 oracle steps (no fp16 rounding, float64)."""
+    import math
+    import torch
+    from transformers import LlamaConfig, LlamaModel
+    rng = np.random.default_rng(3)
+    H, I, nh, nkv, hd, T = 128, 256, 2, 1, 64, 6
+
+    def lin(fi, fo):
+        q = rng.integers(-32768, 32768, (fo, fi // 8)).astype(np.int16)
+        return dict(W_hat=qo.decompress_e8p(q), in_features=fi, out_features=fo, q_in=fi, q_out=fo,
+                    SU=np.sign(rng.standard_normal(fi)), SV=np.sign(rng.standard_normal(fo)), wscale_float=0.05)
+
+    layer = dict(input_norm=1 + 0.1 * rng.standard_normal(H), post_norm=1 + 0.1 * rng.standard_normal(H),
+                 q=lin(H, nh * hd), k=lin(H, nkv * hd), v=lin(H, nkv * hd), o=lin(nh * hd, H),
+                 gate=lin(H, I), up=lin(H, I), down=lin(I, H))
+    # two layers: hidden_states[1] is then layer 0's raw output (HF applies the final norm to the LAST entry only)
+    cfg = LlamaConfig(hidden_size=H, intermediate_size=I, num_hidden_layers=2, num_attention_heads=nh,
+                      num_key_value_heads=nkv, vocab_size=32, rms_norm_eps=1e-5, max_position_embeddings=64,
+                      attn_implementation="eager")
+    model = LlamaModel(cfg).double().eval()
+    hf = model.layers[0]
+    with torch.no_grad():
+        for name, mod in (("q", hf.self_attn.q_proj), ("k", hf.self_attn.k_proj), ("v", hf.self_attn.v_proj),
+                          ("o", hf.self_attn.o_proj), ("gate", hf.mlp.gate_proj), ("up", hf.mlp.up_proj),
+                          ("down", hf.mlp.down_proj)):
+            p = layer[name]
+            W = qo.quantlinear_forward(np.eye(p["in_features"]), rounding="none", **p).T      # [out, in]
+            mod.weight.copy_(torch.from_numpy(W))
+        hf.input_layernorm.weight.copy_(torch.from_numpy(layer["input_norm"]))
+        hf.post_attention_layernorm.weight.copy_(torch.from_numpy(layer["post_norm"]))
+        x = rng.standard_normal((1, T, H))
+        ref = model(inputs_embeds=torch.from_numpy(x), output_hidden_states=True).hidden_states[1][0].numpy()
+    kc, vc = np.zeros((nkv, 16, hd)), np.zeros((nkv, 16, hd))
+    for t in range(T):
+        got = qo.llama_decoder_layer_step(x[0, t], layer, kc, vc, t, n_heads=nh, n_kv_heads=nkv, head_dim=hd, eps=1e-5,
+                                          rounding="none")
+        # HF's LlamaRMSNorm computes its statistics in float32 whatever the module dtype: 1e-6 relative
+        assert np.abs(got - ref[t]).max() <= 2e-6 * max(1.0, np.abs(ref[t]).max()), (t, np.abs(got - ref[t]).max())
