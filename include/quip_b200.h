@@ -200,8 +200,8 @@ int quipb200_attn_decode(const void* q, const void* k, const void* v, void* k_ca
  * flight while the rotation runs.  Arithmetic and rounding points are those of
  * quipb200_linear_group_forward / quipb200_attn_decode.
  *
- * Restrictions (else QUIPB200_EUNSUPPORTED and the caller uses the per-linear entry points): E8P12
- * codebook for every linear, head_dim 128, fp16 everywhere, all seven linears of a layer present,
+ * Restrictions (else QUIPB200_EUNSUPPORTED and the caller uses the per-linear entry points): one codebook
+ * (E8P12, E8P12RVQ4B or D4) for every linear, head_dim 128, fp16 everywhere, all seven linears of a layer present,
  * power-of-two padded attention dims (K_right == 1 for q/k/v, K_left == 1 for o).
  * ------------------------------------------------------------------------------------------- */
 typedef struct quipb200_decode_layer {

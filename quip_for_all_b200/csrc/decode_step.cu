@@ -105,8 +105,9 @@ __device__ __forceinline__ GemvCfg make_cfg(const quipb200_linear_t& L, int bx, 
   GemvCfg c;
   c.q = reinterpret_cast<const unsigned char*>(L.qidxs);
   c.nseg = L.q_in >> 3;
-  c.row_bytes = (int64_t)c.nseg * 2;
-  const int lanes = (c.nseg + 7) >> 3;
+  const int segs = (L.codebook == QUIPB200_CB_E8P12RVQ4B) ? 4 : 8;      // 8-element segments covered by one 16-byte load
+  c.row_bytes = (int64_t)c.nseg * ((L.codebook == QUIPB200_CB_E8P12RVQ4B) ? 4 : 2);
+  const int lanes = (c.nseg + segs - 1) / segs;
   c.C = (lanes + 31) >> 5;
   c.g = c.C >= DS_WARPS ? 1 : DS_WARPS / c.C;
   const int base = L.q_out / G, rem = L.q_out % G;
@@ -115,10 +116,12 @@ __device__ __forceinline__ GemvCfg make_cfg(const quipb200_linear_t& L, int bx, 
   return c;
 }
 
+template <int CB>
 __device__ __forceinline__ void gemv_first(uint4 (&cw)[DS_UNROLL], const GemvCfg& c, int warp, int lane, uint64_t pol) {
+  constexpr int SEGS = CbTraits<CB>::SEGS;
   const int units = c.C * c.g;
   const int chunk = warp / c.g, sub = warp - chunk * c.g;
-  const bool lv = warp < units && (chunk * 32 + lane) * 8 < c.nseg;
+  const bool lv = warp < units && (chunk * 32 + lane) * SEGS < c.nseg;
   const unsigned char* colp = c.q + (size_t)(chunk * 32 + lane) * 16 + (size_t)c.row_begin * c.row_bytes;
 #pragma unroll
   for (int u = 0; u < DS_UNROLL; u++) {
@@ -151,19 +154,21 @@ __device__ __forceinline__ void prefetch_stage(const quipb200_linear_t* const* m
 }
 
 // xq: swizzled 16-byte activation records in shared memory; red: [nrows][C] chunk partials
+template <int CB>
 __device__ __forceinline__ void gemv_run(uint4 (&cw)[DS_UNROLL], const GemvCfg& c, const uint4* xq,
                                          const unsigned char* tab, int* red, int warp, int lane, uint64_t pol) {
+  using T = CbTraits<CB>;
   const int units = c.C * c.g;
   int unit = warp;
   while (unit < units) {
     const int chunk = unit / c.g;
     const int sub = unit - chunk * c.g;
-    const int seg0 = (chunk * 32 + lane) * 8;
+    const int seg0 = (chunk * 32 + lane) * T::SEGS;
     const bool lane_valid = seg0 < c.nseg;
-    uint32_t xs[8][4];
-    int xsum[8];
+    uint32_t xs[T::SEGS][4];
+    int xsum[T::SEGS];
 #pragma unroll
-    for (int sgi = 0; sgi < 8; sgi++) {
+    for (int sgi = 0; sgi < T::SEGS; sgi++) {
       uint4 r = make_uint4(0, 0, 0, 0);
       if (lane_valid) r = xq[swz(seg0 + sgi)];
       xs[sgi][0] = r.x; xs[sgi][1] = r.y; xs[sgi][2] = r.z; xs[sgi][3] = r.w;
@@ -187,15 +192,43 @@ __device__ __forceinline__ void gemv_run(uint4 (&cw)[DS_UNROLL], const GemvCfg& 
         if (r < c.nrows) {
           int aH = 0, aL = 0, aP = 0, cH = 0, cL = 0, cP = 0;
           const uint32_t w[4] = {cw[0].x, cw[0].y, cw[0].z, cw[0].w};
+          if (CB == QUIPB200_CB_E8P12) {
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            e8p_dot((w[i] >> 5) & 0x7f8u, w[i] & 0xffu, tab, xs[2 * i], xsum[2 * i], aH, aL, aP);
-            e8p_dot((w[i] >> 21) & 0x7f8u, __byte_perm(w[i], 0, 0x4442), tab, xs[2 * i + 1], xsum[2 * i + 1], cH, cL, cP);
+            for (int i = 0; i < 4; i++) {
+              e8p_dot((w[i] >> 5) & 0x7f8u, w[i] & 0xffu, tab, xs[2 * i], xsum[2 * i], aH, aL, aP);
+              e8p_dot((w[i] >> 21) & 0x7f8u, __byte_perm(w[i], 0, 0x4442), tab, xs[2 * i + 1], xsum[2 * i + 1], cH, cL, cP);
+            }
+            aH += cH; aL += cL; aP += cP;
+          } else if (CB == QUIPB200_CB_E8P12RVQ4B) {     // main code = hi16 (a*), residual code = lo16 (c*), same x segment
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              e8p_dot((w[i] >> 21) & 0x7f8u, __byte_perm(w[i], 0, 0x4442), tab, xs[i], xsum[i], aH, aL, aP);
+              e8p_dot((w[i] >> 5) & 0x7f8u, w[i] & 0xffu, tab, xs[i], xsum[i], cH, cL, cP);
+            }
+          } else {                                        // D4: byte -> 4 weights; two codes per 8-element segment
+            const uint32_t* t4 = reinterpret_cast<const uint32_t*>(tab);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+#pragma unroll
+              for (int b = 0; b < 4; b++) {
+                const uint32_t v = t4[(w[i] >> (8 * b)) & 0xffu];
+                const int sgi = i * 2 + (b >> 1), half = b & 1;
+                aH = dp4a_ss(v, xs[sgi][half], aH);
+                aL = dp4a_su(v, xs[sgi][2 + half], aL);
+              }
+            }
           }
-          aH += cH; aL += cL; aP += cP;
           int tot = aH * 256 + aL - 2 * aP;
           tot = __reduce_add_sync(0xffffffffu, tot);
-          if (lane == 0) red[r * c.C + chunk] = tot;
+          int tot2 = 0;
+          if (T::ACCS == 2) {
+            tot2 = cH * 256 + cL - 2 * cP;
+            tot2 = __reduce_add_sync(0xffffffffu, tot2);
+          }
+          if (lane == 0) {
+            red[(r * c.C + chunk) * T::ACCS] = tot;
+            if (T::ACCS == 2) red[(r * c.C + chunk) * T::ACCS + 1] = tot2;
+          }
         }
 #pragma unroll
         for (int v = 0; v + 1 < DS_UNROLL; v++) cw[v] = cw[v + 1];
@@ -206,7 +239,7 @@ __device__ __forceinline__ void gemv_run(uint4 (&cw)[DS_UNROLL], const GemvCfg& 
     unit += DS_WARPS;
     if (unit < units) {
       const int chunk2 = unit / c.g, sub2 = unit - chunk2 * c.g;
-      const bool lv = (chunk2 * 32 + lane) * 8 < c.nseg;
+      const bool lv = (chunk2 * 32 + lane) * T::SEGS < c.nseg;
       const unsigned char* colp2 = c.q + (size_t)(chunk2 * 32 + lane) * 16 + (size_t)c.row_begin * c.row_bytes;
 #pragma unroll
       for (int u = 0; u < DS_UNROLL; u++) {
@@ -219,13 +252,22 @@ __device__ __forceinline__ void gemv_run(uint4 (&cw)[DS_UNROLL], const GemvCfg& 
 }
 
 // chunk partials -> global accumulator (fp32 image of the integer dot product)
-__device__ __forceinline__ void gemv_store(const GemvCfg& c, const int* red, __half* acc, float xscale, int tid) {
+template <int CB>
+__device__ __forceinline__ void gemv_store(const GemvCfg& c, const int* red, __half* acc, float xscale, float resid_scale,
+                                           int tid) {
+  using T = CbTraits<CB>;
   __syncthreads();
-  const float xs = xscale * 0.25f;
+  const float xs = xscale * (CB == QUIPB200_CB_D4 ? 0.5f : 0.25f);     // weight unit: 1/4 (E8P) or 1/2 (D4)
+  const float rs = __half2float(__float2half_rn(resid_scale));         // the reference's fp16 hfma operand (origin_order.cu:378)
   for (int r = tid; r < c.nrows; r += DS_THREADS) {
-    long long s = 0;
-    for (int k = 0; k < c.C; k++) s += red[r * c.C + k];
-    acc[c.row_begin + r] = __float2half_rn((float)s * xs);      // origin_order.cu:129 (single fp16 rounding of the mm)
+    long long s = 0, s2 = 0;
+    for (int k = 0; k < c.C; k++) {
+      s += red[(r * c.C + k) * T::ACCS];
+      if (T::ACCS == 2) s2 += red[(r * c.C + k) * T::ACCS + 1];
+    }
+    float f = (float)s;
+    if (T::ACCS == 2) f = fmaf(rs, (float)s2, f);
+    acc[c.row_begin + r] = __float2half_rn(f * xs);      // origin_order.cu:129 (single fp16 rounding of the mm)
   }
 }
 
@@ -804,6 +846,7 @@ __device__ __forceinline__ void slice_finish(const quipb200_linear_t& L, const f
   }
 }
 
+template <int CB>
 __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid_constant__ DsParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -849,12 +892,20 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
   if (tid == 0) bar_target = *reinterpret_cast<volatile unsigned int*>(p.ws.bar + 32);
   const uint64_t pol = l2_evict_first_policy();
 
-  // the E8P abs table (identical for every linear), "+1/4" pre-applied
+  // the codebook table (identical for every linear).  E8P: int8x8 abs entries, "+1/4" pre-applied; D4: fp16 [4] ->
+  // int8 (units of 1/2), byte order (0,2,1,3) to match the record layout of the activations
   if (tid < 256) {
     uint2 t = reinterpret_cast<const uint2*>(P.layers[0].q.grid)[tid];
-    t.x |= 0x01010101u;
-    t.y |= 0x01010101u;
-    reinterpret_cast<uint2*>(tab)[tid] = t;
+    if (CB == QUIPB200_CB_D4) {
+      const __half2 h01 = *reinterpret_cast<const __half2*>(&t.x), h23 = *reinterpret_cast<const __half2*>(&t.y);
+      const int v0 = __float2int_rn(__low2float(h01) * 2.0f) & 0xff, v1 = __float2int_rn(__high2float(h01) * 2.0f) & 0xff;
+      const int v2 = __float2int_rn(__low2float(h23) * 2.0f) & 0xff, v3 = __float2int_rn(__high2float(h23) * 2.0f) & 0xff;
+      reinterpret_cast<uint32_t*>(tab)[tid] = (uint32_t)v0 | ((uint32_t)v2 << 8) | ((uint32_t)v1 << 16) | ((uint32_t)v3 << 24);
+    } else {
+      t.x |= 0x01010101u;
+      t.y |= 0x01010101u;
+      reinterpret_cast<uint2*>(tab)[tid] = t;
+    }
   }
   const int hid8 = P.hidden >> 3;
   if (bid == 0 && tid < hid8) reinterpret_cast<uint4*>(p.ws.hA)[tid] = reinterpret_cast<const uint4*>(p.h_in)[tid];
@@ -936,10 +987,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
           const quipb200_linear_t* nx[1] = {&Ly.o};
           prefetch_stage(nx, &p.geo.G_C, 1, bid, tid);
         }
-        gemv_first(cw, c, warp, lane, pol);
-        gemv_run(cw, c, xq, tab, red, warp, lane, pol);
+        gemv_first<CB>(cw, c, warp, lane, pol);
+        gemv_run<CB>(cw, c, xq, tab, red, warp, lane, pol);
         DS_ST(4);
-        gemv_store(c, red, p.ws.acc[SL_Q + j], xs, tid);
+        gemv_store<CB>(c, red, p.ws.acc[SL_Q + j], xs, L.resid_scale, tid);
         DS_ST(5);
       } else {   // idle in this stage, not in the next
         const quipb200_linear_t* nx[1] = {&Ly.o};
@@ -1231,10 +1282,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
           const quipb200_linear_t* nx[2] = {&Ly.gate, &Ly.up};
           prefetch_stage(nx, p.geo.G_D, 2, bid, tid);
         }
-        gemv_first(cw, c, warp, lane, pol);
-        gemv_run(cw, c, xq, tab, red, warp, lane, pol);
+        gemv_first<CB>(cw, c, warp, lane, pol);
+        gemv_run<CB>(cw, c, xq, tab, red, warp, lane, pol);
         DS_ST(14);
-        gemv_store(c, red, p.ws.acc[SL_O], xs, tid);
+        gemv_store<CB>(c, red, p.ws.acc[SL_O], xs, L.resid_scale, tid);
       } else {
         const quipb200_linear_t* nx[2] = {&Ly.gate, &Ly.up};
         prefetch_stage(nx, p.geo.G_D, 2, bid, tid);
@@ -1284,10 +1335,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
           const quipb200_linear_t* nx[1] = {&Ly.down};
           prefetch_stage(nx, &p.geo.G_E, 1, bid, tid);
         }
-        gemv_first(cw, c, warp, lane, pol);
-        gemv_run(cw, c, xq, tab, red, warp, lane, pol);
+        gemv_first<CB>(cw, c, warp, lane, pol);
+        gemv_run<CB>(cw, c, xq, tab, red, warp, lane, pol);
         DS_ST(18);
-        gemv_store(c, red, p.ws.acc[SL_G + j], xs, tid);
+        gemv_store<CB>(c, red, p.ws.acc[SL_G + j], xs, L.resid_scale, tid);
       } else {
         const quipb200_linear_t* nx[1] = {&Ly.down};
         prefetch_stage(nx, &p.geo.G_E, 1, bid, tid);
@@ -1334,10 +1385,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
           const quipb200_linear_t* nx[3] = {&Ln.q, &Ln.k, &Ln.v};
           prefetch_stage(nx, p.geo.G_A, 3, bid, tid);
         }
-        gemv_first(cw, c, warp, lane, pol);
-        gemv_run(cw, c, xq, tab, red, warp, lane, pol);
+        gemv_first<CB>(cw, c, warp, lane, pol);
+        gemv_run<CB>(cw, c, xq, tab, red, warp, lane, pol);
         DS_ST(23);
-        gemv_store(c, red, p.ws.acc[SL_D], xs, tid);
+        gemv_store<CB>(c, red, p.ws.acc[SL_D], xs, L.resid_scale, tid);
       } else if (l + 1 < P.n_layers) {
         const quipb200_decode_layer_t& Ln = s_desc[(l + 1) & 1];
         const quipb200_linear_t* nx[3] = {&Ln.q, &Ln.k, &Ln.v};
@@ -1382,7 +1433,9 @@ static int ilog2_exact_h(int v) {
 }
 
 static bool linear_ok(const quipb200_linear_t& L) {
-  if (L.codebook != QUIPB200_CB_E8P12 || !L.qidxs || !L.grid) return false;
+  if ((L.codebook != QUIPB200_CB_E8P12 && L.codebook != QUIPB200_CB_E8P12RVQ4B && L.codebook != QUIPB200_CB_D4) ||
+      !L.qidxs || !L.grid)
+    return false;
   if (L.K_left < 1 || L.K_right < 1 || L.q_in % L.K_left || L.q_out % L.K_right) return false;
   if (L.in_features > L.q_in || L.out_features > L.q_out) return false;
   if ((L.K_left > 1 && !L.had_left) || (L.K_right > 1 && !L.had_right)) return false;
@@ -1433,7 +1486,7 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
     const quipb200_linear_t* all[SL_N] = {&Z.q, &Z.k, &Z.v, &Z.o, &Z.gate, &Z.up, &Z.down};
     const quipb200_linear_t* ref[SL_N] = {&Y.q, &Y.k, &Y.v, &Y.o, &Y.gate, &Y.up, &Y.down};
     for (int i = 0; i < SL_N; i++)
-      if (!linear_ok(*all[i]) || !same_shape(*all[i], *ref[i])) return QUIPB200_EUNSUPPORTED;
+      if (!linear_ok(*all[i]) || !same_shape(*all[i], *ref[i]) || all[i]->codebook != Y.q.codebook) return QUIPB200_EUNSUPPORTED;
     if (!Z.input_norm_w || !Z.post_norm_w || !Z.k_cache || !Z.v_cache) return QUIPB200_EINVAL;
   }
   // shape chain of a Llama decoder layer
@@ -1488,9 +1541,10 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
   for (auto& g : groups) {
     for (int i = 0; i < g.n; i++) {
       const quipb200_linear_t& L = *g.m[i];
-      const int nseg = L.q_in / 8, lanes = (nseg + 7) / 8, C = (lanes + 31) / 32;
+      const int segs = L.codebook == QUIPB200_CB_E8P12RVQ4B ? 4 : 8, accs = L.codebook == QUIPB200_CB_E8P12RVQ4B ? 2 : 1;
+      const int nseg = L.q_in / 8, lanes = (nseg + segs - 1) / segs, C = (lanes + 31) / 32;
       const size_t rows = (size_t)L.q_out / g.G[i] + 1;
-      red = std::max(red, rows * C * sizeof(int));
+      red = std::max(red, rows * C * accs * sizeof(int));
       xq = std::max(xq, (size_t)((nseg + 7) / 8 * 8) * 16);
     }
   }
@@ -1586,18 +1640,22 @@ extern "C" int quipb200_decode_step(const quipb200_decode_plan_t* plan, const qu
   int rc = ds_layout(plan, host_layers, sms, &lay);
   if (rc) return rc;
   if (workspace_bytes < lay.ws_bytes) return QUIPB200_EWORKSPACE;
-  static int checked_dev = -1;
+  static int checked_dev[5] = {-1, -1, -1, -1, -1};
   int dev = 0;
   cudaGetDevice(&dev);
-  cudaError_t e = cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.sm.total);
+  const int cb = host_layers[0].q.codebook;
+  const void* fn = cb == QUIPB200_CB_E8P12        ? (const void*)decode_step_kernel<QUIPB200_CB_E8P12>
+                   : cb == QUIPB200_CB_E8P12RVQ4B ? (const void*)decode_step_kernel<QUIPB200_CB_E8P12RVQ4B>
+                                                  : (const void*)decode_step_kernel<QUIPB200_CB_D4>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.sm.total);
   if (e != cudaSuccess) return (int)e;
-  if (checked_dev != dev) {
+  if (checked_dev[cb] != dev) {
     int coop = 0, occ = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_step_kernel, DS_THREADS, lay.sm.total);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, DS_THREADS, lay.sm.total);
     if (e != cudaSuccess) return (int)e;
     if (!coop || occ < 1) return QUIPB200_EUNSUPPORTED;
-    checked_dev = dev;
+    checked_dev[cb] = dev;
   }
   DsParams p{};
   p.plan = *plan;
@@ -1628,7 +1686,7 @@ extern "C" int quipb200_decode_step(const quipb200_decode_plan_t* plan, const qu
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   void* args[] = {&p};
-  e = cudaLaunchKernelExC(&cfg, (const void*)decode_step_kernel, args);
+  e = cudaLaunchKernelExC(&cfg, fn, args);
   if (e != cudaSuccess) return (int)e;
   QB_LAUNCH_CHECK();
   return 0;

@@ -63,8 +63,10 @@ class PersistentDecodeStep:
             at, mlp = lyr.self_attn, lyr.mlp
             mods = (at.q_proj, at.k_proj, at.v_proj, at.o_proj, mlp.gate_proj, mlp.up_proj, mlp.down_proj)
             for m in mods:
-                if getattr(getattr(m, "codebook", None), "id", None) != "E8P12" or getattr(m, "per_channel", False):
-                    raise ValueError("persistent decode step: every block linear must be an E8P12 QuantLinear")
+                cbid = getattr(getattr(m, "codebook", None), "id", None)
+                if cbid not in ("E8P12", "E8P12RVQ4B", "D4") or cbid != mods[0].codebook.id or getattr(m, "per_channel", False):
+                    raise ValueError("persistent decode step: every block linear must be a QuantLinear of one codebook "
+                                     "(E8P12, E8P12RVQ4B or D4)")
                 for t in (m.SU, m.SV, m.bias, m.had_left, m.had_right):
                     if t is not None and t.dtype != torch.float16:
                         raise ValueError("persistent decode step needs fp16 scale / bias / hadK tensors")

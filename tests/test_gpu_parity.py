@@ -743,3 +743,29 @@ def test_persistent_decode_step_matches_cpu_oracle(name):
             assert np.abs(gk - kc[i][:, pos]).max() <= 2.0 ** -7 * np.abs(kc[i][:, pos]).max() + 1e-3
             assert np.abs(gv - vc[i][:, pos]).max() <= 2.0 ** -7 * np.abs(vc[i][:, pos]).max() + 1e-3
         eng.pos.add_(1)
+
+
+@pytest.mark.parametrize("cb", ["E8P12RVQ4B", "D4"])
+def test_persistent_decode_step_other_codebooks(cb):
+    """BASELINE config 4 codebooks through the persistent kernel (two integer accumulators + fp16 residual scale for
+    RVQ4B; 1-byte codes and the half-unit table for D4) against the per-linear launches."""
+    from quip_for_all_b200.modeling import LlamaDecodeEngine, llama_config, make_random_quantized_llama
+    model = make_random_quantized_llama(llama_config("tiny256", num_hidden_layers=2), cb, seed=6, device=DEV)
+    e1 = LlamaDecodeEngine(model, max_cache_len=64, persistent=True, use_cuda_graph=False)
+    assert e1.persistent is not None
+    e2 = LlamaDecodeEngine(model, max_cache_len=64, persistent=False, use_cuda_graph=False)
+    ids = torch.randint(0, 32000, (1, 7), generator=torch.Generator().manual_seed(8)).to(DEV)
+    e1.prefill(ids)
+    e2.prefill(ids)
+    for _ in range(2):
+        with torch.no_grad():
+            h = model.model.embed_tokens(e1.tok).view(1, -1).contiguous()
+            h1 = e1.persistent(h, e1.h_step_out).clone()
+            h2 = h.clone()
+            for li in range(len(e2.layers)):
+                h2 = e2._layer_fused(li, h2)
+        torch.cuda.synchronize()
+        d = (h1.float() - h2.float()).abs().max().item()
+        assert d <= 2.0 ** -8 * h2.float().abs().max().item(), (cb, d)
+        e1.pos.add_(1)
+        e2.pos.add_(1)
