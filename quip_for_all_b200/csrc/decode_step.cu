@@ -566,19 +566,12 @@ __device__ __forceinline__ float in_side_m(const float (&f)[8], bool has_norm, f
 // ---------------------------------------------------------------------------------------------
 struct BlkBuf { __half* Tg; __half* Tu; __half* hkg; __half* hku; __half* hkd; __half* vSVg; __half* vSVu; __half* vSUd; int LS; };
 
-// In-place K x K mix  T <- M T  of one or two block buffers (256 columns, row stride LS) on the tensor path.  The A
-// fragments of the coefficient matrix are loaded once per call and reused for every 8-column tile the warp owns; both
+// In-place K x K mix  T <- M T  of one or two block buffers (256 columns, row stride LS) on the tensor path; both
 // buffers share one barrier pair.  fp16 operands, fp32 accumulate, one fp16 rounding: the reference's `hadK @ y`
 // (quant.py:83).  MT = Kp / 16.
 template <int MT>
 __device__ __forceinline__ void mix_tiles_one(__half* T, const __half* hk, int K, int LS, int warp, int lane) {
   constexpr int Kp = MT * 16;
-  uint32_t af[MT][MT][4];
-#pragma unroll
-  for (int mt = 0; mt < MT; mt++)
-#pragma unroll
-    for (int kt = 0; kt < MT; kt++)
-      ldmatrix_x4(af[mt][kt], hk + (size_t)(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * Kp + kt * 16 + (lane >> 4) * 8);
   const int g = lane >> 2, tq = lane & 3;
   for (int nt_i = warp; nt_i < 32; nt_i += DS_WARPS) {
     const int c0 = nt_i << 3;
@@ -595,7 +588,11 @@ __device__ __forceinline__ void mix_tiles_one(__half* T, const __half* hk, int K
 #pragma unroll
       for (int j = 0; j < 4; j++) acc[mt][j] = 0.f;
 #pragma unroll
-      for (int kt = 0; kt < MT; kt++) mma_16816(acc[mt], af[mt][kt], bf[kt]);
+      for (int kt = 0; kt < MT; kt++) {      // A fragments are re-read per tile: keeping all MT*MT of them live spilled
+        uint32_t af[4];
+        ldmatrix_x4(af, hk + (size_t)(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * Kp + kt * 16 + (lane >> 4) * 8);
+        mma_16816(acc[mt], af, bf[kt]);
+      }
     }
     __syncwarp();                                          // every lane has read its B fragments of this tile
 #pragma unroll
