@@ -13,6 +13,8 @@ extern int g_opt_stage_mask;
 extern int g_opt_fuse;
 extern int g_opt_phase0;
 extern int g_opt_lean;
+extern int g_opt_rot_warp_rows;
+extern int g_ds_rebalance;
 int g_opt_umma = 2;     // in-kernel decode + tcgen05 GEMM (umma_gemm.cu): 0 = never, 1 = whenever the shape is covered
                         // (M <= 256), 2 = auto: where it measured faster than the alternatives (profiles/README.md)
 }  // namespace qb
@@ -82,6 +84,15 @@ extern "C" int quipb200_set_option(const char* name, int value) {
     qb::g_opt_umma = value;
     return 0;
   }
+  if (!strcmp(name, "ds_rebalance")) {
+    qb::g_ds_rebalance = value ? 1 : 0;
+    return 0;
+  }
+  if (!strcmp(name, "rot_warp_rows")) {
+    if (value < 1) return QUIPB200_EINVAL;
+    qb::g_opt_rot_warp_rows = value;
+    return 0;
+  }
   if (!strcmp(name, "fuse")) {
     if (value < 0 || value > 3) return QUIPB200_EINVAL;
     qb::g_opt_fuse = value;
@@ -99,6 +110,8 @@ extern "C" int quipb200_get_option(const char* name) {
   if (!strcmp(name, "fuse")) return qb::g_opt_fuse;
   if (!strcmp(name, "pdl")) return qb::g_opt_pdl;
   if (!strcmp(name, "umma")) return qb::g_opt_umma;
+  if (!strcmp(name, "rot_warp_rows")) return qb::g_opt_rot_warp_rows;
+  if (!strcmp(name, "ds_rebalance")) return qb::g_ds_rebalance;
   return QUIPB200_EINVAL;
 }
 

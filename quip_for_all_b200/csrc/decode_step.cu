@@ -65,6 +65,7 @@ struct DsParams {
   __half* h_out;
   int kv_splits;
   int use_mma;           // hidden-side rotations are 4096-point: tensor-path transforms
+  int rebalance;         // GEMV unit split for wide rows (make_cfg)
   long long* dbg;        // optional [64] clock stamps of one CTA (tools/ds_timeline.py)
   int dbg_cta;
 };
@@ -96,12 +97,20 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 struct GemvCfg {
   const unsigned char* q;
   int64_t row_bytes;
-  int nseg, C, g, row_begin, nrows;
+  int nseg, C, g, rot, row_begin, nrows;
 };
+
+// work unit -> (column chunk, row phase).  rot != 0 (g == 8): every pass over the warps shifts the row phase by rot, so a
+// warp does not get the long row phases (nrows % g of them have one row more) in all of its units.
+__device__ __forceinline__ void unit_of(const GemvCfg& c, int unit, int& chunk, int& sub) {
+  chunk = unit / c.g;
+  sub = unit - chunk * c.g;
+  if (c.rot) sub = (sub + c.rot * (unit / DS_WARPS)) & (c.g - 1);
+}
 
 __device__ __forceinline__ int ilog2_dev(int v) { return 31 - __clz(v); }
 
-__device__ __forceinline__ GemvCfg make_cfg(const quipb200_linear_t& L, int bx, int G) {
+__device__ __forceinline__ GemvCfg make_cfg(const quipb200_linear_t& L, int bx, int G, int rebalance = 0) {
   GemvCfg c;
   c.q = reinterpret_cast<const unsigned char*>(L.qidxs);
   c.nseg = L.q_in >> 3;
@@ -110,6 +119,10 @@ __device__ __forceinline__ GemvCfg make_cfg(const quipb200_linear_t& L, int bx, 
   const int lanes = (c.nseg + segs - 1) / segs;
   c.C = (lanes + 31) >> 5;
   c.g = c.C >= DS_WARPS ? 1 : DS_WARPS / c.C;
+  c.rot = 0;
+  // C * g units on DS_WARPS warps: when an eighth of the warps or more would idle (11008 columns: 6 chunks x 2 = 12 units,
+  // 14 rows each, against 9.4 for a perfect split) switch to 8 row phases per chunk and several units per warp
+  if (rebalance && c.C < DS_WARPS && c.C * c.g * 8 < DS_WARPS * 7) { c.g = 8; c.rot = 4; }
   const int base = L.q_out / G, rem = L.q_out % G;
   c.row_begin = bx * base + min(bx, rem);
   c.nrows = base + (bx < rem ? 1 : 0);
@@ -120,7 +133,8 @@ template <int CB>
 __device__ __forceinline__ void gemv_first(uint4 (&cw)[DS_UNROLL], const GemvCfg& c, int warp, int lane, uint64_t pol) {
   constexpr int SEGS = CbTraits<CB>::SEGS;
   const int units = c.C * c.g;
-  const int chunk = warp / c.g, sub = warp - chunk * c.g;
+  int chunk, sub;
+  unit_of(c, warp, chunk, sub);
   const bool lv = warp < units && (chunk * 32 + lane) * SEGS < c.nseg;
   const unsigned char* colp = c.q + (size_t)(chunk * 32 + lane) * 16 + (size_t)c.row_begin * c.row_bytes;
 #pragma unroll
@@ -161,8 +175,8 @@ __device__ __forceinline__ void gemv_run(uint4 (&cw)[DS_UNROLL], const GemvCfg& 
   const int units = c.C * c.g;
   int unit = warp;
   while (unit < units) {
-    const int chunk = unit / c.g;
-    const int sub = unit - chunk * c.g;
+    int chunk, sub;
+    unit_of(c, unit, chunk, sub);
     const int seg0 = (chunk * 32 + lane) * T::SEGS;
     const bool lane_valid = seg0 < c.nseg;
     uint32_t xs[T::SEGS][4];
@@ -238,7 +252,8 @@ __device__ __forceinline__ void gemv_run(uint4 (&cw)[DS_UNROLL], const GemvCfg& 
     }
     unit += DS_WARPS;
     if (unit < units) {
-      const int chunk2 = unit / c.g, sub2 = unit - chunk2 * c.g;
+      int chunk2, sub2;
+      unit_of(c, unit, chunk2, sub2);
       const bool lv = (chunk2 * 32 + lane) * T::SEGS < c.nseg;
       const unsigned char* colp2 = c.q + (size_t)(chunk2 * 32 + lane) * 16 + (size_t)c.row_begin * c.row_bytes;
 #pragma unroll
@@ -461,10 +476,15 @@ struct Stg {
   __half* nw;      // [4096] RMSNorm weight
   __half* su;      // [4096] SU of the consuming linear
   __half* atto;    // [n_heads * S * 128] split-KV partial outputs (stage C; aliases sv .. nw)
-  __half* wscr;    // [16 warps][256] per-warp scratch (octet -> fragment layout)
 };
+// The staged vectors are read at spread-layout positions, 4 consecutive halfs per lane: stored with the chunk swizzle of
+// fwht_mma.cuh (4 wavefronts per 8-byte read instead of 8 per 4-byte read).
 __device__ __forceinline__ void stg_vec(__half* dst, const __half* src, int n, int tid) {
-  if (src != nullptr && tid * 8 < n) cp_async16(dst + tid * 8, src + tid * 8);
+  if (src != nullptr && tid * 8 < n) cp_async16(dst + stg_chunk(tid) * 8, src + tid * 8);
+}
+// halfs i .. i+3 (i % 4 == 0) of a staged vector
+__device__ __forceinline__ uint2 stg_ld4(const __half* v, int i) {
+  return *reinterpret_cast<const uint2*>(v + stg_chunk(i >> 3) * 8 + (i & 7));
 }
 
 // f[2q], f[2q+1]: fp32 result at elements idx_spread(warp, lane, q) (+1) BEFORE the final fp16 rounding.
@@ -472,37 +492,42 @@ __device__ __forceinline__ void stg_vec(__half* dst, const __half* src, int n, i
 __device__ __forceinline__ uint4 out_side_load(const __half* acc, int warp, int lane) {   // block `warp`, octet `lane`
   return __ldcg(reinterpret_cast<const uint4*>(acc) + warp * 32 + lane);
 }
-__device__ __forceinline__ void out_side_m(const quipb200_linear_t& Lp, const uint4& oct, bool has_resid, const Stg& st,
+__device__ __forceinline__ void out_side_m(const quipb200_linear_t& Lp, const uint4& oct_in, bool has_resid, const Stg& st,
                                            const HFrag& A, float* S, int warp, int lane, float (&f)[8],
                                            long long* dbg = nullptr) {
   const bool has_sv = Lp.SV != nullptr, has_bias = Lp.bias != nullptr;
   const __half* wpc = reinterpret_cast<const __half*>(Lp.wscale_pc);
-  uint32_t p[4];
-  warp_octets_to_frag(oct, st.wscr + warp * 256, lane, p);
-  if (dbg) dbg[40] = clock64() + (p[0] & 0);
-  if (wpc) {
-#pragma unroll
-    for (int q = 0; q < 4; q++) p[q] = as_u32(__hmul2(as_h2(p[q]), as_h2(ldg_h2(wpc, idx_block(warp, lane, q)))));   // qlinear.py:107
-  }
+  uint4 oct = oct_in;
+  if (dbg) dbg[40] = clock64() + (oct.x & 0);
+  if (wpc) oct = hmul2x4(oct, __ldg(reinterpret_cast<const uint4*>(wpc) + warp * 32 + lane));   // qlinear.py:107
+  const uint32_t p[4] = {oct.x, oct.z, oct.y, oct.w};                                // natural placement (fwht_mma.cuh)
   cp_async_wait_all();                                                               // staged vectors: visible after the
   if (dbg) dbg[41] = clock64();
   fwht4096_frag(p, A, S, warp, lane, f);                                             // exchange barrier inside; x 1/64
   if (dbg) dbg[42] = clock64() + (__float_as_int(f[0]) & 0);
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const int i = idx_spread(warp, lane, q);
+  for (int xh = 0; xh < 2; xh++) {
+    const int i = idx_spread(warp, lane, xh);                                        // pairs xh and xh + 2: halfs i .. i+3
     const bool ok = i < Lp.out_features;
-    __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
-    if (has_sv) h = __hmul2(h, *reinterpret_cast<const __half2*>(st.sv + i));        // qlinear.py:112
-    if (has_bias) h = __hadd2(h, *reinterpret_cast<const __half2*>(st.bias + i));    // qlinear.py:114
-    float2 v = __half22float2(h);
-    if (has_resid) {
-      const float2 r = __half22float2(*reinterpret_cast<const __half2*>(st.resid + i));
-      v.x += r.x;
-      v.y += r.y;
+    uint2 sv = make_uint2(0, 0), bi = sv, re = sv;
+    if (has_sv) sv = stg_ld4(st.sv, i);
+    if (has_bias) bi = stg_ld4(st.bias, i);
+    if (has_resid) re = stg_ld4(st.resid, i);
+#pragma unroll
+    for (int yh = 0; yh < 2; yh++) {
+      const int q = xh + 2 * yh;
+      __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
+      if (has_sv) h = __hmul2(h, as_h2(yh ? sv.y : sv.x));                            // qlinear.py:112
+      if (has_bias) h = __hadd2(h, as_h2(yh ? bi.y : bi.x));                          // qlinear.py:114
+      float2 v = __half22float2(h);
+      if (has_resid) {
+        const float2 r = __half22float2(as_h2(yh ? re.y : re.x));
+        v.x += r.x;
+        v.y += r.y;
+      }
+      f[2 * q] = ok ? v.x : 0.f;
+      f[2 * q + 1] = ok ? v.y : 0.f;
     }
-    f[2 * q] = ok ? v.x : 0.f;
-    f[2 * q + 1] = ok ? v.y : 0.f;
   }
 }
 
@@ -529,34 +554,41 @@ __device__ __forceinline__ float in_side_m(const float (&f)[8], bool has_norm, f
   }
   uint32_t p[4];
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const int i = idx_spread(warp, lane, q);
+  for (int xh = 0; xh < 2; xh++) {
+    const int i = idx_spread(warp, lane, xh);                                        // pairs xh and xh + 2: halfs i .. i+3
     const bool ok = i < L.in_features;
-    __half2 h = __floats2half2_rn(f[2 * q] * rstd, f[2 * q + 1] * rstd);
-    if (has_norm) h = __hmul2(*reinterpret_cast<const __half2*>(st.nw + i), h);
-    if (has_su) h = __hmul2(h, *reinterpret_cast<const __half2*>(st.su + i));        // qlinear.py:91
-    p[q] = ok ? as_u32(h) : 0u;
+    uint2 nw = make_uint2(0, 0), su = nw;
+    if (has_norm) nw = stg_ld4(st.nw, i);
+    if (has_su) su = stg_ld4(st.su, i);
+#pragma unroll
+    for (int yh = 0; yh < 2; yh++) {
+      const int q = xh + 2 * yh;
+      __half2 h = __floats2half2_rn(f[2 * q] * rstd, f[2 * q + 1] * rstd);
+      if (has_norm) h = __hmul2(as_h2(yh ? nw.y : nw.x), h);
+      if (has_su) h = __hmul2(h, as_h2(yh ? su.y : su.x));                            // qlinear.py:91
+      p[q] = ok ? as_u32(h) : 0u;
+    }
   }
   float r[8];
   fwht4096_frag(p, A, S, warp, lane, r);                                             // block layout, 1/64 included
+  // block layout with natural placement: this thread now holds octet `tid` of the rotated vector, i.e. its own record
   const float ws = L.wscale_float;
   float mx = 0.f;
+  float o8[8];
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     const __half2 h = __floats2half2_rn(r[2 * q] * ws, r[2 * q + 1] * ws);           // register_lib.py:20 (fp16 out)
     const float2 v = __half22float2(h);
     mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
-    *reinterpret_cast<__half2*>(V + idx_block(warp, lane, q)) = h;
+    const int e = idx_block(0, 0, q);
+    o8[e] = v.x;
+    o8[e + 1] = v.y;
   }
-  mx = block_max1(mx, fred + 32, tid, DS_THREADS);                                   // its barrier also publishes V
+  mx = block_max1(mx, fred + 32, tid, DS_THREADS);
   const float inv = (mx > 0.f) ? 32767.0f / mx : 0.f;
-  {
-    float o8[8];
-    unpack_h8(*reinterpret_cast<const uint4*>(V + tid * 8), o8);
-    uint4 rec;
-    pack_record(o8, inv, rec);
-    xq[swz(tid)] = rec;
-  }
+  uint4 rec;
+  pack_record(o8, inv, rec);
+  xq[swz(tid)] = rec;
   __syncthreads();
   return (mx > 0.f) ? mx / 32767.0f : 0.f;
 }
@@ -631,7 +663,7 @@ __device__ __forceinline__ void mix_blocks(__half* T0, const __half* hk0, __half
 constexpr int DS_EB = 3;   // blocks per warp in flight (K <= 48 in one round)
 __device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, const quipb200_linear_t& Lu,
                                                 const quipb200_linear_t& Ld, const __half* acc_g, const __half* acc_u,
-                                                const __half* hk_blob, const BlkBuf& bb, const HFrag& A, __half* wscr,
+                                                const __half* hk_blob, const BlkBuf& bb, const HFrag& A,
                                                 float* fred, uint4* xq, int tid, long long* dbg) {
 #define DS_E(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   const int lane = tid & 31, warp = tid >> 5;
@@ -694,26 +726,17 @@ __device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, con
     for (int r = 0; r < DS_EB; r++) {
       const int b = b0 + r * DS_WARPS;
       if (b < K) {
-        uint32_t pg[4], pu[4];
-        warp_octets_to_frag(ga[r], wscr + warp * 512, lane, pg);
-        warp_octets_to_frag(ua[r], wscr + warp * 512 + 256, lane, pu);
-        if (wg || wu) {
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int e = b * 256 + frag_x(lane, q) * 16 + frag_y(lane, q);
-            if (wg) pg[q] = as_u32(__hmul2(as_h2(pg[q]), as_h2(ldg_h2(wg, e))));
-            if (wu) pu[q] = as_u32(__hmul2(as_h2(pu[q]), as_h2(ldg_h2(wu, e))));
-          }
-        }
+        // the lane's octet is already a valid fragment (F(x, y) is a bit permutation of the natural index and H_256 is
+        // invariant under it, tools/emu_fwht_frag.py): pairs in, the same octet's transformed pairs out
+        uint4 go = ga[r], uo = ua[r];
+        if (wg) go = hmul2x4(go, __ldg(reinterpret_cast<const uint4*>(wg) + b * 32 + lane));
+        if (wu) uo = hmul2x4(uo, __ldg(reinterpret_cast<const uint4*>(wu) + b * 32 + lane));
+        const uint32_t pg[4] = {go.x, go.z, go.y, go.w}, pu[4] = {uo.x, uo.z, uo.y, uo.w};
         float g[8], u[8];
         fwht256_frag(pg, A, g);
         fwht256_frag(pu, A, u);
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int e = frag_x(lane, q) * 16 + frag_y(lane, q);
-          *reinterpret_cast<__half2*>(bb.Tg + b * LS + e) = __floats2half2_rn(g[2 * q], g[2 * q + 1]);
-          *reinterpret_cast<__half2*>(bb.Tu + b * LS + e) = __floats2half2_rn(u[2 * q], u[2 * q + 1]);
-        }
+        *reinterpret_cast<uint4*>(bb.Tg + b * LS + lane * 8) = frag_to_octet(g, 1.0f);
+        *reinterpret_cast<uint4*>(bb.Tu + b * LS + lane * 8) = frag_to_octet(u, 1.0f);
       }
     }
   }
@@ -724,30 +747,38 @@ __device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, con
   // SV / bias of gate and up, silu(gate) * up, SU of down, block transform of down's input (x wscale/16)
   const float ws_d = Ld.wscale_float;
   for (int b = warp; b < K; b += DS_WARPS) {
-    uint32_t pa[4];
+    const int o = b * 32 + lane;               // octet of the intermediate vector
+    const uint4 g4 = *reinterpret_cast<const uint4*>(bb.Tg + b * LS + lane * 8);
+    const uint4 u4 = *reinterpret_cast<const uint4*>(bb.Tu + b * LS + lane * 8);
+    uint4 sv_g = make_uint4(0, 0, 0, 0), sv_u = sv_g, su_d = sv_g, b_g = sv_g, b_u = sv_g;
+    if (SVg) sv_g = *reinterpret_cast<const uint4*>(bb.vSVg + o * 8);
+    if (SVu) sv_u = *reinterpret_cast<const uint4*>(bb.vSVu + o * 8);
+    if (SUd) su_d = *reinterpret_cast<const uint4*>(bb.vSUd + o * 8);
+    if (bg && o < noct_mid) b_g = __ldg(reinterpret_cast<const uint4*>(bg) + o);
+    if (bu && o < noct_mid) b_u = __ldg(reinterpret_cast<const uint4*>(bu) + o);
+    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, uw[4] = {u4.x, u4.y, u4.z, u4.w};
+    const uint32_t svg[4] = {sv_g.x, sv_g.y, sv_g.z, sv_g.w}, svu[4] = {sv_u.x, sv_u.y, sv_u.z, sv_u.w};
+    const uint32_t sud[4] = {su_d.x, su_d.y, su_d.z, su_d.w};
+    const uint32_t bgw[4] = {b_g.x, b_g.y, b_g.z, b_g.w}, buw[4] = {b_u.x, b_u.y, b_u.z, b_u.w};
+    uint32_t aw[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      const int e = frag_x(lane, q) * 16 + frag_y(lane, q);
-      const int i = b * 256 + e;
-      __half2 g = *reinterpret_cast<const __half2*>(bb.Tg + b * LS + e);
-      __half2 u = *reinterpret_cast<const __half2*>(bb.Tu + b * LS + e);
-      if (SVg) g = __hmul2(g, *reinterpret_cast<const __half2*>(bb.vSVg + i));
-      if (bg) g = __hadd2(g, as_h2(ldg_h2(bg, i)));
-      if (SVu) u = __hmul2(u, *reinterpret_cast<const __half2*>(bb.vSVu + i));
-      if (bu) u = __hadd2(u, as_h2(ldg_h2(bu, i)));
+      __half2 g = as_h2(gw[q]);
+      __half2 u = as_h2(uw[q]);
+      if (SVg) g = __hmul2(g, as_h2(svg[q]));
+      if (bg) g = __hadd2(g, as_h2(bgw[q]));
+      if (SVu) u = __hmul2(u, as_h2(svu[q]));
+      if (bu) u = __hadd2(u, as_h2(buw[q]));
       const float2 gf = __half22float2(g);
       const __half2 sg = __floats2half2_rn(silu_f(gf.x), silu_f(gf.y));
       __half2 a = __hmul2(sg, u);                                    // LlamaMLP: act_fn(gate) * up
-      if (SUd) a = __hmul2(a, *reinterpret_cast<const __half2*>(bb.vSUd + i));
-      pa[q] = (i < (noct_mid << 3)) ? as_u32(a) : 0u;
+      if (SUd) a = __hmul2(a, as_h2(sud[q]));
+      aw[q] = (o < noct_mid) ? as_u32(a) : 0u;
     }
+    const uint32_t pa[4] = {aw[0], aw[2], aw[1], aw[3]};
     float u[8];
     fwht256_frag(pa, A, u);
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int e = frag_x(lane, q) * 16 + frag_y(lane, q);
-      *reinterpret_cast<__half2*>(bb.Tu + b * LS + e) = __floats2half2_rn(u[2 * q] * ws_d, u[2 * q + 1] * ws_d);   // in place
-    }
+    *reinterpret_cast<uint4*>(bb.Tu + b * LS + lane * 8) = frag_to_octet(u, ws_d);      // in place
   }
   DS_E(33);
   mix_blocks(bb.Tu, bb.hkd, nullptr, nullptr, K, LS, tid);
@@ -873,7 +904,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
   Stg stg;                                                   // staging vectors: behind V, same aliasing
   stg.sv = V + 4096; stg.bias = stg.sv + 4096; stg.resid = stg.bias + 4096; stg.nw = stg.resid + 4096;
   stg.atto = stg.sv;                                          // 32 KB (n_heads * S * 128 halfs <= 16384)
-  stg.su = stg.sv + 32768; stg.wscr = stg.su + 4096;
+  stg.su = stg.sv + 32768;
   long long* dbg = (p.dbg && bid == p.dbg_cta && tid == 0) ? p.dbg : nullptr;
 #define DS_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
 #define DS_ST(i) do { if (dbg && l == 1) dbg[i] = clock64(); } while (0)
@@ -927,7 +958,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
       which_member(p.geo.G_A, 3, bid, j, bx);
       if (j >= 0) {
         const quipb200_linear_t L = (j == 0) ? Ly.q : (j == 1 ? Ly.k : Ly.v);
-        const GemvCfg c = make_cfg(L, bx, p.geo.G_A[j]);
+        const GemvCfg c = make_cfg(L, bx, p.geo.G_A[j], p.rebalance);
         DS_ST(1);
         float f[8];
         float xs;
@@ -1193,13 +1224,16 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
       which_member(&p.geo.G_C, 1, bid, j, bx);
       if (j >= 0) {
         const quipb200_linear_t L = Ly.o;
-        const GemvCfg c = make_cfg(L, bx, p.geo.G_C);
+        const GemvCfg c = make_cfg(L, bx, p.geo.G_C, p.rebalance);
         // combine the split-KV partials into the fp16 attention output.  Split weights exp(m_s - M) / sum go through
         // shared memory: [head][split] floats, computed once per CTA
         float* wsm = rb.fred + 64;   // aliases the block buffers (unused in this stage); n_heads * S <= 512 floats
         if (p.use_mma) {             // partial outputs and SU of o_proj -> shared memory, 16 bytes per request
           const int n8 = (P.n_heads * S * DS_HD) >> 3;
-          for (int i = tid; i < n8; i += DS_THREADS) cp_async16(stg.atto + i * 8, p.ws.att_o + i * 8);
+          for (int i = tid; i < n8; i += DS_THREADS) {           // chunk swizzle: see the combine below
+            const int row = i >> 4, hh = row / S;
+            cp_async16(stg.atto + (((row << 4) | ((i & 15) ^ ((hh >> 1) & 7))) << 3), p.ws.att_o + i * 8);
+          }
           stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
         }
         if (tid < P.n_heads) {
@@ -1225,32 +1259,34 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float xs;
         if (p.use_mma) {
-          // register pairs at idx_spread positions: pairs q and q+2 share a head
+          // register pairs at idx_spread positions: pairs xh and xh + 2 are 4 consecutive halfs of one head.  The row
+          // groups of a warp are 2 heads apart (the same banks), so 16-byte chunk c of head row r = h * S + s is staged
+          // at chunk c ^ ((h >> 1) & 7) of that row.
 #pragma unroll
           for (int xh = 0; xh < 2; xh++) {
             const int i0 = idx_spread(warp, lane, xh);
             if (i0 < P.n_heads * DS_HD) {
-              const int h = i0 >> 7;
-              float w[DS_MAX_SPLITS];
+              const int h = i0 >> 7, d0 = i0 & (DS_HD - 1);
+              const int off = ((((d0 >> 3) ^ ((h >> 1) & 7))) << 3) + (d0 & 7);
+              float ax0 = 0.f, ay0 = 0.f, ax1 = 0.f, ay1 = 0.f;
 #pragma unroll
-              for (int s = 0; s < DS_MAX_SPLITS; s++) w[s] = (s < S) ? wsm[h * S + s] : 0.f;
-#pragma unroll
-              for (int yh = 0; yh < 2; yh++) {
-                const int q = xh + 2 * yh;
-                const int d = idx_spread(warp, lane, q) & (DS_HD - 1);
-                float ax = 0.f, ay = 0.f;
-#pragma unroll
-                for (int s = 0; s < DS_MAX_SPLITS; s++) {
-                  if (s < S) {
-                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(stg.atto + (h * S + s) * DS_HD + d));
-                    ax = fmaf(w[s], a.x, ax);
-                    ay = fmaf(w[s], a.y, ay);
-                  }
+              for (int s = 0; s < DS_MAX_SPLITS; s++) {
+                if (s < S) {
+                  const float w = wsm[h * S + s];
+                  const uint2 a = *reinterpret_cast<const uint2*>(stg.atto + (h * S + s) * DS_HD + off);
+                  const float2 a0 = __half22float2(as_h2(a.x)), a1 = __half22float2(as_h2(a.y));
+                  ax0 = fmaf(w, a0.x, ax0);
+                  ay0 = fmaf(w, a0.y, ay0);
+                  ax1 = fmaf(w, a1.x, ax1);
+                  ay1 = fmaf(w, a1.y, ay1);
                 }
-                const float2 v = __half22float2(__floats2half2_rn(ax, ay));
-                f[2 * q] = v.x;
-                f[2 * q + 1] = v.y;
               }
+              const float2 v0 = __half22float2(__floats2half2_rn(ax0, ay0));
+              const float2 v1 = __half22float2(__floats2half2_rn(ax1, ay1));
+              f[2 * xh] = v0.x;
+              f[2 * xh + 1] = v0.y;
+              f[2 * xh + 4] = v1.x;
+              f[2 * xh + 5] = v1.y;
             }
           }
           DS_ST(12);
@@ -1296,7 +1332,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
       which_member(p.geo.G_D, 2, bid, j, bx);
       if (j >= 0) {
         const quipb200_linear_t L = (j == 0) ? Ly.gate : Ly.up;
-        const GemvCfg c = make_cfg(L, bx, p.geo.G_D[j]);
+        const GemvCfg c = make_cfg(L, bx, p.geo.G_D[j], p.rebalance);
         float f[8];
         float xs;
         const quipb200_linear_t Lp = Ly.o;
@@ -1349,11 +1385,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
       which_member(&p.geo.G_E, 1, bid, j, bx);
       if (j >= 0) {
         const quipb200_linear_t L = Ly.down;
-        const GemvCfg c = make_cfg(L, bx, p.geo.G_E);
+        const GemvCfg c = make_cfg(L, bx, p.geo.G_E, p.rebalance);
         float xs;
         if (L.K_left > 1) {
           xs = stage_e_blocks(Ly.gate, Ly.up, L, p.ws.acc[SL_G], p.ws.acc[SL_U], reinterpret_cast<const __half*>(Ly.mlp_hk), bb,
-                              hfrag, reinterpret_cast<__half*>(rb.A), rb.fred, xq, tid, (dbg && l == 1) ? dbg : nullptr);
+                              hfrag, rb.fred, xq, tid, (dbg && l == 1) ? dbg : nullptr);
         } else {
           float g[8], u[8];
           {
@@ -1458,6 +1494,7 @@ static int group_ctas(const quipb200_linear_t* const* mem, int n, int nblk, int*
 }
 
 int g_ds_splits = 0;   // test / tuning hook: force the number of KV splits (0 = automatic)
+int g_ds_rebalance = 0; // tuning hook (option "ds_rebalance"): 8 row phases per column chunk when warps would idle
 
 struct DsLayout {
   DsSmem sm;
@@ -1670,6 +1707,7 @@ extern "C" int quipb200_decode_step(const quipb200_decode_plan_t* plan, const qu
   p.h_out = reinterpret_cast<__half*>(h_out);
   p.kv_splits = lay.splits;
   p.use_mma = lay.use_mma;
+  p.rebalance = g_ds_rebalance;
   p.dbg = g_ds_dbg;
   p.dbg_cta = g_ds_dbg_cta;
   cudaLaunchConfig_t cfg{};

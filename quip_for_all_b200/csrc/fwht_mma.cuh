@@ -34,10 +34,10 @@ __device__ __forceinline__ uint32_t pk_h2(float a, float b) {
 }
 // packed fp16 pairs (p[0] = r0r1, p[1] = r2r3, p[2] = r4r5, p[3] = r6r7) -> transformed tile (fp32)
 __device__ __forceinline__ void hT_packed(const uint32_t (&p)[4], const HFrag& A, float (&r)[8]) {
-  float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+  float d0[4], d1[4];
   const uint32_t b0[2] = {p[0], p[2]}, b1[2] = {p[1], p[3]};
-  mma_16816(d0, A.a, b0);
-  mma_16816(d1, A.a, b1);
+  mma_16816_zero(d0, A.a, b0);
+  mma_16816_zero(d1, A.a, b1);
 #pragma unroll
   for (int j = 0; j < 4; j++) { r[j] = d0[j]; r[4 + j] = d1[j]; }
 }
@@ -51,11 +51,11 @@ __device__ __forceinline__ void hT_split(float (&r)[8], const HFrag& A) {
     hi[q] = *reinterpret_cast<const uint32_t*>(&h);
     lo[q] = pk_h2(r[2 * q] - hf.x, r[2 * q + 1] - hf.y);
   }
-  float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+  float d0[4], d1[4];
   const uint32_t b0h[2] = {hi[0], hi[2]}, b1h[2] = {hi[1], hi[3]};
   const uint32_t b0l[2] = {lo[0], lo[2]}, b1l[2] = {lo[1], lo[3]};
-  mma_16816(d0, A.a, b0h);
-  mma_16816(d1, A.a, b1h);
+  mma_16816_zero(d0, A.a, b0h);
+  mma_16816_zero(d1, A.a, b1h);
   mma_16816(d0, A.a, b0l);
   mma_16816(d1, A.a, b1l);
 #pragma unroll
@@ -99,24 +99,53 @@ __device__ __forceinline__ void fwht4096_frag(const uint32_t (&p)[4], const HFra
     for (int j = 0; j < 8; j++) r[j] = 0.f;
   }
 }
-// element index of register pair q (first element; the second is +1):
-//   block layout   : warp = top 4 bits, x = middle, y = low      (input of the output-side rotation, output of the input side)
-//   spread layout  : x = top 4 bits, warp = middle, y = low      (output of the output-side rotation, input of the input side)
-__device__ __forceinline__ int idx_block(int warp, int lane, int q) { return warp * 256 + frag_x(lane, q) * 16 + frag_y(lane, q); }
-__device__ __forceinline__ int idx_spread(int warp, int lane, int q) { return frag_x(lane, q) * 256 + warp * 16 + frag_y(lane, q); }
+// Element index of register pair q (first element; the second is +1).  Natural placement (see frag_to_octet below):
+// on the block side lane l of warp w holds octet 32 w + l, its 16-byte word j feeding p[{0,2,1,3}[j]]; the transform
+// then leaves the result on the spread side, where pairs q and q + 2 are adjacent (4 halfs = 8 bytes):
+//   block layout   : input of the output-side rotation, output of the input-side rotation (records: octet = thread)
+//   spread layout  : output of the output-side rotation, input of the input-side rotation
+// (tools/emu_fwht_frag.py checks both maps against a dense H_4096 with a numpy model of the fragments.)
+__device__ __forceinline__ int idx_block(int warp, int lane, int q) { return warp * 256 + lane * 8 + 2 * (((q & 1) << 1) | (q >> 1)); }
+__device__ __forceinline__ int idx_spread(int warp, int lane, int q) {
+  return ((lane >> 2) + 8 * (q & 1)) * 256 + (warp & 7) * 32 + (lane & 3) * 8 + (warp >> 3) * 4 + (q >> 1) * 2;
+}
 
+// A 4096-element fp16 vector in shared memory that is accessed at spread-layout positions (4 consecutive halfs per lane,
+// the eight row groups of a warp 512 bytes apart = the same banks) keeps its 16-byte chunk c at chunk c ^ ((c >> 5) & 7).
+__device__ __forceinline__ int stg_chunk(int c) { return c ^ ((c >> 5) & 7); }
 
 __device__ __forceinline__ uint32_t ldg_h2(const __half* p, int i) { return __ldg(reinterpret_cast<const unsigned int*>(p + i)); }
 __device__ __forceinline__ __half2 as_h2(uint32_t v) { return *reinterpret_cast<const __half2*>(&v); }
 __device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
 
-// fragment-layout pairs of one 256-element block held as octets by the lanes of a warp (lane l: elements 8l .. 8l+7)
-__device__ __forceinline__ void warp_octets_to_frag(const uint4& oct, __half* wscr_warp, int lane, uint32_t (&p)[4]) {
-  __syncwarp();
-  *reinterpret_cast<uint4*>(wscr_warp + lane * 8) = oct;
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < 4; q++) p[q] = *reinterpret_cast<const uint32_t*>(wscr_warp + frag_x(lane, q) * 16 + frag_y(lane, q));
+__device__ __forceinline__ uint4 hmul2x4(const uint4& a, const uint4& b) {
+  uint4 r;
+  r.x = as_u32(__hmul2(as_h2(a.x), as_h2(b.x)));
+  r.y = as_u32(__hmul2(as_h2(a.y), as_h2(b.y)));
+  r.z = as_u32(__hmul2(as_h2(a.z), as_h2(b.z)));
+  r.w = as_u32(__hmul2(as_h2(a.w), as_h2(b.w)));
+  return r;
+}
+__device__ __forceinline__ uint4 hadd2x4(const uint4& a, const uint4& b) {
+  uint4 r;
+  r.x = as_u32(__hadd2(as_h2(a.x), as_h2(b.x)));
+  r.y = as_u32(__hadd2(as_h2(a.y), as_h2(b.y)));
+  r.z = as_u32(__hadd2(as_h2(a.z), as_h2(b.z)));
+  r.w = as_u32(__hadd2(as_h2(a.w), as_h2(b.w)));
+  return r;
+}
+
+// Natural placement.  F(x, y) is a bit permutation of the natural index of a 256-element block, and H_256 (Sylvester)
+// is invariant under a simultaneous bit permutation of its row and column index, so lane l may hand the words of its
+// own 16-byte octet (elements 8l .. 8l+7) to fwht256_frag as p = {x, z, y, w} (x, y and z, w stay register pairs: the
+// two B fragments) and gets that octet's transformed elements back in r; this packs them (x scale) in memory order.
+__device__ __forceinline__ uint4 frag_to_octet(const float (&r)[8], float scale) {
+  uint4 v;
+  v.x = pk_h2(r[0] * scale, r[1] * scale);
+  v.z = pk_h2(r[2] * scale, r[3] * scale);
+  v.y = pk_h2(r[4] * scale, r[5] * scale);
+  v.w = pk_h2(r[6] * scale, r[7] * scale);
+  return v;
 }
 
 }  // namespace qb

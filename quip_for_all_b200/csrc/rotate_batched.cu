@@ -22,6 +22,8 @@ constexpr int RB_THREADS = 512;
 constexpr int RB_WARPS = RB_THREADS / 32;
 constexpr int RB_LS = 256 + 8;      // row stride (halfs) of the block buffer: ldmatrix friendly
 
+int g_opt_rot_warp_rows = 2048;   // rows from which the n = 4096 rotation runs one warp per row (rot4096w_kernel)
+
 struct RotBArgs {
   const __half* x; int64_t ldx;     // [M][in_feat]
   __half* y; int64_t ldy;           // [M][out_feat]
@@ -33,29 +35,11 @@ struct RotBArgs {
   float post_scale;                 // scale * sqrt(n / K): what is left after the 1/sqrt(L) built into the H_16/4 factors
 };
 
-__device__ __forceinline__ uint4 hmul2x4(const uint4& a, const uint4& b) {
-  uint4 r;
-  r.x = as_u32(__hmul2(as_h2(a.x), as_h2(b.x)));
-  r.y = as_u32(__hmul2(as_h2(a.y), as_h2(b.y)));
-  r.z = as_u32(__hmul2(as_h2(a.z), as_h2(b.z)));
-  r.w = as_u32(__hmul2(as_h2(a.w), as_h2(b.w)));
-  return r;
-}
-__device__ __forceinline__ uint4 hadd2x4(const uint4& a, const uint4& b) {
-  uint4 r;
-  r.x = as_u32(__hadd2(as_h2(a.x), as_h2(b.x)));
-  r.y = as_u32(__hadd2(as_h2(a.y), as_h2(b.y)));
-  r.z = as_u32(__hadd2(as_h2(a.z), as_h2(b.z)));
-  r.w = as_u32(__hadd2(as_h2(a.w), as_h2(b.w)));
-  return r;
-}
-
 // ---- n == 4096, K == 1: thread t owns octet t of the row --------------------------------------------------
 __global__ void __launch_bounds__(RB_THREADS) rot4096_kernel(const __grid_constant__ RotBArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* S = reinterpret_cast<float*>(smem);                                   // 16 x DS_XROW floats
-  __half* wscr = reinterpret_cast<__half*>(smem + 16 * DS_XROW * sizeof(float));   // [16][256]
-  __half* V = wscr + RB_WARPS * 256;                                           // [4096]
+  __half* V = reinterpret_cast<__half*>(smem + 16 * DS_XROW * sizeof(float));  // [4096]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const HFrag hf = make_hfrag(lane);
   const bool vin = tid * 8 < a.in_feat, vout = tid * 8 < a.out_feat;
@@ -71,19 +55,89 @@ __global__ void __launch_bounds__(RB_THREADS) rot4096_kernel(const __grid_consta
     const int rown = row + gridDim.x;      // the next row's octet is in flight while this one is transformed
     if (vin && rown < a.M) nxt = ldg_stream_v4(a.x + (size_t)rown * a.ldx + tid * 8);
     if (a.pre) oct = hmul2x4(oct, pre);                                        // qlinear.py:91 (fp16 tensor)
-    uint32_t p[4];
-    warp_octets_to_frag(oct, wscr + warp * 256, lane, p);                      // block layout: warp = top 4 index bits
+    const uint32_t p[4] = {oct.x, oct.z, oct.y, oct.w};                        // block layout, natural placement (fwht_mma.cuh)
     float r[8];
     fwht4096_frag(p, hf, S, warp, lane, r);                                    // spread layout, x 1/64
 #pragma unroll
-    for (int q = 0; q < 4; q++)
-      *reinterpret_cast<__half2*>(V + idx_spread(warp, lane, q)) = __floats2half2_rn(r[2 * q] * sc, r[2 * q + 1] * sc);
+    for (int xh = 0; xh < 2; xh++) {                                           // pairs xh and xh + 2 are adjacent
+      const int i = idx_spread(warp, lane, xh);
+      *reinterpret_cast<uint2*>(V + stg_chunk(i >> 3) * 8 + (i & 7)) =
+          make_uint2(pk_h2(r[2 * xh] * sc, r[2 * xh + 1] * sc), pk_h2(r[2 * xh + 4] * sc, r[2 * xh + 5] * sc));
+    }
     __syncthreads();
     if (vout) {
-      uint4 o = *reinterpret_cast<const uint4*>(V + tid * 8);
+      uint4 o = *reinterpret_cast<const uint4*>(V + stg_chunk(tid) * 8);
       if (a.post) o = hmul2x4(o, post);                                        // qlinear.py:112
       if (a.bias) o = hadd2x4(o, bias);                                        // qlinear.py:114
       stg_stream_v4(a.y + (size_t)row * a.ldy + tid * 8, o);
+    }
+  }
+}
+
+// ---- n == 4096, K == 1, many rows: one WARP per row, no shared-memory exchange, no barrier ------------------------
+// The F(x, y) register layout of fwht_mma.cuh is a bit permutation of the natural index, and a Sylvester Hadamard
+// matrix is invariant under a simultaneous bit permutation of its row and column index (H[i][j] = (-1)^popc(i & j)).
+// So a lane that loads octet `lane` of a 256-element block (16 bytes) already holds a valid fragment: its pairs go into
+// fwht256_frag as they are and come back as the transformed elements of the same octet (tools/emu_fwht_frag.py checks
+// this with a numpy model of the mma fragments).  A warp holds the 16 blocks of a row, transforms each on the tensor
+// path and finishes with a radix-16 butterfly across the blocks in fp32 registers.  Rows in flight per SM: 12 (against
+// 2 for the CTA-per-row kernel, which stays for small M where one row per warp would leave most SMs idle).
+constexpr int RW_THREADS = 128;
+constexpr int RW_WARPS = RW_THREADS / 32;
+__global__ void __launch_bounds__(RW_THREADS, 3) rot4096w_kernel(const __grid_constant__ RotBArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint4* s_pre = reinterpret_cast<uint4*>(smem);        // [512] octets each; only the vectors that exist are filled
+  uint4* s_post = s_pre + 512;
+  uint4* s_bias = s_post + 512;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int noct_in = a.in_feat >> 3, noct_out = a.out_feat >> 3;
+  for (int i = tid; i < 512; i += RW_THREADS) {
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    if (a.pre) s_pre[i] = (i < noct_in) ? __ldg(reinterpret_cast<const uint4*>(a.pre) + i) : z4;
+    if (a.post) s_post[i] = (i < noct_out) ? __ldg(reinterpret_cast<const uint4*>(a.post) + i) : z4;
+    if (a.bias) s_bias[i] = (i < noct_out) ? __ldg(reinterpret_cast<const uint4*>(a.bias) + i) : z4;
+  }
+  __syncthreads();
+  const HFrag hf = make_hfrag(lane);
+  const float sc = a.post_scale * 0.25f;      // two H_16/4 factors on the tensor path; the third factor is the plain butterfly
+  for (int row = blockIdx.x * RW_WARPS + warp; row < a.M; row += gridDim.x * RW_WARPS) {
+    const __half* xr = a.x + (size_t)row * a.ldx;
+    uint4 oct[16];
+#pragma unroll
+    for (int z = 0; z < 16; z++) {
+      const int o = z * 32 + lane;
+      oct[z] = make_uint4(0, 0, 0, 0);
+      if (o < noct_in) oct[z] = ldg_stream_v4(xr + o * 8);
+    }
+    float R[16][8];
+#pragma unroll
+    for (int z = 0; z < 16; z++) {
+      uint4 v = oct[z];
+      if (a.pre) v = hmul2x4(v, s_pre[z * 32 + lane]);                          // qlinear.py:91 (fp16 tensor)
+      const uint32_t p[4] = {v.x, v.z, v.y, v.w};      // (x, y) and (z, w) stay register pairs: the two B fragments
+      fwht256_frag(p, hf, R[z]);                                                // x 1/16
+    }
+#pragma unroll
+    for (int h = 1; h < 16; h <<= 1) {
+#pragma unroll
+      for (int z = 0; z < 16; z++) {
+        if (z & h) continue;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float u = R[z][j], w = R[z | h][j];
+          R[z][j] = u + w;
+          R[z | h][j] = u - w;
+        }
+      }
+    }
+    __half* yr = a.y + (size_t)row * a.ldy;
+#pragma unroll
+    for (int z = 0; z < 16; z++) {
+      const int o = z * 32 + lane;
+      uint4 v = frag_to_octet(R[z], sc);                                        // register_lib.py:20 (fp16 out)
+      if (a.post) v = hmul2x4(v, s_post[o]);                                    // qlinear.py:112
+      if (a.bias) v = hadd2x4(v, s_bias[o]);                                    // qlinear.py:114
+      if (o < noct_out) stg_stream_v4(yr + o * 8, v);
     }
   }
 }
@@ -94,8 +148,7 @@ __global__ void __launch_bounds__(RB_THREADS) rotblk_kernel(const __grid_constan
   const int K = a.K, Kp = (K + 15) / 16 * 16;
   __half* T = reinterpret_cast<__half*>(smem);                                 // [(K + 1)][RB_LS]
   __half* hk = T + (size_t)(K + 1) * RB_LS;                                    // [Kp][Kp]
-  __half* wscr = hk + (size_t)Kp * Kp;                                         // [16][256]
-  float* dummy = reinterpret_cast<float*>(wscr + RB_WARPS * 256);              // 64 floats (unused reduction scratch)
+  float* dummy = reinterpret_cast<float*>(hk + (size_t)Kp * Kp);               // 64 floats (unused reduction scratch)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const HFrag hf = make_hfrag(lane);
   if (K > 1)
@@ -131,14 +184,11 @@ __global__ void __launch_bounds__(RB_THREADS) rotblk_kernel(const __grid_constan
       const int oi = b * 32 + lane;
       uint4 oct = cur[j];
       if (a.pre && oi < noct_in) oct = hmul2x4(oct, __ldg(reinterpret_cast<const uint4*>(a.pre) + oi));
-      uint32_t p[4];
-      warp_octets_to_frag(oct, wscr + warp * 256, lane, p);
+      // the octet is already a valid fragment (see rot4096w_kernel): pairs in, the same octet's transformed pairs out
+      const uint32_t p[4] = {oct.x, oct.z, oct.y, oct.w};
       float r[8];
       fwht256_frag(p, hf, r);                                                  // x 1/16
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-        *reinterpret_cast<__half2*>(T + b * RB_LS + frag_x(lane, q) * 16 + frag_y(lane, q)) =
-            __floats2half2_rn(r[2 * q] * sc, r[2 * q + 1] * sc);              // register_lib.py:20 (fp16 out)
+      *reinterpret_cast<uint4*>(T + b * RB_LS + lane * 8) = frag_to_octet(r, sc);   // register_lib.py:20 (fp16 out)
     }
     if (K > 1) rotate_mix(rs, K * 256, K, tid, RB_THREADS);                    // barrier, mma.sync tiles (quant.py:83), barrier
     else __syncthreads();
@@ -176,14 +226,21 @@ extern "C" int quipb200_rotate_batched(const void* x, int64_t ldx, void* y, int6
   if (sms < 1) return (int)cudaErrorNoDevice;
   cudaStream_t st = (cudaStream_t)stream;
   if (K == 1 && n == 4096) {
-    const size_t smem = 16 * DS_XROW * sizeof(float) + RB_WARPS * 256 * 2 + 4096 * 2;
+    const size_t smem = 16 * DS_XROW * sizeof(float) + 4096 * 2;
     cudaError_t e = cudaFuncSetAttribute(rot4096_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    const int grid = M < sms * 4 ? M : sms * 4;
-    rot4096_kernel<<<grid, RB_THREADS, smem, st>>>(a);
+    if (M >= qb::g_opt_rot_warp_rows) {      // enough rows to give every resident warp one
+      const size_t smem_w = 3 * 512 * sizeof(uint4);
+      const int ctas = (M + RW_WARPS - 1) / RW_WARPS;
+      const int grid = ctas < sms * 3 ? ctas : sms * 3;
+      rot4096w_kernel<<<grid, RW_THREADS, smem_w, st>>>(a);
+    } else {
+      const int grid = M < sms * 4 ? M : sms * 4;
+      rot4096_kernel<<<grid, RB_THREADS, smem, st>>>(a);
+    }
   } else if (L == 256 && K <= 64 && (K == 1 || hk_padded)) {
     const int Kp = (K + 15) / 16 * 16;
-    const size_t smem = (size_t)(K + 1) * RB_LS * 2 + (size_t)Kp * Kp * 2 + RB_WARPS * 256 * 2 + 64 * sizeof(float);
+    const size_t smem = (size_t)(K + 1) * RB_LS * 2 + (size_t)Kp * Kp * 2 + 64 * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(rotblk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = (int)((200 * 1024) / (smem + 1024));

@@ -679,6 +679,40 @@ def test_rotate_fused_matches_unfused_op_sequence(n, K, fin, fout, M):
     assert (y2.float() - ref2.float()).abs().max().item() <= 2.0 ** -9 * ref2.float().abs().max().item()
 
 
+@pytest.mark.parametrize("fin,fout", [(4096, 4096), (4000, 3968)])
+@pytest.mark.parametrize("M,force", [(2301, False), (5, True), (148 * 12 * 2 + 3, False)])
+def test_rotate_fused_warp_per_row_kernel(fin, fout, M, force):
+    """The many-rows variant of the n = 4096 rotation (one warp per row, rotate_batched.cu::rot4096w_kernel) against the
+    CTA-per-row kernel (bit-identical inputs; both round once to fp16) and the unfused op sequence."""
+    import math
+    from quip_for_all_b200 import _native
+    from quip_for_all_b200.quant import matmul_hadU_cuda
+    g = torch.Generator().manual_seed(M + fin)
+    x = torch.randn(M, fin, generator=g).half().to(DEV)
+    pre = (1 + 0.1 * torch.randn(fin, generator=g)).half().to(DEV)
+    post = (1 + 0.1 * torch.randn(fout, generator=g)).half().to(DEV)
+    bias = (0.1 * torch.randn(fout, generator=g)).half().to(DEV)
+    scale = 0.37 / math.sqrt(4096)
+    default = _native.get_option("rot_warp_rows")
+    try:
+        _native.set_option("rot_warp_rows", 1 if force else default)
+        y_w = torch.ops.quip_lib.rotate_fused(x, pre, None, post, bias, 4096, 1, fout, scale)
+        y_w2 = torch.ops.quip_lib.rotate_fused(x, None, None, None, None, 4096, 1, 4096, scale)
+        _native.set_option("rot_warp_rows", 1 << 30)
+        y_c = torch.ops.quip_lib.rotate_fused(x, pre, None, post, bias, 4096, 1, fout, scale)
+        y_c2 = torch.ops.quip_lib.rotate_fused(x, None, None, None, None, 4096, 1, 4096, scale)
+    finally:
+        _native.set_option("rot_warp_rows", default)
+    ref = matmul_hadU_cuda(x * pre, None, 1, 4096, scale=0.37)[..., :fout] * post + bias
+    tol = 2.0 ** -9 * ref.float().abs().max().item()
+    assert y_w.shape == ref.shape and y_w2.shape == (M, 4096)
+    assert (y_w.float() - ref.float()).abs().max().item() <= tol
+    assert (y_w.float() - y_c.float()).abs().max().item() <= tol
+    assert (y_w2.float() - y_c2.float()).abs().max().item() <= tol
+    # the two kernels differ only in fp32 summation order before the single fp16 rounding: all but a few elements equal
+    assert (y_w != y_c).float().mean().item() < 0.02
+
+
 @pytest.mark.parametrize("fin,fout,bias", [(4096, 11008, True), (11008, 4096, False), (4096, 4096, True)])
 @pytest.mark.parametrize("M", [17, 40, 300])
 def test_batched_forward_vs_oracle(fin, fout, bias, M):

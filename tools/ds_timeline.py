@@ -1,5 +1,5 @@
 """Stage timeline of the persistent decode-step kernel (clock64 stamps of CTA 0, first layer).
-Usage (GPU box): python tools/ds_timeline.py [n_layers] [ctx]"""
+Usage (GPU box): python tools/ds_timeline.py [n_layers] [ctx] [cta] [option=value ...]   (options: quipb200_set_option)"""
 import os
 import sys
 
@@ -14,6 +14,10 @@ from quip_for_all_b200.modeling import LlamaDecodeEngine, llama_config, make_ran
 nl = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 ctx = int(sys.argv[2]) if len(sys.argv) > 2 else 384
 cta = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+for kv in sys.argv[4:]:
+    k, v = kv.split("=")
+    _native.set_option(k, int(v))
+    print(f"option {k} = {v}")
 dev = torch.device("cuda:0")
 model = make_random_quantized_llama(llama_config("llama2-7b", num_hidden_layers=nl), "E8P12", seed=0, device=dev)
 eng = LlamaDecodeEngine(model, max_cache_len=ctx + 64, use_cuda_graph=False)

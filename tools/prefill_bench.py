@@ -48,13 +48,30 @@ def main():
             t_hin = ev_time(lambda: torch.ops.quip_lib.hadamard(xp.view(-1, L.q_in_features // L.K_left), 0.01))
             yo = torch.randn(M, L.q_out_features, device=dev, dtype=torch.float16)
             t_hout = ev_time(lambda: torch.ops.quip_lib.hadamard(yo.view(-1, L.q_out_features // L.K_right), 0.01))
+            # the one-pass fused rotations the forward actually uses (rotate_batched.cu), both sides, with the n = 4096
+            # side timed on the CTA-per-row kernel and on the warp-per-row kernel
+            from quip_for_all_b200 import _native
+            rot = {}
+            xs_in = x
+            for side, n, K, src in (("in", L.q_in_features, L.K_left, xs_in), ("out", L.q_out_features, L.K_right, yo)):
+                hk = L._hk_padded("left" if side == "in" else "right") if K > 1 else None
+                vec = torch.ones(src.shape[1], device=dev, dtype=torch.float16)
+                call = lambda: torch.ops.quip_lib.rotate_fused(src, vec if side == "in" else None, hk,
+                                                               vec if side == "out" else None, None, n, K, src.shape[1], 0.01)
+                default = _native.get_option("rot_warp_rows")
+                for name, thr in (("cta_per_row", 1 << 30), ("default", default)):
+                    _native.set_option("rot_warp_rows", thr)
+                    t = ev_time(call)
+                    rot[f"{side}_{name}_ms"] = round(t, 3)
+                    rot[f"{side}_{name}_gbs"] = round(2 * src.numel() * 2 / (t * 1e-3) / 1e9, 1)
+                _native.set_option("rot_warp_rows", default)
         flops = 2.0 * M * L.q_in_features * L.q_out_features
         rec = {"shape": f"{fin}x{fout}", "M": M, "codebook": cb, "forward_ms": round(t_all, 3),
                "decompress_ms": round(t_dec, 4), "gemm_ms": round(t_mm, 3), "hadamard_in_ms": round(t_hin, 3),
                "hadamard_out_ms": round(t_hout, 3),
                "gemm_tflops": round(flops / (t_mm * 1e-3) / 1e12, 1), "forward_tflops": round(flops / (t_all * 1e-3) / 1e12, 1),
                "decompress_gbs_written": round(L.q_in_features * L.q_out_features * 2 / (t_dec * 1e-3) / 1e9, 1),
-               "hadamard_in_gbs": round(2 * xp.numel() * 2 / (t_hin * 1e-3) / 1e9, 1)}
+               "hadamard_in_gbs": round(2 * xp.numel() * 2 / (t_hin * 1e-3) / 1e9, 1), "rotate_fused": rot}
         print(json.dumps(rec), flush=True)
         out.append(rec)
         del x, xp, yo, W
