@@ -14,7 +14,7 @@ extern int g_opt_fuse;
 extern int g_opt_phase0;
 extern int g_opt_lean;
 extern int g_opt_rot_warp_rows;
-extern int g_ds_rebalance;
+extern int g_opt_rot_pipe_rows;
 int g_opt_umma = 2;     // in-kernel decode + tcgen05 GEMM (umma_gemm.cu): 0 = never, 1 = whenever the shape is covered
                         // (M <= 256), 2 = auto: where it measured faster than the alternatives (profiles/README.md)
 }  // namespace qb
@@ -84,8 +84,9 @@ extern "C" int quipb200_set_option(const char* name, int value) {
     qb::g_opt_umma = value;
     return 0;
   }
-  if (!strcmp(name, "ds_rebalance")) {
-    qb::g_ds_rebalance = value ? 1 : 0;
+  if (!strcmp(name, "rot_pipe_rows")) {
+    if (value < 1) return QUIPB200_EINVAL;
+    qb::g_opt_rot_pipe_rows = value;
     return 0;
   }
   if (!strcmp(name, "rot_warp_rows")) {
@@ -111,7 +112,7 @@ extern "C" int quipb200_get_option(const char* name) {
   if (!strcmp(name, "pdl")) return qb::g_opt_pdl;
   if (!strcmp(name, "umma")) return qb::g_opt_umma;
   if (!strcmp(name, "rot_warp_rows")) return qb::g_opt_rot_warp_rows;
-  if (!strcmp(name, "ds_rebalance")) return qb::g_ds_rebalance;
+  if (!strcmp(name, "rot_pipe_rows")) return qb::g_opt_rot_pipe_rows;
   return QUIPB200_EINVAL;
 }
 

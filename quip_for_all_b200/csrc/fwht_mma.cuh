@@ -126,12 +126,14 @@ __device__ __forceinline__ uint4 hmul2x4(const uint4& a, const uint4& b) {
   r.w = as_u32(__hmul2(as_h2(a.w), as_h2(b.w)));
   return r;
 }
+// (the _rn form keeps ptxas from contracting a preceding fp16 multiply and this add into one fma: the reference rounds
+// `out * SV` and `+ bias` separately, qlinear.py:112-114)
 __device__ __forceinline__ uint4 hadd2x4(const uint4& a, const uint4& b) {
   uint4 r;
-  r.x = as_u32(__hadd2(as_h2(a.x), as_h2(b.x)));
-  r.y = as_u32(__hadd2(as_h2(a.y), as_h2(b.y)));
-  r.z = as_u32(__hadd2(as_h2(a.z), as_h2(b.z)));
-  r.w = as_u32(__hadd2(as_h2(a.w), as_h2(b.w)));
+  r.x = as_u32(__hadd2_rn(as_h2(a.x), as_h2(b.x)));
+  r.y = as_u32(__hadd2_rn(as_h2(a.y), as_h2(b.y)));
+  r.z = as_u32(__hadd2_rn(as_h2(a.z), as_h2(b.z)));
+  r.w = as_u32(__hadd2_rn(as_h2(a.w), as_h2(b.w)));
   return r;
 }
 

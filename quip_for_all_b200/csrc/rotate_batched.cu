@@ -22,6 +22,7 @@ constexpr int RB_THREADS = 512;
 constexpr int RB_WARPS = RB_THREADS / 32;
 constexpr int RB_LS = 256 + 8;      // row stride (halfs) of the block buffer: ldmatrix friendly
 
+int g_opt_rot_pipe_rows = 1024;   // rows from which the K x 256 rotation streams rows through shared memory (rotblk_pipe_kernel)
 int g_opt_rot_warp_rows = 2048;   // rows from which the n = 4096 rotation runs one warp per row (rot4096w_kernel)
 
 struct RotBArgs {
@@ -203,6 +204,183 @@ __global__ void __launch_bounds__(RB_THREADS) rotblk_kernel(const __grid_constan
   }
 }
 
+// ---- n == K * 256, many rows: persistent CTA per SM, rows streamed through shared memory by bulk copies (TMA) --------
+// One I/O warp moves whole rows: cp.async.bulk global -> shared (mbarrier complete_tx) into one of RP_SLOTS row buffers,
+// cp.async.bulk shared -> global for the finished row.  The 16 compute warps form two groups of 8 that take alternate
+// rows (the barrier waits of one group are filled by the other) and work in place on the row buffer:
+//   P1  H_256 of every block (one warp per block, natural placement), x scale, fp16; block b stores its 16-byte chunk c
+//       at chunk c ^ (b & 7) so the K x K mix can ldmatrix a column tile without bank conflicts on a dense buffer
+//   P2  K x K mix of each 8-column tile (mma.sync, the A fragments of the coefficient matrix stay in registers)
+//   P3  chunk un-swizzle + SV / bias, fence to the async proxy, arrive on the slot's `done` barrier
+// Two named barriers per row inside a group; loads, stores and arithmetic of different rows overlap through the slot
+// ring.  Same arithmetic and rounding points as rotblk_kernel.
+constexpr int RP_SLOTS = 4;
+constexpr int RP_COMPUTE = 512;
+constexpr int RP_THREADS = RP_COMPUTE + 32;
+
+constexpr int RP_GROUPS = 2;                          // row groups inside the CTA
+constexpr int RP_GW = RP_COMPUTE / 32 / RP_GROUPS;    // warps per group
+static_assert(RP_GW == 8, "block b of a warp must keep (b & 7) == warp-in-group");
+__device__ __forceinline__ void rp_bar(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(RP_GW * 32) : "memory"); }
+
+template <int MT>
+__global__ void __launch_bounds__(RP_THREADS, 1) rotblk_pipe_kernel(const __grid_constant__ RotBArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int Kp = MT * 16;
+  const int K = a.K;
+  const int row_halfs = K * 256;
+  __half* buf = reinterpret_cast<__half*>(smem);                                  // [RP_SLOTS][K][256], dense
+  __half* zrow = buf + (size_t)RP_SLOTS * row_halfs;                              // [256] zeros: the rows >= K of a tile
+  __half* hk = zrow + 256;                                                        // [Kp][Kp]
+  __half* s_pre = hk + Kp * Kp;                                                   // [K * 256] each, if present
+  __half* s_post = s_pre + (a.pre ? row_halfs : 0);
+  __half* s_bias = s_post + (a.post ? row_halfs : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + (a.bias ? row_halfs : 0));   // full[RP_SLOTS], done[RP_SLOTS]
+  const uint32_t bar_full = smem_u32(bars), bar_done = smem_u32(bars + RP_SLOTS);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int noct_in = a.in_feat >> 3, noct_out = a.out_feat >> 3, noct = row_halfs >> 3;
+
+  if (tid == 0) {
+    for (int s = 0; s < RP_SLOTS; s++) {
+      mbar_init(bar_full + 8 * s, 1);                    // the I/O thread's arrive.expect_tx
+      mbar_init(bar_done + 8 * s, RP_GW);                // one arrive per warp of the group that owns the row
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < (Kp * Kp) >> 3; i += RP_THREADS)
+    reinterpret_cast<uint4*>(hk)[i] = __ldg(reinterpret_cast<const uint4*>(a.hk) + i);
+  for (int i = tid; i < 32; i += RP_THREADS) reinterpret_cast<uint4*>(zrow)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < noct; i += RP_THREADS) {
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    if (a.pre) reinterpret_cast<uint4*>(s_pre)[i] = (i < noct_in) ? __ldg(reinterpret_cast<const uint4*>(a.pre) + i) : z4;
+    if (a.post) reinterpret_cast<uint4*>(s_post)[i] = (i < noct_out) ? __ldg(reinterpret_cast<const uint4*>(a.post) + i) : z4;
+    if (a.bias) reinterpret_cast<uint4*>(s_bias)[i] = (i < noct_out) ? __ldg(reinterpret_cast<const uint4*>(a.bias) + i) : z4;
+  }
+  __syncthreads();
+
+  const int n_my = (a.M - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // rows blockIdx.x, + gridDim.x, ..
+  const uint32_t bytes_in = (uint32_t)a.in_feat * 2u, bytes_out = (uint32_t)a.out_feat * 2u;
+
+  if (warp == RP_COMPUTE / 32) {
+    // ---------------- I/O warp: one thread drives the slot ring ----------------
+    if (lane == 0) {
+      int issued = 0;
+      for (; issued < n_my && issued < RP_SLOTS; issued++) {
+        const size_t row = (size_t)blockIdx.x + (size_t)issued * gridDim.x;
+        mbar_arrive_expect_tx(bar_full + 8 * issued, bytes_in);
+        bulk_load(smem_u32(buf + (size_t)issued * row_halfs), a.x + row * a.ldx, bytes_in, bar_full + 8 * issued);
+      }
+      for (int done = 0; done < n_my; done++) {
+        const int s = done % RP_SLOTS;
+        mbar_wait(bar_done + 8 * s, (uint32_t)(done / RP_SLOTS) & 1u);
+        const size_t row = (size_t)blockIdx.x + (size_t)done * gridDim.x;
+        bulk_store(a.y + row * a.ldy, smem_u32(buf + (size_t)s * row_halfs), bytes_out);
+        if (issued < n_my) {                             // slot s is refilled with row `issued` == done + RP_SLOTS
+          bulk_store_wait_read();
+          const size_t rown = (size_t)blockIdx.x + (size_t)issued * gridDim.x;
+          mbar_arrive_expect_tx(bar_full + 8 * s, bytes_in);
+          bulk_load(smem_u32(buf + (size_t)s * row_halfs), a.x + rown * a.ldx, bytes_in, bar_full + 8 * s);
+          issued++;
+        }
+      }
+      bulk_store_wait_all();
+    }
+    return;
+  }
+
+  // ---------------- compute warps: two groups of 8, each with its own rows (even / odd) and named barrier ----------------
+  const HFrag hf = make_hfrag(lane);
+  const float sc = a.post_scale;
+  const int g = lane >> 2, tq = lane & 3;
+  const int grp = warp / RP_GW, wg = warp % RP_GW;       // every block b of this warp has (b & 7) == wg
+  uint32_t af[MT][MT][4];                                // coefficient matrix as mma A fragments
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+    for (int kt = 0; kt < MT; kt++)
+      ldmatrix_x4(af[mt][kt], hk + (size_t)(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * Kp + kt * 16 + (lane >> 4) * 8);
+  const int swz_chunk = (lane ^ wg) << 3;                // this lane's chunk inside its (swizzled) blocks
+
+  for (int it = grp; it < n_my; it += RP_GROUPS) {
+    const int s = it % RP_SLOTS;
+    __half* T = buf + (size_t)s * row_halfs;
+    mbar_wait(bar_full + 8 * s, (uint32_t)(it / RP_SLOTS) & 1u);
+    // P1: two blocks per pass for instruction-level parallelism
+    for (int b0 = wg; b0 < K; b0 += 2 * RP_GW) {
+      uint4 oct[2];
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int b = b0 + j * RP_GW, o = b * 32 + lane;
+        oct[j] = make_uint4(0, 0, 0, 0);
+        if (b < K && o < noct_in) oct[j] = *reinterpret_cast<const uint4*>(T + o * 8);
+        if (a.pre && b < K) oct[j] = hmul2x4(oct[j], *reinterpret_cast<const uint4*>(s_pre + o * 8));   // qlinear.py:91
+      }
+      float r[2][8];
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const uint32_t p[4] = {oct[j].x, oct[j].z, oct[j].y, oct[j].w};
+        fwht256_frag(p, hf, r[j]);                                                      // x 1/16; every lane has loaded
+      }
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int b = b0 + j * RP_GW;
+        if (b < K) *reinterpret_cast<uint4*>(T + b * 256 + swz_chunk) = frag_to_octet(r[j], sc);   // register_lib.py:20
+      }
+    }
+    rp_bar(grp);
+    // P2: T <- M T, 8-column tile nt = chunk nt of every block (quant.py:83: fp16 operands, fp32 accumulate, fp16 out)
+#pragma unroll 2
+    for (int ti = 0; ti < 32 / RP_GW; ti++) {
+      const int nt = wg + ti * RP_GW;
+      uint32_t bf[MT][2];
+#pragma unroll
+      for (int kt = 0; kt < MT; kt++) {
+        const int r = kt * 16 + (lane & 15);
+        const __half* src = (r < K) ? T + r * 256 + ((nt ^ (r & 7)) << 3) : zrow;
+        ldmatrix_x2_trans(bf[kt], src);
+      }
+      float acc[MT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) {
+        mma_16816_zero(acc[mt], af[mt][0], bf[0]);
+#pragma unroll
+        for (int kt = 1; kt < MT; kt++) mma_16816(acc[mt], af[mt][kt], bf[kt]);
+      }
+      __syncwarp();                                        // every lane has read its B fragments of this tile
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) {
+        const int r0 = mt * 16 + g, r1 = r0 + 8;
+        const int off = ((nt ^ g) << 3) + tq * 2;          // (r0 & 7) == (r1 & 7) == g
+        if (r0 < K) *reinterpret_cast<__half2*>(T + r0 * 256 + off) = __floats2half2_rn(acc[mt][0], acc[mt][1]);
+        if (r1 < K) *reinterpret_cast<__half2*>(T + r1 * 256 + off) = __floats2half2_rn(acc[mt][2], acc[mt][3]);
+      }
+    }
+    rp_bar(grp);
+    // P3
+    for (int b0 = wg; b0 < K; b0 += 2 * RP_GW) {
+      uint4 v[2];
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int b = b0 + j * RP_GW, o = b * 32 + lane;
+        if (b < K) {
+          v[j] = *reinterpret_cast<const uint4*>(T + b * 256 + swz_chunk);
+          if (a.post) v[j] = hmul2x4(v[j], *reinterpret_cast<const uint4*>(s_post + o * 8));      // qlinear.py:112
+          if (a.bias) v[j] = hadd2x4(v[j], *reinterpret_cast<const uint4*>(s_bias + o * 8));      // qlinear.py:114
+        }
+      }
+      __syncwarp();                                        // both blocks have been read by every lane
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int b = b0 + j * RP_GW;
+        if (b < K) *reinterpret_cast<uint4*>(T + (b * 32 + lane) * 8) = v[j];
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_done + 8 * s);
+  }
+}
+
 }  // namespace qb
 
 using namespace qb;
@@ -238,6 +416,28 @@ extern "C" int quipb200_rotate_batched(const void* x, int64_t ldx, void* y, int6
       const int grid = M < sms * 4 ? M : sms * 4;
       rot4096_kernel<<<grid, RB_THREADS, smem, st>>>(a);
     }
+  } else if (L == 256 && K > 1 && K <= 48 && hk_padded && M >= qb::g_opt_rot_pipe_rows) {
+    // persistent CTA per SM, rows streamed by bulk copies
+    const int Kp = (K + 15) / 16 * 16;
+    const int vecs = (pre ? 1 : 0) + (post ? 1 : 0) + (bias ? 1 : 0);
+    const size_t smem = ((size_t)RP_SLOTS + vecs) * K * 512 + 512 + (size_t)Kp * Kp * 2 + 2 * RP_SLOTS * 8;
+    const int grid = M < sms ? M : sms;
+    cudaError_t e = cudaSuccess;
+    switch (Kp >> 4) {
+      case 1:
+        e = cudaFuncSetAttribute(rotblk_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) rotblk_pipe_kernel<1><<<grid, RP_THREADS, smem, st>>>(a);
+        break;
+      case 2:
+        e = cudaFuncSetAttribute(rotblk_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) rotblk_pipe_kernel<2><<<grid, RP_THREADS, smem, st>>>(a);
+        break;
+      default:
+        e = cudaFuncSetAttribute(rotblk_pipe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) rotblk_pipe_kernel<3><<<grid, RP_THREADS, smem, st>>>(a);
+        break;
+    }
+    if (e != cudaSuccess) return (int)e;
   } else if (L == 256 && K <= 64 && (K == 1 || hk_padded)) {
     const int Kp = (K + 15) / 16 * 16;
     const size_t smem = (size_t)(K + 1) * RB_LS * 2 + (size_t)Kp * Kp * 2 + 64 * sizeof(float);

@@ -713,6 +713,45 @@ def test_rotate_fused_warp_per_row_kernel(fin, fout, M, force):
     assert (y_w != y_c).float().mean().item() < 0.02
 
 
+@pytest.mark.parametrize("n,K,fin,fout", [(11008, 43, 11008, 11008), (2816, 11, 2816, 2800), (2816, 11, 2808, 2816),
+                                          (4096, 16, 4096, 4096), (5120, 20, 5120, 5112)])
+@pytest.mark.parametrize("M,force", [(1500, False), (3, True), (597, True)])
+def test_rotate_fused_row_streaming_kernel(n, K, fin, fout, M, force):
+    """The many-rows variant of the K x 256 rotation (persistent CTAs, rows streamed through shared memory with bulk
+    copies, rotate_batched.cu::rotblk_pipe_kernel) against the CTA-per-row kernel -- same arithmetic in the same order,
+    so bit-identical -- and against the unfused op sequence."""
+    import math
+    from quip_for_all_b200 import _native
+    from quip_for_all_b200.quant import matmul_hadU_cuda
+    g = torch.Generator().manual_seed(M + n + fin)
+    x = torch.randn(M, fin, generator=g).half().to(DEV)
+    pre = (1 + 0.1 * torch.randn(fin, generator=g)).half().to(DEV)
+    post = (1 + 0.1 * torch.randn(fout, generator=g)).half().to(DEV)
+    bias = (0.1 * torch.randn(fout, generator=g)).half().to(DEV)
+    qm, _ = torch.linalg.qr(torch.randn(K, K, generator=g))
+    hadK = qm.half().to(DEV)
+    Kp = (K + 15) // 16 * 16
+    hk = torch.zeros(Kp, Kp, dtype=torch.float16, device=DEV)
+    hk[:K, :K] = hadK
+    scale = 0.37 / math.sqrt(n // K)
+    default = _native.get_option("rot_pipe_rows")
+    try:
+        _native.set_option("rot_pipe_rows", 1 if force else default)
+        y_p = torch.ops.quip_lib.rotate_fused(x, pre, hk, post, bias, n, K, fout, scale)
+        y_p2 = torch.ops.quip_lib.rotate_fused(x, None, hk, None, None, n, K, n, scale)
+        torch.cuda.synchronize()
+        _native.set_option("rot_pipe_rows", 1 << 30)
+        y_c = torch.ops.quip_lib.rotate_fused(x, pre, hk, post, bias, n, K, fout, scale)
+        y_c2 = torch.ops.quip_lib.rotate_fused(x, None, hk, None, None, n, K, n, scale)
+    finally:
+        _native.set_option("rot_pipe_rows", default)
+    assert y_p.shape == (M, fout) and y_p2.shape == (M, n)
+    assert torch.equal(y_p, y_c)
+    assert torch.equal(y_p2, y_c2)
+    ref = matmul_hadU_cuda(x * pre, hadK, K, n, scale=0.37)[..., :fout] * post + bias
+    assert (y_p.float() - ref.float()).abs().max().item() <= 2.0 ** -9 * ref.float().abs().max().item()
+
+
 @pytest.mark.parametrize("fin,fout,bias", [(4096, 11008, True), (11008, 4096, False), (4096, 4096, True)])
 @pytest.mark.parametrize("M", [17, 40, 300])
 def test_batched_forward_vs_oracle(fin, fout, bias, M):

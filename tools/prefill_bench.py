@@ -58,13 +58,15 @@ def main():
                 vec = torch.ones(src.shape[1], device=dev, dtype=torch.float16)
                 call = lambda: torch.ops.quip_lib.rotate_fused(src, vec if side == "in" else None, hk,
                                                                vec if side == "out" else None, None, n, K, src.shape[1], 0.01)
-                default = _native.get_option("rot_warp_rows")
-                for name, thr in (("cta_per_row", 1 << 30), ("default", default)):
-                    _native.set_option("rot_warp_rows", thr)
+                defaults = {k: _native.get_option(k) for k in ("rot_warp_rows", "rot_pipe_rows")}
+                for name in ("cta_per_row", "default"):
+                    for k, v in defaults.items():
+                        _native.set_option(k, (1 << 30) if name == "cta_per_row" else v)
                     t = ev_time(call)
                     rot[f"{side}_{name}_ms"] = round(t, 3)
                     rot[f"{side}_{name}_gbs"] = round(2 * src.numel() * 2 / (t * 1e-3) / 1e9, 1)
-                _native.set_option("rot_warp_rows", default)
+                for k, v in defaults.items():
+                    _native.set_option(k, v)
         flops = 2.0 * M * L.q_in_features * L.q_out_features
         rec = {"shape": f"{fin}x{fout}", "M": M, "codebook": cb, "forward_ms": round(t_all, 3),
                "decompress_ms": round(t_dec, 4), "gemm_ms": round(t_mm, 3), "hadamard_in_ms": round(t_hin, 3),
