@@ -527,11 +527,11 @@ __device__ __forceinline__ void out_side_m(const quipb200_linear_t& Lp, const ui
 }
 
 // f: fp16-valued pairs at idx_spread positions (zeros beyond in_features): [RMSNorm] -> SU -> rotation -> * wscale/64 ->
-// 16-bit fixed point records (via the fp16 vector V, 4096 halfs).  Returns the fixed-point scale.
+// 16-bit fixed point records (each thread ends up holding its own record).  Returns the fixed-point scale.
 // The caller has issued stg_vec() for nw / su and guarantees a CTA barrier after this thread's cp.async.wait_all
 // (staged == true), or passes staged == false and the function synchronises itself.
 __device__ __forceinline__ float in_side_m(const float (&f)[8], bool has_norm, float eps, const quipb200_linear_t& L,
-                                           const Stg& st, bool staged, const HFrag& A, float* S, __half* V, float* fred,
+                                           const Stg& st, bool staged, const HFrag& A, float* S, float* fred,
                                            uint4* xq, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
   const bool has_su = L.SU != nullptr;
@@ -895,9 +895,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
   bb.LS = 256 + 8;
   const HFrag hfrag = make_hfrag(lane);
   float* const XS = rb.A;                                   // exchange buffer of fwht4096_frag (16 x DS_XROW floats)
-  __half* const V = reinterpret_cast<__half*>(rb.fred + 64);   // fp16 [4096] (aliases the block buffers, unused in A / C / D)
-  Stg stg;                                                   // staging vectors: behind V, same aliasing
-  stg.sv = V + 4096; stg.bias = stg.sv + 4096; stg.resid = stg.bias + 4096; stg.nw = stg.resid + 4096;
+  Stg stg;                                                   // staging vectors: alias the block buffers (unused in A / C / D)
+  stg.sv = reinterpret_cast<__half*>(rb.fred + 64) + 4096; stg.bias = stg.sv + 4096; stg.resid = stg.bias + 4096; stg.nw = stg.resid + 4096;
   stg.atto = stg.sv;                                          // 32 KB (n_heads * S * 128 halfs <= 16384)
   stg.su = stg.sv + 32768;
   long long* dbg = (p.dbg && bid == p.dbg_cta && tid == 0) ? p.dbg : nullptr;
@@ -988,7 +987,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             stg_vec(stg.nw, reinterpret_cast<const __half*>(Ly.input_norm_w), L.in_features, tid);
             stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
           }
-          xs = in_side_m(f, true, P.norm_eps, L, stg, l != 0, hfrag, XS, V, rb.fred, xq, tid);
+          xs = in_side_m(f, true, P.norm_eps, L, stg, l != 0, hfrag, XS, rb.fred, xq, tid);
         } else {
           if (l == 0) {
             uint4 hv = make_uint4(0, 0, 0, 0);
@@ -1285,7 +1284,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             }
           }
           DS_ST(12);
-          xs = in_side_m(f, false, 0.f, L, stg, true, hfrag, XS, V, rb.fred, xq, tid);
+          xs = in_side_m(f, false, 0.f, L, stg, true, hfrag, XS, rb.fred, xq, tid);
         } else {
           if (tid < ((P.n_heads * DS_HD) >> 3)) {
             const int h = (tid * 8) / DS_HD, d = (tid * 8) % DS_HD;
@@ -1348,7 +1347,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             f[2 * q + 1] = v.y;
           }
           DS_ST(16);
-          xs = in_side_m(f, true, P.norm_eps, L, stg, true, hfrag, XS, V, rb.fred, xq, tid);
+          xs = in_side_m(f, true, P.norm_eps, L, stg, true, hfrag, XS, rb.fred, xq, tid);
         } else {
           out_side_k1(Lp, p.ws.acc[SL_O], p.ws.hA, rb, tid, f);
           const uint4 hv = pack_h8(f);
@@ -1595,7 +1594,7 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
   out->use_mma = use_mma ? 1 : 0;
   if (use_mma) nmax = std::max(nmax, (size_t)4096);   // the exchange buffer (16 x 388 floats) lives in A | B
   size_t blk = 2 * t_halfs * 2 + 3 * hk_halfs * 2 + 3 * mid_halfs * 2;
-  if (use_mma) blk = std::max(blk, (size_t)90112);    // V (8 KB) + staged vectors / attention partials (72 KB) + warp scratch (8 KB)
+  if (use_mma) blk = std::max(blk, (size_t)90112);    // 8 KB spare + staged vectors / attention partials (72 KB) + 8 KB spare
   size_t scr = 2 * nmax * sizeof(float) + 64 * sizeof(float) + blk;
   scr = std::max(scr, attn);
   auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };

@@ -318,3 +318,25 @@ def test_mm_dispatch_policy_and_rotation_coverage():
         assert rl.umma_preferred(4, 4096, 4096) and rl.umma_preferred(32, 4096, 4096)
         assert not rl.umma_preferred(33, 4096, 4096) and rl.umma_preferred(64, 4096, 11008)
         assert not rl.umma_preferred(16, 4096 + 64, 4096) and not rl.umma_preferred(300, 4096, 4096)
+
+
+def test_tensor_path_fragment_placement_model():
+    """The register-layout claims csrc/fwht_mma.cuh relies on, checked on a numpy model of the mma.sync fragments against
+    dense Sylvester matrices: a lane's own 16-byte octet is a valid fragment of the 256-point transform ("natural
+    placement"), the warp-per-row 4096-point transform, and the block / spread index maps of the CTA-wide transform.
+    The same index formulas must be the ones written in the header."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("emu_fwht_frag", os.path.join(ROOT, "tools", "emu_fwht_frag.py"))
+    emu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(emu)
+    emu.main()
+    emu.check_4096()
+    hdr = open(os.path.join(ROOT, "quip_for_all_b200", "csrc", "fwht_mma.cuh")).read()
+    blk = re.search(r"int idx_block\(int warp, int lane, int q\) \{ return ([^;]+); \}", hdr).group(1)
+    spr = re.search(r"int idx_spread\(int warp, int lane, int q\) \{\s*return ([^;]+);", hdr).group(1)
+    for warp in (0, 5, 9, 15):
+        for lane in (0, 7, 18, 31):
+            for q in range(4):
+                env = {"warp": warp, "lane": lane, "q": q}
+                assert eval(blk, {}, env) == emu.idx_block(warp, lane, q)
+                assert eval(spr, {}, env) == emu.idx_spread(warp, lane, q)
