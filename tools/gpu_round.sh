@@ -15,6 +15,9 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
 NCUARGS="--steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-kernel-bench --no-ref-cuda --prompt-len 8"
 echo "== ncu launch list"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py $NCUARGS > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
 echo "== ncu full decode_step"; timeout 1200 ncu --set full --clock-control none --import-source on -k regex:decode_step -s 4 -c 1 -f -o gpurun_out/decode_step_full python bench.py $NCUARGS > gpurun_out/ncu_ds.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncu_ds.log
+if [ "${SKIP_UMMA_NCU:-0}" != "1" ]; then
 echo "== ncu full umma"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:e8p_umma -s 6 -c 1 -f -o gpurun_out/umma_full python tools/umma_bench.py 128 4096x11008 > gpurun_out/ncu_umma.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncu_umma.log
 fi
+fi
+if [ "${PREFILL_MODEL:-0}" = "1" ]; then echo "== whole-model prefill"; timeout 300 python tools/prefill_model_bench.py 2>&1 | tail -3 | cut -c1-600; fi
 echo done
