@@ -174,7 +174,8 @@ def run_reference_arm(a):
         "steps": steps, "warmup": min(a.warmup, 3), "ms_per_step": 1000.0 * s.n_layers * t_layer,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8xint16 fixed point (ours) / fp16->fp32 (this port)",
         "data": "synthetic",
-        "config": {"workload": f"{a.model} E8P12 2-bit bs=1 decode, random-init packed weights",
+        "config": {"workload": f"{a.model} {a.codebook} bs=1 greedy decode, random-init packed weights "
+                               "(CPU port of the QuantLinear path; bounded sample, see `sampled`)",
                    "sampled": s.describe()},
         "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": s.cores, "kind": "port", "sample": s.describe()},
         "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

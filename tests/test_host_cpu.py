@@ -340,3 +340,24 @@ def test_tensor_path_fragment_placement_model():
                 env = {"warp": warp, "lane": lane, "q": q}
                 assert eval(blk, {}, env) == emu.idx_block(warp, lane, q)
                 assert eval(spr, {}, env) == emu.idx_spread(warp, lane, q)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (CPU port of the path on the host cores) prints one JSON line with the keys the
+    driver reads; ranks other than 0 print nothing and exit 0."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--model", "tiny"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "tokens/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("decode tokens/s bs=1 Llama-2-7B E8P12")
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert "workload" in line["config"]
+    r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                         "--model", "tiny"], capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=300)
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
