@@ -103,6 +103,9 @@ int quipb200_mm(int codebook, const void* x_f16, const void* qidxs, const void* 
  *   scale as passed to quip_lib::hadamard (quant.py:75: scale / sqrt(n/K)).
  *   Covered: n == 4096 with K == 1, and n == 256*K with K <= 64; else QUIPB200_EUNSUPPORTED (caller keeps the
  *   reference's op sequence over quipb200_hadamard).  in/out_features % 8 == 0, row pitches % 8 == 0.
+ *   Kernel choice by M (options "rot_warp_rows", "rot_pipe_rows"): a CTA per row for few rows; for many rows one warp
+ *   per row (n == 4096) or persistent CTAs streaming rows through shared memory with bulk copies (n == 256*K, K <= 48).
+ *   All variants give the same result up to the fp32 summation order before the fp16 roundings.
  * ------------------------------------------------------------------------------------------- */
 int quipb200_rotate_batched(const void* x_f16, int64_t ldx, void* y_f16, int64_t ldy, const void* pre, const void* post,
                             const void* bias, const void* hk_padded, int M, int in_features, int out_features,
@@ -243,7 +246,11 @@ int quipb200_decode_step_debug_cta(int cta);   /* which CTA writes the stamps (d
 int quipb200_decode_step_set_splits(int splits);
 
 /* Tuning / introspection hooks used by bench.py and the tests (not part of the reference surface). */
-int quipb200_set_option(const char* name, int value);   /* e.g. "gemv_table_repl" = 1|16 */
+/* options: "umma" 0|1|2 (tcgen05 decode+GEMM never / whenever covered / where measured faster; default 2),
+ *   "rot_warp_rows", "rot_pipe_rows" (row counts from which the many-rows rotation kernels are used),
+ *   "pdl" 0|1, "fuse" 0..3, "stage_mask" 0..7 (bench only), "gemv_warps", "gemv_ctas_per_sm", "lean", "phase0"
+ *   (tuning hooks of the per-linear launches).  Unknown names / out-of-range values: QUIPB200_EINVAL. */
+int quipb200_set_option(const char* name, int value);
 int quipb200_get_option(const char* name);
 /* profiling hook: when non-NULL, every CTA of the GEMV kernel writes 16 int64 clock64() stamps of its
  * phases into buffer[cta*16 ..] (tools/timeline.py); pass NULL to switch it off. */
