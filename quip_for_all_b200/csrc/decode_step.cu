@@ -162,12 +162,77 @@ __device__ __forceinline__ void prefetch_stage(const quipb200_linear_t* const* m
   gemv_prefetch_l2(c, tid);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Replicated lookup tables (64 KB of shared memory, built once per launch).  Row i (256 bytes) holds
+//   E8P family: [abs-table entry i, "+1/4" pre-applied, x 16 copies][sign-mask entry of sign byte i x 16 copies]
+//   D4        : [int8x4 entry i x 32 copies][unused]
+// so a lane reads its own copy: the address is (index byte << 8) | lane offset = ONE PRMT on the packed word, and the
+// LDS is bank-conflict free whatever the indices are (a half-warp's 16 lanes hit 16 distinct bank pairs).  The
+// sign-mask entry is 0xfc in every negated byte, | 0x02 in every byte when the code's parity is odd: table ^ mask
+// negates (the low bits of every table byte are 11) and subtracts the parity shift of 2 quarter-units in one LOP3 per
+// word -- codebook/e8p12.py:82-103 restated; round 1 computed the mask with popc / 2 x (imad + prmt) and carried a
+// separate parity * sum(x) term (21 instructions per code; 10 now, profiles/r02_gemv_lut_microbench.txt).
+// ---------------------------------------------------------------------------------------------
+constexpr int DS_TAB_BYTES = 65536;
+
+__device__ __forceinline__ uint2 e8p_sign_mask(uint32_t s8) {
+  const uint32_t par = __popc(s8) & 1u;
+  const uint32_t s = s8 ^ par;
+  uint2 m;
+  m.x = (prmt(s * 0x08040201u, 0u, 0xba98u) & 0xfcfcfcfcu) | (par * 0x02020202u);
+  m.y = (prmt(s * 0x80402010u, 0u, 0xba98u) & 0xfcfcfcfcu) | (par * 0x02020202u);
+  return m;
+}
+
+template <int CB>
+__device__ __forceinline__ void build_tables(unsigned char* tab, const void* grid, int tid) {
+  if (CB == QUIPB200_CB_D4) {
+    // fp16 [4] -> int8 (units of 1/2), byte order (0,2,1,3) to match the record layout of the activations
+    for (int e = tid; e < 256 * 32; e += DS_THREADS) {
+      const int i = e >> 5, c = e & 31;
+      const uint2 t = reinterpret_cast<const uint2*>(grid)[i];
+      const __half2 h01 = *reinterpret_cast<const __half2*>(&t.x), h23 = *reinterpret_cast<const __half2*>(&t.y);
+      const int v0 = __float2int_rn(__low2float(h01) * 2.0f) & 0xff, v1 = __float2int_rn(__high2float(h01) * 2.0f) & 0xff;
+      const int v2 = __float2int_rn(__low2float(h23) * 2.0f) & 0xff, v3 = __float2int_rn(__high2float(h23) * 2.0f) & 0xff;
+      reinterpret_cast<uint32_t*>(tab)[i * 64 + c] = (uint32_t)v0 | ((uint32_t)v2 << 8) | ((uint32_t)v1 << 16) | ((uint32_t)v3 << 24);
+    }
+  } else {
+    for (int e = tid; e < 256 * 32; e += DS_THREADS) {
+      const int i = e >> 5, c = e & 31;
+      uint2 v;
+      if (c < 16) {
+        v = reinterpret_cast<const uint2*>(grid)[i];
+        v.x |= 0x01010101u;
+        v.y |= 0x01010101u;
+      } else {
+        v = e8p_sign_mask((uint32_t)i);
+      }
+      reinterpret_cast<uint2*>(tab)[e] = v;
+    }
+  }
+}
+
+// one E8P code (index bytes `ab` / `sb` of packed word w) against one x segment: hi and lo activation planes
+template <int AB, int SB>
+__device__ __forceinline__ void e8p_dot_lut(uint32_t w, const unsigned char* tab, uint32_t offA, uint32_t offS,
+                                            const uint32_t (&xs)[4], int& aH, int& aL) {
+  const uint2 t = *reinterpret_cast<const uint2*>(tab + prmt(w, offA, 0x5504u | (AB << 4)));
+  const uint2 m = *reinterpret_cast<const uint2*>(tab + prmt(w, offS, 0x5504u | (SB << 4)));
+  const uint32_t vx = t.x ^ m.x, vy = t.y ^ m.y;
+  aH = dp4a_ss(vx, xs[0], aH);
+  aH = dp4a_ss(vy, xs[1], aH);
+  aL = dp4a_su(vx, xs[2], aL);   // signed weights x unsigned low bytes
+  aL = dp4a_su(vy, xs[3], aL);
+}
+
 // xq: swizzled 16-byte activation records in shared memory; red: [nrows][C] chunk partials
 template <int CB>
 __device__ __forceinline__ void gemv_run(uint4 (&cw)[DS_UNROLL], const GemvCfg& c, const uint4* xq,
                                          const unsigned char* tab, int* red, int warp, int lane, uint64_t pol) {
   using T = CbTraits<CB>;
   const int units = c.C * c.g;
+  const uint32_t offA = (CB == QUIPB200_CB_D4) ? (uint32_t)lane * 4u : (uint32_t)(lane & 15) * 8u;
+  const uint32_t offS = 128u + offA;
   int unit = warp;
   while (unit < units) {
     int chunk, sub;
@@ -175,15 +240,11 @@ __device__ __forceinline__ void gemv_run(uint4 (&cw)[DS_UNROLL], const GemvCfg& 
     const int seg0 = (chunk * 32 + lane) * T::SEGS;
     const bool lane_valid = seg0 < c.nseg;
     uint32_t xs[T::SEGS][4];
-    int xsum[T::SEGS];
 #pragma unroll
     for (int sgi = 0; sgi < T::SEGS; sgi++) {
       uint4 r = make_uint4(0, 0, 0, 0);
       if (lane_valid) r = xq[swz(seg0 + sgi)];
       xs[sgi][0] = r.x; xs[sgi][1] = r.y; xs[sgi][2] = r.z; xs[sgi][3] = r.w;
-      const int sh = dp4a_ss(r.x, 0x01010101u, dp4a_ss(r.y, 0x01010101u, 0));
-      const int sl = dp4a_su(0x01010101u, r.z, dp4a_su(0x01010101u, r.w, 0));
-      xsum[sgi] = sh * 256 + sl;
     }
     const unsigned char* colp = c.q + (size_t)(chunk * 32 + lane) * 16 + (size_t)c.row_begin * c.row_bytes;
     for (int r0 = sub; r0 < c.nrows; r0 += c.g * DS_UNROLL) {
@@ -195,52 +256,49 @@ __device__ __forceinline__ void gemv_run(uint4 (&cw)[DS_UNROLL], const GemvCfg& 
         nx[u] = make_uint4(0, 0, 0, 0);
         if (lane_valid && r < c.nrows) nx[u] = ldg_stream_v4(colp + (size_t)r * c.row_bytes, pol);
       }
-#pragma unroll 1
-      for (int u = 0; u < DS_UNROLL; u++) {
-        const int r = r0 + u * c.g;
-        if (r < c.nrows) {
-          int aH = 0, aL = 0, aP = 0, cH = 0, cL = 0, cP = 0;
-          const uint32_t w[4] = {cw[0].x, cw[0].y, cw[0].z, cw[0].w};
-          if (CB == QUIPB200_CB_E8P12) {
+      int tot[DS_UNROLL], tot2[DS_UNROLL];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-              e8p_dot((w[i] >> 5) & 0x7f8u, w[i] & 0xffu, tab, xs[2 * i], xsum[2 * i], aH, aL, aP);
-              e8p_dot((w[i] >> 21) & 0x7f8u, __byte_perm(w[i], 0, 0x4442), tab, xs[2 * i + 1], xsum[2 * i + 1], cH, cL, cP);
-            }
-            aH += cH; aL += cL; aP += cP;
-          } else if (CB == QUIPB200_CB_E8P12RVQ4B) {     // main code = hi16 (a*), residual code = lo16 (c*), same x segment
+      for (int u = 0; u < DS_UNROLL; u++) {      // rows past the end hold zero words: harmless, not stored
+        int aH = 0, aL = 0, cH = 0, cL = 0;
+        const uint32_t w[4] = {cw[u].x, cw[u].y, cw[u].z, cw[u].w};
+        if (CB == QUIPB200_CB_E8P12) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-              e8p_dot((w[i] >> 21) & 0x7f8u, __byte_perm(w[i], 0, 0x4442), tab, xs[i], xsum[i], aH, aL, aP);
-              e8p_dot((w[i] >> 5) & 0x7f8u, w[i] & 0xffu, tab, xs[i], xsum[i], cH, cL, cP);
-            }
-          } else {                                        // D4: byte -> 4 weights; two codes per 8-element segment
-            const uint32_t* t4 = reinterpret_cast<const uint32_t*>(tab);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-#pragma unroll
-              for (int b = 0; b < 4; b++) {
-                const uint32_t v = t4[(w[i] >> (8 * b)) & 0xffu];
-                const int sgi = i * 2 + (b >> 1), half = b & 1;
-                aH = dp4a_ss(v, xs[sgi][half], aH);
-                aL = dp4a_su(v, xs[sgi][2 + half], aL);
-              }
-            }
+          for (int i = 0; i < 4; i++) {
+            e8p_dot_lut<1, 0>(w[i], tab, offA, offS, xs[2 * i], aH, aL);
+            e8p_dot_lut<3, 2>(w[i], tab, offA, offS, xs[2 * i + 1], cH, cL);
           }
-          int tot = aH * 256 + aL - 2 * aP;
-          tot = __reduce_add_sync(0xffffffffu, tot);
-          int tot2 = 0;
-          if (T::ACCS == 2) {
-            tot2 = cH * 256 + cL - 2 * cP;
-            tot2 = __reduce_add_sync(0xffffffffu, tot2);
+          aH += cH; aL += cL;
+        } else if (CB == QUIPB200_CB_E8P12RVQ4B) {     // main code = hi16 (a*), residual code = lo16 (c*), same x segment
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            e8p_dot_lut<3, 2>(w[i], tab, offA, offS, xs[i], aH, aL);
+            e8p_dot_lut<1, 0>(w[i], tab, offA, offS, xs[i], cH, cL);
           }
-          if (lane == 0) {
-            red[(r * c.C + chunk) * T::ACCS] = tot;
-            if (T::ACCS == 2) red[(r * c.C + chunk) * T::ACCS + 1] = tot2;
+        } else {                                        // D4: byte -> 4 weights; two codes per 8-element segment
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+              const uint32_t v = *reinterpret_cast<const uint32_t*>(tab + prmt(w[i], offA, 0x5504u | (b << 4)));
+              const int sgi = i * 2 + (b >> 1), half = b & 1;
+              aH = dp4a_ss(v, xs[sgi][half], aH);
+              aL = dp4a_su(v, xs[sgi][2 + half], aL);
+            }
           }
         }
+        tot[u] = aH * 256 + aL;
+        tot2[u] = cH * 256 + cL;
+      }
 #pragma unroll
-        for (int v = 0; v + 1 < DS_UNROLL; v++) cw[v] = cw[v + 1];
+      for (int u = 0; u < DS_UNROLL; u++) {
+        const int r = r0 + u * c.g;
+        const int t1 = __reduce_add_sync(0xffffffffu, tot[u]);
+        int t2 = 0;
+        if (T::ACCS == 2) t2 = __reduce_add_sync(0xffffffffu, tot2[u]);
+        if (lane == 0 && r < c.nrows) {
+          red[(r * c.C + chunk) * T::ACCS] = t1;
+          if (T::ACCS == 2) red[(r * c.C + chunk) * T::ACCS + 1] = t2;
+        }
       }
 #pragma unroll
       for (int u = 0; u < DS_UNROLL; u++) cw[u] = nx[u];
@@ -891,7 +949,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
   bb.hkd = bb.hku + p.sm.hk_halfs;
   bb.vSVg = bb.hkd + p.sm.hk_halfs;
   bb.vSVu = bb.vSVg + p.sm.mid_halfs;
-  bb.vSUd = bb.vSVu + p.sm.mid_halfs;
+  bb.vSUd = reinterpret_cast<__half*>(rb.A);               // A | B is idle in stage E when the MLP side is blocked (K > 1)
   bb.LS = 256 + 8;
   const HFrag hfrag = make_hfrag(lane);
   float* const XS = rb.A;                                   // exchange buffer of fwht4096_frag (16 x DS_XROW floats)
@@ -914,21 +972,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
   if (tid == 0) bar_target = *reinterpret_cast<volatile unsigned int*>(p.ws.bar + 32);
   const uint64_t pol = l2_evict_first_policy();
 
-  // the codebook table (identical for every linear).  E8P: int8x8 abs entries, "+1/4" pre-applied; D4: fp16 [4] ->
-  // int8 (units of 1/2), byte order (0,2,1,3) to match the record layout of the activations
-  if (tid < 256) {
-    uint2 t = reinterpret_cast<const uint2*>(P.layers[0].q.grid)[tid];
-    if (CB == QUIPB200_CB_D4) {
-      const __half2 h01 = *reinterpret_cast<const __half2*>(&t.x), h23 = *reinterpret_cast<const __half2*>(&t.y);
-      const int v0 = __float2int_rn(__low2float(h01) * 2.0f) & 0xff, v1 = __float2int_rn(__high2float(h01) * 2.0f) & 0xff;
-      const int v2 = __float2int_rn(__low2float(h23) * 2.0f) & 0xff, v3 = __float2int_rn(__high2float(h23) * 2.0f) & 0xff;
-      reinterpret_cast<uint32_t*>(tab)[tid] = (uint32_t)v0 | ((uint32_t)v2 << 8) | ((uint32_t)v1 << 16) | ((uint32_t)v3 << 24);
-    } else {
-      t.x |= 0x01010101u;
-      t.y |= 0x01010101u;
-      reinterpret_cast<uint2*>(tab)[tid] = t;
-    }
-  }
+  // the codebook tables (identical for every linear)
+  build_tables<CB>(tab, P.layers[0].q.grid, tid);
   const int hid8 = P.hidden >> 3;
   if (bid == 0 && tid < hid8) reinterpret_cast<uint4*>(p.ws.hA)[tid] = reinterpret_cast<const uint4*>(p.h_in)[tid];
   __syncthreads();
@@ -1549,6 +1594,7 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
     hk_halfs = Kp * Kp;
     mid_halfs = ((size_t)Y.gate.out_features + 7) / 8 * 8;
     nmax = std::max(nmax, (size_t)2048);   // A | B doubles as the per-warp octet -> fragment scratch (16 KB)
+    nmax = std::max(nmax, (mid_halfs + 3) / 4);   // ... and holds the staged SU of down (mid_halfs fp16) in stage E
   }
   if (nmax > 8 * DS_THREADS) return QUIPB200_EUNSUPPORTED;
 
@@ -1593,14 +1639,14 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
                        Y.gate.q_in == 4096 && Y.up.q_in == 4096 && Y.down.q_out == 4096 && P->hidden <= 4096;
   out->use_mma = use_mma ? 1 : 0;
   if (use_mma) nmax = std::max(nmax, (size_t)4096);   // the exchange buffer (16 x 388 floats) lives in A | B
-  size_t blk = 2 * t_halfs * 2 + 3 * hk_halfs * 2 + 3 * mid_halfs * 2;
+  size_t blk = 2 * t_halfs * 2 + 3 * hk_halfs * 2 + 2 * mid_halfs * 2;
   if (use_mma) blk = std::max(blk, (size_t)90112);    // 8 KB spare + staged vectors / attention partials (72 KB) + 8 KB spare
   size_t scr = 2 * nmax * sizeof(float) + 64 * sizeof(float) + blk;
   scr = std::max(scr, attn);
   auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
   DsSmem sm;
   size_t off = 0;
-  sm.tab = 0; off += 2048;
+  sm.tab = 0; off += DS_TAB_BYTES;
   sm.red = (uint32_t)off; off += up16(red);
   sm.xq = (uint32_t)off; off += up16(xq);
   sm.scr = (uint32_t)off; off += up16(scr);
@@ -1609,7 +1655,7 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
   sm.t_halfs = (uint32_t)t_halfs;
   sm.hk_halfs = (uint32_t)hk_halfs;
   sm.mid_halfs = (uint32_t)mid_halfs;
-  if (off > 227 * 1024) return QUIPB200_EUNSUPPORTED;
+  if (off > 227 * 1024 - 2560) return QUIPB200_EUNSUPPORTED;   // static descriptors (1.5 KB) + the 1 KB the system reserves per CTA
   out->sm = sm;
   size_t w = 0;
   auto take = [&](size_t b) { size_t o = w; w += (b + 255) / 256 * 256; return o; };
