@@ -92,12 +92,14 @@ def make_random_quantized_llama(config="llama2-7b", codebook="E8P12", seed=0, de
         import copy
         cfg = copy.deepcopy(cfg)
         cfg.num_hidden_layers = len(layer_range)
-    with torch.device("meta"):
+    from .quantizer import _materialize, init_empty_weights
+    with init_empty_weights():           # parameters on meta, computed buffers (rotary inv_freq) real
         model = LlamaForCausalLM(cfg).to(dtype)
+    # opt_resid_scale=None: the codebook's own default (1/3.45 for RVQ4B, BASELINE config 4); the quantizer's default of -1
+    # (reference quantizer.py:69) is handed to the codebook as a literal scale
     quantizer = QuipQuantizer(codebook=codebook, use_rand=use_rand, per_channel=per_channel, inference=True,
-                              ft_epochs=0)
+                              ft_epochs=0, opt_resid_scale=None)
     model = quantizer.convert_model(model)
-    from .quantizer import _materialize
     _materialize(model, device, dtype)
     model = model.to(device)
     gen = torch.Generator(device=device)

@@ -9,6 +9,7 @@ instantiated on the meta device, every block linear is swapped for a `QuantLinea
 checkpoint shards (`pytorch_model*.bin` or `*.safetensors`, with or without an index json -- what
 `Accelerator.save_model` writes, quantizer.py:718-756) are streamed into it.
 """
+import contextlib
 import json
 import os
 from logging import getLogger
@@ -32,7 +33,7 @@ class QuipQuantizer(object):
                  model_seqlen: int = 2048, quip_tune_iters: int = 10, use_rand: bool = True,
                  rescale_WH: bool = False, sigma_reg: float = 1e-2, sigma_reg2: float = 1e-2,
                  modules_to_not_convert: Optional[List] = None, block_name_to_quantize: Optional[str] = None,
-                 merge_suv: bool = False, per_channel: bool = False, opt_resid_scale: Optional[float] = None,
+                 merge_suv: bool = False, per_channel: bool = False, opt_resid_scale: Optional[float] = -1,
                  inference: bool = False, ft_epochs: int = 5, ft_lr: float = 5e-5, ft_susv_lr: float = 5e-4,
                  ft_valid_size: int = 128, ft_bs: int = 8, ft_update_freq: int = 2, ft_early_stop: int = 3,
                  *args, **kwargs):
@@ -157,9 +158,33 @@ def _read_shard(path: str) -> Dict[str, torch.Tensor]:
     return torch.load(path, map_location="cpu", weights_only=True)
 
 
+@contextlib.contextmanager
+def init_empty_weights():
+    """Parameters are created on the meta device, buffers keep real storage and their computed values (rotary
+    inv_freq, causal masks, ...): the behaviour of accelerate's `init_empty_weights(include_buffers=False)` that the
+    reference relies on (quantizer.py:811), without the accelerate dependency."""
+    old_register = nn.Module.register_parameter
+
+    def register_parameter(module, name, param):
+        old_register(module, name, param)
+        if param is not None:
+            cur = module._parameters[name]
+            kw = dict(cur.__dict__)
+            kw["requires_grad"] = cur.requires_grad
+            module._parameters[name] = cur.__class__(cur.to("meta"), **kw)
+
+    nn.Module.register_parameter = register_parameter
+    try:
+        yield
+    finally:
+        nn.Module.register_parameter = old_register
+
+
 def _materialize(model: nn.Module, device, dtype):
-    """Give real storage to whatever is still on the meta device (everything except the QuantLinears)."""
-    for mod in model.modules():
+    """Give real storage to the parameters that are still on the meta device.  Returns the names of buffers that had no
+    real storage (none when the model was built under init_empty_weights): they must come from the checkpoint."""
+    meta_buffers = []
+    for mname, mod in model.named_modules():
         for name, p in list(mod._parameters.items()):
             if p is not None and p.is_meta:
                 mod._parameters[name] = nn.Parameter(torch.empty(p.shape, dtype=p.dtype, device=device),
@@ -167,16 +192,14 @@ def _materialize(model: nn.Module, device, dtype):
         for name, b in list(mod._buffers.items()):
             if b is not None and b.is_meta:
                 mod._buffers[name] = torch.empty(b.shape, dtype=b.dtype, device=device)
-    # non-persistent computed buffers (rotary inv_freq) do not come from the checkpoint: rebuild them
-    for parent in model.modules():
-        for cname, child in list(parent.named_children()):
-            if "RotaryEmbedding" in child.__class__.__name__ and hasattr(child, "config"):
-                parent.add_module(cname, child.__class__(config=child.config).to(device))
+                meta_buffers.append(f"{mname}.{name}" if mname else name)
+    return meta_buffers
 
 
-def load_state_into(model: nn.Module, files: List[str]):
-    """Stream checkpoint shards into the model.  QuantLinear attributes that the checkpoint lacks
-    because they were merged away at pack time (SU / SV = None, qlinear.py:125-131) are set to None."""
+def load_state_into(model: nn.Module, files: List[str], merge_suv: bool = True):
+    """Stream checkpoint shards into the model.  With `merge_suv` (quantization config), QuantLinear SU / SV vectors
+    that the checkpoint lacks were merged away at pack time (qlinear.py:125-131) and are set to None; without it an
+    absent SU / SV is a missing tensor like any other."""
     own = dict(model.state_dict(keep_vars=True))
     seen = set()
     for f in files:
@@ -192,12 +215,13 @@ def load_state_into(model: nn.Module, files: List[str]):
                 dst.copy_(v.to(dst.dtype) if dst.dtype.is_floating_point and v.dtype.is_floating_point else v)
             seen.add(k)
         del shard
-    for name, mod in model.named_modules():
-        if isinstance(mod, QuantLinear):
-            for attr in ("SU", "SV"):
-                if f"{name}.{attr}" not in seen:
-                    setattr(mod, attr, None)
-    missing = [k for k in own if k not in seen and not k.endswith((".SU", ".SV"))]
+    if merge_suv:
+        for name, mod in model.named_modules():
+            if isinstance(mod, QuantLinear):
+                for attr in ("SU", "SV"):
+                    if f"{name}.{attr}" not in seen:
+                        setattr(mod, attr, None)
+    missing = [k for k in own if k not in seen and not (merge_suv and k.endswith((".SU", ".SV")))]
     return missing
 
 
@@ -223,12 +247,18 @@ def load_quantized_model(save_folder: str, revision: Optional[str] = None,
     requirement -- there is no CPU inference path."""
     if not torch.cuda.is_available():
         raise RuntimeError("No GPU found. A GPU is needed to run quantized model.")
+    return _load_quantized_model(save_folder, revision, torch_dtype, trust_remote_code, use_safetensors, device_map)
+
+
+def _load_quantized_model(save_folder, revision=None, torch_dtype=torch.float16, trust_remote_code=True,
+                          use_safetensors=False, device_map=None):
+    """Body of load_quantized_model (host-side work only; callable without a device by the CPU tests)."""
     from transformers import AutoModelForCausalLM
     folder, config = load_config(save_folder, trust_remote_code=trust_remote_code,
                                  safetensors=use_safetensors, revision=revision)
     if isinstance(torch_dtype, str):
         torch_dtype = getattr(torch, torch_dtype)
-    with torch.device("meta"):
+    with init_empty_weights():
         model = AutoModelForCausalLM.from_config(config, trust_remote_code=trust_remote_code, dtype=torch_dtype)
 
     qcfg = getattr(config, "quantization_config", None)
@@ -248,8 +278,12 @@ def load_quantized_model(save_folder: str, revision: Optional[str] = None,
         device = device_map[""]
     elif device_map is not None:
         device = "cuda"      # whole model on the current GPU; multi-GPU goes through parallel.LayerPipeline
-    _materialize(model, "cpu", torch_dtype)
-    missing = load_state_into(model, _checkpoint_files(folder, use_safetensors))
+    meta_buffers = _materialize(model, "cpu", torch_dtype)
+    missing = load_state_into(model, _checkpoint_files(folder, use_safetensors), merge_suv=quantizer.merge_suv)
+    persistent = set(model.state_dict().keys())
+    lost = [b for b in meta_buffers if b not in persistent]
+    if lost:      # a computed, non-persistent buffer without storage would be read as uninitialised memory
+        raise RuntimeError(f"{len(lost)} non-persistent buffers have no values, e.g. {lost[:5]}")
     if hasattr(model, "tie_weights"):
         model.tie_weights()
     missing = [k for k in missing if not ("lm_head" in k and getattr(config, "tie_word_embeddings", False))]

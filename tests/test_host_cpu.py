@@ -248,11 +248,14 @@ def test_checkpoint_roundtrip_cpu(tmp_path, fmt):
     (tmp_path / f"{base}.{ext}.index.json").write_text(json.dumps({"metadata": {}, "weight_map": wm}))
     files = qz._checkpoint_files(str(tmp_path), use_safetensors=(fmt == "safetensors"))
     assert len(files) == 2
-    with torch.device("meta"):
+    with qz.init_empty_weights():
         dst = cls(cfg).half()
+    assert dst.model.embed_tokens.weight.is_meta and not dst.model.rotary_emb.inv_freq.is_meta
     QuipQuantizer(codebook="E8P12", inference=True).convert_model(dst)
-    qz._materialize(dst, "cpu", torch.float16)
-    missing = qz.load_state_into(dst, files)
+    assert qz._materialize(dst, "cpu", torch.float16) == []
+    missing = qz.load_state_into(dst, files, merge_suv=False)
+    assert missing == ["model.layers.0.self_attn.q_proj.SU"]       # not merged away by config: reported, not dropped
+    missing = qz.load_state_into(dst, files, merge_suv=True)
     assert missing == []
     qz.apply_load_time_tricks(dst)
     assert dst.model.layers[0].self_attn.q_proj.SU is None
@@ -261,7 +264,7 @@ def test_checkpoint_roundtrip_cpu(tmp_path, fmt):
         assert torch.equal(v, sd[k]), k
     l0 = dst.model.layers[1].mlp.up_proj
     assert abs(l0.wscale_float - float(l0.Wscale)) < 1e-9
-    # rotary buffers were rebuilt, not left uninitialised
+    # computed buffers keep their values (parameters only go through the meta device)
     assert torch.isfinite(dst.model.rotary_emb.inv_freq).all() and dst.model.rotary_emb.inv_freq[0] == 1.0
 
 
@@ -361,3 +364,58 @@ def test_bench_reference_arm_prints_the_contract_line():
     r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                          "--model", "tiny"], capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=300)
     assert r2.returncode == 0 and r2.stdout.strip() == ""
+
+
+# ------------------------------------------------------------------------------------------------
+# checkpoint folders written with the REFERENCE's module tree / key layout / config (tests/golden/gen_checkpoint.py)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("folder,st", [("ref_ckpt_e8p12_bin", False), ("ref_ckpt_e8p12_sharded_st", True),
+                                       ("ref_ckpt_e8p12rvq4b_bin", False)])
+def test_loader_consumes_reference_written_checkpoint(golden_dir, folder, st):
+    import json
+    from quip_for_all_b200 import quantizer as qz
+    path = os.path.join(golden_dir, folder)
+    model = qz._load_quantized_model(path, use_safetensors=st)
+    files = qz._checkpoint_files(path, st)
+    ref = {}
+    for f in files:
+        ref.update(qz._read_shard(f))
+    with open(os.path.join(golden_dir, "ref_ckpt_manifest.json")) as f:
+        manifest = json.load(f)
+    if "rvq4b" not in folder:
+        assert set(ref) == set(manifest)
+    sd = model.state_dict()
+    # every tensor the reference's model exposes has a destination of the same shape / dtype and arrives bit-exact
+    for k, v in ref.items():
+        assert k in sd, k
+        assert tuple(sd[k].shape) == tuple(v.shape) and sd[k].dtype == v.dtype, k
+        assert torch.equal(sd[k], v), k
+    assert set(sd) == set(ref)
+    from quip_for_all_b200 import QuantLinear
+    ql = [m for m in model.modules() if isinstance(m, QuantLinear)]
+    assert len(ql) == 14
+    cb = "E8P12RVQ4B" if "rvq4b" in folder else "E8P12"
+    for m in ql:
+        assert m.codebook.id == cb
+        assert m.SU is not None and m.SV is not None              # merge_suv = false in the reference config
+        assert abs(m.wscale_float - float(m.Wscale)) < 1e-9        # quantizer.py:837
+    mlp = model.model.layers[1].mlp                                # 768 = 3 * 256: use_rand blocks, persistent buffers
+    assert mlp.gate_proj.K_right == 3 and tuple(mlp.gate_proj.had_right.shape) == (3, 3)
+    assert mlp.down_proj.K_left == 3 and torch.equal(mlp.down_proj.had_left, ref["model.layers.1.mlp.down_proj.had_left"])
+    if cb == "E8P12RVQ4B":       # the reference hands its default opt_resid_scale = -1 to the codebook as a literal scale
+        assert ql[0].codebook.opt_resid_scale == -1                # (quantizer.py:69,232; e8p12_rvq4.py:23): kept as is
+    assert torch.isfinite(model.model.rotary_emb.inv_freq).all()
+
+
+def test_loader_reports_missing_scale_vectors(golden_dir, tmp_path):
+    """an SU / SV absent from a checkpoint whose config says merge_suv = false is an error, not a silent None."""
+    import shutil
+    from quip_for_all_b200 import quantizer as qz
+    src = os.path.join(golden_dir, "ref_ckpt_e8p12_bin")
+    dst = tmp_path / "broken"
+    shutil.copytree(src, dst)
+    sd = torch.load(dst / "pytorch_model.bin", map_location="cpu", weights_only=True)
+    del sd["model.layers.0.mlp.up_proj.SV"]
+    torch.save(sd, dst / "pytorch_model.bin")
+    with pytest.raises(RuntimeError, match="missing 1 tensors"):
+        qz._load_quantized_model(str(dst))
