@@ -105,6 +105,10 @@ def lib():
     if L.quipb200_abi_version() != 1:
         raise QuipB200Error("libquipb200.so ABI version mismatch")
     _lib = L
+    # tuning switches for A/B runs (tools/ab_bench.sh): QUIPB200_OPTIONS="name=value,name=value"
+    for kv in filter(None, os.environ.get("QUIPB200_OPTIONS", "").split(",")):
+        k, _, v = kv.partition("=")
+        L.quipb200_set_option(k.strip().encode(), int(v))
     return L
 
 

@@ -11,7 +11,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libquipb200.so")
-SOURCES = ["api.cu", "decompress.cu", "hadamard.cu", "quantlinear.cu", "glue.cu", "decode_step.cu", "umma_gemm.cu", "rotate_batched.cu"]
+SOURCES = ["api.cu", "decompress.cu", "hadamard.cu", "quantlinear.cu", "glue.cu", "decode_step.cu", "umma_gemm.cu",
+           "rotate_batched.cu"]
+# (hook for translation units that need relocatable device code; none at present)
+RDC_SOURCES = set()
+RDC_FLAGS = {}
 OBJDIR = os.path.join(HERE, "lib", "obj")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -43,7 +47,7 @@ def build(force=False, verbose=False):
         sp = os.path.join(CSRC, src)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(sp), hdr_t):
             return obj, 0, ""
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, sp]
+        cmd = [nvcc] + NVCC_FLAGS + RDC_FLAGS.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, sp]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         return obj, res.returncode, res.stdout
 
@@ -56,7 +60,16 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if rc != 0:
             raise RuntimeError("nvcc failed building %s:\n%s" % (obj, out[-4000:]))
-    cmd = [nvcc, "-shared", "-o", LIB] + [r[0] for r in results]
+    extra = []
+    rdc_objs = [os.path.join(OBJDIR, f.replace(".cu", ".o")) for f in SOURCES if f in RDC_SOURCES]
+    if rdc_objs:
+        dlink = os.path.join(OBJDIR, "dlink.o")
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-dlink", "-o", dlink] + rdc_objs
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("device link failed:\n" + res.stdout[-4000:])
+        extra = [dlink]
+    cmd = [nvcc, "-shared", "-o", LIB] + [r[0] for r in results] + extra
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed for libquipb200.so:\n" + res.stdout[-4000:])

@@ -11,6 +11,7 @@ extern int g_opt_gemv_warps;
 extern int g_opt_gemv_ctas_per_sm;
 extern int g_opt_stage_mask;
 extern int g_opt_fuse;
+extern int g_ds_flags;
 extern int g_opt_phase0;
 extern int g_opt_lean;
 extern int g_opt_rot_warp_rows;
@@ -94,6 +95,10 @@ extern "C" int quipb200_set_option(const char* name, int value) {
     qb::g_opt_rot_warp_rows = value;
     return 0;
   }
+  if (!strcmp(name, "ds_flags")) {
+    qb::g_ds_flags = value;
+    return 0;
+  }
   if (!strcmp(name, "fuse")) {
     if (value < 0 || value > 3) return QUIPB200_EINVAL;
     qb::g_opt_fuse = value;
@@ -109,6 +114,7 @@ extern "C" int quipb200_get_option(const char* name) {
   if (!strcmp(name, "gemv_ctas_per_sm")) return qb::g_opt_gemv_ctas_per_sm;
   if (!strcmp(name, "stage_mask")) return qb::g_opt_stage_mask;
   if (!strcmp(name, "fuse")) return qb::g_opt_fuse;
+  if (!strcmp(name, "ds_flags")) return qb::g_ds_flags;
   if (!strcmp(name, "pdl")) return qb::g_opt_pdl;
   if (!strcmp(name, "umma")) return qb::g_opt_umma;
   if (!strcmp(name, "rot_warp_rows")) return qb::g_opt_rot_warp_rows;

@@ -65,6 +65,7 @@ struct DsParams {
   __half* h_out;
   int kv_splits;
   int use_mma;           // hidden-side rotations are 4096-point: tensor-path transforms
+  int flags;             // tuning / A-B switches (option "ds_flags")
   long long* dbg;        // optional [64] clock stamps of one CTA (tools/ds_timeline.py)
   int dbg_cta;
 };
@@ -77,6 +78,25 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   if (threadIdx.x == 0) {
     target += nblk;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while ((int)(v - target) < 0);
+  }
+  __syncthreads();
+}
+
+// Split-phase form: arrive (release) first, then issue loads that do not depend on the other CTAs' current stage, then
+// wait.  (Requests issued BEFORE the release are waited for by its fence and delay the arrival: measured +1.9 us.)
+__device__ __forceinline__ void grid_arrive(unsigned int* counter, unsigned int& target, unsigned int nblk) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += nblk;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+  }
+}
+__device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int target) {
+  if (threadIdx.x == 0) {
     unsigned int v;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
@@ -709,6 +729,26 @@ __device__ __forceinline__ void mix_blocks(__half* T0, const __half* hk0, __half
   }
 }
 
+// The layer-constant vectors of stage E (SV of gate / up, SU of down, the coefficient blob): requested between the arrival
+// at stage D's grid barrier and the wait, so that only the raw dot products remain to be fetched after the barrier.
+__device__ __forceinline__ void stage_e_static(const quipb200_linear_t& Lg, const quipb200_linear_t& Lu,
+                                               const quipb200_linear_t& Ld, const __half* hk_blob, const BlkBuf& bb, int tid) {
+  const int K = Lg.K_right, Kp = (K + 15) / 16 * 16;
+  const int noct_mid = Lg.out_features >> 3;
+  const __half* SVg = reinterpret_cast<const __half*>(Lg.SV);
+  const __half* SVu = reinterpret_cast<const __half*>(Lu.SV);
+  const __half* SUd = reinterpret_cast<const __half*>(Ld.SU);
+  for (int o = tid; o < noct_mid; o += DS_THREADS) {
+    if (SVg) cp_async16(bb.vSVg + o * 8, SVg + o * 8);
+    if (SVu) cp_async16(bb.vSVu + o * 8, SVu + o * 8);
+    if (SUd) cp_async16(bb.vSUd + o * 8, SUd + o * 8);
+  }
+  if (hk_blob != nullptr) {
+    const int n16 = (3 * Kp * Kp) >> 3;
+    for (int i = tid; i < n16; i += DS_THREADS) cp_async16(bb.hkg + i * 8, hk_blob + i * 8);
+  }
+}
+
 // Stage-E input construction for K > 1:  x = rot_in_down( SU_d . silu(out(gate)) * out(up) ), records -> xq.
 // Everything the stage reads from global memory is requested up front (one L2 round trip): the raw dot
 // products of this warp's blocks into registers, SV_gate / SV_up / SU_down into shared memory with cp.async,
@@ -717,7 +757,7 @@ constexpr int DS_EB = 3;   // blocks per warp in flight (K <= 48 in one round)
 __device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, const quipb200_linear_t& Lu,
                                                 const quipb200_linear_t& Ld, const __half* acc_g, const __half* acc_u,
                                                 const __half* hk_blob, const BlkBuf& bb, const HFrag& A,
-                                                float* fred, uint4* xq, int tid, long long* dbg) {
+                                                float* fred, uint4* xq, int tid, bool staged, long long* dbg) {
 #define DS_E(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   const int lane = tid & 31, warp = tid >> 5;
   const int K = Lg.K_right, Kp = (K + 15) / 16 * 16, LS = bb.LS;
@@ -729,16 +769,20 @@ __device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, con
   const __half* bu = reinterpret_cast<const __half*>(Lu.bias);
   const __half* wg = reinterpret_cast<const __half*>(Lg.wscale_pc);
   const __half* wu = reinterpret_cast<const __half*>(Lu.wscale_pc);
-  for (int o = tid; o < noct_mid; o += DS_THREADS) {
-    if (SVg) cp_async16(bb.vSVg + o * 8, SVg + o * 8);
-    if (SVu) cp_async16(bb.vSVu + o * 8, SVu + o * 8);
-    if (SUd) cp_async16(bb.vSUd + o * 8, SUd + o * 8);
+  if (!staged) {
+    for (int o = tid; o < noct_mid; o += DS_THREADS) {
+      if (SVg) cp_async16(bb.vSVg + o * 8, SVg + o * 8);
+      if (SVu) cp_async16(bb.vSVu + o * 8, SVu + o * 8);
+      if (SUd) cp_async16(bb.vSUd + o * 8, SUd + o * 8);
+    }
   }
   // coefficient matrices M[k_out][k_in], zero padded to Kp <= 64 (input side of down: hadK^T): one pre-padded blob per
   // layer when the caller provides it (16-byte requests), else gathered from the raw K x K tensors
   if (hk_blob != nullptr) {
-    const int n16 = (3 * Kp * Kp) >> 3;
-    for (int i = tid; i < n16; i += DS_THREADS) cp_async16(bb.hkg + i * 8, hk_blob + i * 8);
+    if (!staged) {
+      const int n16 = (3 * Kp * Kp) >> 3;
+      for (int i = tid; i < n16; i += DS_THREADS) cp_async16(bb.hkg + i * 8, hk_blob + i * 8);
+    }
   } else {
     const __half* src[3] = {reinterpret_cast<const __half*>(Lg.had_right), reinterpret_cast<const __half*>(Lu.had_right),
                             reinterpret_cast<const __half*>(Ld.had_left)};
@@ -905,8 +949,10 @@ __device__ __forceinline__ void warp_fwht128(float (&v)[4], int lane) {
   }
 }
 
-// finish one head slice in a single warp: transform, output-side scalings of the linear (qlinear.py:108-114)
-__device__ __forceinline__ void slice_finish(const quipb200_linear_t& L, const float* part, int j, int lane, float (&v)[4]) {
+// finish one head slice in a single warp: transform, output-side scalings of the linear (qlinear.py:108-114).
+// svv / bv: the 4 SV / bias halfs of this lane's outputs (j * 128 + 4 * lane ..), loaded by the caller ahead of time.
+__device__ __forceinline__ void slice_finish(const quipb200_linear_t& L, const float* part, uint2 svv, uint2 bv, int lane,
+                                             float (&v)[4]) {
 #pragma unroll
   for (int e = 0; e < 4; e++) v[e] = 0.f;
 #pragma unroll
@@ -916,15 +962,46 @@ __device__ __forceinline__ void slice_finish(const quipb200_linear_t& L, const f
   }
   warp_fwht128(v, lane);
   const float sc = 1.0f / sqrtf((float)L.q_out);
-  const __half* SV = reinterpret_cast<const __half*>(L.SV);
-  const __half* bias = reinterpret_cast<const __half*>(L.bias);
+  const float2 s01 = __half22float2(as_h2(svv.x)), s23 = __half22float2(as_h2(svv.y));
+  const float2 b01 = __half22float2(as_h2(bv.x)), b23 = __half22float2(as_h2(bv.y));
+  const float sv4[4] = {s01.x, s01.y, s23.x, s23.y}, b4[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
   for (int e = 0; e < 4; e++) {
-    const int i = j * 128 + lane * 4 + e;
     v[e] = f16_round(v[e] * sc);
-    if (SV) v[e] = f16_round(v[e] * __half2float(SV[i]));
-    if (bias) v[e] = f16_round(v[e] + __half2float(bias[i]));
+    if (L.SV) v[e] = f16_round(v[e] * sv4[e]);
+    if (L.bias) v[e] = f16_round(v[e] + b4[e]);
   }
+}
+
+constexpr int DS_ATT_UN = 4;       // positions per half-warp (scores) / per 16-thread group (P.V) in one pass
+
+// Layer-constant vectors of stages D and A (SV / bias of the producing linear, the skip connection written two barriers
+// earlier, norm weight, SU of the consuming linear): requested between the arrival at the previous stage's grid barrier
+// and the wait (see grid_arrive).
+__device__ __forceinline__ void stage_d_static(const DsParams& p, const quipb200_decode_layer_t& Ly, const Stg& stg, int bid, int tid) {
+  int j2, bx2;
+  which_member(p.geo.G_D, 2, bid, j2, bx2);
+  if (j2 < 0) return;
+  const quipb200_linear_t& Lp = Ly.o;
+  const quipb200_linear_t& Ln = (j2 == 0) ? Ly.gate : Ly.up;
+  stg_vec(stg.sv, reinterpret_cast<const __half*>(Lp.SV), Lp.out_features, tid);
+  stg_vec(stg.bias, reinterpret_cast<const __half*>(Lp.bias), Lp.out_features, tid);
+  stg_vec(stg.resid, p.ws.hA, Lp.out_features, tid);
+  stg_vec(stg.nw, reinterpret_cast<const __half*>(Ly.post_norm_w), Ln.in_features, tid);
+  stg_vec(stg.su, reinterpret_cast<const __half*>(Ln.SU), Ln.in_features, tid);
+}
+__device__ __forceinline__ void stage_a_static(const DsParams& p, const quipb200_decode_layer_t& Ly, const quipb200_decode_layer_t& Lnx,
+                                               const Stg& stg, int bid, int tid) {
+  int j2, bx2;
+  which_member(p.geo.G_A, 3, bid, j2, bx2);
+  if (j2 < 0) return;
+  const quipb200_linear_t& Lp = Ly.down;
+  const quipb200_linear_t& Ln = (j2 == 0) ? Lnx.q : (j2 == 1 ? Lnx.k : Lnx.v);
+  stg_vec(stg.sv, reinterpret_cast<const __half*>(Lp.SV), Lp.out_features, tid);
+  stg_vec(stg.bias, reinterpret_cast<const __half*>(Lp.bias), Lp.out_features, tid);
+  stg_vec(stg.resid, p.ws.hB, Lp.out_features, tid);
+  stg_vec(stg.nw, reinterpret_cast<const __half*>(Lnx.input_norm_w), Ln.in_features, tid);
+  stg_vec(stg.su, reinterpret_cast<const __half*>(Ln.SU), Ln.in_features, tid);
 }
 
 template <int CB>
@@ -1011,11 +1088,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             }
           } else {
             const quipb200_linear_t Lp = s_desc[(l - 1) & 1].down;
-            stg_vec(stg.sv, reinterpret_cast<const __half*>(Lp.SV), Lp.out_features, tid);
-            stg_vec(stg.bias, reinterpret_cast<const __half*>(Lp.bias), Lp.out_features, tid);
-            stg_vec(stg.resid, p.ws.hB, Lp.out_features, tid);
-            stg_vec(stg.nw, reinterpret_cast<const __half*>(Ly.input_norm_w), L.in_features, tid);
-            stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
+            if (p.flags & 1) {      // (else staged during the wait of the previous layer's last barrier: stage_a_static)
+              stg_vec(stg.sv, reinterpret_cast<const __half*>(Lp.SV), Lp.out_features, tid);
+              stg_vec(stg.bias, reinterpret_cast<const __half*>(Lp.bias), Lp.out_features, tid);
+              stg_vec(stg.resid, p.ws.hB, Lp.out_features, tid);
+              stg_vec(stg.nw, reinterpret_cast<const __half*>(Ly.input_norm_w), L.in_features, tid);
+              stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
+            }
             const uint4 oct = out_side_load(p.ws.acc[SL_D], warp, lane);
             out_side_m(Lp, oct, true, stg, hfrag, XS, warp, lane, f);
 #pragma unroll
@@ -1094,6 +1173,26 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         float* sc = sout + DS_PV_GROUPS * 128;                // [chunk] scores
         __half* kc = reinterpret_cast<__half*>(Ly.k_cache) + (size_t)kvh * P.max_len * DS_HD;
         __half* vc = reinterpret_cast<__half*>(Ly.v_cache) + (size_t)kvh * P.max_len * DS_HD;
+        // Everything this CTA needs that does not depend on the q/k/v stage is requested first and travels while the head
+        // slices are rotated: cached K rows of the first scores pass, the RoPE table row, SV / bias of the slices.
+        uint4 kfirst[DS_ATT_UN];
+#pragma unroll
+        for (int u = 0; u < DS_ATT_UN; u++) {
+          const int tk = t_begin + warp * 2 + (lane >> 4) + u * DS_WARPS * 2;
+          kfirst[u] = make_uint4(0, 0, 0, 0);
+          if (tk < t_end && tk != pos) kfirst[u] = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)tk * DS_HD) + (lane & 15));
+        }
+        uint2 rope_c = make_uint2(0, 0), rope_s = rope_c, sl_sv = rope_c, sl_b = rope_c;
+        if (warp < 2) {
+          rope_c = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(P.cos_t) + (size_t)pos * DS_HD) + lane);
+          rope_s = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(P.sin_t) + (size_t)pos * DS_HD) + lane);
+        }
+        if (warp < 3) {
+          const quipb200_linear_t& Ls = warp == 0 ? Ly.q : (warp == 1 ? Ly.k : Ly.v);
+          const int jj = warp == 0 ? h : kvh;
+          if (Ls.SV) sl_sv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(Ls.SV) + jj * 128) + lane);
+          if (Ls.bias) sl_b = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(Ls.bias) + jj * 128) + lane);
+        }
         {
           const int nbq = Ly.q.q_out >> 7, nbk = Ly.k.q_out >> 7, nbv = Ly.v.q_out >> 7;
           const uint4 aq = slice_load(nbq, p.ws.acc[SL_Q], tid);
@@ -1113,28 +1212,36 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         if (warp < (has_new ? 3 : 1)) {
           float v[4];
           const quipb200_linear_t& L = warp == 0 ? Ly.q : (warp == 1 ? Ly.k : Ly.v);
-          slice_finish(L, part + warp * DS_WARPS * 128, warp == 0 ? h : kvh, lane, v);
+          slice_finish(L, part + warp * DS_WARPS * 128, sl_sv, sl_b, lane, v);
           if (warp < 2) {   // RoPE, HF rotate_half convention: x*cos + rotate_half(x)*sin
-            const __half* ct = reinterpret_cast<const __half*>(P.cos_t) + (size_t)pos * DS_HD;
-            const __half* st = reinterpret_cast<const __half*>(P.sin_t) + (size_t)pos * DS_HD;
+            const float2 c01 = __half22float2(as_h2(rope_c.x)), c23 = __half22float2(as_h2(rope_c.y));
+            const float2 s01 = __half22float2(as_h2(rope_s.x)), s23 = __half22float2(as_h2(rope_s.y));
+            const float cv[4] = {c01.x, c01.y, c23.x, c23.y}, sv4[4] = {s01.x, s01.y, s23.x, s23.y};
             const float sgn = (lane < 16) ? -1.f : 1.f;
+            float r4[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-              const int d = lane * 4 + e;
               const float pv = __shfl_xor_sync(0xffffffffu, v[e], 16);
-              const float r = f16_round(v[e] * __half2float(ct[d]) + sgn * pv * __half2float(st[d]));
-              if (warp == 0) sq[d] = r * attn_scale;
-              else {
-                sk[d] = r;
-                if (h % group == 0) kc[(size_t)pos * DS_HD + d] = __float2half_rn(r);
+              r4[e] = f16_round(v[e] * cv[e] + sgn * pv * sv4[e]);
+            }
+            if (warp == 0) {
+              *reinterpret_cast<float4*>(sq + lane * 4) = make_float4(r4[0] * attn_scale, r4[1] * attn_scale, r4[2] * attn_scale, r4[3] * attn_scale);
+            } else {
+              *reinterpret_cast<float4*>(sk + lane * 4) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+              if (h % group == 0) {
+                uint2 o;
+                o.x = pk_h2(r4[0], r4[1]);
+                o.y = pk_h2(r4[2], r4[3]);
+                *reinterpret_cast<uint2*>(kc + (size_t)pos * DS_HD + lane * 4) = o;
               }
             }
           } else {
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const int d = lane * 4 + e;
-              sv[d] = v[e];
-              if (h % group == 0) vc[(size_t)pos * DS_HD + d] = __float2half_rn(v[e]);
+            *reinterpret_cast<float4*>(sv + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+            if (h % group == 0) {
+              uint2 o;
+              o.x = pk_h2(v[0], v[1]);
+              o.y = pk_h2(v[2], v[3]);
+              *reinterpret_cast<uint2*>(vc + (size_t)pos * DS_HD + lane * 4) = o;
             }
           }
         }
@@ -1146,15 +1253,26 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
 #pragma unroll
         for (int e = 0; e < 8; e++) qv[e] = sq[l16 * 8 + e];
         float lmax = -INFINITY;
-        constexpr int UN = 4;
+        uint4 vfirst[DS_ATT_UN];                       // V rows of the first P.V pass: in flight under the scores / softmax
+#pragma unroll
+        for (int u = 0; u < DS_ATT_UN; u++) {
+          const int tv = t_begin + (tid >> 4) + u * DS_PV_GROUPS;
+          vfirst[u] = make_uint4(0, 0, 0, 0);
+          if (tv < t_end && tv != pos) vfirst[u] = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)tv * DS_HD) + (tid & 15));
+        }
+        constexpr int UN = DS_ATT_UN;
         for (int tb = t_begin + warp * 2; tb < t_end; tb += DS_WARPS * 2 * UN) {   // warp-uniform trip count (full-mask shuffles inside)
           const int t0 = tb + hw;
           uint4 raw[UN];
+          const bool first = tb == t_begin + warp * 2;                              // first pass: requested at the top of the stage
 #pragma unroll
           for (int u = 0; u < UN; u++) {
             const int t = t0 + u * DS_WARPS * 2;
-            raw[u] = make_uint4(0, 0, 0, 0);
-            if (t < t_end && t != pos) raw[u] = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)t * DS_HD) + l16);
+            raw[u] = kfirst[u];
+            if (!first) {
+              raw[u] = make_uint4(0, 0, 0, 0);
+              if (t < t_end && t != pos) raw[u] = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)t * DS_HD) + l16);
+            }
           }
           float d[UN];
 #pragma unroll
@@ -1210,14 +1328,18 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         {
           const int pg = tid >> 4, t16 = tid & 15;
           float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          constexpr int UV = 4;
+          constexpr int UV = DS_ATT_UN;
           for (int t0 = t_begin + pg; t0 < t_end; t0 += DS_PV_GROUPS * UV) {
             uint4 vr[UV];
+            const bool first = t0 == t_begin + pg;
 #pragma unroll
             for (int u = 0; u < UV; u++) {
               const int t = t0 + u * DS_PV_GROUPS;
-              vr[u] = make_uint4(0, 0, 0, 0);
-              if (t < t_end && t != pos) vr[u] = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)t * DS_HD) + t16);
+              vr[u] = vfirst[u];
+              if (!first) {
+                vr[u] = make_uint4(0, 0, 0, 0);
+                if (t < t_end && t != pos) vr[u] = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)t * DS_HD) + t16);
+              }
             }
 #pragma unroll
             for (int u = 0; u < UV; u++) {
@@ -1362,7 +1484,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         const quipb200_linear_t* nx[2] = {&Ly.gate, &Ly.up};
         prefetch_stage(nx, p.geo.G_D, 2, bid, tid);
       }
-      grid_barrier(p.ws.bar, bar_target, nblk);
+      grid_arrive(p.ws.bar, bar_target, nblk);
+      if (p.use_mma && !(p.flags & 1)) stage_d_static(p, Ly, stg, bid, tid);
+      grid_wait(p.ws.bar, bar_target);
       DS_ST(15);
     }
     // ======================= stage D: gate, up =======================
@@ -1376,11 +1500,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         float xs;
         const quipb200_linear_t Lp = Ly.o;
         if (p.use_mma) {
-          stg_vec(stg.sv, reinterpret_cast<const __half*>(Lp.SV), Lp.out_features, tid);
-          stg_vec(stg.bias, reinterpret_cast<const __half*>(Lp.bias), Lp.out_features, tid);
-          stg_vec(stg.resid, p.ws.hA, Lp.out_features, tid);
-          stg_vec(stg.nw, reinterpret_cast<const __half*>(Ly.post_norm_w), L.in_features, tid);
-          stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
+          if (p.flags & 1) {        // (else staged during the wait of stage C's barrier: stage_d_static)
+            stg_vec(stg.sv, reinterpret_cast<const __half*>(Lp.SV), Lp.out_features, tid);
+            stg_vec(stg.bias, reinterpret_cast<const __half*>(Lp.bias), Lp.out_features, tid);
+            stg_vec(stg.resid, p.ws.hA, Lp.out_features, tid);
+            stg_vec(stg.nw, reinterpret_cast<const __half*>(Ly.post_norm_w), L.in_features, tid);
+            stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
+          }
           const uint4 oct = out_side_load(p.ws.acc[SL_O], warp, lane);
           out_side_m(Lp, oct, true, stg, hfrag, XS, warp, lane, f, (dbg && l == 1) ? dbg : nullptr);
 #pragma unroll
@@ -1415,7 +1541,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         const quipb200_linear_t* nx[1] = {&Ly.down};
         prefetch_stage(nx, &p.geo.G_E, 1, bid, tid);
       }
-      grid_barrier(p.ws.bar, bar_target, nblk);
+      grid_arrive(p.ws.bar, bar_target, nblk);
+      if (!(p.flags & 1) && Ly.down.K_left > 1)
+        stage_e_static(Ly.gate, Ly.up, Ly.down, reinterpret_cast<const __half*>(Ly.mlp_hk), bb, tid);
+      grid_wait(p.ws.bar, bar_target);
       DS_ST(19);
     }
     // ======================= stage E: down =======================
@@ -1428,7 +1557,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         float xs;
         if (L.K_left > 1) {
           xs = stage_e_blocks(Ly.gate, Ly.up, L, p.ws.acc[SL_G], p.ws.acc[SL_U], reinterpret_cast<const __half*>(Ly.mlp_hk), bb,
-                              hfrag, rb.fred, xq, tid, (dbg && l == 1) ? dbg : nullptr);
+                              hfrag, rb.fred, xq, tid, !(p.flags & 1), (dbg && l == 1) ? dbg : nullptr);
         } else {
           float g[8], u[8];
           {
@@ -1466,7 +1595,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         const quipb200_linear_t* nx[3] = {&Ln.q, &Ln.k, &Ln.v};
         prefetch_stage(nx, p.geo.G_A, 3, bid, tid);
       }
-      grid_barrier(p.ws.bar, bar_target, nblk);
+      grid_arrive(p.ws.bar, bar_target, nblk);
+      if (p.use_mma && !(p.flags & 1) && l + 1 < P.n_layers) stage_a_static(p, Ly, s_desc[(l + 1) & 1], stg, bid, tid);
+      grid_wait(p.ws.bar, bar_target);
       DS_ST(24);
     }
   }
@@ -1533,6 +1664,7 @@ static int group_ctas(const quipb200_linear_t* const* mem, int n, int nblk, int*
 }
 
 int g_ds_splits = 0;   // test / tuning hook: force the number of KV splits (0 = automatic)
+int g_ds_flags = 0;    // option "ds_flags"
 
 struct DsLayout {
   DsSmem sm;
@@ -1746,6 +1878,7 @@ extern "C" int quipb200_decode_step(const quipb200_decode_plan_t* plan, const qu
   p.h_out = reinterpret_cast<__half*>(h_out);
   p.kv_splits = lay.splits;
   p.use_mma = lay.use_mma;
+  p.flags = g_ds_flags;
   p.dbg = g_ds_dbg;
   p.dbg_cta = g_ds_dbg_cta;
   cudaLaunchConfig_t cfg{};

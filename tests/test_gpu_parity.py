@@ -240,6 +240,20 @@ CASES = [
     (2048, 2048, "E8P12", False, True, False, 16),
     (2048, 2048, "E8P12", False, True, False, 40),       # M >= 32: reference op sequence (decompress + GEMM)
     (448, 320, "E8P12", True, True, False, 4),           # K_left = 7, K_right = 5, 64 | q_in
+    # BASELINE config 4 codebooks on the 7B MLP shapes (K_right / K_left = 43)
+    (4096, 11008, "E8P12RVQ4B", False, True, False, 1),
+    (11008, 4096, "E8P12RVQ4B", False, True, False, 1),
+    (4096, 11008, "D4", False, True, False, 1),
+    (11008, 4096, "D4", True, True, False, 1),
+    # BASELINE config 5: every Llama-2-70B linear: 8192-point rotations, 28672 = 7 x 4096
+    (8192, 8192, "E8P12", False, True, False, 1),        # q, o
+    (8192, 1024, "E8P12", False, True, False, 1),        # k, v
+    (8192, 28672, "E8P12", False, True, False, 1),       # gate, up: K_right = 7
+    (28672, 8192, "E8P12", False, True, False, 1),       # down: K_left = 7
+    (8192, 8192, "E8P12", False, True, False, 40),
+    (8192, 1024, "E8P12", False, True, False, 40),
+    (8192, 28672, "E8P12", False, True, False, 40),
+    (28672, 8192, "E8P12", False, True, False, 40),
 ]
 
 
@@ -309,6 +323,32 @@ def test_non_fp16_activations_and_3d_input():
     assert (y32 - y16.float()).abs().max() <= 2.0 ** -8 * y16.abs().max()
 
 
+@pytest.mark.parametrize("fin,fout,cbid,pc", [(512, 768, "E8P12", False), (768, 512, "E8P12RVQ4B", True), (1024, 1024, "D4", False)])
+def test_calc_weight_vs_oracle_dense_weight(fin, fout, cbid, pc):
+    """calc_weight (qlinear.py:144-159) against the oracle's effective dense matrix: the float64 forward of the identity,
+    W_eff^T = forward(I) without bias (SURVEY A.5 forward identity), and the training-mode forward against the oracle."""
+    layer = make_layer(fin, fout, cbid, bias=True, per_channel=pc, seed=fin + 3, device=DEV)
+    with torch.no_grad():
+        W = layer.calc_weight().float().cpu().numpy()             # [out, in]
+    assert W.shape == (fout, fin)
+    eye = torch.eye(fin).half()
+    bias = layer.bias
+    layer.bias = None
+    try:
+        W_ref = oracle_forward(layer, eye, rounding="none").T      # forward(e_i) = column i of W_eff
+    finally:
+        layer.bias = bias
+    # fp16 dense weight: two fp16 Hadamard passes + scalings, 2^-8 of the largest entry
+    assert np.abs(W - W_ref).max() <= 2.0 ** -8 * np.abs(W_ref).max(), (np.abs(W - W_ref).max(), np.abs(W_ref).max())
+    x = torch.randn(5, fin, generator=torch.Generator().manual_seed(4)).half()
+    with torch.no_grad():
+        layer.train()
+        y_train = layer(x.to(DEV)).float().cpu().numpy()
+        layer.eval()
+    ref = oracle_forward(layer, x, rounding="none")
+    assert np.abs(y_train - ref).max() <= 2.0 ** -7 * np.abs(ref).max()
+
+
 def test_training_mode_dense_weight_matches_eval():
     """calc_weight (dense dequant + two-sided Hadamard, qlinear.py:144-159) reproduces the eval forward."""
     layer = make_layer(512, 768, "E8P12", bias=True, seed=9, device=DEV)   # 768 = 3 * 256
@@ -347,8 +387,8 @@ def test_cuda_graph_capture_of_fused_forward():
 def _ref_mod():
     import build_ref
     m = build_ref.load_ref_module()
-    if m is None:
-        pytest.skip("oracle/_ref/quiptools_cuda.so not present")
+    if m is None:      # the compiled reference extension is part of the snapshot (oracle/build_ref.py via build()): its absence on
+        pytest.fail("oracle/_ref/quiptools_cuda.so not present: run __graft_entry__.build() where /root/reference exists")
     return m
 
 
@@ -811,6 +851,40 @@ def test_persistent_decode_step_matches_cpu_oracle(name):
         tol = 2.0 ** -6 * np.abs(ref).max()        # two layers of chained fp16 rounding points (cf. the unfused-engine test)
         assert np.abs(got - ref).max() <= tol, (np.abs(got - ref).max(), tol)
         for i in range(2):                          # the appended rows of the KV cache
+            gk = eng.k_cache[i, 0, :, pos].float().cpu().numpy()
+            gv = eng.v_cache[i, 0, :, pos].float().cpu().numpy()
+            assert np.abs(gk - kc[i][:, pos]).max() <= 2.0 ** -7 * np.abs(kc[i][:, pos]).max() + 1e-3
+            assert np.abs(gv - vc[i][:, pos]).max() <= 2.0 ** -7 * np.abs(vc[i][:, pos]).max() + 1e-3
+        eng.pos.add_(1)
+
+
+def test_persistent_decode_step_matches_cpu_oracle_at_llama2_7b_dims():
+    """The headline kernel at BASELINE config 2's layer shapes (hidden 4096, intermediate 11008 = 43 x 256, 32 heads),
+    two decoder layers, DIRECTLY against the CPU oracle of the decode loop body (not via the grouped launches)."""
+    from quip_for_all_b200.modeling import LlamaDecodeEngine, llama_config, make_random_quantized_llama
+    cfg = llama_config("llama2-7b", num_hidden_layers=2)
+    model = make_random_quantized_llama(cfg, "E8P12", seed=21, device=DEV)
+    eng = LlamaDecodeEngine(model, max_cache_len=160, persistent=True, use_cuda_graph=False)
+    assert eng.persistent is not None
+    ids = torch.randint(0, 32000, (1, 131), generator=torch.Generator().manual_seed(5)).to(DEV)
+    eng.prefill(ids)
+    nh, nkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, eng.hd
+    params = [_oracle_layer_params(l) for l in model.model.layers]
+    for _ in range(2):
+        pos = int(eng.pos.item())
+        kc = [eng.k_cache[i, 0].float().cpu().numpy().astype(np.float64) for i in range(2)]
+        vc = [eng.v_cache[i, 0].float().cpu().numpy().astype(np.float64) for i in range(2)]
+        with torch.no_grad():
+            h = model.model.embed_tokens(eng.tok).view(1, -1).contiguous()
+            got = eng.persistent(h, eng.h_step_out).float().cpu().numpy()[0]
+        torch.cuda.synchronize()
+        ref = h.float().cpu().numpy()[0].astype(np.float64)
+        for i in range(2):
+            ref = qo.llama_decoder_layer_step(ref, params[i], kc[i], vc[i], pos, n_heads=nh, n_kv_heads=nkv, head_dim=hd,
+                                              eps=cfg.rms_norm_eps)
+        tol = 2.0 ** -7 * np.abs(ref).max()
+        assert np.abs(got - ref).max() <= tol, (np.abs(got - ref).max(), tol)
+        for i in range(2):
             gk = eng.k_cache[i, 0, :, pos].float().cpu().numpy()
             gv = eng.v_cache[i, 0, :, pos].float().cpu().numpy()
             assert np.abs(gk - kc[i][:, pos]).max() <= 2.0 ** -7 * np.abs(kc[i][:, pos]).max() + 1e-3
