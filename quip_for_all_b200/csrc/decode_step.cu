@@ -117,7 +117,17 @@ struct GemvCfg {
   const unsigned char* q;
   int64_t row_bytes;
   int nseg, C, g, row_begin, nrows;
+  // local row r of the CTA -> matrix row  row_begin + (r / nu) * rstride + r % nu.  Rows are 1 .. 3.5 KB contiguous each, so
+  // a CTA may own ANY set of rows at full load efficiency: contiguous ranges (nu = rstride = 1) or, for gate / up, every
+  // row k * 256 + c of a few columns c of the K x 256 output blocks (nu columns, rstride = 256) -- then the K x K
+  // orthogonal mix over k of the output-side rotation is local to the producing CTA (gemv_store_mix).
+  int nu, rstride;
+  uint32_t inv_nu;       // ceil(65536 / nu): r / nu == (r * inv_nu) >> 16 for r < 4096, nu <= 8
 };
+__device__ __forceinline__ int grow(const GemvCfg& c, int r) {
+  const int q = (int)(((uint32_t)r * c.inv_nu) >> 16);
+  return q * c.rstride + (r - q * c.nu);
+}
 
 // work unit -> (column chunk, row phase)
 __device__ __forceinline__ void unit_of(const GemvCfg& c, int unit, int& chunk, int& sub) {
@@ -141,6 +151,19 @@ __device__ __forceinline__ GemvCfg make_cfg(const quipb200_linear_t& L, int bx, 
   const int base = L.q_out / G, rem = L.q_out % G;
   c.row_begin = bx * base + min(bx, rem);
   c.nrows = base + (bx < rem ? 1 : 0);
+  c.nu = 1; c.rstride = 1; c.inv_nu = 65536u;
+  return c;
+}
+// column-unit ownership for a linear whose output side is K blocks of Lb: CTA bx of G owns columns [c0, c0 + nu) of every block
+__device__ __forceinline__ GemvCfg make_cfg_cols(const quipb200_linear_t& L, int bx, int G) {
+  GemvCfg c = make_cfg(L, bx, G);
+  const int Lb = L.q_out / L.K_right;
+  const int base = Lb / G, rem = Lb % G;
+  c.row_begin = bx * base + min(bx, rem);
+  c.nu = base + (bx < rem ? 1 : 0);
+  c.nrows = c.nu * L.K_right;
+  c.rstride = Lb;
+  c.inv_nu = (65536u + (uint32_t)c.nu - 1u) / (uint32_t)c.nu;
   return c;
 }
 
@@ -156,20 +179,27 @@ __device__ __forceinline__ void gemv_first(uint4 (&cw)[DS_UNROLL], const GemvCfg
   for (int u = 0; u < DS_UNROLL; u++) {
     const int r = sub + u * c.g;
     cw[u] = make_uint4(0, 0, 0, 0);
-    if (lv && r < c.nrows) cw[u] = ldg_stream_v4(colp + (size_t)r * c.row_bytes, pol);
+    if (lv && r < c.nrows) cw[u] = ldg_stream_v4(colp + (size_t)grow(c, r) * c.row_bytes, pol);
   }
 }
 
 // pull this CTA's whole row range into L2 (no registers held): used when the stage's prologue is long
 __device__ __forceinline__ void gemv_prefetch_l2(const GemvCfg& c, int tid) {
+  // runs of nu consecutive rows, rstride rows apart (one run for contiguous ownership: nu = 1 is folded below)
+  const int runs = (c.nu == 1 && c.rstride == 1) ? 1 : c.nrows / c.nu;
+  const size_t run_bytes = (size_t)(runs == 1 ? c.nrows : c.nu) * c.row_bytes;
+  const int lines = (int)((run_bytes + 127) >> 7);
   const unsigned char* base = c.q + (size_t)c.row_begin * c.row_bytes;
-  const int lines = (int)(((size_t)c.nrows * c.row_bytes + 127) >> 7);
-  for (int i = tid; i < lines; i += DS_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * 128));
+  for (int i = tid; i < lines * runs; i += DS_THREADS) {
+    const int run = i / lines, li = i - run * lines;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)run * c.rstride * c.row_bytes + (size_t)li * 128));
+  }
 }
 
 // Packed codes of this CTA's share of a later stage -> L2.  Issued when the current stage's GEMV starts, so the HBM
 // fetch of stage X+1 runs under the (compute-bound) GEMV of stage X and never in front of a prologue's own requests.
-__device__ __forceinline__ void prefetch_stage(const quipb200_linear_t* const* mem, const int* G, int n, int bid, int tid) {
+__device__ __forceinline__ void prefetch_stage(const quipb200_linear_t* const* mem, const int* G, int n, int bid, int tid,
+                                               bool cols = false) {
   int j, bx = 0;
   j = -1;
   int begin = 0;
@@ -178,7 +208,7 @@ __device__ __forceinline__ void prefetch_stage(const quipb200_linear_t* const* m
     begin += G[i];
   }
   if (j < 0) return;
-  const GemvCfg c = make_cfg(*mem[j], bx, G[j]);
+  const GemvCfg c = cols ? make_cfg_cols(*mem[j], bx, G[j]) : make_cfg(*mem[j], bx, G[j]);
   gemv_prefetch_l2(c, tid);
 }
 
@@ -274,7 +304,7 @@ __device__ __forceinline__ void gemv_run(uint4 (&cw)[DS_UNROLL], const GemvCfg& 
       for (int u = 0; u < DS_UNROLL; u++) {
         const int r = rn + u * c.g;
         nx[u] = make_uint4(0, 0, 0, 0);
-        if (lane_valid && r < c.nrows) nx[u] = ldg_stream_v4(colp + (size_t)r * c.row_bytes, pol);
+        if (lane_valid && r < c.nrows) nx[u] = ldg_stream_v4(colp + (size_t)grow(c, r) * c.row_bytes, pol);
       }
       int tot[DS_UNROLL], tot2[DS_UNROLL];
 #pragma unroll
@@ -333,7 +363,7 @@ __device__ __forceinline__ void gemv_run(uint4 (&cw)[DS_UNROLL], const GemvCfg& 
       for (int u = 0; u < DS_UNROLL; u++) {
         const int r = sub2 + u * c.g;
         cw[u] = make_uint4(0, 0, 0, 0);
-        if (lv && r < c.nrows) cw[u] = ldg_stream_v4(colp2 + (size_t)r * c.row_bytes, pol);
+        if (lv && r < c.nrows) cw[u] = ldg_stream_v4(colp2 + (size_t)grow(c, r) * c.row_bytes, pol);
       }
     }
   }
@@ -355,7 +385,44 @@ __device__ __forceinline__ void gemv_store(const GemvCfg& c, const int* red, __h
     }
     float f = (float)s;
     if (T::ACCS == 2) f = fmaf(rs, (float)s2, f);
-    acc[c.row_begin + r] = __float2half_rn(f * xs);      // origin_order.cu:129 (single fp16 rounding of the mm)
+    acc[c.row_begin + grow(c, r)] = __float2half_rn(f * xs);      // origin_order.cu:129 (single fp16 rounding of the mm)
+  }
+}
+
+// Column-unit variant for gate / up (make_cfg_cols): the CTA holds every block's row of its nu columns, so it applies the
+// K x K orthogonal factor of the output-side rotation itself:  t[k'][c] = f16( sum_k M[k'][k] * v[k][c] ),  v = the fp16 mm
+// output (origin_order.cu:129) [* per-channel Wscale, qlinear.py:106-107].  fp16 operands, fp32 accumulate, one fp16
+// rounding -- the arithmetic of the reference's `hadK @ y` (quant.py:83); the 256-point transform over c then runs in the
+// consuming stage.  (The reference transforms first and mixes second; the two factors of M (x) H commute, the rounding
+// point between them moves.)  M: fp16 [Kp][Kp] in shared memory; vbuf: float [nu <= 8][64] scratch.
+template <int CB>
+__device__ __forceinline__ void gemv_store_mix(const GemvCfg& c, const int* red, __half* acc, float xscale, float resid_scale,
+                                               const __half* wpc, const __half* M, int K, float* vbuf, int tid) {
+  using T = CbTraits<CB>;
+  const int Kp = (K + 15) / 16 * 16;
+  __syncthreads();
+  const float xs = xscale * (CB == QUIPB200_CB_D4 ? 0.5f : 0.25f);
+  const float rs = __half2float(__float2half_rn(resid_scale));
+  for (int r = tid; r < c.nrows; r += DS_THREADS) {
+    long long s = 0, s2 = 0;
+    for (int k = 0; k < c.C; k++) {
+      s += red[(r * c.C + k) * T::ACCS];
+      if (T::ACCS == 2) s2 += red[(r * c.C + k) * T::ACCS + 1];
+    }
+    float f = (float)s;
+    if (T::ACCS == 2) f = fmaf(rs, (float)s2, f);
+    f = f16_round(f * xs);
+    const int k = (int)(((uint32_t)r * c.inv_nu) >> 16), i = r - k * c.nu;
+    if (wpc) f = f16_round(f * __half2float(wpc[k * c.rstride + c.row_begin + i]));
+    vbuf[i * 64 + k] = f;
+  }
+  cp_async_wait_all();      // M was requested when the stage's GEMV started
+  __syncthreads();
+  const int i = tid >> 6, ko = tid & 63;
+  if (i < c.nu && ko < K) {
+    float a = 0.f;
+    for (int k = 0; k < K; k++) a = fmaf(__half2float(M[ko * Kp + k]), vbuf[i * 64 + k], a);
+    acc[ko * c.rstride + c.row_begin + i] = __float2half_rn(a);
   }
 }
 
@@ -743,139 +810,91 @@ __device__ __forceinline__ void stage_e_static(const quipb200_linear_t& Lg, cons
     if (SVu) cp_async16(bb.vSVu + o * 8, SVu + o * 8);
     if (SUd) cp_async16(bb.vSUd + o * 8, SUd + o * 8);
   }
-  if (hk_blob != nullptr) {
-    const int n16 = (3 * Kp * Kp) >> 3;
-    for (int i = tid; i < n16; i += DS_THREADS) cp_async16(bb.hkg + i * 8, hk_blob + i * 8);
-  }
+  // slot 2 of the layer's coefficient blob: M[k_out][k_in] = had_left^T of down (the input-side mix; slots 0 / 1, the
+  // factors of gate / up, are applied by the producing CTAs)
+  const int n16 = (Kp * Kp) >> 3;
+  const __half* src = hk_blob + (size_t)2 * Kp * Kp;
+  for (int i = tid; i < n16; i += DS_THREADS) cp_async16(bb.hkd + i * 8, src + i * 8);
 }
 
 // Stage-E input construction for K > 1:  x = rot_in_down( SU_d . silu(out(gate)) * out(up) ), records -> xq.
 // Everything the stage reads from global memory is requested up front (one L2 round trip): the raw dot
 // products of this warp's blocks into registers, SV_gate / SV_up / SU_down into shared memory with cp.async,
 // the three K x K coefficient matrices with batched 2-byte loads.
-constexpr int DS_EB = 3;   // blocks per warp in flight (K <= 48 in one round)
+constexpr int DS_EB = 4;   // blocks per warp (K <= 64: all of them in one round)
 __device__ __forceinline__ float stage_e_blocks(const quipb200_linear_t& Lg, const quipb200_linear_t& Lu,
                                                 const quipb200_linear_t& Ld, const __half* acc_g, const __half* acc_u,
                                                 const __half* hk_blob, const BlkBuf& bb, const HFrag& A,
                                                 float* fred, uint4* xq, int tid, bool staged, long long* dbg) {
 #define DS_E(i) do { if (dbg) dbg[i] = clock64(); } while (0)
   const int lane = tid & 31, warp = tid >> 5;
-  const int K = Lg.K_right, Kp = (K + 15) / 16 * 16, LS = bb.LS;
+  const int K = Lg.K_right, LS = bb.LS;
   const int noct_mid = Lg.out_features >> 3;
   const __half* SVg = reinterpret_cast<const __half*>(Lg.SV);
   const __half* SVu = reinterpret_cast<const __half*>(Lu.SV);
   const __half* SUd = reinterpret_cast<const __half*>(Ld.SU);
   const __half* bg = reinterpret_cast<const __half*>(Lg.bias);
   const __half* bu = reinterpret_cast<const __half*>(Lu.bias);
-  const __half* wg = reinterpret_cast<const __half*>(Lg.wscale_pc);
-  const __half* wu = reinterpret_cast<const __half*>(Lu.wscale_pc);
-  if (!staged) {
-    for (int o = tid; o < noct_mid; o += DS_THREADS) {
-      if (SVg) cp_async16(bb.vSVg + o * 8, SVg + o * 8);
-      if (SVu) cp_async16(bb.vSVu + o * 8, SVu + o * 8);
-      if (SUd) cp_async16(bb.vSUd + o * 8, SUd + o * 8);
-    }
-  }
-  // coefficient matrices M[k_out][k_in], zero padded to Kp <= 64 (input side of down: hadK^T): one pre-padded blob per
-  // layer when the caller provides it (16-byte requests), else gathered from the raw K x K tensors
-  if (hk_blob != nullptr) {
-    if (!staged) {
-      const int n16 = (3 * Kp * Kp) >> 3;
-      for (int i = tid; i < n16; i += DS_THREADS) cp_async16(bb.hkg + i * 8, hk_blob + i * 8);
-    }
-  } else {
-    const __half* src[3] = {reinterpret_cast<const __half*>(Lg.had_right), reinterpret_cast<const __half*>(Lu.had_right),
-                            reinterpret_cast<const __half*>(Ld.had_left)};
-    __half* dst[3] = {bb.hkg, bb.hku, bb.hkd};
-    const int ki = tid & 63;
-    __half hv[3][8];
-#pragma unroll
-    for (int m = 0; m < 3; m++) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int ko = (tid >> 6) + 8 * i;
-        hv[m][i] = __float2half_rn(0.f);
-        if (ko < K && ki < K) hv[m][i] = (m == 2) ? src[m][ki * K + ko] : src[m][ko * K + ki];
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < 3; m++) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int ko = (tid >> 6) + 8 * i;
-        if (ko < Kp && ki < Kp) dst[m][ko * Kp + ki] = hv[m][i];
-      }
-    }
-  }
+  if (!staged) stage_e_static(Lg, Lu, Ld, hk_blob, bb, tid);
   DS_E(30);
-  // block transforms of the raw dot products (256-point WHT per warp on the tensor path, x 1/16), fp16
-  for (int b0 = warp; b0 < K; b0 += DS_WARPS * DS_EB) {
-    uint4 ga[DS_EB], ua[DS_EB];      // one 16-byte octet per lane per block
+  // acc_g / acc_u hold t = (M (x) I) v: the producing CTAs applied the K x K factor (gemv_store_mix).  What is left of the
+  // output-side rotation is the 256-point transform of every block, so one pass per block takes the dot products all the
+  // way to down's block-transformed input: H_256 (x 1/16) -> SV / bias -> silu(gate) * up -> SU -> H_256 (x wscale/16).
+  const float ws_d = Ld.wscale_float;
+  uint4 ga[DS_EB], ua[DS_EB];      // one 16-byte octet per lane per block; all of the warp's blocks requested up front
 #pragma unroll
-    for (int r = 0; r < DS_EB; r++) {
-      const int b = b0 + r * DS_WARPS;
-      if (b < K) {
-        ga[r] = __ldcg(reinterpret_cast<const uint4*>(acc_g) + b * 32 + lane);
-        ua[r] = __ldcg(reinterpret_cast<const uint4*>(acc_u) + b * 32 + lane);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < DS_EB; r++) {
-      const int b = b0 + r * DS_WARPS;
-      if (b < K) {
-        // the lane's octet is already a valid fragment (F(x, y) is a bit permutation of the natural index and H_256 is
-        // invariant under it, tools/emu_fwht_frag.py): pairs in, the same octet's transformed pairs out
-        uint4 go = ga[r], uo = ua[r];
-        if (wg) go = hmul2x4(go, __ldg(reinterpret_cast<const uint4*>(wg) + b * 32 + lane));
-        if (wu) uo = hmul2x4(uo, __ldg(reinterpret_cast<const uint4*>(wu) + b * 32 + lane));
-        const uint32_t pg[4] = {go.x, go.z, go.y, go.w}, pu[4] = {uo.x, uo.z, uo.y, uo.w};
-        float g[8], u[8];
-        fwht256_frag(pg, A, g);
-        fwht256_frag(pu, A, u);
-        *reinterpret_cast<uint4*>(bb.Tg + b * LS + lane * 8) = frag_to_octet(g, 1.0f);
-        *reinterpret_cast<uint4*>(bb.Tu + b * LS + lane * 8) = frag_to_octet(u, 1.0f);
-      }
+  for (int r = 0; r < DS_EB; r++) {
+    const int b = warp + r * DS_WARPS;
+    ga[r] = ua[r] = make_uint4(0, 0, 0, 0);
+    if (b < K) {
+      ga[r] = __ldcg(reinterpret_cast<const uint4*>(acc_g) + b * 32 + lane);
+      ua[r] = __ldcg(reinterpret_cast<const uint4*>(acc_u) + b * 32 + lane);
     }
   }
-  cp_async_wait_all();
-  DS_E(31);
-  mix_blocks(bb.Tg, bb.hkg, bb.Tu, bb.hku, K, LS, tid);
-  DS_E(32);
-  // SV / bias of gate and up, silu(gate) * up, SU of down, block transform of down's input (x wscale/16)
-  const float ws_d = Ld.wscale_float;
-  for (int b = warp; b < K; b += DS_WARPS) {
-    const int o = b * 32 + lane;               // octet of the intermediate vector
-    const uint4 g4 = *reinterpret_cast<const uint4*>(bb.Tg + b * LS + lane * 8);
-    const uint4 u4 = *reinterpret_cast<const uint4*>(bb.Tu + b * LS + lane * 8);
-    uint4 sv_g = make_uint4(0, 0, 0, 0), sv_u = sv_g, su_d = sv_g, b_g = sv_g, b_u = sv_g;
-    if (SVg) sv_g = *reinterpret_cast<const uint4*>(bb.vSVg + o * 8);
-    if (SVu) sv_u = *reinterpret_cast<const uint4*>(bb.vSVu + o * 8);
-    if (SUd) su_d = *reinterpret_cast<const uint4*>(bb.vSUd + o * 8);
-    if (bg && o < noct_mid) b_g = __ldg(reinterpret_cast<const uint4*>(bg) + o);
-    if (bu && o < noct_mid) b_u = __ldg(reinterpret_cast<const uint4*>(bu) + o);
-    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, uw[4] = {u4.x, u4.y, u4.z, u4.w};
-    const uint32_t svg[4] = {sv_g.x, sv_g.y, sv_g.z, sv_g.w}, svu[4] = {sv_u.x, sv_u.y, sv_u.z, sv_u.w};
-    const uint32_t sud[4] = {su_d.x, su_d.y, su_d.z, su_d.w};
-    const uint32_t bgw[4] = {b_g.x, b_g.y, b_g.z, b_g.w}, buw[4] = {b_u.x, b_u.y, b_u.z, b_u.w};
-    uint32_t aw[4];
+  cp_async_wait_all();             // staged SV / SU / coefficients: every thread's requests, then the CTA barrier
+  __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      __half2 g = as_h2(gw[q]);
-      __half2 u = as_h2(uw[q]);
-      if (SVg) g = __hmul2(g, as_h2(svg[q]));
-      if (bg) g = __hadd2_rn(g, as_h2(bgw[q]));
-      if (SVu) u = __hmul2(u, as_h2(svu[q]));
-      if (bu) u = __hadd2_rn(u, as_h2(buw[q]));
-      const float2 gf = __half22float2(g);
-      const __half2 sg = __floats2half2_rn(silu_f(gf.x), silu_f(gf.y));
-      __half2 a = __hmul2(sg, u);                                    // LlamaMLP: act_fn(gate) * up
-      if (SUd) a = __hmul2(a, as_h2(sud[q]));
-      aw[q] = (o < noct_mid) ? as_u32(a) : 0u;
+  for (int r = 0; r < DS_EB; r++) {
+    const int b = warp + r * DS_WARPS;
+    if (b < K) {
+      const int o = b * 32 + lane;               // octet of the intermediate vector
+      // the lane's octet is already a valid fragment (F(x, y) is a bit permutation of the natural index and H_256 is
+      // invariant under it, tools/emu_fwht_frag.py): pairs in, the same octet's transformed pairs out
+      const uint32_t pg[4] = {ga[r].x, ga[r].z, ga[r].y, ga[r].w}, pu[4] = {ua[r].x, ua[r].z, ua[r].y, ua[r].w};
+      float g[8], u[8];
+      fwht256_frag(pg, A, g);
+      fwht256_frag(pu, A, u);
+      const uint4 g4 = frag_to_octet(g, 1.0f), u4 = frag_to_octet(u, 1.0f);     // fp16: the rotated mm outputs
+      uint4 sv_g = make_uint4(0, 0, 0, 0), sv_u = sv_g, su_d = sv_g, b_g = sv_g, b_u = sv_g;
+      if (SVg) sv_g = *reinterpret_cast<const uint4*>(bb.vSVg + o * 8);
+      if (SVu) sv_u = *reinterpret_cast<const uint4*>(bb.vSVu + o * 8);
+      if (SUd) su_d = *reinterpret_cast<const uint4*>(bb.vSUd + o * 8);
+      if (bg && o < noct_mid) b_g = __ldg(reinterpret_cast<const uint4*>(bg) + o);
+      if (bu && o < noct_mid) b_u = __ldg(reinterpret_cast<const uint4*>(bu) + o);
+      const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, uw[4] = {u4.x, u4.y, u4.z, u4.w};
+      const uint32_t svg[4] = {sv_g.x, sv_g.y, sv_g.z, sv_g.w}, svu[4] = {sv_u.x, sv_u.y, sv_u.z, sv_u.w};
+      const uint32_t sud[4] = {su_d.x, su_d.y, su_d.z, su_d.w};
+      const uint32_t bgw[4] = {b_g.x, b_g.y, b_g.z, b_g.w}, buw[4] = {b_u.x, b_u.y, b_u.z, b_u.w};
+      uint32_t aw[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        __half2 gg = as_h2(gw[q]);
+        __half2 uu = as_h2(uw[q]);
+        if (SVg) gg = __hmul2(gg, as_h2(svg[q]));
+        if (bg) gg = __hadd2_rn(gg, as_h2(bgw[q]));
+        if (SVu) uu = __hmul2(uu, as_h2(svu[q]));
+        if (bu) uu = __hadd2_rn(uu, as_h2(buw[q]));
+        const float2 gf = __half22float2(gg);
+        const __half2 sg = __floats2half2_rn(silu_f(gf.x), silu_f(gf.y));
+        __half2 a = __hmul2(sg, uu);                                   // LlamaMLP: act_fn(gate) * up
+        if (SUd) a = __hmul2(a, as_h2(sud[q]));
+        aw[q] = (o < noct_mid) ? as_u32(a) : 0u;
+      }
+      const uint32_t pa[4] = {aw[0], aw[2], aw[1], aw[3]};
+      float w8[8];
+      fwht256_frag(pa, A, w8);
+      *reinterpret_cast<uint4*>(bb.Tu + b * LS + lane * 8) = frag_to_octet(w8, ws_d);
     }
-    const uint32_t pa[4] = {aw[0], aw[2], aw[1], aw[3]};
-    float u[8];
-    fwht256_frag(pa, A, u);
-    *reinterpret_cast<uint4*>(bb.Tu + b * LS + lane * 8) = frag_to_octet(u, ws_d);      // in place
   }
   DS_E(33);
   mix_blocks(bb.Tu, bb.hkd, nullptr, nullptr, K, LS, tid);
@@ -1474,7 +1493,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         DS_ST(13);
         {
           const quipb200_linear_t* nx[2] = {&Ly.gate, &Ly.up};
-          prefetch_stage(nx, p.geo.G_D, 2, bid, tid);
+          prefetch_stage(nx, p.geo.G_D, 2, bid, tid, Ly.gate.K_right > 1);
         }
         gemv_first<CB>(cw, c, warp, lane, pol);
         gemv_run<CB>(cw, c, xq, tab, red, warp, lane, pol);
@@ -1482,7 +1501,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         gemv_store<CB>(c, red, p.ws.acc[SL_O], xs, L.resid_scale, tid);
       } else {
         const quipb200_linear_t* nx[2] = {&Ly.gate, &Ly.up};
-        prefetch_stage(nx, p.geo.G_D, 2, bid, tid);
+        prefetch_stage(nx, p.geo.G_D, 2, bid, tid, Ly.gate.K_right > 1);
       }
       grid_arrive(p.ws.bar, bar_target, nblk);
       if (p.use_mma && !(p.flags & 1)) stage_d_static(p, Ly, stg, bid, tid);
@@ -1495,7 +1514,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
       which_member(p.geo.G_D, 2, bid, j, bx);
       if (j >= 0) {
         const quipb200_linear_t L = (j == 0) ? Ly.gate : Ly.up;
-        const GemvCfg c = make_cfg(L, bx, p.geo.G_D[j]);
+        const bool colmix = L.K_right > 1;       // column-unit ownership + local K x K mix (gemv_store_mix)
+        const GemvCfg c = colmix ? make_cfg_cols(L, bx, p.geo.G_D[j]) : make_cfg(L, bx, p.geo.G_D[j]);
         float f[8];
         float xs;
         const quipb200_linear_t Lp = Ly.o;
@@ -1533,10 +1553,19 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
           const quipb200_linear_t* nx[1] = {&Ly.down};
           prefetch_stage(nx, &p.geo.G_E, 1, bid, tid);
         }
+        if (colmix) {     // this member's padded K x K factor (gate: slot 0, up: slot 1 of the layer's blob) -> shared memory
+          const int Kp = (L.K_right + 15) / 16 * 16;
+          const __half* src = reinterpret_cast<const __half*>(Ly.mlp_hk) + (size_t)j * Kp * Kp;
+          for (int i = tid; i < (Kp * Kp) >> 3; i += DS_THREADS) cp_async16(bb.hkg + i * 8, src + i * 8);
+        }
         gemv_first<CB>(cw, c, warp, lane, pol);
         gemv_run<CB>(cw, c, xq, tab, red, warp, lane, pol);
         DS_ST(18);
-        gemv_store<CB>(c, red, p.ws.acc[SL_G + j], xs, L.resid_scale, tid);
+        if (colmix)
+          gemv_store_mix<CB>(c, red, p.ws.acc[SL_G + j], xs, L.resid_scale, reinterpret_cast<const __half*>(L.wscale_pc), bb.hkg,
+                             L.K_right, reinterpret_cast<float*>(bb.hku), tid);
+        else
+          gemv_store<CB>(c, red, p.ws.acc[SL_G + j], xs, L.resid_scale, tid);
       } else {
         const quipb200_linear_t* nx[1] = {&Ly.down};
         prefetch_stage(nx, &p.geo.G_E, 1, bid, tid);
@@ -1692,6 +1721,7 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
     for (int i = 0; i < SL_N; i++)
       if (!linear_ok(*all[i]) || !same_shape(*all[i], *ref[i]) || all[i]->codebook != Y.q.codebook) return QUIPB200_EUNSUPPORTED;
     if (!Z.input_norm_w || !Z.post_norm_w || !Z.k_cache || !Z.v_cache) return QUIPB200_EINVAL;
+    if (Z.gate.K_right > 1 && !Z.mlp_hk) return QUIPB200_EINVAL;      // the padded coefficient blob is required for blocked MLP dims
   }
   // shape chain of a Llama decoder layer
   if (Y.q.in_features != P->hidden || Y.k.in_features != P->hidden || Y.v.in_features != P->hidden) return QUIPB200_EUNSUPPORTED;
@@ -1738,6 +1768,8 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
   group_ctas(gA, 3, nblk, geo.G_A);
   group_ctas(gC, 1, nblk, &geo.G_C);
   group_ctas(gD, 2, nblk, geo.G_D);
+  if (K > 1)
+    for (int i = 0; i < 2; i++) geo.G_D[i] = std::min(geo.G_D[i], Y.gate.q_out / K);
   group_ctas(gE, 1, nblk, &geo.G_E);
   out->geo = geo;
   struct { const quipb200_linear_t* const* m; int n; const int* G; } groups[4] = {
@@ -1748,7 +1780,12 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
       const quipb200_linear_t& L = *g.m[i];
       const int segs = L.codebook == QUIPB200_CB_E8P12RVQ4B ? 4 : 8, accs = L.codebook == QUIPB200_CB_E8P12RVQ4B ? 2 : 1;
       const int nseg = L.q_in / 8, lanes = (nseg + segs - 1) / segs, C = (lanes + 31) / 32;
-      const size_t rows = (size_t)L.q_out / g.G[i] + 1;
+      size_t rows = (size_t)L.q_out / g.G[i] + 1;
+      if (g.m == gD && L.K_right > 1) {              // column-unit ownership (make_cfg_cols): ceil(Lb / G) columns x K blocks
+        const size_t Lb = (size_t)L.q_out / L.K_right;
+        rows = (Lb + g.G[i] - 1) / g.G[i] * L.K_right;
+        if (rows / L.K_right > 8 || rows > 4096) return QUIPB200_EUNSUPPORTED;      // vbuf rows / the grow() magic division
+      }
       red = std::max(red, rows * C * accs * sizeof(int));
       xq = std::max(xq, (size_t)((nseg + 7) / 8 * 8) * 16);
     }
