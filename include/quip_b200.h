@@ -191,6 +191,16 @@ int quipb200_attn_decode(const void* q, const void* k, const void* v, void* k_ca
                          const void* cos_t, const void* sin_t, const int64_t* pos, void* out,
                          int n_heads, int n_kv_heads, int head_dim, int max_len, void* stream);
 
+/* Tail of a bs=1 greedy decode step in one launch: LlamaRMSNorm(h) -> lm_head (fp16 [vocab, hidden], fp32 accumulate, fp16
+ * logits) -> argmax (ties: lowest index, as torch.argmax) -> *tok_out; optionally h_next = emb[tok] and *pos += 1.
+ * Replaces HF's final norm + nn.Linear + torch.argmax (+ nn.Embedding + `input_pos += 1`) of example_generate.py:29-56.
+ * emb / h_next / pos / logits_out may be NULL.  workspace: quipb200_lm_tail_workspace_bytes() bytes, 256-byte aligned,
+ * zero-filled ONCE by the caller (the arrival counter resets itself); one launch at a time per workspace. */
+size_t quipb200_lm_tail_workspace_bytes(void);
+int quipb200_lm_tail(const void* h_f16, const void* norm_w_f16, float eps, const void* lm_head_f16, const void* emb_f16,
+                     int hidden, int vocab, int64_t* tok_out, void* h_next_f16, int64_t* pos, void* logits_out_f16,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Whole decode step of a Llama-style stack of QuantLinears in ONE persistent cooperative kernel
  * (bs = 1).  Replaces, per token, what the reference runs as 32 x (7 QuantLinear.forward + HF

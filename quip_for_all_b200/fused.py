@@ -74,3 +74,21 @@ def attn_decode(q, k, v, k_cache, v_cache, cos, sin, pos, out, n_heads, n_kv_hea
                                      out.data_ptr(), n_heads, n_kv_heads, head_dim, max_len, _stream()),
           "attn_decode")
     return out
+
+
+class LmTail:
+    """Final RMSNorm -> lm_head -> argmax (-> position increment) in one launch (csrc/lm_tail.cu)."""
+
+    def __init__(self, norm_weight, eps, lm_head_weight):
+        if lm_head_weight.dtype != torch.float16 or norm_weight.dtype != torch.float16 or not lm_head_weight.is_contiguous():
+            raise ValueError("lm_tail needs contiguous fp16 lm_head / norm weights")
+        self.nw, self.eps, self.W = norm_weight, float(eps), lm_head_weight
+        self.vocab, self.hidden = lm_head_weight.shape
+        nbytes = lib().quipb200_lm_tail_workspace_bytes()
+        self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=lm_head_weight.device)
+
+    def __call__(self, h, tok_out, pos=None, logits_out=None):
+        check(lib().quipb200_lm_tail(h.data_ptr(), self.nw.data_ptr(), self.eps, self.W.data_ptr(), None, self.hidden,
+                                     self.vocab, tok_out.data_ptr(), None, _p(pos), _p(logits_out), self.ws.data_ptr(),
+                                     self.ws.numel(), _stream()), "lm_tail")
+        return tok_out

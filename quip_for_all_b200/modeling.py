@@ -171,6 +171,10 @@ class LlamaDecodeEngine:
             self._build_fused()
         if fused and persistent and self.fused is not None:
             self._build_persistent()
+        self.tail = None
+        if self.persistent is not None and self.last:
+            self._build_tail()
+        self._host_pos = 0          # host mirror of self.pos (cache-full check without a device sync)
 
     def _build_fused(self):
         """Per-layer launch groups for the fused decode step (5 launches of ours per layer + 1 prologue):
@@ -201,6 +205,17 @@ class LlamaDecodeEngine:
             self.h_step_out = torch.empty(1, self.cfg.hidden_size, dtype=torch.float16, device=self.dev)
         except ValueError:
             self.persistent = None
+
+    def _build_tail(self):
+        """Final norm -> lm_head -> argmax -> position increment in one launch (lm_tail.cu) for fp16 bias-free lm_heads."""
+        from .fused import LmTail
+        head = self.model.lm_head
+        try:
+            if getattr(head, "bias", None) is not None:
+                raise ValueError("lm_head has a bias")
+            self.tail = LmTail(self.model.model.norm.weight, self.eps, head.weight)
+        except ValueError:
+            self.tail = None
 
     def _layer_fused(self, li, h):
         """h: fp16 [1, hidden]; one decode position (self.pos)."""
@@ -279,12 +294,18 @@ class LlamaDecodeEngine:
         pos = torch.arange(T, device=self.dev)
         out = self._forward(ids_or_hidden, pos)
         self.pos.fill_(T)
+        self._host_pos = T
         if self.last:
             self.tok.copy_(out)
         return out
 
     @torch.no_grad()
     def _step_body(self):
+        if self.tail is not None:        # [embedding] -> persistent decode step -> fused tail (token id + position)
+            h = self.model.model.embed_tokens(self.tok).view(1, -1) if self.first else self.hidden_in.view(1, -1)
+            self.persistent(h.contiguous(), self.h_step_out)
+            self.tail(self.h_step_out, self.tok, pos=self.pos)
+            return
         out = self._forward(self.tok if self.first else self.hidden_in, self.pos)
         if self.last:
             self.tok.copy_(out)
@@ -297,6 +318,9 @@ class LlamaDecodeEngine:
         """Warm up and capture one decode step into a CUDA graph (state is restored afterwards)."""
         if not self.use_graph:
             return
+        if self._host_pos + 3 > self.max_len:      # two warm-up steps and the captured one write at pos, pos+1, pos+2
+            raise RuntimeError(f"KV cache too small to capture a decode step: position {self._host_pos}, "
+                               f"max_cache_len {self.max_len}")
         saved = (self.tok.clone(), self.pos.clone(), self.k_cache.clone(), self.v_cache.clone())
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
@@ -318,6 +342,9 @@ class LlamaDecodeEngine:
     @torch.no_grad()
     def step(self):
         """One decode step: consumes self.tok / self.pos, leaves the next token in self.tok."""
+        if self._host_pos >= self.max_len:          # the kernels clamp the position: refuse instead of overwriting the last slot
+            raise RuntimeError(f"KV cache is full ({self.max_len} positions): allocate a larger max_cache_len")
+        self._host_pos += 1
         if self.graph is not None:
             self.graph.replay()
         else:
@@ -327,6 +354,8 @@ class LlamaDecodeEngine:
     def generate(self, input_ids, max_new_tokens):
         """Greedy decode; returns the generated ids [1, max_new_tokens] (device tensor)."""
         assert self.first and self.last
+        if input_ids.shape[1] + max_new_tokens - 1 > self.max_len:
+            raise ValueError(f"prompt ({input_ids.shape[1]}) + max_new_tokens ({max_new_tokens}) exceeds max_cache_len {self.max_len}")
         self.prefill(input_ids.to(self.dev))
         if self.use_graph and self.graph is None:
             self.capture()

@@ -916,3 +916,39 @@ def test_persistent_decode_step_other_codebooks(cb):
         assert d <= 2.0 ** -8 * h2.float().abs().max().item(), (cb, d)
         e1.pos.add_(1)
         e2.pos.add_(1)
+
+
+@pytest.mark.parametrize("hidden,vocab", [(4096, 32000), (256, 1000), (8192, 517)])
+def test_lm_tail_matches_torch_norm_head_argmax(hidden, vocab):
+    """Fused tail (csrc/lm_tail.cu): LlamaRMSNorm -> fp16 lm_head -> argmax -> position increment, against the torch ops
+    HF runs.  Logits: one fp16 ulp (accumulation order differs from cuBLAS); the token must be a maximiser of the torch
+    logits up to that ulp; exact ties go to the lowest index."""
+    from quip_for_all_b200.fused import LmTail
+    g = torch.Generator().manual_seed(hidden + vocab)
+    W = (0.02 * torch.randn(vocab, hidden, generator=g)).half().to(DEV)
+    nw = (1 + 0.1 * torch.randn(hidden, generator=g)).half().to(DEV)
+    h = torch.randn(1, hidden, generator=g).half().to(DEV)
+    tail = LmTail(nw, 1e-5, W)
+    tok = torch.zeros(1, 1, dtype=torch.long, device=DEV)
+    pos = torch.full((1,), 41, dtype=torch.long, device=DEV)
+    logits = torch.empty(vocab, dtype=torch.float16, device=DEV)
+    for rep in range(2):                                   # second launch: the arrival counter reset itself
+        tail(h, tok, pos=pos, logits_out=logits)
+    torch.cuda.synchronize()
+    v = h.float()
+    x = nw * (v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + 1e-5)).half()
+    ref = (x.float() @ W.float().t()).half().view(-1)
+    d = (logits.float() - ref.float()).abs().max().item()
+    assert d <= 2.0 ** -10 * ref.float().abs().max().item() + 1e-6, d
+    assert int(pos.item()) == 43
+    t = int(tok.item())
+    assert 0 <= t < vocab
+    assert logits[t].item() == logits.max().item() and t == int(torch.nonzero(logits == logits.max())[0].item())
+    assert ref[t].item() >= ref.max().item() - 2.0 ** -9 * abs(ref.max().item())
+    # exact ties: duplicated rows -> the lowest index wins (torch.argmax)
+    W2 = W.clone()
+    W2[vocab - 1] = W2[t]
+    W2[min(t + 3, vocab - 2)] = W2[t]
+    tail2 = LmTail(nw, 1e-5, W2)
+    tail2(h, tok)
+    assert int(tok.item()) == t
