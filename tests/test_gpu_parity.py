@@ -325,19 +325,21 @@ def test_non_fp16_activations_and_3d_input():
 
 @pytest.mark.parametrize("fin,fout,cbid,pc", [(512, 768, "E8P12", False), (768, 512, "E8P12RVQ4B", True), (1024, 1024, "D4", False)])
 def test_calc_weight_vs_oracle_dense_weight(fin, fout, cbid, pc):
-    """calc_weight (qlinear.py:144-159) against the oracle's effective dense matrix: the float64 forward of the identity,
-    W_eff^T = forward(I) without bias (SURVEY A.5 forward identity), and the training-mode forward against the oracle."""
+    """calc_weight (qlinear.py:144-159) against the oracle's dense matrix M_L W_hat^T M_R^T * Wscale: the float64
+    forward of the identity without SU / SV / bias, and the training-mode forward against the oracle."""
     layer = make_layer(fin, fout, cbid, bias=True, per_channel=pc, seed=fin + 3, device=DEV)
     with torch.no_grad():
-        W = layer.calc_weight().float().cpu().numpy()             # [out, in]
-    assert W.shape == (fout, fin)
-    eye = torch.eye(fin).half()
-    bias = layer.bias
-    layer.bias = None
-    try:
-        W_ref = oracle_forward(layer, eye, rounding="none").T      # forward(e_i) = column i of W_eff
-    finally:
-        layer.bias = bias
+        W = layer.calc_weight(cache=False).float().cpu().numpy()   # [q_in, q_out] for `x @ W`; SU / SV / bias are applied around it
+    qi, qo_ = layer.q_in_features, layer.q_out_features
+    assert W.shape == (qi, qo_)
+    cb = layer.codebook
+    W_hat = oracle_w_hat(cb.id, layer.Qidxs.cpu().numpy(), getattr(cb, "opt_resid_scale", None))
+    npy = lambda t: None if t is None else t.detach().float().cpu().numpy()
+    W_ref = qo.quantlinear_forward(                               # rows of the identity through the rotations and the codebook
+        np.eye(qi, dtype=np.float16), W_hat=W_hat, in_features=qi, out_features=qo_, q_in=qi, q_out=qo_, SU=None, SV=None,
+        bias=None, wscale_float=layer.wscale_float, Wscale_per_channel=npy(layer.Wscale) if pc else None,
+        had_left=npy(layer.had_left), K_left=layer.K_left, had_right=npy(layer.had_right), K_right=layer.K_right,
+        rounding="none")
     # fp16 dense weight: two fp16 Hadamard passes + scalings, 2^-8 of the largest entry
     assert np.abs(W - W_ref).max() <= 2.0 ** -8 * np.abs(W_ref).max(), (np.abs(W - W_ref).max(), np.abs(W_ref).max())
     x = torch.randn(5, fin, generator=torch.Generator().manual_seed(4)).half()
