@@ -335,11 +335,17 @@ def test_calc_weight_vs_oracle_dense_weight(fin, fout, cbid, pc):
     cb = layer.codebook
     W_hat = oracle_w_hat(cb.id, layer.Qidxs.cpu().numpy(), getattr(cb, "opt_resid_scale", None))
     npy = lambda t: None if t is None else t.detach().float().cpu().numpy()
-    W_ref = qo.quantlinear_forward(                               # rows of the identity through the rotations and the codebook
-        np.eye(qi, dtype=np.float16), W_hat=W_hat, in_features=qi, out_features=qo_, q_in=qi, q_out=qo_, SU=None, SV=None,
-        bias=None, wscale_float=layer.wscale_float, Wscale_per_channel=npy(layer.Wscale) if pc else None,
-        had_left=npy(layer.had_left), K_left=layer.K_left, had_right=npy(layer.had_right), K_right=layer.K_right,
-        rounding="none")
+    # calc_weight takes its global scale from Wscale.mean() and, per channel, multiplies the ROTATED matrix by
+    # Wscale / Wscale.mean() (qlinear.py:146,155-156): after the load-time normalisation (quantizer.py:838-839) that mean is
+    # 1, not wscale_float, and the per-channel factor sits after the output rotation, not before it as in the eval forward
+    # (qlinear.py:106-109).  Reference behaviour, restated as is.
+    wsf = float(layer.Wscale.mean())
+    W_ref = qo.quantlinear_forward(np.eye(qi, dtype=np.float16), W_hat=W_hat, in_features=qi, out_features=qo_, q_in=qi,
+                                   q_out=qo_, SU=None, SV=None, bias=None, wscale_float=wsf, Wscale_per_channel=None,
+                                   had_left=npy(layer.had_left), K_left=layer.K_left, had_right=npy(layer.had_right),
+                                   K_right=layer.K_right, rounding="none")     # rows of the identity through the path
+    if pc:
+        W_ref = W_ref * npy(layer.Wscale / layer.Wscale.mean())[None, :]
     # fp16 dense weight: two fp16 Hadamard passes + scalings, 2^-8 of the largest entry
     assert np.abs(W - W_ref).max() <= 2.0 ** -8 * np.abs(W_ref).max(), (np.abs(W - W_ref).max(), np.abs(W_ref).max())
     x = torch.randn(5, fin, generator=torch.Generator().manual_seed(4)).half()
@@ -347,7 +353,9 @@ def test_calc_weight_vs_oracle_dense_weight(fin, fout, cbid, pc):
         layer.train()
         y_train = layer(x.to(DEV)).float().cpu().numpy()
         layer.eval()
-    ref = oracle_forward(layer, x, rounding="none")
+    xs = np.zeros((5, qi))
+    xs[:, :fin] = x.double().numpy() * npy(layer.SU).astype(np.float64)
+    ref = (xs @ W_ref)[:, :fout] * npy(layer.SV).astype(np.float64) + npy(layer.bias).astype(np.float64)   # qlinear.py:93-97,111-114
     assert np.abs(y_train - ref).max() <= 2.0 ** -7 * np.abs(ref).max()
 
 
