@@ -28,13 +28,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="llama2-7b")
+    ap.add_argument("--model", default=None,
+                    help="default: llama2-7b on one GPU (BASELINE config 2), llama2-70b for the multi-GPU layer pipeline (config 5)")
+    ap.add_argument("--no-secondary", dest="no_secondary", action="store_true",
+                    help="N > 1: skip the additional 7B pipeline measurement")
     ap.add_argument("--codebook", default="E8P12")
     ap.add_argument("--prompt-len", type=int, default=128)
     ap.add_argument("--cache-len", type=int, default=0, help="KV cache length (0: prompt + steps + warmup + 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-bench", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-hf-dropin", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--engine", default="auto", choices=["auto", "persistent", "grouped"],
                     help="decode engine: one persistent whole-step kernel, or one launch per linear group")
@@ -117,66 +121,102 @@ LLAMA_LINEARS = {
 }
 
 
-class CpuLayerSample:
-    """One decoder layer's 7 QuantLinear forwards (decode-every-call, bs=1) through oracle/quip_oracle.c.
-    tokens/s is extrapolated as 1 / (n_layers * t_layer): attention / norms / lm_head are not timed."""
+def _host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
-    def __init__(self, model_name):
+
+class CpuTokenPass:
+    """The QuantLinear forwards of ONE decode token (bs=1, decode-every-call: 7 per decoder layer, every layer with its own
+    packed weights) through oracle/quip_oracle.c on all host threads.  Attention / norms / lm_head are not part of the
+    reference's quantised path and are not timed (they are < 2 % of the CPU time of a token).
+    `n_run` <= n_layers distinct layers are allocated and run per pass; tokens/s = 1 / (t_pass * n_layers / n_run)."""
+
+    def __init__(self, model_name, n_run=None):
+        # torchrun exports OMP_NUM_THREADS=1: the CPU arm is meant to use the host, so the thread count is set explicitly
+        os.environ["OMP_NUM_THREADS"] = str(_host_threads())
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import numpy as np
         import quip_oracle as qo
         import quip_oracle_c as qc
         self.np, self.qo, self.qc = np, qo, qc
         self.n_layers, shapes = LLAMA_LINEARS[model_name]
+        self.n_run = self.n_layers if n_run is None else max(1, min(n_run, self.n_layers))
         rng = np.random.default_rng(0)
         self.tab = qo.e8p_abs_table()
-        self.lin = []
+        self.layers = []
+        orth = lambda k: np.linalg.qr(rng.standard_normal((k, k)))[0].astype(np.float32) if k > 1 else None
+        base = []
         for fin, fout in shapes:
             Kl, q_in, _ = qo.hadK_shape(fin, True)
             Kr, q_out, _ = qo.hadK_shape(fout, True)
-            q = rng.integers(-32768, 32768, (q_out, q_in // 8)).astype(np.int16)
-            orth = lambda k: np.linalg.qr(rng.standard_normal((k, k)))[0].astype(np.float32) if k > 1 else None
-            self.lin.append(dict(fin=fin, fout=fout, q_in=q_in, q_out=q_out, q=q, Kl=Kl, Kr=Kr,
-                                 hl=orth(Kl), hr=orth(Kr),
-                                 SU=np.sign(rng.standard_normal(fin)).astype(np.float32),
-                                 SV=np.sign(rng.standard_normal(fout)).astype(np.float32),
-                                 x=rng.standard_normal((1, fin)).astype(np.float16)))
+            base.append(dict(fin=fin, fout=fout, q_in=q_in, q_out=q_out, Kl=Kl, Kr=Kr, hl=orth(Kl), hr=orth(Kr),
+                             q=rng.integers(-32768, 32768, (q_out, q_in // 8)).astype(np.int16),
+                             SU=np.sign(rng.standard_normal(fin)).astype(np.float32),
+                             SV=np.sign(rng.standard_normal(fout)).astype(np.float32),
+                             x=rng.standard_normal((1, fin)).astype(np.float16)))
+        for li in range(self.n_run):      # distinct weight arrays per layer (rolled copies: same statistics, no cache reuse)
+            self.layers.append([dict(L, q=np.roll(L["q"], li + 1, axis=0).copy() if li else L["q"]) for L in base])
         self.cores = qc.num_threads()
 
     def run_once(self):
         t0 = time.perf_counter()
-        for L in self.lin:
-            self.qc.quantlinear_forward_e8p(L["x"], L["q"], self.tab, L["fin"], L["fout"], L["q_in"], L["q_out"],
-                                            SU=L["SU"], SV=L["SV"], wscale_float=0.0183,
-                                            had_left=L["hl"], K_left=L["Kl"], had_right=L["hr"], K_right=L["Kr"])
+        for lin in self.layers:
+            for L in lin:
+                self.qc.quantlinear_forward_e8p(L["x"], L["q"], self.tab, L["fin"], L["fout"], L["q_in"], L["q_out"],
+                                                SU=L["SU"], SV=L["SV"], wscale_float=0.0183,
+                                                had_left=L["hl"], K_left=L["Kl"], had_right=L["hr"], K_right=L["Kr"])
         return time.perf_counter() - t0
 
+    def tok_s(self, t_pass):
+        return 1.0 / (t_pass * self.n_layers / self.n_run)
+
     def describe(self):
-        return (f"1 of {self.n_layers} decoder layers: its 7 QuantLinear forwards (decode-every-call, bs=1, "
-                f"E8P12) via oracle/quip_oracle.c with OpenMP; tokens/s = 1/({self.n_layers} x t_layer)")
+        what = (f"all {self.n_layers} decoder layers" if self.n_run == self.n_layers else
+                f"{self.n_run} of {self.n_layers} decoder layers (distinct weights; tokens/s scaled by {self.n_layers}/{self.n_run})")
+        return (f"one decode token = the 7 QuantLinear forwards (decode-every-call, bs=1, E8P12) of {what} via "
+                f"oracle/quip_oracle.c, OpenMP, {self.cores} threads")
+
+
+def _cpu_layers_for_budget(model_name, steps, warmup, budget_s=150.0):
+    """How many decoder layers a pass may run so that (steps + warmup) passes fit the time budget: probed with a
+    two-layer pass on this host."""
+    probe = CpuTokenPass(model_name, n_run=2)
+    probe.run_once()
+    t2 = min(probe.run_once() for _ in range(2))
+    per_layer = t2 / 2
+    n_layers = probe.n_layers
+    fit = int(budget_s / max(1e-9, per_layer * max(1, steps + warmup)))
+    return max(1, min(n_layers, fit)), per_layer
 
 
 def run_reference_arm(a):
-    """`--impl reference`: the reference has no CPU implementation of its own ops (register_lib.py:
-    CUDA-only), so the CPU statement of the path is the oracle port; timed on all host threads."""
+    """`--impl reference`: the reference has no CPU implementation of its own ops (register_lib.py: CUDA-only), so the
+    CPU statement of the path is the oracle port; timed on all host threads.  Every step is a whole-token pass when
+    `steps + warmup` of them fit the time budget on this host, else the largest whole number of layers that does (stated
+    in `sample`); `steps` and `warmup` are used as given."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    s = CpuLayerSample(a.model)
-    for _ in range(max(1, min(a.warmup, 3))):
+    n_run, _ = _cpu_layers_for_budget(a.model, a.steps, a.warmup)
+    s = CpuTokenPass(a.model, n_run=n_run)
+    for _ in range(a.warmup):
         s.run_once()
-    steps = max(1, min(a.steps, 20))
-    ts = [s.run_once() for _ in range(steps)]
-    t_layer = sum(ts) / len(ts)
-    val = 1.0 / (s.n_layers * t_layer)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        s.run_once()
+    t_pass = (time.perf_counter() - t0) / a.steps
+    val = s.tok_s(t_pass)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "tokens/s", "n_gpus": a.gpus,
-        "steps": steps, "warmup": min(a.warmup, 3), "ms_per_step": 1000.0 * s.n_layers * t_layer,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8xint16 fixed point (ours) / fp16->fp32 (this port)",
-        "data": "synthetic",
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * t_pass * s.n_layers / s.n_run,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int8xint16 fixed point (ours) / fp16->fp32 (this port)", "data": "synthetic",
         "config": {"workload": f"{a.model} {a.codebook} bs=1 greedy decode, random-init packed weights "
-                               "(CPU port of the QuantLinear path; bounded sample, see `sampled`)",
-                   "sampled": s.describe()},
+                               "(CPU port of the QuantLinear path on the host cores; see `sampled`)",
+                   "sampled": s.describe(), "timed_s": t_pass * a.steps},
         "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": s.cores, "kind": "port", "sample": s.describe()},
         "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -324,6 +364,52 @@ def ref_cuda_bench(model, torch, reps=3):
             "launches": len(layers)}
 
 
+def hf_dropin_bench(model, torch, prompt, steps, warmup):
+    """The API the north_star names: UNMODIFIED HF LlamaForCausalLM.forward over drop-in QuantLinear modules, static KV
+    cache, one token per forward, the step captured in a CUDA graph (what the reference's example_generate.py:29-56,
+    62-70 does with torch.compile(mode="reduce-overhead")).  Greedy, bs=1.  Returns tokens/s (CUDA events)."""
+    try:
+        from transformers import StaticCache
+        dev = prompt.device
+        T = prompt.shape[1]
+        cache = StaticCache(config=model.config, max_cache_len=T + 2 * (steps + warmup) + 16)
+        with torch.no_grad():
+            out = model(input_ids=prompt, past_key_values=cache, use_cache=True,
+                        cache_position=torch.arange(T, device=dev))
+            tok = out.logits[:, -1:].argmax(-1)                      # static buffers of the captured step
+            pos = torch.full((1,), T, dtype=torch.long, device=dev)
+
+            def step():
+                logits = model(input_ids=tok, past_key_values=cache, use_cache=True, cache_position=pos).logits
+                tok.copy_(logits[:, -1:].argmax(-1))
+                pos.add_(1)
+
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    step()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+            for _ in range(warmup):
+                g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                g.replay()
+            e1.record()
+            e1.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": 1000.0 / ms, "unit": "tokens/s", "ms_per_step": ms, "steps": steps,
+                "how": "transformers LlamaForCausalLM.forward (unmodified) with quip_for_all_b200.QuantLinear modules, "
+                       "StaticCache, one CUDA graph per decode step (torch.cuda.graph), greedy, bs=1"}
+    except Exception as e:       # informational leg: never fail the headline line
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -332,7 +418,7 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from quip_for_all_b200.parallel import run_pipeline_bench
-        return run_pipeline_bench(a, METRIC, ClockSampler)
+        return run_pipeline_bench(a, METRIC, ClockSampler, peak_gbs=measured_peaks()[0])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     from quip_for_all_b200 import _native
@@ -422,20 +508,25 @@ def run_ours(a):
             line["roofline_per_linear_kernel"] = roof      # the drop-in op path (one launch per QuantLinear)
         else:
             line["roofline"] = roof
+    if not a.no_hf_dropin:
+        line["hf_dropin"] = hf_dropin_bench(model, torch, prompt.to(dev), min(a.steps, 64), 4)
     if not a.no_ref_cuda:
         line["ref_cuda"] = ref_cuda_bench(model, torch)
     if not a.no_cpu_baseline:
-        s = CpuLayerSample(a.model if a.model in LLAMA_LINEARS else "llama2-7b")
+        mname = a.model if a.model in LLAMA_LINEARS else "llama2-7b"
+        n_run, _ = _cpu_layers_for_budget(mname, 3, 1, budget_s=20.0)     # ~10-30 s of CPU work
+        s = CpuTokenPass(mname, n_run=n_run)
         s.run_once()
-        ts = [s.run_once() for _ in range(3)]
-        t_layer = min(ts)
-        line["cpu_baseline"] = {"value": 1.0 / (s.n_layers * t_layer), "unit": "tokens/s", "cores": s.cores,
+        t_pass = min(s.run_once() for _ in range(3))
+        line["cpu_baseline"] = {"value": s.tok_s(t_pass), "unit": "tokens/s", "cores": s.cores,
                                 "kind": "port", "sample": s.describe()}
     print(json.dumps(line))
 
 
 def main():
     a = parse()
+    if a.model is None:
+        a.model = "llama2-70b" if max(a.gpus, int(os.environ.get("WORLD_SIZE", "1"))) > 1 else "llama2-7b"
     if a.impl == "reference":
         run_reference_arm(a)
     else:

@@ -134,18 +134,12 @@ class LlamaStage:
             e.capture()
 
 
-def run_pipeline_bench(a, metric, clock_sampler_cls=None):
-    """bench.py body for WORLD_SIZE > 1 (launched by torchrun, one rank per GPU)."""
-    import json
-    world = int(os.environ["WORLD_SIZE"])
-    rank = int(os.environ["RANK"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+def _pipeline_measure(a, model_name, world, rank, local, dev, clock_sampler_cls=None):
+    """One layer-pipeline measurement of `model_name` on the already initialised process group.  Returns (on every
+    rank) a dict with the device-timed and the end-to-end aggregate tokens/s."""
     S = world
-    cache_len = a.cache_len or (a.prompt_len + (a.steps + a.warmup) // S * 2 + 3 * S + 32)
-    stage = LlamaStage(a.model, a.codebook, rank, world, dev, S, cache_len, use_graph=not a.no_graph)
+    cache_len = a.cache_len or (a.prompt_len + (a.steps * 2 + a.warmup) // S * 2 + 4 * S + 32)
+    stage = LlamaStage(model_name, a.codebook, rank, world, dev, S, cache_len, use_graph=not a.no_graph)
     pipe = RingPipeline(stage, rank, world, S)
     g = torch.Generator().manual_seed(0)
     vocab = stage.model.config.vocab_size
@@ -154,14 +148,12 @@ def run_pipeline_bench(a, metric, clock_sampler_cls=None):
     # fill + warm-up ticks
     for _ in range(world - 1 + max(a.warmup, 3)):
         pipe.tick()
-    from . import _native
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
     clocks = clock_sampler_cls(local) if (clock_sampler_cls is not None and rank == 0) else None
     if clocks is not None:
         clocks.start()
-    lc0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
@@ -177,28 +169,52 @@ def run_pipeline_bench(a, metric, clock_sampler_cls=None):
     # own kernels enqueued per tick on this rank (graph replays re-run what was captured: count one eager tick)
     launches = torch.tensor([float(getattr(stage.engines[0], "launches_per_step", 0) or 0)], device=dev)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
-    del lc0
-    # ---- e2e: every tick the emitted token id goes device -> pinned host on the last stage and the next input token
-    # pinned host -> device on the first stage, with a stream sync per tick; wall clock, max over ranks
-    h_tok = torch.zeros(1, 1, dtype=torch.long).pin_memory()
-    d_tok_in = torch.zeros(1, 1, dtype=torch.long, device=dev)
+    # ---- e2e: every tick the first stage takes the input token of the sequence it is about to run from pinned host
+    # memory (H2D into that engine's token buffer, which the step consumes) and the last stage returns the emitted token
+    # id to pinned host memory (D2H), with a stream sync per tick on every rank; wall clock, max over ranks
+    h_tok = torch.randint(0, vocab, (1, 1), generator=g).pin_memory()
     dist.barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
         if stage.first:
-            d_tok_in.copy_(h_tok, non_blocking=True)
+            slot = (pipe.t - rank) % S
+            stage.engines[slot].tok.copy_(h_tok, non_blocking=True)
         pipe.tick()
         if stage.last:
-            h_tok.copy_(stage.engines[0].tok, non_blocking=True)
+            h_tok.copy_(stage.engines[(pipe.t - 1 - rank) % S].tok, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
     dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_tok_s = a.steps / t_e2e.item()
+    from .modeling import quantized_bytes
+    code_bytes = torch.tensor([float(quantized_bytes(stage.model))], device=dev)
+    dist.all_reduce(code_bytes, op=dist.ReduceOp.SUM)
+    persistent = stage.engines[0].persistent is not None
+    out = {"tok_s": a.steps / (ms * 1e-3), "ms_per_step": ms / a.steps, "e2e_tok_s": a.steps / t_e2e.item(),
+           "launches": int(launches.item()) * a.steps, "clocks": ck, "code_bytes": code_bytes.item(),
+           "engine": "persistent whole-step kernel per stage" if persistent else "grouped launches (6 per decoder layer)"}
+    del stage, pipe
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_pipeline_bench(a, metric, clock_sampler_cls=None, peak_gbs=None):
+    """bench.py body for WORLD_SIZE > 1 (launched by torchrun, one rank per GPU).  Workload = BASELINE config 5: the
+    Llama-2-70B layer pipeline; the 7B pipeline of round 1 is measured as well and reported under `secondary`."""
+    import json
+    world = int(os.environ["WORLD_SIZE"])
+    rank = int(os.environ["RANK"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    main = _pipeline_measure(a, a.model, world, rank, local, dev, clock_sampler_cls)
+    second = None
+    if a.model != "llama2-7b" and not getattr(a, "no_secondary", False):
+        second = _pipeline_measure(a, "llama2-7b", world, rank, local, dev, None)
     if rank == 0:
-        from .modeling import LLAMA2_SHAPES
         line = {
-            "metric": metric, "value": a.steps / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
-            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "metric": metric, "value": main["tok_s"], "unit": "tokens/s", "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 weights x int16 fixed-point activations (exact int32 dp4a), fp16 in/out",
             "data": "synthetic",
@@ -206,11 +222,23 @@ def run_pipeline_bench(a, metric, clock_sampler_cls=None):
                                    f"({world} independent bs=1 sequences in flight, one per stage), random-init "
                                    f"packed weights, synthetic {a.prompt_len}-token prompts",
                        "parallelism": f"pp{world} (whole decoder layers per stage, NCCL p2p ring exchange per tick)",
-                       "l2": "inputs larger than L2 (each stage streams its slice of the 1.6 GB of codes per tick)"},
-            "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8,
-                    "how": "per tick: token id pinned host -> device (first stage) and device -> pinned host (last stage), "
-                           "stream sync on every rank, wall clock, max over ranks"},
-            "gpu_launches": int(launches.item()) * a.steps, "clocks": ck,
+                       "engine": main["engine"],
+                       "l2": "inputs larger than L2 (each stage streams its slice of the %.1f GB of codes per tick)"
+                             % (main["code_bytes"] / 1e9)},
+            "e2e": {"value": main["e2e_tok_s"], "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8,
+                    "how": "per tick: input token id pinned host -> the running engine's token buffer (first stage) and "
+                           "emitted token id device -> pinned host (last stage), stream sync on every rank, wall clock, "
+                           "max over ranks"},
+            "gpu_launches": main["launches"], "clocks": main["clocks"],
         }
+        if peak_gbs:
+            # aggregate roofline: one token leaves per tick and every stage streams its slice once per tick
+            roof = world * peak_gbs * 1e9 / main["code_bytes"]
+            line["model_roofline"] = {"packed_code_bytes_per_token": main["code_bytes"],
+                                      "tok_s_at_hbm_peak_all_gpus": roof, "frac_of_hbm_roofline": main["tok_s"] / roof}
+        if second is not None:
+            line["secondary"] = {"workload": f"llama2-7b {a.codebook} bs=1 decode, same pipeline ({second['engine']})",
+                                 "value": second["tok_s"], "unit": "tokens/s", "ms_per_step": second["ms_per_step"],
+                                 "e2e": second["e2e_tok_s"]}
         print(json.dumps(line))
     dist.destroy_process_group()

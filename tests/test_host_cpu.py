@@ -361,6 +361,12 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert "workload" in line["config"]
+    assert line["steps"] == 1 and line["warmup"] == 0                     # used as given, not capped
+    assert "all 2 decoder layers" in line["config"]["sampled"]            # a whole-token pass, not one layer x n_layers
+    # under torchrun (OMP_NUM_THREADS=1 exported) the arm still uses the host's cores
+    r3 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                         "--model", "tiny"], capture_output=True, text=True, env=dict(env, OMP_NUM_THREADS="1"), timeout=300)
+    assert json.loads(r3.stdout.strip().splitlines()[-1])["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                          "--model", "tiny"], capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=300)
     assert r2.returncode == 0 and r2.stdout.strip() == ""
