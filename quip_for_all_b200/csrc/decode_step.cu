@@ -1194,12 +1194,15 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         __half* vc = reinterpret_cast<__half*>(Ly.v_cache) + (size_t)kvh * P.max_len * DS_HD;
         // Everything this CTA needs that does not depend on the q/k/v stage is requested first and travels while the head
         // slices are rotated: cached K rows of the first scores pass, the RoPE table row, SV / bias of the slices.
-        uint4 kfirst[DS_ATT_UN];
+        uint4 kfirst[DS_ATT_UN], vfirst[DS_ATT_UN];
 #pragma unroll
         for (int u = 0; u < DS_ATT_UN; u++) {
           const int tk = t_begin + warp * 2 + (lane >> 4) + u * DS_WARPS * 2;
-          kfirst[u] = make_uint4(0, 0, 0, 0);
-          if (tk < t_end && tk != pos) kfirst[u] = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)tk * DS_HD) + (lane & 15));
+          kfirst[u] = vfirst[u] = make_uint4(0, 0, 0, 0);
+          if (tk < t_end && tk != pos) {
+            kfirst[u] = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)tk * DS_HD) + (lane & 15));
+            vfirst[u] = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)tk * DS_HD) + (lane & 15));
+          }
         }
         uint2 rope_c = make_uint2(0, 0), rope_s = rope_c, sl_sv = rope_c, sl_b = rope_c;
         if (warp < 2) {
@@ -1266,31 +1269,29 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         }
         __syncthreads();
         DS_ST(8);
-        // ---- scores over [t_begin, t_end): a half-warp per cached position, 16-byte loads (8 dims per lane) ----
+        // ---- scores, softmax and P.V in one sweep: a half-warp owns a cached position (lane l16: dims 8 * l16 .. + 7 of its K
+        // and V rows, 16-byte loads) and keeps a running (max, sum, weighted V) of its own positions; the 32 half-warp
+        // partials meet once in shared memory.  (Round 1 ran scores -> block max -> exp / block sum -> P.V with four block
+        // barriers and a second mapping for V.)
         const int l16 = lane & 15, hw = lane >> 4;
         float qv[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) qv[e] = sq[l16 * 8 + e];
-        float lmax = -INFINITY;
-        uint4 vfirst[DS_ATT_UN];                       // V rows of the first P.V pass: in flight under the scores / softmax
-#pragma unroll
-        for (int u = 0; u < DS_ATT_UN; u++) {
-          const int tv = t_begin + (tid >> 4) + u * DS_PV_GROUPS;
-          vfirst[u] = make_uint4(0, 0, 0, 0);
-          if (tv < t_end && tv != pos) vfirst[u] = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)tv * DS_HD) + (tid & 15));
-        }
+        float m_run = -INFINITY, l_run = 0.f;
+        float oacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         constexpr int UN = DS_ATT_UN;
         for (int tb = t_begin + warp * 2; tb < t_end; tb += DS_WARPS * 2 * UN) {   // warp-uniform trip count (full-mask shuffles inside)
           const int t0 = tb + hw;
-          uint4 raw[UN];
-          const bool first = tb == t_begin + warp * 2;                              // first pass: requested at the top of the stage
+          uint4 raw[UN], vr[UN];
+          const bool first = tb == t_begin + warp * 2;                              // first pass: K requested at the top of the stage
 #pragma unroll
           for (int u = 0; u < UN; u++) {
             const int t = t0 + u * DS_WARPS * 2;
             raw[u] = kfirst[u];
-            if (!first) {
-              raw[u] = make_uint4(0, 0, 0, 0);
-              if (t < t_end && t != pos) raw[u] = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)t * DS_HD) + l16);
+            vr[u] = vfirst[u];
+            if (!first && t < t_end && t != pos) {
+              raw[u] = __ldcg(reinterpret_cast<const uint4*>(kc + (size_t)t * DS_HD) + l16);
+              vr[u] = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)t * DS_HD) + l16);
             }
           }
           float d[UN];
@@ -1314,83 +1315,74 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
 #pragma unroll
             for (int u = 0; u < UN; u++) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
           }
+          // online softmax over this half-warp's (up to UN) positions of the pass
+          float mx = m_run;
+#pragma unroll
+          for (int u = 0; u < UN; u++)
+            if (t0 + u * DS_WARPS * 2 < t_end) mx = fmaxf(mx, d[u]);
+          const float resc = (m_run == -INFINITY) ? 0.f : __expf(m_run - mx);
+          l_run *= resc;
+#pragma unroll
+          for (int e = 0; e < 8; e++) oacc[e] *= resc;
 #pragma unroll
           for (int u = 0; u < UN; u++) {
             const int t = t0 + u * DS_WARPS * 2;
             if (t < t_end) {
-              if (l16 == 0) sc[t - t_begin] = d[u];
-              lmax = fmaxf(lmax, d[u]);
+              const float pr = __expf(d[u] - mx);
+              l_run += pr;
+              float vf[8];
+              if (t == pos) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) vf[e] = sv[l16 * 8 + e];
+              } else {
+                unpack_h8(vr[u], vf);
+              }
+#pragma unroll
+              for (int e = 0; e < 8; e++) oacc[e] = fmaf(pr, vf[e], oacc[e]);
             }
           }
+          m_run = mx;
         }
-        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, 16));
-        if (lane == 0) sred[warp] = lmax;
-        __syncthreads();
-        float mx = -INFINITY;
-#pragma unroll
-        for (int w = 0; w < DS_WARPS; w++) mx = fmaxf(mx, sred[w]);
-        __syncthreads();
-        float lsum = 0.f;
-        for (int t = t_begin + tid; t < t_end; t += DS_THREADS) {
-          const float pr = __expf(sc[t - t_begin] - mx);
-          sc[t - t_begin] = pr;
-          lsum += pr;
-        }
-        lsum = warp_sum(lsum);
-        if (lane == 0) sred[warp] = lsum;
-        __syncthreads();
-        float tot = 0.f;
-#pragma unroll
-        for (int w = 0; w < DS_WARPS; w++) tot += sred[w];
-        DS_ST(9);
-        // ---- partial out = P . V: 16 threads per position (8 dims each, 16-byte loads), 32 positions per pass ----
+        // the warp's two half-warps merge through shuffles, then warp partials -> shared memory: sout[16][128] weighted V,
+        // sc[16][2] (max, sum)
         {
-          const int pg = tid >> 4, t16 = tid & 15;
-          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          constexpr int UV = DS_ATT_UN;
-          for (int t0 = t_begin + pg; t0 < t_end; t0 += DS_PV_GROUPS * UV) {
-            uint4 vr[UV];
-            const bool first = t0 == t_begin + pg;
+          const float m_o = __shfl_xor_sync(0xffffffffu, m_run, 16), l_o = __shfl_xor_sync(0xffffffffu, l_run, 16);
+          const float mw = fmaxf(m_run, m_o);
+          const float wa = (m_run == -INFINITY) ? 0.f : __expf(m_run - mw), wb = (m_o == -INFINITY) ? 0.f : __expf(m_o - mw);
 #pragma unroll
-            for (int u = 0; u < UV; u++) {
-              const int t = t0 + u * DS_PV_GROUPS;
-              vr[u] = vfirst[u];
-              if (!first) {
-                vr[u] = make_uint4(0, 0, 0, 0);
-                if (t < t_end && t != pos) vr[u] = __ldcg(reinterpret_cast<const uint4*>(vc + (size_t)t * DS_HD) + t16);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < UV; u++) {
-              const int t = t0 + u * DS_PV_GROUPS;
-              if (t < t_end) {
-                float vf[8];
-                if (t == pos) {
-#pragma unroll
-                  for (int e = 0; e < 8; e++) vf[e] = sv[t16 * 8 + e];
-                } else {
-                  unpack_h8(vr[u], vf);
-                }
-                const float pr = sc[t - t_begin];
-#pragma unroll
-                for (int e = 0; e < 8; e++) acc[e] = fmaf(pr, vf[e], acc[e]);
-              }
+          for (int e = 0; e < 8; e++) {
+            const float o_o = __shfl_xor_sync(0xffffffffu, oacc[e], 16);
+            oacc[e] = wa * oacc[e] + wb * o_o;
+          }
+          if (hw == 0) {
+            float4* so = reinterpret_cast<float4*>(sout + warp * 128 + l16 * 8);
+            so[0] = make_float4(oacc[0], oacc[1], oacc[2], oacc[3]);
+            so[1] = make_float4(oacc[4], oacc[5], oacc[6], oacc[7]);
+            if (l16 == 0) {
+              sc[2 * warp] = mw;
+              sc[2 * warp + 1] = wa * l_run + wb * l_o;
             }
           }
-          float4* so = reinterpret_cast<float4*>(sout + pg * 128 + t16 * 8);
-          so[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-          so[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
         __syncthreads();
+        DS_ST(9);
         if (tid < DS_HD) {
-          float r = 0.f;
+          float mx = -INFINITY;
 #pragma unroll
-          for (int g2 = 0; g2 < DS_PV_GROUPS; g2++) r += sout[g2 * 128 + tid];
+          for (int g2 = 0; g2 < DS_WARPS; g2++) mx = fmaxf(mx, sc[2 * g2]);
+          float tot = 0.f, r = 0.f;
+#pragma unroll
+          for (int g2 = 0; g2 < DS_WARPS; g2++) {
+            const float mg = sc[2 * g2];
+            const float w = (mg == -INFINITY) ? 0.f : __expf(mg - mx);
+            tot = fmaf(w, sc[2 * g2 + 1], tot);
+            r = fmaf(w, sout[g2 * 128 + tid], r);
+          }
           p.ws.att_o[(size_t)(h * S + s) * DS_HD + tid] = __float2half_rn(tot > 0.f ? r / tot : 0.f);
-        }
-        if (tid == 0) {
-          __stcg(p.ws.att_ml + (size_t)(h * S + s) * 2, mx);
-          __stcg(p.ws.att_ml + (size_t)(h * S + s) * 2 + 1, tot);
+          if (tid == 0) {
+            __stcg(p.ws.att_ml + (size_t)(h * S + s) * 2, mx);
+            __stcg(p.ws.att_ml + (size_t)(h * S + s) * 2 + 1, tot);
+          }
         }
         DS_ST(10);
       }
@@ -1802,7 +1794,7 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
   if (P->n_heads * S > 512 || P->n_heads * S * DS_HD > 16384) return QUIPB200_EUNSUPPORTED;
   out->splits = S;
   const size_t chunk = S > 1 ? ((size_t)P->max_len + S - 2) / (S - 1) : (size_t)P->max_len;
-  const size_t attn = (3 * DS_WARPS * 128 + 3 * 128 + 32 + DS_PV_GROUPS * 128 + chunk) * sizeof(float);
+  const size_t attn = (3 * DS_WARPS * 128 + 3 * 128 + 32 + DS_PV_GROUPS * 128 + std::max(chunk, (size_t)(4 * DS_WARPS))) * sizeof(float);   // sc: scores (grouped path) or the 32 half-warp (max, sum) pairs
   // tensor-path rotations when every hidden-side rotation has exactly 4096 points
   const bool use_mma = Y.q.q_in == 4096 && Y.k.q_in == 4096 && Y.v.q_in == 4096 && Y.o.q_in == 4096 && Y.o.q_out == 4096 &&
                        Y.gate.q_in == 4096 && Y.up.q_in == 4096 && Y.down.q_out == 4096 && P->hidden <= 4096;

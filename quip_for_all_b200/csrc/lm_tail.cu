@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lm_tail_kernel(const __grid_con
   // ---- GEMV: one warp per row, rows strided over all warps of the grid ----
   const int gw = blockIdx.x * LT_WARPS + warp, nw = gridDim.x * LT_WARPS;
   const int iters = (noct + 31) >> 5;                      // 16-byte pieces per lane per row
+  const uint64_t pol = l2_evict_first_policy();            // 262 MB pass through the L2 once: do not evict the KV cache for it
   unsigned long long best = 0ull;
   for (int row = gw; row < p.vocab; row += nw) {
     const uint4* wr = reinterpret_cast<const uint4*>(p.W + (size_t)row * H);
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lm_tail_kernel(const __grid_con
       for (int u = 0; u < LT_U; u++) {
         const int o = (i0 + u) * 32 + lane;
         wv[u] = make_uint4(0, 0, 0, 0);
-        if (i0 + u < iters && o < noct) wv[u] = ldg_stream_v4(wr + o);
+        if (i0 + u < iters && o < noct) wv[u] = ldg_stream_v4(wr + o, pol);
       }
 #pragma unroll
       for (int u = 0; u < LT_U; u++) {
