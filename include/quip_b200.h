@@ -119,6 +119,9 @@ int quipb200_rotate_batched(const void* x_f16, int64_t ldx, void* y_f16, int64_t
  *   layout.  Requires N % 128 == 0 and K % 64 == 0 (else QUIPB200_EUNSUPPORTED -> caller uses the dense path).
  *   workspace: >= quipb200_e8p_mm_umma_workspace_bytes(M_max, N, K) bytes, 256-byte aligned, zero-filled ONCE
  *   by the caller; the kernel returns it zeroed (split-K partial sums are cleared by the CTA that converts them).
+ *   A workspace carries partial sums and arrival tickets of ONE launch at a time: launches that may overlap (different
+ *   streams or threads) need separate workspaces (the Python binding keeps one per device, stream and N, and never
+ *   creates one while a CUDA graph is being captured).
  * ------------------------------------------------------------------------------------------- */
 size_t quipb200_e8p_mm_umma_workspace_bytes(int M, int N, int K);
 int quipb200_e8p_mm_umma(const void* x_f16, const void* qidxs, const void* grid_packed_abs, void* out_f16,
@@ -151,6 +154,10 @@ typedef struct quipb200_linear {
   const void* wscale_pc;     /* fp16 [q_out] per-channel Wscale (already mean-normalised) or NULL */
 } quipb200_linear_t;
 
+/* Fused-path launches take a "last CTA finishes the output side" ticket slot from a device-global table of 4096 slots,
+ * handed out round-robin by the host and reset by the consuming CTA: launches that could land on the same slot must not
+ * overlap in time, i.e. issue fused forwards of one device from one stream (or serialise streams with events).  A captured
+ * 7B decode step uses 224 slots. */
 size_t quipb200_linear_workspace_bytes(const quipb200_linear_t* layer, int M);
 /* x: fp16 [M, in_features] with row pitch ldx elements; y: fp16 [M, out_features] pitch ldy. */
 int quipb200_linear_forward(const quipb200_linear_t* layer, const void* x_f16, int64_t ldx,

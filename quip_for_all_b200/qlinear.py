@@ -122,6 +122,10 @@ class QuantLinear(nn.Module):
 
     def forward(self, input):
         x = input.reshape(-1, input.shape[-1])
+        # the kernels want 16-byte aligned rows (8-element row pitch): sliced / offset activation views that the reference
+        # accepts are copied once instead of being rejected by the C ABI
+        if x.is_cuda and (x.stride(-1) != 1 or x.data_ptr() % 16 or (x.shape[0] > 1 and (x.stride(0) * x.element_size()) % 16)):
+            x = x.clone(memory_format=torch.contiguous_format)
         x_dtype = x.dtype
         if self.training:
             if self.SU is not None:

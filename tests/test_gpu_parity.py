@@ -962,3 +962,17 @@ def test_lm_tail_matches_torch_norm_head_argmax(hidden, vocab):
     tail2 = LmTail(nw, 1e-5, W2)
     tail2(h, tok)
     assert int(tok.item()) == t
+
+
+def test_forward_accepts_sliced_and_offset_activation_views():
+    """activation views that are not 16-byte aligned / have an odd row pitch work in the reference; the fast paths
+    must take them too (copied once) instead of raising from the C ABI."""
+    layer = make_layer(512, 256, "E8P12", bias=True, seed=13, device=DEV)
+    big = torch.randn(24, 515, generator=torch.Generator().manual_seed(5)).half().to(DEV)
+    with torch.no_grad():
+        for M in (1, 3, 20):
+            xv = big[:M, 3:]                   # offset by 6 bytes, row pitch 515 elements
+            assert xv.data_ptr() % 16 != 0
+            y = layer(xv)
+            y_ref = layer(xv.contiguous())
+            assert torch.equal(y, y_ref)
