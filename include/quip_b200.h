@@ -124,6 +124,11 @@ int quipb200_rotate_batched(const void* x_f16, int64_t ldx, void* y_f16, int64_t
  *   creates one while a CUDA graph is being captured).
  * ------------------------------------------------------------------------------------------- */
 size_t quipb200_e8p_mm_umma_workspace_bytes(int M, int N, int K);
+/* The same kernel with the producers' decode templated on the codebook: QUIPB200_CB_E8P12 (origin_order.cu:388-555, K1),
+ * QUIPB200_CB_E8P12RVQ4B (K2, :337-385, :698-743; `scale` = the residual scale, rounded to fp16 and applied with one fp16
+ * fma as the reference does) and QUIPB200_CB_D4 (K3, :143-168, :557-602; grid = fp16 [256][4]).  Same workspace rules. */
+int quipb200_mm_umma(int codebook, const void* x_f16, const void* qidxs, const void* grid, float scale, void* out_f16,
+                     int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
 int quipb200_e8p_mm_umma(const void* x_f16, const void* qidxs, const void* grid_packed_abs, void* out_f16,
                          int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
 

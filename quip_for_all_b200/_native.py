@@ -24,7 +24,7 @@ EXPORTS = [
     "quipb200_linear_workspace_bytes", "quipb200_linear_forward",
     "quipb200_linear_group_workspace_bytes", "quipb200_linear_group_forward", "quipb200_attn_decode",
     "quipb200_decode_step_workspace_bytes", "quipb200_decode_step", "quipb200_decode_step_debug", "quipb200_decode_step_debug_cta", "quipb200_decode_step_set_splits",
-    "quipb200_e8p_mm_umma_workspace_bytes", "quipb200_e8p_mm_umma", "quipb200_rotate_batched",
+    "quipb200_e8p_mm_umma_workspace_bytes", "quipb200_e8p_mm_umma", "quipb200_mm_umma", "quipb200_rotate_batched",
     "quipb200_lm_tail_workspace_bytes", "quipb200_lm_tail",
     "quipb200_set_option", "quipb200_get_option", "quipb200_launch_count", "quipb200_debug_timeline",
 ]
@@ -89,6 +89,8 @@ def lib():
     L.quipb200_e8p_mm_umma_workspace_bytes.argtypes = [c_int, c_int, c_int]
     L.quipb200_e8p_mm_umma.restype = c_int
     L.quipb200_e8p_mm_umma.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, vp, c_size_t, vp]
+    L.quipb200_mm_umma.restype = c_int
+    L.quipb200_mm_umma.argtypes = [c_int, vp, vp, vp, c_float, vp, c_int, c_int, c_int, vp, c_size_t, vp]
     L.quipb200_rotate_batched.restype = c_int
     L.quipb200_rotate_batched.argtypes = [vp, c_int64, vp, c_int64, vp, vp, vp, vp, c_int, c_int, c_int, c_int, c_int,
                                           c_float, vp]

@@ -70,9 +70,10 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t sdst, const void* gsrc
 }
 
 struct UmmaArgs {
-  const unsigned char* codes;   // [N][K/8] int16
+  const unsigned char* codes;   // [N][K/8] int16 (E8P12) / int32 (E8P12RVQ4B) or [N][K/4] uint8 (D4)
   const __half* x;              // [M][K]
-  const uint2* table;           // int64[256] abs table
+  const uint2* table;           // E8P family: int64[256] abs table; D4: fp16 [256][4]
+  float resid_scale;            // E8P12RVQ4B
   __half* out;                  // [M][N]
   float* ws;                    // [256][N] fp32 split-K partials (zero on entry, zero on exit)
   unsigned int* tickets;        // [N/128]
@@ -90,7 +91,8 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 // Warp-specialised: 16 producer warps fill the stage slots (no CTA-wide barrier in the main loop), warp 16 waits on
 // full[s], issues the 8 MMAs of the stage and commits to empty[s].
-template <int NTOK, int STAGES>
+// CB: the producers' decode (QUIPB200_CB_E8P12 / _E8P12RVQ4B / _D4); everything else is shared.
+template <int CB, int NTOK, int STAGES>
 __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_constant__ UmmaArgs a) {
   extern __shared__ unsigned char smem_raw[];
   constexpr uint32_t A_SUB = UG_BM * 128, B_SUB = NTOK * 128;           // one 64-wide swizzle tile
@@ -122,8 +124,10 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), NTOK);
   if (tid < 256) {
     uint2 t = a.table[tid];
-    t.x |= 0x01010101u;
-    t.y |= 0x01010101u;
+    if (CB != QUIPB200_CB_D4) {      // E8P abs entries with the "+1/4" pre-applied; D4: the fp16 grid rows as they are
+      t.x |= 0x01010101u;
+      t.y |= 0x01010101u;
+    }
     reinterpret_cast<uint2*>(tab)[tid] = t;
   }
   tc_fence_before();
@@ -153,11 +157,19 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
     }
     __syncwarp();
   } else {
-    // ===== producers: thread -> (weight row, 4 of its 16 codes of the stage); activations: 16-byte chunks round-robin
+    // ===== producers: thread -> (weight row, 32 of its 128 weights of the stage = 4 swizzle chunks); activations: 16-byte
+    // chunks round-robin.  Packed bytes per thread per stage: 8 (E8P12: 4 codes, D4: 8 codes) or 16 (RVQ4B: 4 codes).
+    constexpr int CBYTES = (CB == QUIPB200_CB_E8P12RVQ4B) ? 16 : 8;
     const int wrow = tid >> 2, wq = tid & 3;
-    const unsigned char* wsrc = a.codes + (size_t)(n0 + wrow) * (a.K >> 2) + wq * 8;
+    const size_t row_bytes = (CB == QUIPB200_CB_E8P12RVQ4B) ? (size_t)(a.K >> 1) : (size_t)(a.K >> 2);
+    const unsigned char* wsrc = a.codes + (size_t)(n0 + wrow) * row_bytes + wq * CBYTES;
     const uint64_t pol = l2_evict_first_policy();
-    auto load_codes = [&](int it) -> uint2 { return ldg_stream_v2(wsrc + (size_t)(kb_begin + it) * 32, pol); };
+    auto load_codes = [&](int it) -> uint4 {
+      const unsigned char* p = wsrc + (size_t)(kb_begin + it) * (4 * CBYTES);
+      if (CB == QUIPB200_CB_E8P12RVQ4B) return ldg_stream_v4(p, pol);
+      const uint2 v = ldg_stream_v2(p, pol);
+      return make_uint4(v.x, v.y, 0u, 0u);
+    };
     auto issue_acts = [&](int it) {
       const int s = it % STAGES;
       const __half* xs = a.x + (size_t)(kb_begin + it) * UG_BK2;
@@ -168,7 +180,8 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
         cp_async16_zfill(sB + s * B_BYTES + h * B_SUB + tok * 128 + ((ch ^ (tok & 7)) << 4), src, ok ? 16u : 0u);
       }
     };
-    uint2 cur = make_uint2(0, 0);
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    const __half2 rs2 = __float2half2_rn(a.resid_scale);      // the reference's fp16 hfma2 operand (origin_order.cu:378)
     if (nit > 0) {
       cur = load_codes(0);
       issue_acts(0);
@@ -176,7 +189,7 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
     asm volatile("cp.async.commit_group;" ::: "memory");
     for (int it = 0; it < nit; it++) {
       const int s = it % STAGES;
-      uint2 nxt = make_uint2(0, 0);
+      uint4 nxt = make_uint4(0, 0, 0, 0);
       if (it + 1 < nit) {
         nxt = load_codes(it + 1);
         if (it + 1 >= STAGES) mbar_wait(bar_empty + 8 * ((it + 1) % STAGES), (uint32_t)(((it + 1) / STAGES - 1) & 1));
@@ -185,21 +198,37 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
       asm volatile("cp.async.commit_group;" ::: "memory");
       // weights of stage `it` -> slot s (free: empty[s] was waited on one iteration ago, or it < STAGES)
       {
-        const uint32_t w[2] = {cur.x, cur.y};
+        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
         unsigned char* arow = gbase + (size_t)s * A_BYTES + (wq >> 1) * A_SUB + wrow * 128;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const uint32_t code = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
-          const uint2 t1 = *reinterpret_cast<const uint2*>(tab + ((code >> 8) << 3));
-          const uint2 q = e8p_decode_q(t1, code);
-          __half2 e0, o0, e1, o1;
-          q4_to_half2(q.x, e0, o0);     // weights (0,1) = bytes (0,2); (2,3) = bytes (1,3)
-          q4_to_half2(q.y, e1, o1);
           uint4 v;
-          v.x = *reinterpret_cast<const uint32_t*>(&e0);
-          v.y = *reinterpret_cast<const uint32_t*>(&o0);
-          v.z = *reinterpret_cast<const uint32_t*>(&e1);
-          v.w = *reinterpret_cast<const uint32_t*>(&o1);
+          if (CB == QUIPB200_CB_D4) {            // two 1-byte codes -> 2 x 4 fp16 weights (table rows, natural order)
+            const uint32_t b0 = (w[j >> 1] >> ((j & 1) * 16)) & 0xffu, b1 = (w[j >> 1] >> ((j & 1) * 16 + 8)) & 0xffu;
+            const uint2 g0 = *reinterpret_cast<const uint2*>(tab + (b0 << 3)), g1 = *reinterpret_cast<const uint2*>(tab + (b1 << 3));
+            v = make_uint4(g0.x, g0.y, g1.x, g1.y);
+          } else {
+            const uint32_t code = (CB == QUIPB200_CB_E8P12RVQ4B) ? (w[j] >> 16) : ((w[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+            const uint2 t1 = *reinterpret_cast<const uint2*>(tab + ((code >> 8) << 3));
+            const uint2 q = e8p_decode_q(t1, code);
+            __half2 e0, o0, e1, o1;
+            q4_to_half2(q.x, e0, o0);     // weights (0,1) = bytes (0,2); (2,3) = bytes (1,3)
+            q4_to_half2(q.y, e1, o1);
+            if (CB == QUIPB200_CB_E8P12RVQ4B) {   // W = g[main] + fp16(scale) * g[resid], one fp16 fma rounding (e8p12_rvq4.py:23)
+              const uint32_t rc = w[j] & 0xffffu;
+              const uint2 t2 = *reinterpret_cast<const uint2*>(tab + ((rc >> 8) << 3));
+              const uint2 q2 = e8p_decode_q(t2, rc);
+              __half2 re0, ro0, re1, ro1;
+              q4_to_half2(q2.x, re0, ro0);
+              q4_to_half2(q2.y, re1, ro1);
+              e0 = __hfma2(rs2, re0, e0); o0 = __hfma2(rs2, ro0, o0);
+              e1 = __hfma2(rs2, re1, e1); o1 = __hfma2(rs2, ro1, o1);
+            }
+            v.x = *reinterpret_cast<const uint32_t*>(&e0);
+            v.y = *reinterpret_cast<const uint32_t*>(&o0);
+            v.z = *reinterpret_cast<const uint32_t*>(&e1);
+            v.w = *reinterpret_cast<const uint32_t*>(&o1);
+          }
           const int ch = (wq & 1) * 4 + j;
           *reinterpret_cast<uint4*>(arow + ((ch ^ (wrow & 7)) << 4)) = v;
         }
@@ -256,14 +285,21 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
   }
 }
 
-template <int NTOK, int STAGES>
+template <int CB, int NTOK, int STAGES>
 static int launch_umma(const UmmaArgs& a, dim3 grid, cudaStream_t st) {
   const size_t smem = (size_t)STAGES * 2 * (UG_BM * 128 + NTOK * 128) + 2048 + 8 * (2 * STAGES + 1) + 16 + 1024;
-  cudaError_t e = cudaFuncSetAttribute(e8p_umma_kernel<NTOK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(e8p_umma_kernel<CB, NTOK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  e8p_umma_kernel<NTOK, STAGES><<<grid, UG_THREADS2, smem, st>>>(a);
+  e8p_umma_kernel<CB, NTOK, STAGES><<<grid, UG_THREADS2, smem, st>>>(a);
   QB_LAUNCH_CHECK();
   return 0;
+}
+template <int CB>
+static int launch_umma_m(const UmmaArgs& a, dim3 grid, cudaStream_t st) {
+  if (a.M <= 32) return launch_umma<CB, 32, 4>(a, grid, st);
+  if (a.M <= 64) return launch_umma<CB, 64, 4>(a, grid, st);
+  if (a.M <= 128) return launch_umma<CB, 128, 3>(a, grid, st);
+  return launch_umma<CB, 256, 2>(a, grid, st);
 }
 
 }  // namespace qb
@@ -275,9 +311,11 @@ extern "C" size_t quipb200_e8p_mm_umma_workspace_bytes(int M, int N, int K) {
   return (size_t)N * UG_WS_LD * sizeof(float) + (size_t)(N / UG_BM + 1) * sizeof(unsigned int) + 256;
 }
 
-extern "C" int quipb200_e8p_mm_umma(const void* x, const void* qidxs, const void* grid, void* out, int M, int N, int K,
-                                    void* workspace, size_t ws_bytes, void* stream) {
+extern "C" int quipb200_mm_umma(int codebook, const void* x, const void* qidxs, const void* grid, float scale, void* out,
+                                int M, int N, int K, void* workspace, size_t ws_bytes, void* stream) {
   if (!x || !qidxs || !grid || !out) return QUIPB200_EINVAL;
+  if (codebook != QUIPB200_CB_E8P12 && codebook != QUIPB200_CB_E8P12RVQ4B && codebook != QUIPB200_CB_D4)
+    return QUIPB200_EUNSUPPORTED;
   if (M < 1 || M > 256 || N < UG_BM || N % UG_BM || K < UG_BK2 || K % UG_BK2) return QUIPB200_EUNSUPPORTED;
   if (!aligned16(x) || !aligned16(qidxs) || !aligned16(grid) || !aligned16(out)) return QUIPB200_EALIGN;
   const int sms = quipb200_sm_count();
@@ -287,6 +325,7 @@ extern "C" int quipb200_e8p_mm_umma(const void* x, const void* qidxs, const void
   while (ksplit < 16 && tiles * ksplit * 2 <= sms && nkb / (ksplit * 2) >= 4) ksplit *= 2;
   UmmaArgs a{};
   a.codes = (const unsigned char*)qidxs; a.x = (const __half*)x; a.table = (const uint2*)grid; a.out = (__half*)out;
+  a.resid_scale = scale;
   a.M = M; a.N = N; a.K = K;
   a.ksplit = ksplit;
   a.kb_per_split = (nkb + ksplit - 1) / ksplit;
@@ -298,8 +337,12 @@ extern "C" int quipb200_e8p_mm_umma(const void* x, const void* qidxs, const void
   }
   const dim3 grid_dim(tiles, ksplit);
   cudaStream_t st = (cudaStream_t)stream;
-  if (M <= 32) return launch_umma<32, 4>(a, grid_dim, st);
-  if (M <= 64) return launch_umma<64, 4>(a, grid_dim, st);
-  if (M <= 128) return launch_umma<128, 3>(a, grid_dim, st);
-  return launch_umma<256, 2>(a, grid_dim, st);
+  if (codebook == QUIPB200_CB_E8P12) return launch_umma_m<QUIPB200_CB_E8P12>(a, grid_dim, st);
+  if (codebook == QUIPB200_CB_E8P12RVQ4B) return launch_umma_m<QUIPB200_CB_E8P12RVQ4B>(a, grid_dim, st);
+  return launch_umma_m<QUIPB200_CB_D4>(a, grid_dim, st);
+}
+
+extern "C" int quipb200_e8p_mm_umma(const void* x, const void* qidxs, const void* grid, void* out, int M, int N, int K,
+                                    void* workspace, size_t ws_bytes, void* stream) {
+  return quipb200_mm_umma(QUIPB200_CB_E8P12, x, qidxs, grid, 0.f, out, M, N, K, workspace, ws_bytes, stream);
 }

@@ -99,8 +99,9 @@ class QuantLinear(nn.Module):
         """4 <= M <= 16 rows: rotations as one pass each + the tcgen05 mm (codes decoded once for all rows) beats the
         single fused launch, whose GEMV runs once per row."""
         from .register_lib import umma_preferred
-        return (self.codebook.id == "E8P12" and not self.per_channel and self._batched_fused_ok(x)
-                and umma_preferred(x.shape[0], self.q_out_features, self.q_in_features))
+        cb = CODEBOOK_ENUM.get(self.codebook.id)
+        return (self.codebook.id in ("E8P12", "E8P12RVQ4B", "D4") and not self.per_channel and self._batched_fused_ok(x)
+                and umma_preferred(x.shape[0], self.q_out_features, self.q_in_features, cb))
 
     def _hk_padded(self, side):
         """Zero-padded [Kp, Kp] coefficient matrix M[k_out][k_in] of the K x K block mix: hadK^T on the input side

@@ -182,23 +182,28 @@ def _mm_fused(codebook, x, Qidxs, grid, scale, K):
 _UMMA_WS = {}
 
 
-def umma_preferred(M: int, N: int, K: int) -> bool:
-    """Dispatch policy of the E8P12 mm (measured on B200, profiles/README.md): the tcgen05 kernel decodes every code once
-    for all rows, the integer-dp4a GEMV once per row (1 row: 10 us, 4 rows: 37 us, 16 rows: 121 us at 4096 x 4096), and
-    decompress + cuBLAS catches up from ~64 rows on."""
+def umma_preferred(M: int, N: int, K: int, codebook=None) -> bool:
+    """Dispatch policy of the codebook mm ops (measured on B200, profiles/README.md): the tcgen05 kernel decodes every code
+    once for all rows, the integer-dp4a GEMV once per row (1 row: 10 us, 4 rows: 37 us, 16 rows: 121 us at 4096 x 4096),
+    and decompress + cuBLAS catches up from ~64 rows on.  RVQ4B / D4: the reference's own small-M kernels (K2 / K3) stop at
+    32 / 24 rows; the tcgen05 route covers 4 .. 32 rows for them."""
     opt = _native.get_option("umma")
     if opt == 0 or N % 128 or K % 128 or M < 1 or M > 256:
         return False
+    if codebook is not None and codebook != _native.CB_E8P12:
+        return 4 <= M <= 32
     if opt == 1:
         return M > 16
     return 4 <= M <= 32 or (M <= 64 and N * K >= (32 << 20))
 
 
-def _mm_umma(x, Qidxs, grid, K):
-    """17 <= M <= 256, E8P12: in-kernel decode + tcgen05 GEMM (csrc/umma_gemm.cu); None if the shape is not covered."""
+def _mm_umma(x, Qidxs, grid, K, codebook=None, scale=0.0):
+    """1 <= M <= 256: in-kernel decode + tcgen05 GEMM (csrc/umma_gemm.cu); None if the shape is not covered."""
     M, N = x.shape[0], Qidxs.shape[0]
     if M < 1 or M > 256 or N % 128 or K % 128:
         return None
+    if codebook is None:
+        codebook = _native.CB_E8P12
     L = lib()
     # The kernel accumulates fp32 split-K partials and arrival tickets in the workspace and leaves it zero again; two
     # launches that overlap in time must not share one.  Launches on one stream are ordered, so the workspace is keyed by
@@ -216,11 +221,11 @@ def _mm_umma(x, Qidxs, grid, K):
     off = (-ws.data_ptr()) % 256
     out = torch.empty((M, N), dtype=torch.float16, device=x.device)
     with torch.cuda.device(x.device):
-        rc = L.quipb200_e8p_mm_umma(_ptr(x), _ptr(Qidxs), _ptr(grid), _ptr(out), M, N, K,
-                                    ctypes.c_void_p(ws.data_ptr() + off), ws.numel() - 256, _stream())
+        rc = L.quipb200_mm_umma(int(codebook), _ptr(x), _ptr(Qidxs), _ptr(grid), float(scale), _ptr(out), M, N, K,
+                                ctypes.c_void_p(ws.data_ptr() + off), ws.numel() - 256, _stream())
     if rc == _native.EUNSUPPORTED:
         return None
-    check(rc, "e8p_mm_umma")
+    check(rc, "mm_umma")
     return out
 
 
@@ -235,8 +240,8 @@ def _mm(codebook, name, x, Qidxs, grid, scale, K, dense):
     q = _contig(Qidxs)
     out = None
     M = xh.shape[0]
-    if codebook == _native.CB_E8P12 and umma_preferred(M, q.shape[0], K):
-        out = _mm_umma(xh, q, grid, K)        # tcgen05: decode once, all rows (the dp4a path re-decodes per row)
+    if codebook is not None and umma_preferred(M, q.shape[0], K, codebook):
+        out = _mm_umma(xh, q, grid, K, codebook, scale)   # tcgen05: decode once, all rows (the dp4a path re-decodes per row)
     if out is None and codebook is not None:
         out = _mm_fused(codebook, xh, q, grid, scale, K)
     if out is None and codebook == _native.CB_E8P12 and _native.get_option("umma") == 1:

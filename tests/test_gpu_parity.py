@@ -685,6 +685,41 @@ def test_e8p_mm_umma_matches_oracle(M, N, K):
     assert d <= 2.0 ** -9 * dense.float().abs().max().item() + 1e-6, d
 
 
+@pytest.mark.parametrize("M", [4, 8, 16, 23, 31, 32])
+@pytest.mark.parametrize("cb", ["E8P12RVQ4B", "D4"])
+@pytest.mark.parametrize("N,K", [(4096, 4096), (11008, 4096), (4096, 11008 + 128 - 11008 % 128)])
+def test_rvq4_d4_small_m_tcgen05_route(cb, M, N, K):
+    """4 <= M <= 32 for the RVQ4B / D4 mm ops (the reference's K2 / K3 range, origin_order.cu:337-385, :143-168): ONE launch
+    of the codebook-templated tcgen05 kernel (codes decoded once for all rows) against the oracle and the dense route."""
+    from quip_for_all_b200 import _native
+    from quip_for_all_b200.codebook.d4 import build_D4_CB
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    x = torch.randn(M, K, generator=g).half()
+    xd = x.to(DEV)
+    lc0 = _native.launch_count()
+    if cb == "D4":
+        q = torch.randint(0, 256, (N, K // 4), generator=g).to(torch.uint8)
+        grid = build_D4_CB().half().to(DEV)
+        call = lambda: torch.ops.quip_lib.d4_mm_origorder(xd, q.to(DEV), grid)
+        W = qo.decompress_d4(q.numpy())
+    else:
+        q = torch.randint(-2**31, 2**31, (N, K // 8), generator=g, dtype=torch.int64).to(torch.int32)
+        call = lambda: torch.ops.quip_lib.e8prvq4_mm_origorder(xd, q.to(DEV), _grid(), 1 / 3.45)
+        W = qo.decompress_e8prvq4(q.numpy(), 1 / 3.45)
+    out = call()
+    out2 = call()
+    assert _native.launch_count() - lc0 == 2                  # one launch of ours per call
+    _mm_check(out, x, W)
+    _mm_check(out2, x, W)
+    _native.set_option("umma", 0)
+    try:
+        dense = call()                                        # per-row dp4a GEMV / decompress + cuBLAS
+    finally:
+        _native.set_option("umma", 2)
+    d = (out.float() - dense.float()).abs().max().item()
+    assert d <= 2.0 ** -9 * dense.float().abs().max().item() + 1e-6, d
+
+
 def test_e8p_mm_umma_unsupported_shapes_take_dense_path():
     g = torch.Generator().manual_seed(5)
     q = torch.randint(-32768, 32768, (96, 32), generator=g).to(torch.int16)      # N % 128 != 0
