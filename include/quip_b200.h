@@ -120,8 +120,8 @@ int quipb200_rotate_batched(const void* x_f16, int64_t ldx, void* y_f16, int64_t
  *   workspace: >= quipb200_e8p_mm_umma_workspace_bytes(M_max, N, K) bytes, 256-byte aligned, zero-filled ONCE
  *   by the caller; the kernel returns it zeroed (split-K partial sums are cleared by the CTA that converts them).
  *   A workspace carries partial sums and arrival tickets of ONE launch at a time: launches that may overlap (different
- *   streams or threads) need separate workspaces (the Python binding keeps one per device, stream and N, and never
- *   creates one while a CUDA graph is being captured).
+ *   streams or threads) need separate workspaces (the Python binding keeps one per device, stream and N; a workspace
+ *   created during CUDA-graph capture belongs to the capture stream and its zero fill is part of the graph).
  * ------------------------------------------------------------------------------------------- */
 size_t quipb200_e8p_mm_umma_workspace_bytes(int M, int N, int K);
 /* The same kernel with the producers' decode templated on the codebook: QUIPB200_CB_E8P12 (origin_order.cu:388-555, K1),

@@ -207,14 +207,13 @@ def _mm_umma(x, Qidxs, grid, K, codebook=None, scale=0.0):
     L = lib()
     # The kernel accumulates fp32 split-K partials and arrival tickets in the workspace and leaves it zero again; two
     # launches that overlap in time must not share one.  Launches on one stream are ordered, so the workspace is keyed by
-    # (device, stream, N); it is zero-filled once, eagerly -- never while a CUDA graph is being captured (a captured
-    # fill would only run at replay and later eager calls would see stale tickets).
+    # (device, stream, N).  A workspace first needed while a CUDA graph is being captured belongs to the capture stream
+    # (torch captures on a stream of its own, so eager calls never share it): its zero fill is captured with it and
+    # re-runs at the head of every replay, which is harmless because the kernel leaves the workspace zeroed anyway.
     stream = torch.cuda.current_stream(x.device)
     key = (x.device.index, stream.cuda_stream, N)
     ws = _UMMA_WS.get(key)
     if ws is None:
-        if torch.cuda.is_current_stream_capturing():
-            return None          # first use of this (stream, N) inside a capture: take the dense route
         nbytes = L.quipb200_e8p_mm_umma_workspace_bytes(256, N, K)
         ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=x.device)
         _UMMA_WS[key] = ws
