@@ -194,7 +194,7 @@ def umma_preferred(M: int, N: int, K: int, codebook=None) -> bool:
         return 4 <= M <= 32
     if opt == 1:
         return M > 16
-    return 4 <= M <= 32 or (M <= 64 and N * K >= (32 << 20))
+    return 4 <= M <= 32 or (32 < M <= 64 and N * K >= (32 << 20))     # (1 .. 3 rows: the integer GEMV, one pass per row)
 
 
 def _mm_umma(x, Qidxs, grid, K, codebook=None, scale=0.0):
