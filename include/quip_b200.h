@@ -124,11 +124,15 @@ int quipb200_rotate_batched(const void* x_f16, int64_t ldx, void* y_f16, int64_t
  *   created during CUDA-graph capture belongs to the capture stream and its zero fill is part of the graph).
  * ------------------------------------------------------------------------------------------- */
 size_t quipb200_e8p_mm_umma_workspace_bytes(int M, int N, int K);
-/* The same kernel with the producers' decode templated on the codebook: QUIPB200_CB_E8P12 (origin_order.cu:388-555, K1),
- * QUIPB200_CB_E8P12RVQ4B (K2, :337-385, :698-743; `scale` = the residual scale, rounded to fp16 and applied with one fp16
- * fma as the reference does) and QUIPB200_CB_D4 (K3, :143-168, :557-602; grid = fp16 [256][4]).  Same workspace rules. */
-int quipb200_mm_umma(int codebook, const void* x_f16, const void* qidxs, const void* grid, float scale, void* out_f16,
-                     int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
+/* The same kernel with the producers' decode templated on the codebook, covering the reference's small-M mm kernels:
+ *   QUIPB200_CB_E8P12       K1  origin_order.cu:388-555
+ *   QUIPB200_CB_E8P12RVQ4B  K2  :337-385, :698-743   `scale` = residual scale, rounded to fp16, one fp16 fma (as the reference)
+ *   QUIPB200_CB_D4          K3  :143-168, :557-602   grid = fp16 [256][4]
+ *   QUIPB200_CB_E8P12RVQ3B  K4  :287-335, :650-696   grid2 = e81b residual table, int32[256]; `scale` as for RVQ4B
+ *   QUIPB200_CB_HI          K5  :170-206, :745-788   no table (grid may be NULL)
+ * grid2 is NULL except for RVQ3B.  Same shape and workspace rules as quipb200_e8p_mm_umma. */
+int quipb200_mm_umma(int codebook, const void* x_f16, const void* qidxs, const void* grid, const void* grid2, float scale,
+                     void* out_f16, int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
 int quipb200_e8p_mm_umma(const void* x_f16, const void* qidxs, const void* grid_packed_abs, void* out_f16,
                          int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
 

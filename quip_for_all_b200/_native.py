@@ -90,7 +90,7 @@ def lib():
     L.quipb200_e8p_mm_umma.restype = c_int
     L.quipb200_e8p_mm_umma.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, vp, c_size_t, vp]
     L.quipb200_mm_umma.restype = c_int
-    L.quipb200_mm_umma.argtypes = [c_int, vp, vp, vp, c_float, vp, c_int, c_int, c_int, vp, c_size_t, vp]
+    L.quipb200_mm_umma.argtypes = [c_int, vp, vp, vp, vp, c_float, vp, c_int, c_int, c_int, vp, c_size_t, vp]
     L.quipb200_rotate_batched.restype = c_int
     L.quipb200_rotate_batched.argtypes = [vp, c_int64, vp, c_int64, vp, vp, vp, vp, c_int, c_int, c_int, c_int, c_int,
                                           c_float, vp]

@@ -72,8 +72,9 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t sdst, const void* gsrc
 struct UmmaArgs {
   const unsigned char* codes;   // [N][K/8] int16 (E8P12) / int32 (E8P12RVQ4B) or [N][K/4] uint8 (D4)
   const __half* x;              // [M][K]
-  const uint2* table;           // E8P family: int64[256] abs table; D4: fp16 [256][4]
-  float resid_scale;            // E8P12RVQ4B
+  const uint2* table;           // E8P family: int64[256] abs table; D4: fp16 [256][4]; HI: unused
+  const uint32_t* table2;       // E8P12RVQ3B: e81b residual table, int32[256] (8 nibbles of 2 * v)
+  float resid_scale;            // E8P12RVQ4B / E8P12RVQ3B
   __half* out;                  // [M][N]
   float* ws;                    // [256][N] fp32 split-K partials (zero on entry, zero on exit)
   unsigned int* tickets;        // [N/128]
@@ -91,7 +92,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 // Warp-specialised: 16 producer warps fill the stage slots (no CTA-wide barrier in the main loop), warp 16 waits on
 // full[s], issues the 8 MMAs of the stage and commits to empty[s].
-// CB: the producers' decode (QUIPB200_CB_E8P12 / _E8P12RVQ4B / _D4); everything else is shared.
+// CB: the producers' decode (QUIPB200_CB_E8P12 / _E8P12RVQ4B / _D4 / _E8P12RVQ3B / _HI); everything else is shared.
 template <int CB, int NTOK, int STAGES>
 __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_constant__ UmmaArgs a) {
   extern __shared__ unsigned char smem_raw[];
@@ -101,10 +102,11 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
   const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle atoms need 1024-byte alignment
   unsigned char* gbase = smem_raw + (base - raw);
   const uint32_t sA = base, sB = base + STAGES * A_BYTES;
-  unsigned char* tab = gbase + STAGES * (A_BYTES + B_BYTES);    // 2 KB table
-  const uint32_t sbar = base + STAGES * (A_BYTES + B_BYTES) + 2048;   // full[STAGES], empty[STAGES], done
+  unsigned char* tab = gbase + STAGES * (A_BYTES + B_BYTES);    // 2 KB table + 1 KB residual table (RVQ3B)
+  const uint32_t* tab2 = reinterpret_cast<const uint32_t*>(tab + 2048);
+  const uint32_t sbar = base + STAGES * (A_BYTES + B_BYTES) + 3072;   // full[STAGES], empty[STAGES], done
   const uint32_t bar_full = sbar, bar_empty = sbar + 8 * STAGES, bar_done = sbar + 16 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + STAGES * (A_BYTES + B_BYTES) + 2048 + 8 * (2 * STAGES + 1));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + STAGES * (A_BYTES + B_BYTES) + 3072 + 8 * (2 * STAGES + 1));
   __shared__ int s_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -122,13 +124,14 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), NTOK);
-  if (tid < 256) {
+  if (tid < 256 && CB != QUIPB200_CB_HI) {
     uint2 t = a.table[tid];
     if (CB != QUIPB200_CB_D4) {      // E8P abs entries with the "+1/4" pre-applied; D4: the fp16 grid rows as they are
       t.x |= 0x01010101u;
       t.y |= 0x01010101u;
     }
     reinterpret_cast<uint2*>(tab)[tid] = t;
+    if (CB == QUIPB200_CB_E8P12RVQ3B) reinterpret_cast<uint32_t*>(tab + 2048)[tid] = a.table2[tid];
   }
   tc_fence_before();
   __syncthreads();
@@ -159,14 +162,19 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
   } else {
     // ===== producers: thread -> (weight row, 32 of its 128 weights of the stage = 4 swizzle chunks); activations: 16-byte
     // chunks round-robin.  Packed bytes per thread per stage: 8 (E8P12: 4 codes, D4: 8 codes) or 16 (RVQ4B: 4 codes).
-    constexpr int CBYTES = (CB == QUIPB200_CB_E8P12RVQ4B) ? 16 : 8;
+    // Packed bytes per thread per stage: 8 (E8P12 4 codes, D4 8 codes), 16 (RVQ4B 4 codes, HI 4 words), 12 (RVQ3B 4 codes).
+    constexpr int CBYTES = (CB == QUIPB200_CB_E8P12RVQ4B || CB == QUIPB200_CB_HI) ? 16 : (CB == QUIPB200_CB_E8P12RVQ3B ? 12 : 8);
     const int wrow = tid >> 2, wq = tid & 3;
-    const size_t row_bytes = (CB == QUIPB200_CB_E8P12RVQ4B) ? (size_t)(a.K >> 1) : (size_t)(a.K >> 2);
+    const size_t row_bytes = (size_t)(a.K >> 5) * CBYTES;            // CBYTES per 32 weights
     const unsigned char* wsrc = a.codes + (size_t)(n0 + wrow) * row_bytes + wq * CBYTES;
     const uint64_t pol = l2_evict_first_policy();
     auto load_codes = [&](int it) -> uint4 {
       const unsigned char* p = wsrc + (size_t)(kb_begin + it) * (4 * CBYTES);
-      if (CB == QUIPB200_CB_E8P12RVQ4B) return ldg_stream_v4(p, pol);
+      if (CBYTES == 16) return ldg_stream_v4(p, pol);
+      if (CBYTES == 12) {      // 4-byte aligned only (row pitch 3K/8)
+        const uint32_t* p4 = reinterpret_cast<const uint32_t*>(p);
+        return make_uint4(__ldg(p4), __ldg(p4 + 1), __ldg(p4 + 2), 0u);
+      }
       const uint2 v = ldg_stream_v2(p, pol);
       return make_uint4(v.x, v.y, 0u, 0u);
     };
@@ -203,7 +211,47 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           uint4 v;
-          if (CB == QUIPB200_CB_D4) {            // two 1-byte codes -> 2 x 4 fp16 weights (table rows, natural order)
+          if (CB == QUIPB200_CB_HI) {            // 8 nibbles of one word: w = nib - 7.5, elements (0,2,4,6,1,3,5,7) (hi.py:41-50)
+            uint32_t qa = w[j];
+            const uint32_t c0 = 0x64086408u;     // 1024 + 8 (+ 16 * nibble); the reference's constants (origin_order.cu:1028-1051)
+            const __half2 y16 = __float2half2_rn(1.0f / 16.0f), z16 = __float2half2_rn(-1024.0f / 16.0f - 8.0f);
+            uint32_t hw4[4];
+            hw4[0] = ((qa & 0x000f000fu) << 4) | c0;
+            hw4[1] = (qa & 0x00f000f0u) | c0;
+            qa >>= 8;
+            hw4[2] = ((qa & 0x000f000fu) << 4) | c0;
+            hw4[3] = (qa & 0x00f000f0u) | c0;
+            uint32_t o4[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const __half2 h = __hfma2(*reinterpret_cast<const __half2*>(&hw4[e]), y16, z16);
+              o4[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            v = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+          } else if (CB == QUIPB200_CB_E8P12RVQ3B) {   // byte triplets [resid, main lo, main hi] (e8p12_rvq3.py:97-107)
+            const uint32_t lo = w[(3 * j) >> 2], hi = w[((3 * j) >> 2) + 1 < 3 ? ((3 * j) >> 2) + 1 : 2];
+            const uint32_t c24 = __funnelshift_r(lo, hi, ((3 * j) & 3) * 8) & 0xffffffu;
+            const uint32_t rc = c24 & 0xffu, code = c24 >> 8;
+            const uint2 t1 = *reinterpret_cast<const uint2*>(tab + ((code >> 8) << 3));
+            const uint2 q = e8p_decode_q(t1, code);
+            __half2 e0, o0, e1, o1;
+            q4_to_half2(q.x, e0, o0);
+            q4_to_half2(q.y, e1, o1);
+            const uint32_t c = tab2[rc];          // 8 nibbles of 2 * v (two's complement), nibble j + 4 h <-> element 2 j + h
+            const __half2 adj = __float2half2_rn(-516.0f);
+            __half2 r4[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              uint32_t b = ((c >> (4 * e)) & 0x000f000fu) ^ 0x60086008u;      // 512 + (nib ^ 8) / 2 (origin_order.cu:323-327)
+              r4[e] = __hadd2(*reinterpret_cast<const __half2*>(&b), adj);
+            }
+            e0 = __hfma2(rs2, r4[0], e0); o0 = __hfma2(rs2, r4[1], o0);
+            e1 = __hfma2(rs2, r4[2], e1); o1 = __hfma2(rs2, r4[3], o1);
+            v.x = *reinterpret_cast<const uint32_t*>(&e0);
+            v.y = *reinterpret_cast<const uint32_t*>(&o0);
+            v.z = *reinterpret_cast<const uint32_t*>(&e1);
+            v.w = *reinterpret_cast<const uint32_t*>(&o1);
+          } else if (CB == QUIPB200_CB_D4) {            // two 1-byte codes -> 2 x 4 fp16 weights (table rows, natural order)
             const uint32_t b0 = (w[j >> 1] >> ((j & 1) * 16)) & 0xffu, b1 = (w[j >> 1] >> ((j & 1) * 16 + 8)) & 0xffu;
             const uint2 g0 = *reinterpret_cast<const uint2*>(tab + (b0 << 3)), g1 = *reinterpret_cast<const uint2*>(tab + (b1 << 3));
             v = make_uint4(g0.x, g0.y, g1.x, g1.y);
@@ -287,7 +335,7 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
 
 template <int CB, int NTOK, int STAGES>
 static int launch_umma(const UmmaArgs& a, dim3 grid, cudaStream_t st) {
-  const size_t smem = (size_t)STAGES * 2 * (UG_BM * 128 + NTOK * 128) + 2048 + 8 * (2 * STAGES + 1) + 16 + 1024;
+  const size_t smem = (size_t)STAGES * 2 * (UG_BM * 128 + NTOK * 128) + 3072 + 8 * (2 * STAGES + 1) + 16 + 1024;
   cudaError_t e = cudaFuncSetAttribute(e8p_umma_kernel<CB, NTOK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   e8p_umma_kernel<CB, NTOK, STAGES><<<grid, UG_THREADS2, smem, st>>>(a);
@@ -311,13 +359,14 @@ extern "C" size_t quipb200_e8p_mm_umma_workspace_bytes(int M, int N, int K) {
   return (size_t)N * UG_WS_LD * sizeof(float) + (size_t)(N / UG_BM + 1) * sizeof(unsigned int) + 256;
 }
 
-extern "C" int quipb200_mm_umma(int codebook, const void* x, const void* qidxs, const void* grid, float scale, void* out,
-                                int M, int N, int K, void* workspace, size_t ws_bytes, void* stream) {
-  if (!x || !qidxs || !grid || !out) return QUIPB200_EINVAL;
-  if (codebook != QUIPB200_CB_E8P12 && codebook != QUIPB200_CB_E8P12RVQ4B && codebook != QUIPB200_CB_D4)
-    return QUIPB200_EUNSUPPORTED;
+extern "C" int quipb200_mm_umma(int codebook, const void* x, const void* qidxs, const void* grid, const void* grid2, float scale,
+                                void* out, int M, int N, int K, void* workspace, size_t ws_bytes, void* stream) {
+  if (!x || !qidxs || !out) return QUIPB200_EINVAL;
+  if (codebook < QUIPB200_CB_E8P12 || codebook > QUIPB200_CB_HI) return QUIPB200_EUNSUPPORTED;
+  if (codebook != QUIPB200_CB_HI && !grid) return QUIPB200_EINVAL;
+  if (codebook == QUIPB200_CB_E8P12RVQ3B && !grid2) return QUIPB200_EINVAL;
   if (M < 1 || M > 256 || N < UG_BM || N % UG_BM || K < UG_BK2 || K % UG_BK2) return QUIPB200_EUNSUPPORTED;
-  if (!aligned16(x) || !aligned16(qidxs) || !aligned16(grid) || !aligned16(out)) return QUIPB200_EALIGN;
+  if (!aligned16(x) || !aligned16(qidxs) || !aligned16(grid) || !aligned16(out) || ((uintptr_t)grid2 & 3)) return QUIPB200_EALIGN;
   const int sms = quipb200_sm_count();
   if (sms < 1) return (int)cudaErrorNoDevice;
   const int tiles = N / UG_BM, nkb = K / UG_BK2;
@@ -325,6 +374,7 @@ extern "C" int quipb200_mm_umma(int codebook, const void* x, const void* qidxs, 
   while (ksplit < 16 && tiles * ksplit * 2 <= sms && nkb / (ksplit * 2) >= 4) ksplit *= 2;
   UmmaArgs a{};
   a.codes = (const unsigned char*)qidxs; a.x = (const __half*)x; a.table = (const uint2*)grid; a.out = (__half*)out;
+  a.table2 = (const uint32_t*)grid2;
   a.resid_scale = scale;
   a.M = M; a.N = N; a.K = K;
   a.ksplit = ksplit;
@@ -339,10 +389,12 @@ extern "C" int quipb200_mm_umma(int codebook, const void* x, const void* qidxs, 
   cudaStream_t st = (cudaStream_t)stream;
   if (codebook == QUIPB200_CB_E8P12) return launch_umma_m<QUIPB200_CB_E8P12>(a, grid_dim, st);
   if (codebook == QUIPB200_CB_E8P12RVQ4B) return launch_umma_m<QUIPB200_CB_E8P12RVQ4B>(a, grid_dim, st);
+  if (codebook == QUIPB200_CB_E8P12RVQ3B) return launch_umma_m<QUIPB200_CB_E8P12RVQ3B>(a, grid_dim, st);
+  if (codebook == QUIPB200_CB_HI) return launch_umma_m<QUIPB200_CB_HI>(a, grid_dim, st);
   return launch_umma_m<QUIPB200_CB_D4>(a, grid_dim, st);
 }
 
 extern "C" int quipb200_e8p_mm_umma(const void* x, const void* qidxs, const void* grid, void* out, int M, int N, int K,
                                     void* workspace, size_t ws_bytes, void* stream) {
-  return quipb200_mm_umma(QUIPB200_CB_E8P12, x, qidxs, grid, 0.f, out, M, N, K, workspace, ws_bytes, stream);
+  return quipb200_mm_umma(QUIPB200_CB_E8P12, x, qidxs, grid, nullptr, 0.f, out, M, N, K, workspace, ws_bytes, stream);
 }

@@ -190,6 +190,8 @@ def umma_preferred(M: int, N: int, K: int, codebook=None) -> bool:
     opt = _native.get_option("umma")
     if opt == 0 or N % 128 or K % 128 or M < 1 or M > 256:
         return False
+    if codebook in (_native.CB_E8P12RVQ3B, _native.CB_HI):
+        return M <= 32           # no integer-GEMV route for these: the tcgen05 kernel serves the whole K4 / K5 range
     if codebook is not None and codebook != _native.CB_E8P12:
         return 4 <= M <= 32
     if opt == 1:
@@ -197,7 +199,7 @@ def umma_preferred(M: int, N: int, K: int, codebook=None) -> bool:
     return 4 <= M <= 32 or (32 < M <= 64 and N * K >= (32 << 20))     # (1 .. 3 rows: the integer GEMV, one pass per row)
 
 
-def _mm_umma(x, Qidxs, grid, K, codebook=None, scale=0.0):
+def _mm_umma(x, Qidxs, grid, K, codebook=None, scale=0.0, grid2=None):
     """1 <= M <= 256: in-kernel decode + tcgen05 GEMM (csrc/umma_gemm.cu); None if the shape is not covered."""
     M, N = x.shape[0], Qidxs.shape[0]
     if M < 1 or M > 256 or N % 128 or K % 128:
@@ -220,7 +222,7 @@ def _mm_umma(x, Qidxs, grid, K, codebook=None, scale=0.0):
     off = (-ws.data_ptr()) % 256
     out = torch.empty((M, N), dtype=torch.float16, device=x.device)
     with torch.cuda.device(x.device):
-        rc = L.quipb200_mm_umma(int(codebook), _ptr(x), _ptr(Qidxs), _ptr(grid), float(scale), _ptr(out), M, N, K,
+        rc = L.quipb200_mm_umma(int(codebook), _ptr(x), _ptr(Qidxs), _ptr(grid), _ptr(grid2), float(scale), _ptr(out), M, N, K,
                                 ctypes.c_void_p(ws.data_ptr() + off), ws.numel() - 256, _stream())
     if rc == _native.EUNSUPPORTED:
         return None
@@ -228,7 +230,7 @@ def _mm_umma(x, Qidxs, grid, K, codebook=None, scale=0.0):
     return out
 
 
-def _mm(codebook, name, x, Qidxs, grid, scale, K, dense):
+def _mm(codebook, name, x, Qidxs, grid, scale, K, dense, grid2=None):
     if x.dim() != 2 or Qidxs.dim() != 2:
         raise RuntimeError(f"quip_lib::{name}: x and Qidxs must be 2-D")
     if x.shape[1] != K:
@@ -240,8 +242,8 @@ def _mm(codebook, name, x, Qidxs, grid, scale, K, dense):
     out = None
     M = xh.shape[0]
     if codebook is not None and umma_preferred(M, q.shape[0], K, codebook):
-        out = _mm_umma(xh, q, grid, K, codebook, scale)   # tcgen05: decode once, all rows (the dp4a path re-decodes per row)
-    if out is None and codebook is not None:
+        out = _mm_umma(xh, q, grid, K, codebook, scale, grid2)   # tcgen05: decode once, all rows (the dp4a path re-decodes per row)
+    if out is None and codebook in (_native.CB_E8P12, _native.CB_E8P12RVQ4B, _native.CB_D4):
         out = _mm_fused(codebook, xh, q, grid, scale, K)
     if out is None and codebook == _native.CB_E8P12 and _native.get_option("umma") == 1:
         out = _mm_umma(xh, q, grid, K)
@@ -268,12 +270,12 @@ def _d4_mm(x: Tensor, Qidxs: Tensor, grid: Tensor) -> Tensor:
 
 
 def _e8prvq3_mm(x: Tensor, Qidxs: Tensor, grid: Tensor, grid2: Tensor, scale: float) -> Tensor:
-    return _mm(None, "e8prvq3_mm_origorder", x, Qidxs, grid, scale, Qidxs.shape[1] * 32 // 3,
-               lambda q: _decompress_e8prvq3(q, grid, grid2, scale))
+    return _mm(_native.CB_E8P12RVQ3B, "e8prvq3_mm_origorder", x, Qidxs, _contig(grid), scale, Qidxs.shape[1] * 32 // 3,
+               lambda q: _decompress_e8prvq3(q, grid, grid2, scale), grid2=_contig(grid2))
 
 
 def _hi_mm(x: Tensor, Qidxs: Tensor) -> Tensor:
-    return _mm(None, "hi_mm_origorder", x, Qidxs, None, 0.0, Qidxs.shape[1] * 8, _decompress_hi)
+    return _mm(_native.CB_HI, "hi_mm_origorder", x, Qidxs, None, 0.0, Qidxs.shape[1] * 8, _decompress_hi)
 
 
 def _fake_mm(x, Qidxs, *a):

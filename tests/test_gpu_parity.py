@@ -186,6 +186,39 @@ def test_rvq3_and_hi_mm_dense_path():
     _mm_check(out, x, qo.decompress_hi(qh.numpy()), slack=2.0)
 
 
+@pytest.mark.parametrize("M", [1, 3, 8, 17, 31, 32, 40])
+@pytest.mark.parametrize("N,K", [(128, 128), (4096, 4096), (1408, 1152)])
+def test_rvq3_and_hi_mm_tcgen05_route(M, N, K):
+    """K4 / K5 replacements (origin_order.cu:287-335 / :170-206 with hosts :650-696 / :745-788): for M <= 32 the RVQ3B and HI
+    mm ops are ONE launch of the codebook-templated tcgen05 kernel (3-byte codes + nibble residual table with one fp16
+    fma; 4-bit scalar codes); above that the reference's own route, decompress + GEMM.  Against the oracle's dequantised
+    weights (bit-exact on their own, test_decompress_rvq4_d4_rvq3_hi_bit_exact)."""
+    from quip_for_all_b200 import _native
+    from quip_for_all_b200.codebook.e8p12_rvq3 import get_e81bgrid, pack_e81b
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).half()
+    xd = x.to(DEV)
+    e81b = pack_e81b(get_e81bgrid()).to(DEV)
+    q3 = torch.randint(-2**31, 2**31, (N, 3 * K // 32), generator=g, dtype=torch.int64).to(torch.int32)
+    qh = torch.randint(-2**31, 2**31, (N, K // 8), generator=g, dtype=torch.int64).to(torch.int32)
+    lc0 = _native.launch_count()
+    o3 = torch.ops.quip_lib.e8prvq3_mm_origorder(xd, q3.to(DEV), _grid(), e81b, 1 / 2.04)
+    oh = torch.ops.quip_lib.hi_mm_origorder(xd, qh.to(DEV))
+    n_launch = _native.launch_count() - lc0
+    assert n_launch == (2 if M <= 32 else 2)      # M <= 32: one tcgen05 launch each; above: one decompress launch each (+ cuBLAS)
+    _mm_check(o3, x, qo.decompress_e8prvq3(q3.numpy(), 1 / 2.04))
+    _mm_check(oh, x, qo.decompress_hi(qh.numpy()))
+    if M <= 32:        # and against the dense route on the same device
+        _native.set_option("umma", 0)
+        try:
+            d3 = torch.ops.quip_lib.e8prvq3_mm_origorder(xd, q3.to(DEV), _grid(), e81b, 1 / 2.04)
+            dh = torch.ops.quip_lib.hi_mm_origorder(xd, qh.to(DEV))
+        finally:
+            _native.set_option("umma", 2)
+        for a_, b_ in ((o3, d3), (oh, dh)):
+            assert (a_.float() - b_.float()).abs().max().item() <= 2.0 ** -9 * b_.float().abs().max().item() + 1e-6
+
+
 # ------------------------------------------------------------------------------------------------
 # fused QuantLinear.forward
 # ------------------------------------------------------------------------------------------------
