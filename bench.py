@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--no-kernel-bench", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-hf-dropin", action="store_true")
+    ap.add_argument("--no-70b", action="store_true", help="N = 1: skip the single-GPU Llama-2-70B leg (the base of the N > 1 scaling)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--engine", default="auto", choices=["auto", "persistent", "grouped"],
                     help="decode engine: one persistent whole-step kernel, or one launch per linear group")
@@ -410,6 +411,39 @@ def hf_dropin_bench(model, torch, prompt, steps, warmup):
         return {"unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
 
 
+def single_gpu_70b(a, torch, dev, peak):
+    """BASELINE config 5 on ONE GPU (17.1 GB of packed codes fit): the N = 1 point of the 70B layer-pipeline scaling that
+    `--gpus N` (N > 1) measures.  Same engine as a pipeline stage (grouped launches: the persistent kernel does not cover
+    hidden 8192 / 7 x 4096 blocks), CUDA-graph replay, CUDA events."""
+    try:
+        from quip_for_all_b200.modeling import LlamaDecodeEngine, make_random_quantized_llama, quantized_bytes
+        steps, warm = min(a.steps, 48), 4
+        model = make_random_quantized_llama("llama2-70b", a.codebook, seed=0, device=dev)
+        code_bytes = quantized_bytes(model)
+        eng = LlamaDecodeEngine(model, max_cache_len=a.prompt_len + 2 * (steps + warm) + 16, use_cuda_graph=not a.no_graph)
+        g = torch.Generator().manual_seed(0)
+        eng.prefill(torch.randint(0, model.config.vocab_size, (1, a.prompt_len), generator=g).to(dev))
+        eng.capture()
+        for _ in range(warm):
+            eng.step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            eng.step()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out = {"workload": f"llama2-70b {a.codebook} bs=1 greedy decode on one GPU, random-init packed weights",
+               "value": 1000.0 / ms, "unit": "tokens/s", "ms_per_step": ms, "steps": steps,
+               "engine": "persistent whole-step kernel" if eng.persistent is not None else "grouped launches (6 per decoder layer)",
+               "packed_code_bytes_per_token": code_bytes, "frac_of_hbm_roofline": (1000.0 / ms) * code_bytes / (peak * 1e9)}
+        del eng, model
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -512,6 +546,11 @@ def run_ours(a):
         line["hf_dropin"] = hf_dropin_bench(model, torch, prompt.to(dev), min(a.steps, 64), 4)
     if not a.no_ref_cuda:
         line["ref_cuda"] = ref_cuda_bench(model, torch)
+    if not a.no_70b and a.model == "llama2-7b":
+        del eng
+        model = None
+        torch.cuda.empty_cache()
+        line["llama2_70b_1gpu"] = single_gpu_70b(a, torch, dev, peak)
     if not a.no_cpu_baseline:
         mname = a.model if a.model in LLAMA_LINEARS else "llama2-7b"
         n_run, _ = _cpu_layers_for_budget(mname, 3, 1, budget_s=20.0)     # ~10-30 s of CPU work

@@ -68,6 +68,7 @@ struct DsParams {
   int flags;             // tuning / A-B switches (option "ds_flags")
   long long* dbg;        // optional [64] clock stamps of one CTA (tools/ds_timeline.py)
   int dbg_cta;
+  int dbg_layer;         // which layer's stage stamps are recorded (default 1)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1055,7 +1056,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
   stg.su = stg.sv + 32768;
   long long* dbg = (p.dbg && bid == p.dbg_cta && tid == 0) ? p.dbg : nullptr;
 #define DS_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
-#define DS_ST(i) do { if (dbg && l == 1) dbg[i] = clock64(); } while (0)
+#define DS_ST(i) do { if (dbg && l == p.dbg_layer) dbg[i] = clock64(); } while (0)
   DS_STAMP(0);
 
   // layer descriptors: two slots in shared memory, layer l+1 is fetched (cp.async) while layer l runs
@@ -1520,7 +1521,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             stg_vec(stg.su, reinterpret_cast<const __half*>(L.SU), L.in_features, tid);
           }
           const uint4 oct = out_side_load(p.ws.acc[SL_O], warp, lane);
-          out_side_m(Lp, oct, true, stg, hfrag, XS, warp, lane, f, (dbg && l == 1) ? dbg : nullptr);
+          out_side_m(Lp, oct, true, stg, hfrag, XS, warp, lane, f, (dbg && l == p.dbg_layer) ? dbg : nullptr);
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             const __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
@@ -1578,7 +1579,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         float xs;
         if (L.K_left > 1) {
           xs = stage_e_blocks(Ly.gate, Ly.up, L, p.ws.acc[SL_G], p.ws.acc[SL_U], reinterpret_cast<const __half*>(Ly.mlp_hk), bb,
-                              hfrag, rb.fred, xq, tid, !(p.flags & 1), (dbg && l == 1) ? dbg : nullptr);
+                              hfrag, rb.fred, xq, tid, !(p.flags & 1), (dbg && l == p.dbg_layer) ? dbg : nullptr);
         } else {
           float g[8], u[8];
           {
@@ -1833,6 +1834,7 @@ static int ds_layout(const quipb200_decode_plan_t* P, const quipb200_decode_laye
 
 long long* g_ds_dbg = nullptr;
 int g_ds_dbg_cta = 0;
+int g_ds_dbg_layer = 1;
 
 }  // namespace qb
 
@@ -1850,7 +1852,8 @@ extern "C" int quipb200_decode_step_debug(void* device_int64_buffer) {
 }
 
 extern "C" int quipb200_decode_step_debug_cta(int cta) {
-  g_ds_dbg_cta = cta < 0 ? 0 : cta;
+  g_ds_dbg_cta = cta < 0 ? 0 : (cta & 0xffff);
+  g_ds_dbg_layer = cta < 0 ? 1 : ((cta >> 16) ? (cta >> 16) - 1 : 1);      // bits 16..: layer + 1 (0 = default layer 1)
   return 0;
 }
 
@@ -1910,6 +1913,7 @@ extern "C" int quipb200_decode_step(const quipb200_decode_plan_t* plan, const qu
   p.flags = g_ds_flags;
   p.dbg = g_ds_dbg;
   p.dbg_cta = g_ds_dbg_cta;
+  p.dbg_layer = g_ds_dbg_layer;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(sms);
   cfg.blockDim = dim3(DS_THREADS);

@@ -13,7 +13,7 @@ from quip_for_all_b200.modeling import LlamaDecodeEngine, llama_config, make_ran
 
 nl = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 ctx = int(sys.argv[2]) if len(sys.argv) > 2 else 384
-cta = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+cta = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # cta | (layer + 1) << 16 selects the stamped layer
 for kv in sys.argv[4:]:
     k, v = kv.split("=")
     _native.set_option(k, int(v))

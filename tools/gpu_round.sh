@@ -9,10 +9,10 @@ echo "== smoke" ; timeout 600 python -c "import __graft_entry__ as g; g.smoke()"
 echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q --maxfail=3 --timeout 90 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
 if [ "${SKIP_LAYER:-0}" != "1" ]; then echo "== layer bench"; timeout 600 python tools/layer_bench.py E8P12 1 2>&1 | tail -9 | cut -c1-400; fi
 echo "== bench"; timeout 900 python bench.py --steps ${BENCH_STEPS:-256} --warmup 16 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-echo "== bench grouped"; timeout 900 python bench.py --steps 128 --warmup 8 --engine grouped --no-cpu-baseline --no-ref-cuda > gpurun_out/bench_grouped.json 2>> gpurun_out/bench.err; cut -c1-300 gpurun_out/bench_grouped.json
+echo "== bench grouped"; timeout 900 python bench.py --steps 128 --warmup 8 --engine grouped --no-cpu-baseline --no-ref-cuda --no-hf-dropin --no-70b > gpurun_out/bench_grouped.json 2>> gpurun_out/bench.err; cut -c1-300 gpurun_out/bench_grouped.json
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference.json 2>> gpurun_out/bench.err; cut -c1-400 gpurun_out/bench_reference.json
 if [ "${SKIP_NCU:-0}" != "1" ]; then
-NCUARGS="--steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-kernel-bench --no-ref-cuda --prompt-len 8"
+NCUARGS="--steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-kernel-bench --no-ref-cuda --no-hf-dropin --no-70b --prompt-len 8"
 echo "== ncu launch list"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py $NCUARGS > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
 echo "== ncu full decode_step"; timeout 1200 ncu --set full --clock-control none --import-source on -k regex:decode_step -s 4 -c 1 -f -o gpurun_out/decode_step_full python bench.py $NCUARGS > gpurun_out/ncu_ds.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncu_ds.log
 if [ "${SKIP_UMMA_NCU:-0}" != "1" ]; then
