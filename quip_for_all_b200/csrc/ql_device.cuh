@@ -731,6 +731,52 @@ __device__ __forceinline__ void e8p_dot(uint32_t absoff, uint32_t sgn, const uns
   aP += (int)par * xsum;          // "- 2 per byte when parity odd" folded out: sum_j x_j
 }
 
+// ---------------------------------------------------------------------------------------------
+// Replicated lookup tables for the decode (the scheme of decode_step.cu, see the comment there): row i (256 bytes) =
+// [abs entry i x 16 copies][sign-mask entry of sign byte i x 16 copies] (D4: [int8x4 entry i x 32 copies][unused]); a
+// lane reads its own copy, the address is one PRMT on the packed word, the LDS.64 is conflict-free, and
+// table ^ mask is the decoded int8 x 8 word pair (parity shift folded into the mask as ^0x02).
+// ---------------------------------------------------------------------------------------------
+constexpr int LUT_TAB_BYTES = 65536;
+__device__ __forceinline__ uint2 lut_sign_mask(uint32_t s8) {
+  const uint32_t par = __popc(s8) & 1u;
+  const uint32_t s = s8 ^ par;
+  uint2 m;
+  m.x = (prmt(s * 0x08040201u, 0u, 0xba98u) & 0xfcfcfcfcu) | (par * 0x02020202u);
+  m.y = (prmt(s * 0x80402010u, 0u, 0xba98u) & 0xfcfcfcfcu) | (par * 0x02020202u);
+  return m;
+}
+template <int CB>
+__device__ __forceinline__ void lut_build_tables(unsigned char* tab, const void* grid, int tid, int nt) {
+  for (int e = tid; e < 256 * 32; e += nt) {
+    const int i = e >> 5, c = e & 31;
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(grid) + i);
+    if (CB == QUIPB200_CB_D4) {     // fp16 [4] -> int8 (units of 1/2), byte order (0,2,1,3) as the activation records
+      const __half2 h01 = *reinterpret_cast<const __half2*>(&t.x), h23 = *reinterpret_cast<const __half2*>(&t.y);
+      const int v0 = __float2int_rn(__low2float(h01) * 2.0f) & 0xff, v1 = __float2int_rn(__high2float(h01) * 2.0f) & 0xff;
+      const int v2 = __float2int_rn(__low2float(h23) * 2.0f) & 0xff, v3 = __float2int_rn(__high2float(h23) * 2.0f) & 0xff;
+      reinterpret_cast<uint32_t*>(tab)[i * 64 + c] = (uint32_t)v0 | ((uint32_t)v2 << 8) | ((uint32_t)v1 << 16) | ((uint32_t)v3 << 24);
+    } else {
+      uint2 v;
+      if (c < 16) v = make_uint2(t.x | 0x01010101u, t.y | 0x01010101u);
+      else v = lut_sign_mask((uint32_t)i);
+      reinterpret_cast<uint2*>(tab)[e] = v;
+    }
+  }
+}
+// one E8P code (index bytes AB / SB of packed word w) against one x segment: hi and lo activation planes
+template <int AB, int SB>
+__device__ __forceinline__ void lut_e8p_dot(uint32_t w, const unsigned char* tab, uint32_t offA, uint32_t offS,
+                                            const uint32_t (&xs)[4], int& aH, int& aL) {
+  const uint2 t = *reinterpret_cast<const uint2*>(tab + prmt(w, offA, 0x5504u | (AB << 4)));
+  const uint2 m = *reinterpret_cast<const uint2*>(tab + prmt(w, offS, 0x5504u | (SB << 4)));
+  const uint32_t vx = t.x ^ m.x, vy = t.y ^ m.y;
+  aH = dp4a_ss(vx, xs[0], aH);
+  aH = dp4a_ss(vy, xs[1], aH);
+  aL = dp4a_su(vx, xs[2], aL);   // signed weights x unsigned low bytes
+  aL = dp4a_su(vy, xs[3], aL);
+}
+
 // both 16-bit codes of a 32-bit word
 __device__ __forceinline__ void e8p_dot2(uint32_t w, const unsigned char* tab, const uint32_t (&x0)[4], int s0,
                                          const uint32_t (&x1)[4], int s1, int& aH, int& aL, int& aP) {

@@ -28,7 +28,7 @@ namespace qb {
 // ---------------------------------------------------------------------------------------------
 // options (bench / tests)
 // ---------------------------------------------------------------------------------------------
-int g_opt_table_repl = 1;    // kept for set_option compatibility; the plain 2 KB table is used
+int g_opt_table_repl = 16;   // 16: replicated lookup tables (64 KB) when they fit; 1: always the plain 2 KB table + computed signs
 int g_opt_gemv_warps = 0;    // 0: auto (16)
 int g_opt_gemv_ctas_per_sm = 1;
 int g_opt_stage_mask = 7;    // bench only: bit0 prologue, bit1 gemv, bit2 epilogue
@@ -59,14 +59,16 @@ __global__ void __launch_bounds__(PRO_THREADS) ql_epilogue_kernel(EpilogueArgs a
   epilogue_body<false>(a, smem_raw, blockIdx.x, a.xscale[blockIdx.x], threadIdx.x, PRO_THREADS);
 }
 
-template <int CB, bool LEAN, bool LEAN_EPI>
+// LUT: the decode uses the replicated abs + sign-mask tables (64 KB, ql_device.cuh) instead of the 2 KB table + computed
+// signs: 10 instead of 21 instructions per code; chosen by the host when the shared memory is there (every Llama shape).
+template <int CB, bool LEAN, bool LEAN_EPI, bool LUT>
 __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const __grid_constant__ GroupArgs ga) {
   using T = CbTraits<CB>;
   constexpr int UNROLL = GEMV_UNROLL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // [table][red: rows_per_cta * C * ACCS ints][x records][rotation workspace]
   unsigned char* tab = smem_raw;
-  int* red = reinterpret_cast<int*>(smem_raw + T::TAB_BYTES);
+  int* red = reinterpret_cast<int*>(smem_raw + (LUT ? LUT_TAB_BYTES : T::TAB_BYTES));
   __shared__ float s_xscale;
   __shared__ int s_last;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
 
   // ---- table entry for this thread: issue the load now, park it in shared memory after phase 1 ----
   uint2 tabv = make_uint2(0, 0);
-  if (tid < 256) tabv = reinterpret_cast<const uint2*>(a.table)[tid];   // E8P: int8x8 entry; D4: 4 x fp16
+  if (!LUT && tid < 256) tabv = reinterpret_cast<const uint2*>(a.table)[tid];   // E8P: int8x8 entry; D4: 4 x fp16
 
   QB_STAMP(1);
   // everything above read only weights; from here on we consume what earlier kernels produced
@@ -139,7 +141,9 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
     xq = a.pro.xq + (size_t)m * a.nseg;
     xscale = a.pro.xscale[m];
   }
-  if (tid < 256) {
+  if (LUT) {
+    lut_build_tables<CB>(tab, a.table, tid, nt);
+  } else if (tid < 256) {
     if (CB == QUIPB200_CB_D4) {
       // fp16 [4] -> int8 (units of 1/2), byte order (0,2,1,3) to match perm_0213'd activations
       const __half2 h01 = *reinterpret_cast<const __half2*>(&tabv.x), h23 = *reinterpret_cast<const __half2*>(&tabv.y);
@@ -175,6 +179,7 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
     const bool lane_valid = seg0 < a.nseg;   // row pitch is a multiple of 16 B => all-or-nothing
     uint32_t xs[T::SEGS][4];
     int xsum[T::SEGS];
+    const uint32_t offA = (CB == QUIPB200_CB_D4) ? (uint32_t)lane * 4u : (uint32_t)(lane & 15) * 8u, offS = 128u + offA;
 #pragma unroll
     for (int sgi = 0; sgi < T::SEGS; sgi++) {
       uint4 r = make_uint4(0, 0, 0, 0);
@@ -183,9 +188,12 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
       xs[sgi][1] = r.y;
       xs[sgi][2] = r.z;
       xs[sgi][3] = r.w;
-      const int sh = dp4a_ss(r.x, 0x01010101u, dp4a_ss(r.y, 0x01010101u, 0));
-      const int sl = dp4a_su(0x01010101u, r.z, dp4a_su(0x01010101u, r.w, 0));
-      xsum[sgi] = sh * 256 + sl;
+      xsum[sgi] = 0;
+      if (!LUT) {      // (the table path folds the parity shift into the sign mask: no sum(x) term)
+        const int sh = dp4a_ss(r.x, 0x01010101u, dp4a_ss(r.y, 0x01010101u, 0));
+        const int sl = dp4a_su(0x01010101u, r.z, dp4a_su(0x01010101u, r.w, 0));
+        xsum[sgi] = sh * 256 + sl;
+      }
     }
     const unsigned char* colp = a.qidxs + (size_t)(chunk * 32 + lane) * 16 + (size_t)row_begin * a.row_bytes;
     if (first_unit) { QB_STAMP(4); first_unit = false; }
@@ -214,16 +222,26 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
             int cH = 0, cL = 0, cP = 0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-              e8p_dot((w[i] >> 5) & 0x7f8u, w[i] & 0xffu, tab, xs[2 * i], xsum[2 * i], aH, aL, aP);
-              e8p_dot((w[i] >> 21) & 0x7f8u, __byte_perm(w[i], 0, 0x4442), tab, xs[2 * i + 1], xsum[2 * i + 1], cH, cL, cP);
+              if (LUT) {
+                lut_e8p_dot<1, 0>(w[i], tab, offA, offS, xs[2 * i], aH, aL);
+                lut_e8p_dot<3, 2>(w[i], tab, offA, offS, xs[2 * i + 1], cH, cL);
+              } else {
+                e8p_dot((w[i] >> 5) & 0x7f8u, w[i] & 0xffu, tab, xs[2 * i], xsum[2 * i], aH, aL, aP);
+                e8p_dot((w[i] >> 21) & 0x7f8u, __byte_perm(w[i], 0, 0x4442), tab, xs[2 * i + 1], xsum[2 * i + 1], cH, cL, cP);
+              }
             }
             aH += cH; aL += cL; aP += cP;
           } else if (CB == QUIPB200_CB_E8P12RVQ4B) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
               // main code = hi16, residual code = lo16, same x segment
-              e8p_dot((w[i] >> 21) & 0x7f8u, __byte_perm(w[i], 0, 0x4442), tab, xs[i], xsum[i], aH, aL, aP);
-              e8p_dot((w[i] >> 5) & 0x7f8u, w[i] & 0xffu, tab, xs[i], xsum[i], bH, bL, bP);
+              if (LUT) {
+                lut_e8p_dot<3, 2>(w[i], tab, offA, offS, xs[i], aH, aL);
+                lut_e8p_dot<1, 0>(w[i], tab, offA, offS, xs[i], bH, bL);
+              } else {
+                e8p_dot((w[i] >> 21) & 0x7f8u, __byte_perm(w[i], 0, 0x4442), tab, xs[i], xsum[i], aH, aL, aP);
+                e8p_dot((w[i] >> 5) & 0x7f8u, w[i] & 0xffu, tab, xs[i], xsum[i], bH, bL, bP);
+              }
             }
           } else {  // D4: byte c -> 4 weights; two codes per 8-element segment
             const uint32_t* t4 = reinterpret_cast<const uint32_t*>(tab);
@@ -231,7 +249,8 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
             for (int i = 0; i < 4; i++) {
 #pragma unroll
               for (int b = 0; b < 4; b++) {
-                const uint32_t v = t4[(w[i] >> (8 * b)) & 0xffu];
+                const uint32_t v = LUT ? *reinterpret_cast<const uint32_t*>(tab + prmt(w[i], offA, 0x5504u | (b << 4)))
+                                       : t4[(w[i] >> (8 * b)) & 0xffu];
                 const int sgi = i * 2 + (b >> 1), half = b & 1;
                 aH = dp4a_ss(v, xs[sgi][half], aH);
                 aL = dp4a_su(v, xs[sgi][2 + half], aL);
@@ -408,7 +427,8 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
   int Gtot = sms * (g_opt_gemv_ctas_per_sm > 0 ? g_opt_gemv_ctas_per_sm : 1);
   int cta = 0;
   size_t smem = 0;
-  bool any_unfused_pro = false, any_unfused_epi = false;
+  bool any_unfused_pro = false, any_unfused_epi = false, lut_fits = true;
+  uint32_t xq_rel[3] = {0, 0, 0}, rot_rel[3] = {0, 0, 0};
   for (int j = 0; j < n; j++) {
     Member& mj = mem[j];
     const bool two = plan[j].accs == 2;
@@ -448,6 +468,9 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
       else return QUIPB200_EUNSUPPORTED;
     }
     if (need > smem) smem = need;
+    if (need - plan[j].tab_bytes + LUT_TAB_BYTES > SMEM_LIMIT) lut_fits = false;   // same fusion choices must still fit
+    xq_rel[j] = (uint32_t)red_bytes;
+    rot_rel[j] = (uint32_t)(red_bytes + (fuse_pro ? xq_bytes : 0));
     any_unfused_pro |= !fuse_pro;
     any_unfused_epi |= !fuse_epi;
 
@@ -457,8 +480,6 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
     g.rows_base = mj.N / G; g.rows_rem = mj.N % G;
     g.fuse_pro = fuse_pro ? 1 : 0; g.fuse_epi = fuse_epi ? 1 : 0;
     g.pro = mj.pa; g.epi = mj.ea;
-    g.xq_off = (uint32_t)(plan[j].tab_bytes + red_bytes);
-    g.rot_off = (uint32_t)(plan[j].tab_bytes + red_bytes + (fuse_pro ? xq_bytes : 0));
     g.counters = nullptr;
     if (fuse_epi) {
       unsigned int* counters = nullptr;
@@ -468,6 +489,18 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
                                   QUIPB200_MM_MAX_M;
     }
   }
+
+  // replicated lookup tables (64 KB) when every member keeps its fusion choices with them and the layers are big enough
+  // to repay the ~0.5 us table build (option "gemv_table_repl": 1 = never)
+  long long weights = 0;
+  for (int j = 0; j < n; j++) weights += (long long)mem[j].N * mem[j].K;
+  const bool use_lut = lut_fits && g_opt_table_repl != 1 && weights >= (8ll << 20);
+  for (int j = 0; j < n; j++) {
+    const uint32_t tb = use_lut ? (uint32_t)LUT_TAB_BYTES : (uint32_t)plan[j].tab_bytes;
+    ga.a[j].xq_off = tb + xq_rel[j];
+    ga.a[j].rot_off = tb + rot_rel[j];
+  }
+  if (use_lut) smem = smem - plan[0].tab_bytes + LUT_TAB_BYTES;
 
   // lean instantiations (instruction-cache footprint): fused, pure power-of-two rotation, every vector 16-byte
   // aligned, one octet per thread.  Input and output side qualify independently (gate/up: lean in, 43-block out).
@@ -501,13 +534,26 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
     const void* fn = nullptr;
     switch (mem[0].codebook) {
       case QUIPB200_CB_E8P12:
-        if (lean_pro && lean_epi) fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, true, true>;
-        else if (lean_pro) fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, true, false>;
-        else if (lean_epi) fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, false, true>;
-        else fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, false, false>;
+        if (use_lut) {
+          if (lean_pro && lean_epi) fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, true, true, true>;
+          else if (lean_pro) fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, true, false, true>;
+          else if (lean_epi) fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, false, true, true>;
+          else fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, false, false, true>;
+        } else {
+          if (lean_pro && lean_epi) fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, true, true, false>;
+          else if (lean_pro) fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, true, false, false>;
+          else if (lean_epi) fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, false, true, false>;
+          else fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12, false, false, false>;
+        }
         break;
-      case QUIPB200_CB_E8P12RVQ4B: fn = (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12RVQ4B, false, false>; break;
-      case QUIPB200_CB_D4: fn = (const void*)ql_gemv_kernel<QUIPB200_CB_D4, false, false>; break;
+      case QUIPB200_CB_E8P12RVQ4B:
+        fn = use_lut ? (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12RVQ4B, false, false, true>
+                     : (const void*)ql_gemv_kernel<QUIPB200_CB_E8P12RVQ4B, false, false, false>;
+        break;
+      case QUIPB200_CB_D4:
+        fn = use_lut ? (const void*)ql_gemv_kernel<QUIPB200_CB_D4, false, false, true>
+                     : (const void*)ql_gemv_kernel<QUIPB200_CB_D4, false, false, false>;
+        break;
       default: return QUIPB200_EUNSUPPORTED;
     }
     if ((rc = set_smem_attr(fn, smem))) return rc;
