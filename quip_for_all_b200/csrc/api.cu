@@ -7,6 +7,7 @@ namespace qb {
 int64_t g_launch_count = 0;
 int g_opt_pdl = 1;   // programmatic dependent launch between our kernels
 extern int g_opt_table_repl;
+extern int g_opt_rot_cluster;
 extern int g_opt_gemv_warps;
 extern int g_opt_gemv_ctas_per_sm;
 extern int g_opt_stage_mask;
@@ -51,6 +52,10 @@ extern "C" int quipb200_set_option(const char* name, int value) {
   if (!strcmp(name, "gemv_table_repl")) {
     if (value != 1 && value != 16) return QUIPB200_EINVAL;
     qb::g_opt_table_repl = value;
+    return 0;
+  }
+  if (!strcmp(name, "rot_cluster")) {
+    qb::g_opt_rot_cluster = value ? 1 : 0;
     return 0;
   }
   if (!strcmp(name, "gemv_warps")) {
@@ -110,6 +115,7 @@ extern "C" int quipb200_set_option(const char* name, int value) {
 extern "C" int quipb200_get_option(const char* name) {
   if (!name) return QUIPB200_EINVAL;
   if (!strcmp(name, "gemv_table_repl")) return qb::g_opt_table_repl;
+  if (!strcmp(name, "rot_cluster")) return qb::g_opt_rot_cluster;
   if (!strcmp(name, "gemv_warps")) return qb::g_opt_gemv_warps;
   if (!strcmp(name, "gemv_ctas_per_sm")) return qb::g_opt_gemv_ctas_per_sm;
   if (!strcmp(name, "stage_mask")) return qb::g_opt_stage_mask;

@@ -32,7 +32,7 @@ struct RotSmem {
   int log2L;
 };
 
-static inline int kpad(int K) { return (K + 15) / 16 * 16; }
+__host__ __device__ static inline int kpad(int K) { return (K + 15) / 16 * 16; }
 static inline size_t rot_t_halfs(int q, int K) { return K > 1 ? (size_t)(K + 1) * (q / K + 8) : (size_t)q; }
 // ping-pong (Stockham) layout whenever two fp32 copies fit comfortably; else the in-place padded layout
 static inline bool rot_pingpong(int q, int K) {
@@ -92,10 +92,10 @@ __device__ __forceinline__ void load_hadK(const RotSmem& sm, const __half* hadK,
 // of that tile before it writes, so in-place is safe.  fp16 operands, fp32 accumulate, one fp16
 // rounding -- the arithmetic of the reference's `hadK @ input` fp16 GEMM (quant.py:83).
 template <int MT>   // MT = Kp / 16 (1..4); larger blocks (use_rand=False K=172) take the CUDA-core mix
-__device__ __forceinline__ void mix_mma_tiles(const RotSmem& sm, int K, int warp, int lane, int nwarps) {
-  const int L = 1 << sm.log2L, Kp = MT * 16;
+__device__ __forceinline__ void mix_mma_tiles(const RotSmem& sm, int K, int warp, int lane, int nwarps, int ntiles) {
+  const int Kp = MT * 16;
   const int g = lane >> 2, tq = lane & 3;
-  for (int nt_i = warp; nt_i < (L >> 3); nt_i += nwarps) {
+  for (int nt_i = warp; nt_i < ntiles; nt_i += nwarps) {
     const int c0 = nt_i << 3;
     uint32_t bf[MT][2];
 #pragma unroll
@@ -138,10 +138,10 @@ static __device__ __noinline__ void rotate_mix(RotSmem sm, int q, int K, int tid
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
     switch (Kp >> 4) {
-      case 1: mix_mma_tiles<1>(sm, K, warp, lane, nwarps); break;
-      case 2: mix_mma_tiles<2>(sm, K, warp, lane, nwarps); break;
-      case 3: mix_mma_tiles<3>(sm, K, warp, lane, nwarps); break;
-      default: mix_mma_tiles<4>(sm, K, warp, lane, nwarps); break;
+      case 1: mix_mma_tiles<1>(sm, K, warp, lane, nwarps, L >> 3); break;
+      case 2: mix_mma_tiles<2>(sm, K, warp, lane, nwarps, L >> 3); break;
+      case 3: mix_mma_tiles<3>(sm, K, warp, lane, nwarps, L >> 3); break;
+      default: mix_mma_tiles<4>(sm, K, warp, lane, nwarps, L >> 3); break;
     }
     __syncthreads();
     return;
@@ -156,6 +156,43 @@ static __device__ __noinline__ void rotate_mix(RotSmem sm, int q, int K, int tid
     for (int kp = 0; kp < K; kp++)
       acc = fmaf(__half2float(sm.hk[ko * Kp + kp]), sm.s[s_index(sm, (kp << sm.log2L) + c)], acc);
     sm.t[t_index(sm, K, i)] = __float2half_rn(acc);
+  }
+  __syncthreads();
+}
+
+// 512..4096-wide blocks with an orthogonal mix (Llama-2-70B: 28672 = 7 x 4096).  The caller has already run
+// warp_fwht256 on every 256-wide sub-block (registers + shuffles) and stored the fp32 result in s; this finishes
+// the block transform with ONE shared-memory pass -- the H_NO butterflies across the NO = L / 256 sub-blocks, two
+// adjacent columns per thread -- then scales, rounds and writes the fp16 rows the mix reads.
+template <int NO>
+__device__ __forceinline__ void cross256_tile(const RotSmem& sm, int K, float scale, int tid, int nt) {
+  constexpr int L = NO * 256;
+  for (int it = tid; it < K * 128; it += nt) {
+    const int base = (it >> 7) * L + (it & 127) * 2;
+    float2 v[NO];
+#pragma unroll
+    for (int c = 0; c < NO; c++) v[c] = *reinterpret_cast<const float2*>(sm.s + s_index(sm, base + c * 256));
+#pragma unroll
+    for (int h = 1; h < NO; h <<= 1)
+#pragma unroll
+      for (int c = 0; c < NO; c++)
+        if (!(c & h)) {
+          const float2 a = v[c], b = v[c | h];
+          v[c] = make_float2(a.x + b.x, a.y + b.y);
+          v[c | h] = make_float2(a.x - b.x, a.y - b.y);
+        }
+#pragma unroll
+    for (int c = 0; c < NO; c++)
+      *reinterpret_cast<__half2*>(sm.t + t_index(sm, K, base + c * 256)) = __floats2half2_rn(v[c].x * scale, v[c].y * scale);
+  }
+}
+
+static __device__ __noinline__ void rotate_cross256(RotSmem sm, int K, float scale, int tid, int nt) {
+  switch (sm.log2L) {
+    case 9: cross256_tile<2>(sm, K, scale, tid, nt); break;
+    case 10: cross256_tile<4>(sm, K, scale, tid, nt); break;
+    case 11: cross256_tile<8>(sm, K, scale, tid, nt); break;
+    default: cross256_tile<16>(sm, K, scale, tid, nt); break;
   }
   __syncthreads();
 }
@@ -299,6 +336,8 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
   float rstd = 1.f;
   // 256-wide blocks (11008 = 43 x 256): each warp transforms whole blocks in registers + shuffles
   const bool wf = !LEAN && vec && a.transform && a.K > 1 && a.log2L == 8 && (nt & 31) == 0;
+  // wider blocks (28672 = 7 x 4096): sub-blocks of 256 in registers here, one shared-memory pass (rotate_cross256) after
+  const bool wfb = !LEAN && vec && a.transform && a.K > 1 && a.log2L >= 9 && a.log2L <= 12 && (nt & 31) == 0;
   if (vec) {
     const bool single = noct <= nt * CH;    // everything fits one round: no re-read for the norm
     uint4 xv[CH];
@@ -355,6 +394,7 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
             for (int j = 0; j < 8; j++) f[j] *= a.scale;
             *reinterpret_cast<uint4*>(sm.t + t_index(sm, a.K, idx * 8)) = pack_h8(f);
           } else {
+            if (wfb) warp_fwht256(f, tid & 31);
             float4* d = reinterpret_cast<float4*>(sm.s + s_index(sm, idx * 8));
             d[0] = make_float4(f[0], f[1], f[2], f[3]);
             d[1] = make_float4(f[4], f[5], f[6], f[7]);
@@ -405,7 +445,8 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
     return (mx > 0.f) ? mx / 32767.0f : 0.f;
   }
   if (LEAN) return 0.f;   // unreachable
-  if (wf) rotate_mix(sm, a.q_in, a.K, tid, nt);
+  if (wfb) rotate_cross256(sm, a.K, a.scale, tid, nt);
+  if (wf || wfb) rotate_mix(sm, a.q_in, a.K, tid, nt);
   else rotate_smem(sm, a.q_in, a.K, a.scale, a.transform, tid, nt);
   QB_DSTAMP(10);
 
@@ -520,6 +561,7 @@ __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned ch
     }
   }
   const bool wf = !LEAN && vec_in && a.transform && a.K > 1 && a.log2L == 8 && (nt & 31) == 0;
+  const bool wfb = !LEAN && vec_in && a.transform && a.K > 1 && a.log2L >= 9 && a.log2L <= 12 && (nt & 31) == 0;
   if (vec_in) {
     for (int base = 0; base < noct; base += nt * CH) {
       float4 v0[CH], v1[CH], w0[CH], w1[CH];
@@ -558,6 +600,7 @@ __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned ch
             for (int j = 0; j < 8; j++) f[j] *= a.scale;
             *reinterpret_cast<uint4*>(sm.t + t_index(sm, a.K, idx * 8)) = pack_h8(f);
           } else {
+            if (wfb) warp_fwht256(f, tid & 31);
             float4* d = reinterpret_cast<float4*>(sm.s + s_index(sm, idx * 8));
             d[0] = make_float4(f[0], f[1], f[2], f[3]);
             d[1] = make_float4(f[4], f[5], f[6], f[7]);
@@ -613,7 +656,8 @@ __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned ch
     return;
   }
   if (LEAN) return;   // unreachable
-  if (wf) rotate_mix(sm, a.q_out, a.K, tid, nt);
+  if (wfb) rotate_cross256(sm, a.K, a.scale, tid, nt);
+  if (wf || wfb) rotate_mix(sm, a.q_out, a.K, tid, nt);
   else rotate_smem(sm, a.q_out, a.K, a.scale, a.transform, tid, nt);
   QB_DSTAMP(14);
 

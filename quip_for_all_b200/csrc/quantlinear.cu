@@ -22,6 +22,7 @@
 // dot products are exact; the only approximation is the fixed-point activation (|err| <= max|x| *
 // 2^-16 per element, below the fp16 rounding the reference applies to the same vector).
 #include "ql_device.cuh"
+#include "rot_cluster.cuh"
 
 namespace qb {
 
@@ -33,6 +34,7 @@ int g_opt_gemv_warps = 0;    // 0: auto (16)
 int g_opt_gemv_ctas_per_sm = 1;
 int g_opt_stage_mask = 7;    // bench only: bit0 prologue, bit1 gemv, bit2 epilogue
 int g_opt_fuse = 3;          // bit0: fuse prologue into the GEMV kernel, bit1: last-CTA epilogue
+int g_opt_rot_cluster = 1;  // block rotations with an orthogonal mix run on a thread-block cluster (rot_cluster.cuh); 0: one CTA
 int g_opt_lean = 1;          // use the instruction-cache-lean kernel instantiation when eligible
 int g_opt_phase0 = 1;        // experiment: 0 = no early code prefetch
 long long* g_dbg_timeline = nullptr;   // profiling hook: per-CTA clock64 stamps of the GEMV kernel phases
@@ -405,6 +407,18 @@ struct Member {
 
 // Enqueue a group of 1..3 linears of the same codebook in one GEMV launch (+ prologue / epilogue
 // kernels where they cannot be fused).
+// the cluster rotation kernels take only the vectorised layout: whole octets, 16-byte aligned rows
+static bool rotc_pro_ok(const PrologueArgs& a, int M) {
+  return g_opt_rot_cluster && a.transform && rotc_supported(a.q_in, a.K, a.log2L) && (a.in_features & 7) == 0 && aligned16(a.x) &&
+         aligned16(a.gate) && aligned16(a.SU) && aligned16(a.norm_w) && aligned16(a.hadK) &&
+         (M == 1 || ((a.ldx & 7) == 0 && (a.ldgate & 7) == 0));
+}
+static bool rotc_epi_ok(const EpilogueArgs& a, int M) {
+  return g_opt_rot_cluster && a.transform && rotc_supported(a.q_out, a.K, a.log2L) && (a.out_features & 7) == 0 &&
+         aligned16(a.wscale_pc) && aligned16(a.SV) && aligned16(a.bias) && aligned16(a.residual) && aligned16(a.y) &&
+         (M == 1 || ((a.ldres & 7) == 0 && (a.ldy & 7) == 0));
+}
+
 static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes, cudaStream_t st) {
   if (n < 1 || n > QUIPB200_MAX_GROUP) return QUIPB200_EINVAL;
   const int sms = quipb200_sm_count();
@@ -455,7 +469,9 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
     // fused prologue only for pure-FWHT (or identity) input sides: the orthogonal-block mix is too
     // much work to repeat in every CTA
     bool fuse_pro = (g_opt_fuse & 1) && mj.pa.K == 1;
-    bool fuse_epi = (g_opt_fuse & 2) != 0;
+    // orthogonal-mix output sides go to the cluster kernel (one CTA would spend longer on a 28672-point rotation than
+    // the whole GEMV takes); the last-CTA epilogue keeps the pure power-of-two case
+    bool fuse_epi = (g_opt_fuse & 2) != 0 && !rotc_epi_ok(mj.ea, M);
     size_t need;
     for (;;) {
       size_t rot = 0;
@@ -522,6 +538,16 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
   if (any_unfused_pro && (g_opt_stage_mask & 1)) {
     for (int j = 0; j < n; j++) {
       if (ga.a[j].fuse_pro) continue;
+      if (rotc_pro_ok(ga.a[j].pro, M)) {
+        RotcPlan rp = rotc_plan(ga.a[j].pro.K, ga.a[j].pro.log2L);
+        const size_t csm = rotc_smem_bytes(ga.a[j].pro.K, ga.a[j].pro.log2L, rp);
+        if ((rc = set_smem_attr((const void*)ql_prologue_cluster_kernel, csm))) return rc;
+        void* cargs[] = {&ga.a[j].pro, &rp};
+        cudaError_t ce = launch_cluster_kernel((const void*)ql_prologue_cluster_kernel, dim3(rp.C, M), rp.C, cargs, csm, st);
+        if (ce != cudaSuccess) return (int)ce;
+        QB_LAUNCH_CHECK();
+        continue;
+      }
       const size_t pro_smem = rot_smem_bytes(mem[j].pa.q_in, mem[j].pa.K);
       if ((rc = set_smem_attr((const void*)ql_prologue_kernel, pro_smem))) return rc;
       void* pargs[] = {&ga.a[j].pro};
@@ -565,6 +591,16 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
   if (any_unfused_epi && (g_opt_stage_mask & 4)) {
     for (int j = 0; j < n; j++) {
       if (ga.a[j].fuse_epi) continue;
+      if (rotc_epi_ok(ga.a[j].epi, M)) {
+        RotcPlan rp = rotc_plan(ga.a[j].epi.K, ga.a[j].epi.log2L);
+        const size_t csm = rotc_smem_bytes(ga.a[j].epi.K, ga.a[j].epi.log2L, rp);
+        if ((rc = set_smem_attr((const void*)ql_epilogue_cluster_kernel, csm))) return rc;
+        void* cargs[] = {&ga.a[j].epi, &rp};
+        cudaError_t ce = launch_cluster_kernel((const void*)ql_epilogue_cluster_kernel, dim3(rp.C, M), rp.C, cargs, csm, st);
+        if (ce != cudaSuccess) return (int)ce;
+        QB_LAUNCH_CHECK();
+        continue;
+      }
       const size_t epi_smem = rot_smem_bytes(mem[j].ea.q_out, mem[j].ea.K);
       if ((rc = set_smem_attr((const void*)ql_epilogue_kernel, epi_smem))) return rc;
       void* eargs[] = {&ga.a[j].epi};

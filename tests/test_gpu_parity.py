@@ -287,6 +287,11 @@ CASES = [
     (8192, 1024, "E8P12", False, True, False, 40),
     (8192, 28672, "E8P12", False, True, False, 40),
     (28672, 8192, "E8P12", False, True, False, 40),
+    # Llama-2-13B dims: 5120 = 5 x 1024, 13824 = 27 x 512 (wide rotation blocks with an orthogonal mix), and 3 x 2048
+    (5120, 5120, "E8P12", False, True, False, 1),
+    (5120, 13824, "E8P12", False, True, False, 1),
+    (13824, 5120, "E8P12", True, True, False, 2),
+    (6144, 6144, "E8P12", False, True, True, 1),
 ]
 
 
