@@ -160,6 +160,33 @@ static __device__ __noinline__ void rotate_mix(RotSmem sm, int q, int K, int tid
   __syncthreads();
 }
 
+// Pure power-of-two rotations of 4096 / 8192 points on 512 threads (hidden sizes of Llama-2-7B / 70B): instead of
+// 3-4 radix-8 passes through shared memory, every warp transforms its 256-wide sub-blocks in registers + shuffles as
+// it loads them (warp_fwht256), parks them as rows of an [NO][256 (+16 pad)] fp32 array, and ONE pass finishes the
+// log2(NO) remaining levels: thread (column w, half h) reads rows 2j + h, runs the levels over j in registers, the
+// last level against its partner lane (xor 16), scales, rounds and writes the fp16 result.  The row pad puts the two
+// half-warps on disjoint banks.
+constexpr int WK1_STRIDE = 272;
+template <int NPT>   // rows per thread = NO / 2: 8 (4096 points) or 16 (8192)
+__device__ __forceinline__ void cross_rows_to_t(const float* s, __half* t, float sc, int tid) {
+  const int w = (tid >> 5) * 16 + (tid & 15), h = (tid >> 4) & 1;
+  float v[NPT];
+#pragma unroll
+  for (int j = 0; j < NPT; j++) v[j] = s[(2 * j + h) * WK1_STRIDE + w];
+#pragma unroll
+  for (int d = 1; d < NPT; d <<= 1)
+#pragma unroll
+    for (int j = 0; j < NPT; j++)
+      if (!(j & d)) { const float a = v[j], b = v[j | d]; v[j] = a + b; v[j | d] = a - b; }
+  const float sg = h ? -1.f : 1.f;
+#pragma unroll
+  for (int j = 0; j < NPT; j++) {
+    const float p = __shfl_xor_sync(0xffffffffu, v[j], 16);
+    t[(2 * j + h) * 256 + w] = __float2half_rn(fmaf(sg, v[j], p) * sc);
+  }
+}
+__device__ __forceinline__ int wk1_index(int oct) { return (oct >> 5) * WK1_STRIDE + (oct & 31) * 8; }
+
 // 512..4096-wide blocks with an orthogonal mix (Llama-2-70B: 28672 = 7 x 4096).  The caller has already run
 // warp_fwht256 on every 256-wide sub-block (registers + shuffles) and stored the fp32 result in s; this finishes
 // the block transform with ONE shared-memory pass -- the H_NO butterflies across the NO = L / 256 sub-blocks, two
@@ -338,6 +365,8 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
   const bool wf = !LEAN && vec && a.transform && a.K > 1 && a.log2L == 8 && (nt & 31) == 0;
   // wider blocks (28672 = 7 x 4096): sub-blocks of 256 in registers here, one shared-memory pass (rotate_cross256) after
   const bool wfb = !LEAN && vec && a.transform && a.K > 1 && a.log2L >= 9 && a.log2L <= 12 && (nt & 31) == 0;
+  // 4096 / 8192-point pure FWHT: sub-blocks in registers on load, one cross pass (cross_rows_to_t)
+  const bool wk1 = vec && a.transform && a.K == 1 && nt == 512 && (a.log2L == 12 || a.log2L == 13);
   if (vec) {
     const bool single = noct <= nt * CH;    // everything fits one round: no re-read for the norm
     uint4 xv[CH];
@@ -394,8 +423,8 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
             for (int j = 0; j < 8; j++) f[j] *= a.scale;
             *reinterpret_cast<uint4*>(sm.t + t_index(sm, a.K, idx * 8)) = pack_h8(f);
           } else {
-            if (wfb) warp_fwht256(f, tid & 31);
-            float4* d = reinterpret_cast<float4*>(sm.s + s_index(sm, idx * 8));
+            if (wfb || wk1) warp_fwht256(f, tid & 31);
+            float4* d = reinterpret_cast<float4*>(sm.s + (wk1 ? wk1_index(idx) : s_index(sm, idx * 8)));
             d[0] = make_float4(f[0], f[1], f[2], f[3]);
             d[1] = make_float4(f[4], f[5], f[6], f[7]);
           }
@@ -410,22 +439,32 @@ __device__ __forceinline__ float prologue_body(const PrologueArgs& a, unsigned c
   if (LEAN || (a.K == 1 && noct <= nt * CH && (!a.transform || a.log2L >= 3))) {
     // register-resident tail: last butterflies, abs-max and quantisation without another smem round trip
     const float* fin = sm.s;
-    if (a.transform) {
+    const float sc = a.transform ? a.scale : 1.0f;
+    if (wk1) {
+      if (LEAN || a.log2L == 12) cross_rows_to_t<8>(sm.s, sm.t, sc, tid);   // (lean instantiations: q <= 4096)
+      else cross_rows_to_t<16>(sm.s, sm.t, sc, tid);
+      __syncthreads();
+    } else if (a.transform) {
       if (LEAN || sm.pp) fin = stockham_hi(sm.s, sm.s2, a.q_in, a.log2L, tid, nt);
       else fwht_hi(sm.s, a.q_in, a.log2L, tid, nt);
     }
-    const float sc = a.transform ? a.scale : 1.0f;
     float f[CH][8];
     float mx = 0.f;
 #pragma unroll
     for (int c = 0; c < CH; c++) {
       const int o = c * nt + tid;
       if (o < noct) {
-        final_octet(sm, fin, a.transform, o, f[c]);
+        if (wk1) {
+          unpack_h8(*reinterpret_cast<const uint4*>(sm.t + (size_t)o * 8), f[c]);   // already scaled and rounded
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          f[c][j] = f16_round(f[c][j] * sc);   // the rotated vector is an fp16 tensor in the reference
-          mx = fmaxf(mx, fabsf(f[c][j]));
+          for (int j = 0; j < 8; j++) mx = fmaxf(mx, fabsf(f[c][j]));
+        } else {
+          final_octet(sm, fin, a.transform, o, f[c]);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            f[c][j] = f16_round(f[c][j] * sc);   // the rotated vector is an fp16 tensor in the reference
+            mx = fmaxf(mx, fabsf(f[c][j]));
+          }
         }
       }
     }
@@ -562,6 +601,7 @@ __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned ch
   }
   const bool wf = !LEAN && vec_in && a.transform && a.K > 1 && a.log2L == 8 && (nt & 31) == 0;
   const bool wfb = !LEAN && vec_in && a.transform && a.K > 1 && a.log2L >= 9 && a.log2L <= 12 && (nt & 31) == 0;
+  const bool wk1 = vec_in && (LEAN || pre_out) && a.transform && a.K == 1 && nt == 512 && (a.log2L == 12 || a.log2L == 13);
   if (vec_in) {
     for (int base = 0; base < noct; base += nt * CH) {
       float4 v0[CH], v1[CH], w0[CH], w1[CH];
@@ -600,8 +640,8 @@ __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned ch
             for (int j = 0; j < 8; j++) f[j] *= a.scale;
             *reinterpret_cast<uint4*>(sm.t + t_index(sm, a.K, idx * 8)) = pack_h8(f);
           } else {
-            if (wfb) warp_fwht256(f, tid & 31);
-            float4* d = reinterpret_cast<float4*>(sm.s + s_index(sm, idx * 8));
+            if (wfb || wk1) warp_fwht256(f, tid & 31);
+            float4* d = reinterpret_cast<float4*>(sm.s + (wk1 ? wk1_index(idx) : s_index(sm, idx * 8)));
             d[0] = make_float4(f[0], f[1], f[2], f[3]);
             d[1] = make_float4(f[4], f[5], f[6], f[7]);
           }
@@ -621,20 +661,28 @@ __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned ch
   __syncthreads();
   if (LEAN || (a.K == 1 && pre_out && noct <= nt * CH && (!a.transform || a.log2L >= 3))) {
     const float* fin = sm.s;
-    if (a.transform) {
+    const float sc = a.transform ? a.scale : 1.0f;
+    if (wk1) {
+      if (LEAN || a.log2L == 12) cross_rows_to_t<8>(sm.s, sm.t, sc, tid);   // (lean instantiations: q <= 4096)
+      else cross_rows_to_t<16>(sm.s, sm.t, sc, tid);
+      __syncthreads();
+    } else if (a.transform) {
       if (LEAN || sm.pp) fin = stockham_hi(sm.s, sm.s2, a.q_out, a.log2L, tid, nt);
       else fwht_hi(sm.s, a.q_out, a.log2L, tid, nt);
     }
     QB_DSTAMP(14);
-    const float sc = a.transform ? a.scale : 1.0f;
 #pragma unroll
     for (int c = 0; c < CH; c++) {
       const int o = c * nt + tid;
       if (o < noct_out) {
         float f[8], o8[8];
-        final_octet(sm, fin, a.transform, o, f);
+        if (wk1) {
+          unpack_h8(*reinterpret_cast<const uint4*>(sm.t + (size_t)o * 8), f);   // already scaled and rounded
+        } else {
+          final_octet(sm, fin, a.transform, o, f);
 #pragma unroll
-        for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] * sc);
+          for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] * sc);
+        }
         if (a.SV) {
           unpack_h8(psv[c], o8);
 #pragma unroll
@@ -806,6 +854,25 @@ __device__ __forceinline__ void lut_build_tables(unsigned char* tab, const void*
       else v = lut_sign_mask((uint32_t)i);
       reinterpret_cast<uint2*>(tab)[e] = v;
     }
+  }
+}
+// Same E8P tables, ~15x fewer instructions: half-row h = 2 i + half per thread -- half 0 replicates codebook entry i, half 1
+// the sign mask of sign byte i (computed, no load); 128-bit stores with the chunk order rotated by the lane so a
+// quarter-warp covers all 32 banks.  (Used by the lean kernel instantiations only: in the general ones ptxas answers
+// this body with a GEMV loop that rematerialises shared-memory addresses, 133 instead of 114 instructions per 8 codes.)
+__device__ __forceinline__ void lut_build_tables_e8p_fast(unsigned char* tab, const void* grid, int tid, int nt) {
+  for (int h = tid; h < 512; h += nt) {
+    const int i = h >> 1, half = h & 1;
+    uint2 v;
+    if (half) {
+      v = lut_sign_mask((uint32_t)i);
+    } else {
+      const uint2 t = __ldg(reinterpret_cast<const uint2*>(grid) + i);
+      v = make_uint2(t.x | 0x01010101u, t.y | 0x01010101u);
+    }
+    uint4* d = reinterpret_cast<uint4*>(tab + i * 256 + half * 128);
+#pragma unroll
+    for (int k = 0; k < 8; k++) d[(k + tid) & 7] = make_uint4(v.x, v.y, v.x, v.y);
   }
 }
 // one E8P code (index bytes AB / SB of packed word w) against one x segment: hi and lo activation planes

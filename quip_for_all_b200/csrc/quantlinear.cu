@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(GEMV_MAX_WARPS * 32, 1) ql_gemv_kernel(const _
     xscale = a.pro.xscale[m];
   }
   if (LUT) {
-    lut_build_tables<CB>(tab, a.table, tid, nt);
+    if (LEAN && CB == QUIPB200_CB_E8P12) lut_build_tables_e8p_fast(tab, a.table, tid, nt);
+    else lut_build_tables<CB>(tab, a.table, tid, nt);
   } else if (tid < 256) {
     if (CB == QUIPB200_CB_D4) {
       // fp16 [4] -> int8 (units of 1/2), byte order (0,2,1,3) to match perm_0213'd activations
@@ -471,7 +472,10 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
     bool fuse_pro = (g_opt_fuse & 1) && mj.pa.K == 1;
     // orthogonal-mix output sides go to the cluster kernel (one CTA would spend longer on a 28672-point rotation than
     // the whole GEMV takes); the last-CTA epilogue keeps the pure power-of-two case
-    bool fuse_epi = (g_opt_fuse & 2) != 0 && !rotc_epi_ok(mj.ea, M);
+    // ... and only behind a fused input side: when the input rotation is its own kernel anyway (K_left > 1), a separate
+    // epilogue kernel -- launched early through PDL, its vector loads issued before the dependency wait -- measured
+    // 3-4 us faster than the ticketed last CTA (11008x4096: 19.2 vs 22.0 us, 28672x8192: 41.2 vs 45.3 us)
+    bool fuse_epi = (g_opt_fuse & 2) != 0 && !rotc_epi_ok(mj.ea, M) && (fuse_pro || g_opt_fuse == 2);
     size_t need;
     for (;;) {
       size_t rot = 0;
@@ -536,18 +540,28 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
   }
 
   if (any_unfused_pro && (g_opt_stage_mask & 1)) {
+    // cluster kernel: members of the same block shape share one launch
+    bool done[QUIPB200_MAX_GROUP] = {false, false, false};
     for (int j = 0; j < n; j++) {
-      if (ga.a[j].fuse_pro) continue;
-      if (rotc_pro_ok(ga.a[j].pro, M)) {
-        RotcPlan rp = rotc_plan(ga.a[j].pro.K, ga.a[j].pro.log2L);
-        const size_t csm = rotc_smem_bytes(ga.a[j].pro.K, ga.a[j].pro.log2L, rp);
-        if ((rc = set_smem_attr((const void*)ql_prologue_cluster_kernel, csm))) return rc;
-        void* cargs[] = {&ga.a[j].pro, &rp};
-        cudaError_t ce = launch_cluster_kernel((const void*)ql_prologue_cluster_kernel, dim3(rp.C, M), rp.C, cargs, csm, st);
-        if (ce != cudaSuccess) return (int)ce;
-        QB_LAUNCH_CHECK();
-        continue;
+      if (ga.a[j].fuse_pro || done[j] || !rotc_pro_ok(ga.a[j].pro, M)) continue;
+      RotcProGroup grp{};
+      int cnt = 0;
+      for (int i = j; i < n; i++) {
+        if (ga.a[i].fuse_pro || done[i] || !rotc_pro_ok(ga.a[i].pro, M)) continue;
+        if (ga.a[i].pro.K != ga.a[j].pro.K || ga.a[i].pro.log2L != ga.a[j].pro.log2L) continue;
+        grp.a[cnt++] = ga.a[i].pro;
+        done[i] = true;
       }
+      RotcPlan rp = rotc_plan(ga.a[j].pro.K, ga.a[j].pro.log2L);
+      const size_t csm = rotc_smem_bytes(ga.a[j].pro.K, ga.a[j].pro.log2L, rp);
+      if ((rc = set_smem_attr((const void*)ql_prologue_cluster_kernel, csm))) return rc;
+      void* cargs[] = {&grp, &rp};
+      cudaError_t ce = launch_cluster_kernel((const void*)ql_prologue_cluster_kernel, dim3(rp.C, M, cnt), rp.C, cargs, csm, st);
+      if (ce != cudaSuccess) return (int)ce;
+      QB_LAUNCH_CHECK();
+    }
+    for (int j = 0; j < n; j++) {
+      if (ga.a[j].fuse_pro || done[j]) continue;
       const size_t pro_smem = rot_smem_bytes(mem[j].pa.q_in, mem[j].pa.K);
       if ((rc = set_smem_attr((const void*)ql_prologue_kernel, pro_smem))) return rc;
       void* pargs[] = {&ga.a[j].pro};
@@ -589,18 +603,27 @@ static int run_group(Member* mem, int n, int M, void* workspace, size_t ws_bytes
     QB_LAUNCH_CHECK();
   }
   if (any_unfused_epi && (g_opt_stage_mask & 4)) {
+    bool done[QUIPB200_MAX_GROUP] = {false, false, false};
     for (int j = 0; j < n; j++) {
-      if (ga.a[j].fuse_epi) continue;
-      if (rotc_epi_ok(ga.a[j].epi, M)) {
-        RotcPlan rp = rotc_plan(ga.a[j].epi.K, ga.a[j].epi.log2L);
-        const size_t csm = rotc_smem_bytes(ga.a[j].epi.K, ga.a[j].epi.log2L, rp);
-        if ((rc = set_smem_attr((const void*)ql_epilogue_cluster_kernel, csm))) return rc;
-        void* cargs[] = {&ga.a[j].epi, &rp};
-        cudaError_t ce = launch_cluster_kernel((const void*)ql_epilogue_cluster_kernel, dim3(rp.C, M), rp.C, cargs, csm, st);
-        if (ce != cudaSuccess) return (int)ce;
-        QB_LAUNCH_CHECK();
-        continue;
+      if (ga.a[j].fuse_epi || done[j] || !rotc_epi_ok(ga.a[j].epi, M)) continue;
+      RotcEpiGroup grp{};
+      int cnt = 0;
+      for (int i = j; i < n; i++) {
+        if (ga.a[i].fuse_epi || done[i] || !rotc_epi_ok(ga.a[i].epi, M)) continue;
+        if (ga.a[i].epi.K != ga.a[j].epi.K || ga.a[i].epi.log2L != ga.a[j].epi.log2L) continue;
+        grp.a[cnt++] = ga.a[i].epi;
+        done[i] = true;
       }
+      RotcPlan rp = rotc_plan(ga.a[j].epi.K, ga.a[j].epi.log2L);
+      const size_t csm = rotc_smem_bytes(ga.a[j].epi.K, ga.a[j].epi.log2L, rp);
+      if ((rc = set_smem_attr((const void*)ql_epilogue_cluster_kernel, csm))) return rc;
+      void* cargs[] = {&grp, &rp};
+      cudaError_t ce = launch_cluster_kernel((const void*)ql_epilogue_cluster_kernel, dim3(rp.C, M, cnt), rp.C, cargs, csm, st);
+      if (ce != cudaSuccess) return (int)ce;
+      QB_LAUNCH_CHECK();
+    }
+    for (int j = 0; j < n; j++) {
+      if (ga.a[j].fuse_epi || done[j]) continue;
       const size_t epi_smem = rot_smem_bytes(mem[j].ea.q_out, mem[j].ea.K);
       if ((rc = set_smem_attr((const void*)ql_epilogue_kernel, epi_smem))) return rc;
       void* eargs[] = {&ga.a[j].epi};

@@ -34,6 +34,12 @@ struct RotcPlan {
   int nblk_max;     // ceil(K / C)
 };
 
+struct PrologueArgs;
+struct EpilogueArgs;
+// up to QUIPB200_MAX_GROUP rows of the same shape in one launch (blockIdx.z): the members of a q/k/v or gate/up group
+struct RotcProGroup { PrologueArgs a[QUIPB200_MAX_GROUP]; };
+struct RotcEpiGroup { EpilogueArgs a[QUIPB200_MAX_GROUP]; };
+
 static inline bool rotc_supported(int q, int K, int log2L) { return K > 1 && K <= 64 && log2L >= 8 && log2L <= 12 && q == (K << log2L); }
 
 static inline RotcPlan rotc_plan(int K, int log2L) {
@@ -179,10 +185,11 @@ __device__ __forceinline__ void rotc_setup(const RotcSmem& sm, const RotcPlan& p
 }
 
 // ---------------------------------------------------------------------------------------------
-// input side.  grid (C, M), cluster (C, 1, 1).  Host guarantees: rotc_supported, in_features % 8 == 0, x / gate / SU /
+// input side.  grid (C, M, members), cluster (C, 1, 1).  Host guarantees: rotc_supported, in_features % 8 == 0, x / gate / SU /
 // norm_w rows 16-byte aligned.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ROTC_THREADS) ql_prologue_cluster_kernel(PrologueArgs a, RotcPlan p) {
+__global__ void __launch_bounds__(ROTC_THREADS) ql_prologue_cluster_kernel(const __grid_constant__ RotcProGroup grp, RotcPlan p) {
+  const PrologueArgs& a = grp.a[blockIdx.z];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
   const int r = (int)cluster.block_rank();
@@ -268,7 +275,8 @@ __global__ void __launch_bounds__(ROTC_THREADS) ql_prologue_cluster_kernel(Prolo
 // output side.  Host guarantees: rotc_supported, out_features % 8 == 0, acc / acc2 / wscale_pc / SV / bias / residual /
 // y rows 16-byte aligned.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ROTC_THREADS) ql_epilogue_cluster_kernel(EpilogueArgs a, RotcPlan p) {
+__global__ void __launch_bounds__(ROTC_THREADS) ql_epilogue_cluster_kernel(const __grid_constant__ RotcEpiGroup grp, RotcPlan p) {
+  const EpilogueArgs& a = grp.a[blockIdx.z];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
   const int r = (int)cluster.block_rank();

@@ -71,7 +71,7 @@ def main():
             def sweep():
                 for L in layers:
                     L(x)
-            for name, fuse, mask, pdl in (("fused", 3, 7, 1), ("fused_nopdl", 3, 7, 0), ("unfused_all", 0, 7, 1),
+            for name, fuse, mask, pdl in (("fused", 3, 7, 1), ("fused_nopdl", 3, 7, 0), ("unfused_all", 0, 7, 1), ("fused_pro_only", 1, 7, 1),
                                           ("gemv_only", 0, 2, 0), ("prologue_only", 0, 1, 0), ("epilogue_only", 0, 4, 0)):
                 _native.set_option("fuse", fuse)
                 _native.set_option("stage_mask", mask)
