@@ -17,6 +17,7 @@ extern int g_opt_phase0;
 extern int g_opt_lean;
 extern int g_opt_rot_warp_rows;
 extern int g_opt_rot_pipe_rows;
+int g_opt_umma_ksplit = 0;   // experiments: force the split-K factor of the tcgen05 kernel (0 = auto)
 int g_opt_umma = 2;     // in-kernel decode + tcgen05 GEMM (umma_gemm.cu): 0 = never, 1 = whenever the shape is covered
                         // (M <= 256), 2 = auto: where it measured faster than the alternatives (profiles/README.md)
 }  // namespace qb
@@ -85,6 +86,11 @@ extern "C" int quipb200_set_option(const char* name, int value) {
     qb::g_opt_pdl = value ? 1 : 0;
     return 0;
   }
+  if (!strcmp(name, "umma_ksplit")) {
+    if (value < 0 || value > 16) return QUIPB200_EINVAL;
+    qb::g_opt_umma_ksplit = value;
+    return 0;
+  }
   if (!strcmp(name, "umma")) {
     if (value < 0 || value > 2) return QUIPB200_EINVAL;
     qb::g_opt_umma = value;
@@ -122,6 +128,7 @@ extern "C" int quipb200_get_option(const char* name) {
   if (!strcmp(name, "fuse")) return qb::g_opt_fuse;
   if (!strcmp(name, "ds_flags")) return qb::g_ds_flags;
   if (!strcmp(name, "pdl")) return qb::g_opt_pdl;
+  if (!strcmp(name, "umma_ksplit")) return qb::g_opt_umma_ksplit;
   if (!strcmp(name, "umma")) return qb::g_opt_umma;
   if (!strcmp(name, "rot_warp_rows")) return qb::g_opt_rot_warp_rows;
   if (!strcmp(name, "rot_pipe_rows")) return qb::g_opt_rot_pipe_rows;

@@ -21,9 +21,14 @@
 //
 // Numerics: fp16 x fp16 products accumulated in fp32 (hardware order), one fp16 rounding -- the same
 // class as the reference's mma.sync kernel and cuBLAS path; decoded weights are bit-exact.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace qb {
+
+namespace cg = cooperative_groups;
+extern int g_opt_umma_ksplit;
 
 constexpr int UG_THREADS = 256;
 constexpr int UG_BM = 128;   // weight rows per CTA = UMMA M
@@ -107,7 +112,6 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
   const uint32_t sbar = base + STAGES * (A_BYTES + B_BYTES) + 3072;   // full[STAGES], empty[STAGES], done
   const uint32_t bar_full = sbar, bar_empty = sbar + 8 * STAGES, bar_done = sbar + 16 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + STAGES * (A_BYTES + B_BYTES) + 3072 + 8 * (2 * STAGES + 1));
-  __shared__ int s_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * UG_BM;
@@ -188,18 +192,21 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
         cp_async16_zfill(sB + s * B_BYTES + h * B_SUB + tok * 128 + ((ch ^ (tok & 7)) << 4), src, ok ? 16u : 0u);
       }
     };
-    uint4 cur = make_uint4(0, 0, 0, 0);
+    // packed codes come from HBM (read once, ~1 us away): three stages of them ride in registers ahead of the decode
+    uint4 cur = make_uint4(0, 0, 0, 0), nx1 = cur, nx2 = cur;
     const __half2 rs2 = __float2half2_rn(a.resid_scale);      // the reference's fp16 hfma2 operand (origin_order.cu:378)
     if (nit > 0) {
       cur = load_codes(0);
       issue_acts(0);
     }
+    if (nit > 1) nx1 = load_codes(1);
+    if (nit > 2) nx2 = load_codes(2);
     asm volatile("cp.async.commit_group;" ::: "memory");
     for (int it = 0; it < nit; it++) {
       const int s = it % STAGES;
-      uint4 nxt = make_uint4(0, 0, 0, 0);
+      uint4 nx3 = make_uint4(0, 0, 0, 0);
+      if (it + 3 < nit) nx3 = load_codes(it + 3);
       if (it + 1 < nit) {
-        nxt = load_codes(it + 1);
         if (it + 1 >= STAGES) mbar_wait(bar_empty + 8 * ((it + 1) % STAGES), (uint32_t)(((it + 1) / STAGES - 1) & 1));
         issue_acts(it + 1);
       }
@@ -285,51 +292,74 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * s);
-      cur = nxt;
+      cur = nx1; nx1 = nx2; nx2 = nx3;
     }
   }
   mbar_wait(bar_done, 0);
   tc_fence_after();
 
   // ---- epilogue: TMEM lane = weight row, column = token.  Producer warp w: lane quadrant w % 4, column quarter w / 4.
-  if (warp < UG_PRODUCERS / 32 && nit > 0) {
-    const int quad = warp & 3, cq = warp >> 2;
-    const int n = n0 + quad * 32 + lane;
-    constexpr int CW = NTOK / 4 < 16 ? 16 : NTOK / 4;        // columns per warp (>= one 16-column load)
-    for (int c0 = cq * CW; c0 < (cq + 1) * CW && c0 < NTOK; c0 += 16) {
-      if (c0 >= a.M) break;                        // warp-uniform: token columns beyond M hold zeros
-      float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-      if (a.ksplit == 1) {
+  const int quad = warp & 3, cq = warp >> 2;
+  constexpr int CW = NTOK / 4 < 16 ? 16 : NTOK / 4;        // columns per warp (>= one 16-column load)
+  if (a.ksplit == 1) {
+    if (warp < UG_PRODUCERS / 32 && nit > 0) {
+      const int n = n0 + quad * 32 + lane;
+      for (int c0 = cq * CW; c0 < (cq + 1) * CW && c0 < NTOK; c0 += 16) {
+        if (c0 >= a.M) break;                        // warp-uniform: token columns beyond M hold zeros
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
         for (int j = 0; j < 16; j++)
           if (c0 + j < a.M) a.out[(size_t)(c0 + j) * a.N + n] = __float2half_rn(v[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; j++)      // a warp adds 32 consecutive floats of one token row: one 128-byte L2 reduction
-          if (c0 + j < a.M) atomicAdd(a.ws + (size_t)(c0 + j) * a.N + n, v[j]);
       }
     }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, NTOK);
+    return;
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, NTOK);
-  if (a.ksplit == 1) return;
-  // ---- split-K: the last CTA of this row tile converts the fp32 partial sums and clears them
-  if (tid == 0) {
-    __threadfence();
-    const unsigned int prev = atomicAdd(a.tickets + blockIdx.x, 1u);
-    s_last = (prev == (unsigned int)(a.ksplit - 1));
-    if (s_last) a.tickets[blockIdx.x] = 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int i = tid; i < a.M * UG_BM; i += UG_THREADS2) {
-    const int tok = i >> 7, n = n0 + (i & 127);
-    float* p = a.ws + (size_t)tok * a.N + n;
-    a.out[(size_t)tok * a.N + n] = __float2half_rn(__ldcg(p));
-    __stcg(p, 0.f);
+  // ---- split-K: the ksplit CTAs of a row tile form a cluster (1, ksplit, 1) and reduce-scatter their accumulators through
+  // distributed shared memory: CTA r owns the token columns [r * NTOK / ksplit, ...), every CTA pushes each 16-column
+  // group of its TMEM tile into the owner's receive buffer (the stage ring, idle now), the owner adds the ksplit partial
+  // tiles and stores fp16.  No atomics, no workspace, no second pass through L2.
+  {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = (int)cluster.block_rank();
+    const int cols_per = NTOK / a.ksplit;                       // >= 4 (NTOK >= 32, ksplit <= 8); a multiple of 4
+    float* recv = reinterpret_cast<float*>(gbase);              // [ksplit sources][cols_per][128 rows]
+    cluster.sync();                                             // every CTA of the tile is done with its stage ring
+    if (warp < UG_PRODUCERS / 32) {
+      const int row = quad * 32 + lane;
+      for (int c0 = cq * CW; c0 < (cq + 1) * CW && c0 < NTOK; c0 += 16) {
+        if (c0 >= a.M) break;
+        float v[16];
+        if (nit > 0) {
+          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+        } else {                                               // (a split with no k-blocks contributes zeros)
+#pragma unroll
+          for (int j = 0; j < 16; j++) v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const int c = c0 + j;
+          const int d = c / cols_per, lc = c - d * cols_per;
+          float* dst = cluster.map_shared_rank(recv, d) + ((size_t)(r * cols_per + lc) << 7) + row;
+          *dst = v[j];
+        }
+      }
+    }
+    tc_fence_before();
+    cluster.sync();                                             // all partial tiles delivered
+    if (warp == 0) tmem_dealloc(tmem_base, NTOK);
+    const int tok0 = r * cols_per;
+    for (int i = tid; i < cols_per * UG_BM; i += UG_THREADS2) {
+      const int lc = i >> 7, row = i & 127;
+      const int tok = tok0 + lc;
+      if (tok >= a.M) break;
+      float acc = 0.f;
+      for (int src = 0; src < a.ksplit; src++) acc += recv[((size_t)(src * cols_per + lc) << 7) + row];
+      a.out[(size_t)tok * a.N + n0 + row] = __float2half_rn(acc);
+    }
   }
 }
 
@@ -338,7 +368,21 @@ static int launch_umma(const UmmaArgs& a, dim3 grid, cudaStream_t st) {
   const size_t smem = (size_t)STAGES * 2 * (UG_BM * 128 + NTOK * 128) + 3072 + 8 * (2 * STAGES + 1) + 16 + 1024;
   cudaError_t e = cudaFuncSetAttribute(e8p_umma_kernel<CB, NTOK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  e8p_umma_kernel<CB, NTOK, STAGES><<<grid, UG_THREADS2, smem, st>>>(a);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(UG_THREADS2);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;      // the split-K CTAs of one row tile
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = grid.y;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  void* args[] = {const_cast<UmmaArgs*>(&a)};
+  e = cudaLaunchKernelExC(&cfg, (const void*)e8p_umma_kernel<CB, NTOK, STAGES>, args);
+  if (e != cudaSuccess) return (int)e;
   QB_LAUNCH_CHECK();
   return 0;
 }
@@ -371,7 +415,10 @@ extern "C" int quipb200_mm_umma(int codebook, const void* x, const void* qidxs, 
   if (sms < 1) return (int)cudaErrorNoDevice;
   const int tiles = N / UG_BM, nkb = K / UG_BK2;
   int ksplit = 1;
-  while (ksplit < 16 && tiles * ksplit * 2 <= sms && nkb / (ksplit * 2) >= 4) ksplit *= 2;
+  while (ksplit < 8 && tiles * ksplit * 2 <= sms && nkb / (ksplit * 2) >= 4) ksplit *= 2;   // <= 8: one portable cluster
+  if (g_opt_umma_ksplit > 0 && g_opt_umma_ksplit <= 8 && !(g_opt_umma_ksplit & (g_opt_umma_ksplit - 1)) &&
+      nkb / g_opt_umma_ksplit >= 1)
+    ksplit = g_opt_umma_ksplit;
   UmmaArgs a{};
   a.codes = (const unsigned char*)qidxs; a.x = (const __half*)x; a.table = (const uint2*)grid; a.out = (__half*)out;
   a.table2 = (const uint32_t*)grid2;
@@ -379,12 +426,7 @@ extern "C" int quipb200_mm_umma(int codebook, const void* x, const void* qidxs, 
   a.M = M; a.N = N; a.K = K;
   a.ksplit = ksplit;
   a.kb_per_split = (nkb + ksplit - 1) / ksplit;
-  if (ksplit > 1) {
-    if (!workspace || ((uintptr_t)workspace & 255) || ws_bytes < quipb200_e8p_mm_umma_workspace_bytes(M, N, K))
-      return QUIPB200_EWORKSPACE;
-    a.ws = (float*)workspace;
-    a.tickets = (unsigned int*)((unsigned char*)workspace + (size_t)N * UG_WS_LD * sizeof(float));
-  }
+  (void)workspace; (void)ws_bytes;   // split-K partial tiles are reduced through distributed shared memory: no workspace
   const dim3 grid_dim(tiles, ksplit);
   cudaStream_t st = (cudaStream_t)stream;
   if (codebook == QUIPB200_CB_E8P12) return launch_umma_m<QUIPB200_CB_E8P12>(a, grid_dim, st);
