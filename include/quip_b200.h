@@ -117,11 +117,10 @@ int quipb200_rotate_batched(const void* x_f16, int64_t ldx, void* y_f16, int64_t
  *   "decompress_e8p_origorder + input @ W.T" (codebook/e8p12.py:153-155, origin_order.cu:837-885) without
  *   ever materialising the dense weight: packed codes are decoded straight into the UMMA shared-memory
  *   layout.  Requires N % 128 == 0 and K % 64 == 0 (else QUIPB200_EUNSUPPORTED -> caller uses the dense path).
- *   workspace: >= quipb200_e8p_mm_umma_workspace_bytes(M_max, N, K) bytes, 256-byte aligned, zero-filled ONCE
- *   by the caller; the kernel returns it zeroed (split-K partial sums are cleared by the CTA that converts them).
- *   A workspace carries partial sums and arrival tickets of ONE launch at a time: launches that may overlap (different
- *   streams or threads) need separate workspaces (the Python binding keeps one per device, stream and N; a workspace
- *   created during CUDA-graph capture belongs to the capture stream and its zero fill is part of the graph).
+ *   The activation tile is staged by TMA (tensor map over x, encoded per call) and the split-K partial tiles are reduced
+ *   through distributed shared memory inside a thread-block cluster, so the call needs NO workspace:
+ *   quipb200_e8p_mm_umma_workspace_bytes returns 0 and workspace / workspace_bytes are ignored (kept for ABI stability).
+ *   Concurrent launches on different streams share nothing.
  * ------------------------------------------------------------------------------------------- */
 size_t quipb200_e8p_mm_umma_workspace_bytes(int M, int N, int K);
 /* The same kernel with the producers' decode templated on the codebook, covering the reference's small-M mm kernels:
@@ -130,7 +129,7 @@ size_t quipb200_e8p_mm_umma_workspace_bytes(int M, int N, int K);
  *   QUIPB200_CB_D4          K3  :143-168, :557-602   grid = fp16 [256][4]
  *   QUIPB200_CB_E8P12RVQ3B  K4  :287-335, :650-696   grid2 = e81b residual table, int32[256]; `scale` as for RVQ4B
  *   QUIPB200_CB_HI          K5  :170-206, :745-788   no table (grid may be NULL)
- * grid2 is NULL except for RVQ3B.  Same shape and workspace rules as quipb200_e8p_mm_umma. */
+ * grid2 is NULL except for RVQ3B.  Same shape rules as quipb200_e8p_mm_umma. */
 int quipb200_mm_umma(int codebook, const void* x_f16, const void* qidxs, const void* grid, const void* grid2, float scale,
                      void* out_f16, int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
 int quipb200_e8p_mm_umma(const void* x_f16, const void* qidxs, const void* grid_packed_abs, void* out_f16,

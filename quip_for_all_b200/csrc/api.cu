@@ -17,6 +17,7 @@ extern int g_opt_phase0;
 extern int g_opt_lean;
 extern int g_opt_rot_warp_rows;
 extern int g_opt_rot_pipe_rows;
+int g_opt_umma_rt = 0;       // experiments: 1 = one 128-row tile per CTA at every M (0 = auto: two when M > 64)
 int g_opt_umma_ksplit = 0;   // experiments: force the split-K factor of the tcgen05 kernel (0 = auto)
 int g_opt_umma = 2;     // in-kernel decode + tcgen05 GEMM (umma_gemm.cu): 0 = never, 1 = whenever the shape is covered
                         // (M <= 256), 2 = auto: where it measured faster than the alternatives (profiles/README.md)
@@ -84,6 +85,10 @@ extern "C" int quipb200_set_option(const char* name, int value) {
   }
   if (!strcmp(name, "pdl")) {
     qb::g_opt_pdl = value ? 1 : 0;
+    return 0;
+  }
+  if (!strcmp(name, "umma_rt")) {
+    qb::g_opt_umma_rt = value;
     return 0;
   }
   if (!strcmp(name, "umma_ksplit")) {

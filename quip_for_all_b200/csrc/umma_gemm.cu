@@ -10,18 +10,22 @@
 // thread feeds it to tcgen05.mma (kind::f16, fp32 accumulators in TMEM).
 //
 //   MMA shape : D[128 weight rows x NTOK tokens] += A[128 x 16] . B[NTOK x 16]^T   (cta_group::1, M = 128)
-//   grid      : (N / 128 row tiles) x (split-K so that ~all SMs have a CTA)
-//   pipeline  : STAGES shared-memory slots of 128 k; 16 producer warps (weights: table lookup + sign decode +
-//               int8 -> fp16 with the reference's exact 0x5c80 trick, one 16-byte swizzled store per code;
-//               activations: cp.async one stage ahead) arrive on full[s]; a 17th warp waits on it, issues the 8
-//               MMAs of the stage and tcgen05.commit's to empty[s], which gates the slot's reuse.  No CTA-wide
-//               barrier inside the main loop.
-//   epilogue  : tcgen05.ld (32 lanes x 32 bit x 16 columns) -> fp16 store, or fp32 atomics into a
-//               self-cleaning split-K workspace whose last CTA (ticket) converts the tile.
+//   grid      : (N / 128 row tiles) x (split-K <= 4 so that ~all SMs have a CTA); the K splits of a row tile form a
+//               thread-block cluster (1, ksplit, 1)
+//   pipeline  : STAGES shared-memory slots of 128 k.  16 producer warps decode the packed codes of the slot (table
+//               lookup + sign decode + int8 -> fp16 with the reference's exact 0x5c80 trick, one 16-byte swizzled store
+//               per code; codes ride three stages ahead in registers) and arrive on full[s]; the activation tile of the
+//               slot comes in by TMA (cp.async.bulk.tensor, tensor map over x with SWIZZLE_128B, rows beyond M zero
+//               filled), its bytes counted on the same barrier; a 17th warp waits on full[s], issues the 8 MMAs of the
+//               stage and tcgen05.commit's to empty[s], which gates the slot's reuse.  No CTA-wide barrier, no thread
+//               waiting on activation data in the main loop.
+//   epilogue  : tcgen05.ld (32 lanes x 32 bit x 16 columns) -> fp16 store; with split-K the cluster reduce-scatters
+//               the partial tiles through distributed shared memory (each CTA owns NTOK / ksplit token columns).
 //
 // Numerics: fp16 x fp16 products accumulated in fp32 (hardware order), one fp16 rounding -- the same
 // class as the reference's mma.sync kernel and cuBLAS path; decoded weights are bit-exact.
 #include <cooperative_groups.h>
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include "common.cuh"
 
@@ -29,6 +33,7 @@ namespace qb {
 
 namespace cg = cooperative_groups;
 extern int g_opt_umma_ksplit;
+extern int g_opt_umma_rt;
 
 constexpr int UG_THREADS = 256;
 constexpr int UG_BM = 128;   // weight rows per CTA = UMMA M
@@ -74,6 +79,13 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t sdst, const void* gsrc
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 
+// TMA: one [box rows x 64 k] fp16 tile of the activation matrix (tensor map with SWIZZLE_128B: the layout the UMMA
+// descriptor expects), rows beyond M zero-filled; completion is counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_2d(uint32_t sdst, const CUtensorMap* tmap, uint32_t bar, int crd0, int crd1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(sdst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(crd0), "r"(crd1) : "memory");
+}
+
 struct UmmaArgs {
   const unsigned char* codes;   // [N][K/8] int16 (E8P12) / int32 (E8P12RVQ4B) or [N][K/4] uint8 (D4)
   const __half* x;              // [M][K]
@@ -98,11 +110,17 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // Warp-specialised: 16 producer warps fill the stage slots (no CTA-wide barrier in the main loop), warp 16 waits on
 // full[s], issues the 8 MMAs of the stage and commits to empty[s].
 // CB: the producers' decode (QUIPB200_CB_E8P12 / _E8P12RVQ4B / _D4 / _E8P12RVQ3B / _HI); everything else is shared.
-template <int CB, int NTOK, int STAGES>
-__global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_constant__ UmmaArgs a) {
+// RT: 128-row weight tiles per CTA.  RT = 1: a stage is 128 rows x 128 k (two 64-wide swizzle tiles of A and of B).
+// RT = 2 (M > 64): a stage is 256 rows x 64 k -- two A tiles against ONE activation tile, two TMEM accumulators -- which
+// halves the activation bytes every CTA pulls from L2 per weight (at M = 256 that re-read, not the decode or the MMAs,
+// bounded the kernel: 64 KB per stage per CTA).
+template <int CB, int NTOK, int STAGES, int RT>
+__global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_constant__ UmmaArgs a,
+                                                                  const __grid_constant__ CUtensorMap tmap_x) {
   extern __shared__ unsigned char smem_raw[];
   constexpr uint32_t A_SUB = UG_BM * 128, B_SUB = NTOK * 128;           // one 64-wide swizzle tile
-  constexpr uint32_t A_BYTES = 2 * A_SUB, B_BYTES = 2 * B_SUB;
+  constexpr uint32_t A_BYTES = 2 * A_SUB, B_BYTES = (RT == 2 ? 1 : 2) * B_SUB;
+  constexpr int BK = RT == 2 ? 64 : 128;                                // k per stage
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle atoms need 1024-byte alignment
   unsigned char* gbase = smem_raw + (base - raw);
@@ -114,20 +132,20 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + STAGES * (A_BYTES + B_BYTES) + 3072 + 8 * (2 * STAGES + 1));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * UG_BM;
-  const int kb_begin = blockIdx.y * a.kb_per_split;                       // in units of UG_BK2
-  const int nit = min(a.kb_per_split, a.K / UG_BK2 - kb_begin);
+  const int n0 = blockIdx.x * (UG_BM * RT);
+  const int kb_begin = blockIdx.y * a.kb_per_split;                       // in units of BK
+  const int nit = min(a.kb_per_split, a.K / BK - kb_begin);
 
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(bar_full + 8 * s, UG_PRODUCERS / 32);    // one arrive per producer warp
+      mbar_init(bar_full + 8 * s, UG_PRODUCERS / 32 + 1);    // one arrive per producer warp + the TMA issuer's expect_tx
       mbar_init(bar_empty + 8 * s, 1);                   // tcgen05.commit
     }
     mbar_init(bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), NTOK);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), RT * NTOK);
   if (tid < 256 && CB != QUIPB200_CB_HI) {
     uint2 t = a.table[tid];
     if (CB != QUIPB200_CB_D4) {      // E8P abs entries with the "+1/4" pre-applied; D4: the fp16 grid rows as they are
@@ -152,11 +170,13 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
         mbar_wait(bar_full + 8 * s, (uint32_t)((it / STAGES) & 1));
         tc_fence_after();
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const uint64_t ad = umma_smem_desc(sA + s * A_BYTES + h * A_SUB), bd = umma_smem_desc(sB + s * B_BYTES + h * B_SUB);
+        for (int h = 0; h < 2; h++) {      // RT = 1: the two k halves of the stage; RT = 2: the two row tiles (accumulator h)
+          const uint64_t ad = umma_smem_desc(sA + s * A_BYTES + h * A_SUB);
+          const uint64_t bd = umma_smem_desc(sB + s * B_BYTES + (RT == 2 ? 0 : h) * B_SUB);
+          const uint32_t td = tmem_base + (RT == 2 ? (uint32_t)(h * NTOK) : 0u);
 #pragma unroll
           for (int k = 0; k < 4; k++)    // +32 bytes along K inside the swizzled row = +2 in the address field
-            umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, (it > 0 || h > 0 || k > 0) ? 1u : 0u);
+            umma_f16(td, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, (it > 0 || (RT == 1 && h > 0) || k > 0) ? 1u : 0u);
         }
         umma_commit(bar_empty + 8 * s);          // slot s is free again when these MMAs retire
       }
@@ -168,12 +188,14 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
     // chunks round-robin.  Packed bytes per thread per stage: 8 (E8P12: 4 codes, D4: 8 codes) or 16 (RVQ4B: 4 codes).
     // Packed bytes per thread per stage: 8 (E8P12 4 codes, D4 8 codes), 16 (RVQ4B 4 codes, HI 4 words), 12 (RVQ3B 4 codes).
     constexpr int CBYTES = (CB == QUIPB200_CB_E8P12RVQ4B || CB == QUIPB200_CB_HI) ? 16 : (CB == QUIPB200_CB_E8P12RVQ3B ? 12 : 8);
-    const int wrow = tid >> 2, wq = tid & 3;
+    // RT = 1: thread -> row tid / 4, k quarter tid % 4 of the stage's 128;  RT = 2: row tid / 2 (of 256), k half tid % 2 of 64
+    const int wrow = RT == 2 ? (tid >> 1) : (tid >> 2), wq = RT == 2 ? (tid & 1) : (tid & 3);
+    const int asub = RT == 2 ? (wrow >> 7) : (wq >> 1);              // which 16 KB A tile of the stage
     const size_t row_bytes = (size_t)(a.K >> 5) * CBYTES;            // CBYTES per 32 weights
     const unsigned char* wsrc = a.codes + (size_t)(n0 + wrow) * row_bytes + wq * CBYTES;
     const uint64_t pol = l2_evict_first_policy();
     auto load_codes = [&](int it) -> uint4 {
-      const unsigned char* p = wsrc + (size_t)(kb_begin + it) * (4 * CBYTES);
+      const unsigned char* p = wsrc + (size_t)(kb_begin + it) * ((BK / 32) * CBYTES);
       if (CBYTES == 16) return ldg_stream_v4(p, pol);
       if (CBYTES == 12) {      // 4-byte aligned only (row pitch 3K/8)
         const uint32_t* p4 = reinterpret_cast<const uint32_t*>(p);
@@ -182,15 +204,15 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
       const uint2 v = ldg_stream_v2(p, pol);
       return make_uint4(v.x, v.y, 0u, 0u);
     };
+    // activations: thread 0 posts the stage's byte count on full[s] and issues the tile loads; the copy engine does the
+    // rest (address generation, swizzle, zero fill of the rows beyond M), so no thread ever waits on activation data
     auto issue_acts = [&](int it) {
+      if (tid != 0) return;
       const int s = it % STAGES;
-      const __half* xs = a.x + (size_t)(kb_begin + it) * UG_BK2;
-      for (int c = tid; c < NTOK * 16; c += UG_PRODUCERS) {
-        const int tok = c >> 4, h = (c >> 3) & 1, ch = c & 7;
-        const bool ok = tok < a.M;
-        const __half* src = xs + (size_t)(ok ? tok : 0) * a.K + h * 64 + ch * 8;
-        cp_async16_zfill(sB + s * B_BYTES + h * B_SUB + tok * 128 + ((ch ^ (tok & 7)) << 4), src, ok ? 16u : 0u);
-      }
+      mbar_arrive_expect_tx(bar_full + 8 * s, B_BYTES);
+#pragma unroll
+      for (int h = 0; h < (RT == 2 ? 1 : 2); h++)
+        tma_load_2d(sB + s * B_BYTES + h * B_SUB, &tmap_x, bar_full + 8 * s, (kb_begin + it) * BK + h * 64, 0);
     };
     // packed codes come from HBM (read once, ~1 us away): three stages of them ride in registers ahead of the decode
     uint4 cur = make_uint4(0, 0, 0, 0), nx1 = cur, nx2 = cur;
@@ -201,7 +223,6 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
     }
     if (nit > 1) nx1 = load_codes(1);
     if (nit > 2) nx2 = load_codes(2);
-    asm volatile("cp.async.commit_group;" ::: "memory");
     for (int it = 0; it < nit; it++) {
       const int s = it % STAGES;
       uint4 nx3 = make_uint4(0, 0, 0, 0);
@@ -210,11 +231,10 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
         if (it + 1 >= STAGES) mbar_wait(bar_empty + 8 * ((it + 1) % STAGES), (uint32_t)(((it + 1) / STAGES - 1) & 1));
         issue_acts(it + 1);
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
       // weights of stage `it` -> slot s (free: empty[s] was waited on one iteration ago, or it < STAGES)
       {
         const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
-        unsigned char* arow = gbase + (size_t)s * A_BYTES + (wq >> 1) * A_SUB + wrow * 128;
+        unsigned char* arow = gbase + (size_t)s * A_BYTES + asub * A_SUB + (wrow & 127) * 128;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           uint4 v;
@@ -288,7 +308,6 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
           *reinterpret_cast<uint4*>(arow + ((ch ^ (wrow & 7)) << 4)) = v;
         }
       }
-      asm volatile("cp.async.wait_group 1;" ::: "memory");           // this thread's activation chunks of stage `it`
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * s);
@@ -298,76 +317,113 @@ __global__ void __launch_bounds__(UG_THREADS2, 1) e8p_umma_kernel(const __grid_c
   mbar_wait(bar_done, 0);
   tc_fence_after();
 
-  // ---- epilogue: TMEM lane = weight row, column = token.  Producer warp w: lane quadrant w % 4, column quarter w / 4.
+  // ---- epilogue: TMEM lane = weight row (of row tile `sub`), column = sub * NTOK + token.  Producer warp w: lane quadrant
+  // w % 4, column quarter w / 4.
   const int quad = warp & 3, cq = warp >> 2;
   constexpr int CW = NTOK / 4 < 16 ? 16 : NTOK / 4;        // columns per warp (>= one 16-column load)
   if (a.ksplit == 1) {
     if (warp < UG_PRODUCERS / 32 && nit > 0) {
-      const int n = n0 + quad * 32 + lane;
-      for (int c0 = cq * CW; c0 < (cq + 1) * CW && c0 < NTOK; c0 += 16) {
-        if (c0 >= a.M) break;                        // warp-uniform: token columns beyond M hold zeros
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; j++)
-          if (c0 + j < a.M) a.out[(size_t)(c0 + j) * a.N + n] = __float2half_rn(v[j]);
+      for (int sub = 0; sub < RT; sub++) {
+        const int n = n0 + sub * UG_BM + quad * 32 + lane;
+        for (int c0 = cq * CW; c0 < (cq + 1) * CW && c0 < NTOK; c0 += 16) {
+          if (c0 >= a.M) break;                        // warp-uniform: token columns beyond M hold zeros
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sub * NTOK + c0), v);
+#pragma unroll
+          for (int j = 0; j < 16; j++)
+            if (c0 + j < a.M) a.out[(size_t)(c0 + j) * a.N + n] = __float2half_rn(v[j]);
+        }
       }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, NTOK);
+    if (warp == 0) tmem_dealloc(tmem_base, RT * NTOK);
     return;
   }
   // ---- split-K: the ksplit CTAs of a row tile form a cluster (1, ksplit, 1) and reduce-scatter their accumulators through
   // distributed shared memory: CTA r owns the token columns [r * NTOK / ksplit, ...), every CTA pushes each 16-column
   // group of its TMEM tile into the owner's receive buffer (the stage ring, idle now), the owner adds the ksplit partial
-  // tiles and stores fp16.  No atomics, no workspace, no second pass through L2.
+  // tiles and stores fp16.  No atomics, no workspace, no second pass through L2.  (RT = 2: one round per row tile.)
   {
     cg::cluster_group cluster = cg::this_cluster();
     const int r = (int)cluster.block_rank();
-    const int cols_per = NTOK / a.ksplit;                       // >= 4 (NTOK >= 32, ksplit <= 8); a multiple of 4
+    const int cols_per = NTOK / a.ksplit;                       // >= 4 (NTOK >= 32, ksplit <= 8)
     float* recv = reinterpret_cast<float*>(gbase);              // [ksplit sources][cols_per][128 rows]
-    cluster.sync();                                             // every CTA of the tile is done with its stage ring
-    if (warp < UG_PRODUCERS / 32) {
-      const int row = quad * 32 + lane;
-      for (int c0 = cq * CW; c0 < (cq + 1) * CW && c0 < NTOK; c0 += 16) {
-        if (c0 >= a.M) break;
-        float v[16];
-        if (nit > 0) {
-          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-        } else {                                               // (a split with no k-blocks contributes zeros)
+    const int tok0 = r * cols_per;
+#pragma unroll 1
+    for (int sub = 0; sub < RT; sub++) {
+      cluster.sync();                                           // every CTA is done with its stage ring / the previous round
+      if (warp < UG_PRODUCERS / 32) {
+        const int row = quad * 32 + lane;
+        for (int c0 = cq * CW; c0 < (cq + 1) * CW && c0 < NTOK; c0 += 16) {
+          if (c0 >= a.M) break;
+          float v[16];
+          if (nit > 0) {
+            tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sub * NTOK + c0), v);
+          } else {                                               // (a split with no k-blocks contributes zeros)
 #pragma unroll
-          for (int j = 0; j < 16; j++) v[j] = 0.f;
-        }
+            for (int j = 0; j < 16; j++) v[j] = 0.f;
+          }
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-          const int c = c0 + j;
-          const int d = c / cols_per, lc = c - d * cols_per;
-          float* dst = cluster.map_shared_rank(recv, d) + ((size_t)(r * cols_per + lc) << 7) + row;
-          *dst = v[j];
+          for (int j = 0; j < 16; j++) {
+            const int c = c0 + j;
+            const int d = c / cols_per, lc = c - d * cols_per;
+            float* dst = cluster.map_shared_rank(recv, d) + ((size_t)(r * cols_per + lc) << 7) + row;
+            *dst = v[j];
+          }
         }
+      }
+      cluster.sync();                                           // all partial tiles of this round delivered
+      for (int i = tid; i < cols_per * UG_BM; i += UG_THREADS2) {
+        const int lc = i >> 7, row = i & 127;
+        const int tok = tok0 + lc;
+        if (tok >= a.M) break;
+        float acc = 0.f;
+        for (int src = 0; src < a.ksplit; src++) acc += recv[((size_t)(src * cols_per + lc) << 7) + row];
+        a.out[(size_t)tok * a.N + n0 + sub * UG_BM + row] = __float2half_rn(acc);
       }
     }
     tc_fence_before();
-    cluster.sync();                                             // all partial tiles delivered
-    if (warp == 0) tmem_dealloc(tmem_base, NTOK);
-    const int tok0 = r * cols_per;
-    for (int i = tid; i < cols_per * UG_BM; i += UG_THREADS2) {
-      const int lc = i >> 7, row = i & 127;
-      const int tok = tok0 + lc;
-      if (tok >= a.M) break;
-      float acc = 0.f;
-      for (int src = 0; src < a.ksplit; src++) acc += recv[((size_t)(src * cols_per + lc) << 7) + row];
-      a.out[(size_t)tok * a.N + n0 + row] = __float2half_rn(acc);
-    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, RT * NTOK);
+    cluster.sync();                                             // nobody exits while a peer may still read its buffer
   }
 }
 
-template <int CB, int NTOK, int STAGES>
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (the library does not link libcuda)
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (TmapEncodeFn)p;
+  }
+  return fn;
+}
+
+template <int CB, int NTOK, int STAGES, int RT>
 static int launch_umma(const UmmaArgs& a, dim3 grid, cudaStream_t st) {
-  const size_t smem = (size_t)STAGES * 2 * (UG_BM * 128 + NTOK * 128) + 3072 + 8 * (2 * STAGES + 1) + 16 + 1024;
-  cudaError_t e = cudaFuncSetAttribute(e8p_umma_kernel<CB, NTOK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)STAGES * (2 * UG_BM * 128 + (RT == 2 ? 1 : 2) * NTOK * 128) + 3072 + 8 * (2 * STAGES + 1) + 16 + 1024;
+  const void* fn = (const void*)e8p_umma_kernel<CB, NTOK, STAGES, RT>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
+  // x as a 2-D tensor {K (contiguous), M}; one box = 64 k x NTOK token rows = one 128-byte-swizzled UMMA B tile
+  TmapEncodeFn enc = tmap_encoder();
+  if (!enc) return QUIPB200_EUNSUPPORTED;
+  alignas(64) CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)a.K, (cuuint64_t)a.M};
+  const cuuint64_t gstride[1] = {(cuuint64_t)a.K * sizeof(__half)};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)NTOK};
+  const cuuint32_t estr[2] = {1u, 1u};
+  if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(a.x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return QUIPB200_EINVAL;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(UG_THREADS2);
@@ -380,18 +436,23 @@ static int launch_umma(const UmmaArgs& a, dim3 grid, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  void* args[] = {const_cast<UmmaArgs*>(&a)};
-  e = cudaLaunchKernelExC(&cfg, (const void*)e8p_umma_kernel<CB, NTOK, STAGES>, args);
+  void* args[] = {const_cast<UmmaArgs*>(&a), &tmap};
+  e = cudaLaunchKernelExC(&cfg, fn, args);
   if (e != cudaSuccess) return (int)e;
   QB_LAUNCH_CHECK();
   return 0;
 }
+// rt: row tiles per CTA chosen by the host (2 needs N % 256 == 0)
 template <int CB>
-static int launch_umma_m(const UmmaArgs& a, dim3 grid, cudaStream_t st) {
-  if (a.M <= 32) return launch_umma<CB, 32, 4>(a, grid, st);
-  if (a.M <= 64) return launch_umma<CB, 64, 4>(a, grid, st);
-  if (a.M <= 128) return launch_umma<CB, 128, 3>(a, grid, st);
-  return launch_umma<CB, 256, 2>(a, grid, st);
+static int launch_umma_m(const UmmaArgs& a, dim3 grid, int rt, cudaStream_t st) {
+  if (rt == 2) {
+    if (a.M <= 128) return launch_umma<CB, 128, 4, 2>(a, grid, st);
+    return launch_umma<CB, 256, 3, 2>(a, grid, st);
+  }
+  if (a.M <= 32) return launch_umma<CB, 32, 4, 1>(a, grid, st);
+  if (a.M <= 64) return launch_umma<CB, 64, 4, 1>(a, grid, st);
+  if (a.M <= 128) return launch_umma<CB, 128, 3, 1>(a, grid, st);
+  return launch_umma<CB, 256, 2, 1>(a, grid, st);
 }
 
 }  // namespace qb
@@ -399,8 +460,8 @@ static int launch_umma_m(const UmmaArgs& a, dim3 grid, cudaStream_t st) {
 using namespace qb;
 
 extern "C" size_t quipb200_e8p_mm_umma_workspace_bytes(int M, int N, int K) {
-  if (M < 1 || N < 1 || K < 1) return 0;
-  return (size_t)N * UG_WS_LD * sizeof(float) + (size_t)(N / UG_BM + 1) * sizeof(unsigned int) + 256;
+  (void)M; (void)N; (void)K;
+  return 0;   // split-K partial tiles are reduced through distributed shared memory: no workspace since round 2
 }
 
 extern "C" int quipb200_mm_umma(int codebook, const void* x, const void* qidxs, const void* grid, const void* grid2, float scale,
@@ -413,9 +474,13 @@ extern "C" int quipb200_mm_umma(int codebook, const void* x, const void* qidxs, 
   if (!aligned16(x) || !aligned16(qidxs) || !aligned16(grid) || !aligned16(out) || ((uintptr_t)grid2 & 3)) return QUIPB200_EALIGN;
   const int sms = quipb200_sm_count();
   if (sms < 1) return (int)cudaErrorNoDevice;
-  const int tiles = N / UG_BM, nkb = K / UG_BK2;
+  // (option umma_rt=2: 256 rows x 64 k per stage.  Measured slower at every shape -- the pipeline is bound by per-stage
+  // latency, and halving k per stage doubles the stage count -- so one row tile per CTA is the default.)
+  const int rt = (g_opt_umma_rt == 2 && M > 64 && N % (2 * UG_BM) == 0) ? 2 : 1;
+  const int tiles = N / (UG_BM * rt), nkb = K / (rt == 2 ? 64 : UG_BK2);
   int ksplit = 1;
-  while (ksplit < 8 && tiles * ksplit * 2 <= sms && nkb / (ksplit * 2) >= 4) ksplit *= 2;   // <= 8: one portable cluster
+  // <= 4: clusters of 8 of these one-per-SM CTAs do not all fit in one wave (measured 2x slower at 4096 x 4096)
+  while (ksplit < 4 && tiles * ksplit * 2 <= sms && nkb / (ksplit * 2) >= 4 * rt) ksplit *= 2;
   if (g_opt_umma_ksplit > 0 && g_opt_umma_ksplit <= 8 && !(g_opt_umma_ksplit & (g_opt_umma_ksplit - 1)) &&
       nkb / g_opt_umma_ksplit >= 1)
     ksplit = g_opt_umma_ksplit;
@@ -429,11 +494,11 @@ extern "C" int quipb200_mm_umma(int codebook, const void* x, const void* qidxs, 
   (void)workspace; (void)ws_bytes;   // split-K partial tiles are reduced through distributed shared memory: no workspace
   const dim3 grid_dim(tiles, ksplit);
   cudaStream_t st = (cudaStream_t)stream;
-  if (codebook == QUIPB200_CB_E8P12) return launch_umma_m<QUIPB200_CB_E8P12>(a, grid_dim, st);
-  if (codebook == QUIPB200_CB_E8P12RVQ4B) return launch_umma_m<QUIPB200_CB_E8P12RVQ4B>(a, grid_dim, st);
-  if (codebook == QUIPB200_CB_E8P12RVQ3B) return launch_umma_m<QUIPB200_CB_E8P12RVQ3B>(a, grid_dim, st);
-  if (codebook == QUIPB200_CB_HI) return launch_umma_m<QUIPB200_CB_HI>(a, grid_dim, st);
-  return launch_umma_m<QUIPB200_CB_D4>(a, grid_dim, st);
+  if (codebook == QUIPB200_CB_E8P12) return launch_umma_m<QUIPB200_CB_E8P12>(a, grid_dim, rt, st);
+  if (codebook == QUIPB200_CB_E8P12RVQ4B) return launch_umma_m<QUIPB200_CB_E8P12RVQ4B>(a, grid_dim, rt, st);
+  if (codebook == QUIPB200_CB_E8P12RVQ3B) return launch_umma_m<QUIPB200_CB_E8P12RVQ3B>(a, grid_dim, rt, st);
+  if (codebook == QUIPB200_CB_HI) return launch_umma_m<QUIPB200_CB_HI>(a, grid_dim, rt, st);
+  return launch_umma_m<QUIPB200_CB_D4>(a, grid_dim, rt, st);
 }
 
 extern "C" int quipb200_e8p_mm_umma(const void* x, const void* qidxs, const void* grid, void* out, int M, int N, int K,

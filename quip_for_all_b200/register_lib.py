@@ -179,13 +179,12 @@ def _mm_fused(codebook, x, Qidxs, grid, scale, K):
     return out
 
 
-_UMMA_WS = {}
 
 
 def umma_preferred(M: int, N: int, K: int, codebook=None) -> bool:
     """Dispatch policy of the codebook mm ops (measured on B200, profiles/README.md): the tcgen05 kernel decodes every code
     once for all rows, the integer-dp4a GEMV once per row (1 row: 10 us, 4 rows: 37 us, 16 rows: 121 us at 4096 x 4096),
-    and decompress + cuBLAS catches up from ~64 rows on.  RVQ4B / D4: the reference's own small-M kernels (K2 / K3) stop at
+    and decompress + cuBLAS catches up at ~128 rows for 4096 x 4096 and beyond 128 rows for the larger layers.  RVQ4B / D4: the reference's own small-M kernels (K2 / K3) stop at
     32 / 24 rows; the tcgen05 route covers 4 .. 32 rows for them."""
     opt = _native.get_option("umma")
     if opt == 0 or N % 128 or K % 128 or M < 1 or M > 256:
@@ -196,7 +195,11 @@ def umma_preferred(M: int, N: int, K: int, codebook=None) -> bool:
         return 4 <= M <= 32
     if opt == 1:
         return M > 16
-    return 4 <= M <= 32 or (32 < M <= 64 and N * K >= (32 << 20))     # (1 .. 3 rows: the integer GEMV, one pass per row)
+    if 4 <= M <= 64:                 # (1 .. 3 rows: the integer GEMV, one pass per row)
+        return True
+    # beyond 64 rows the activation tile every CTA re-reads from L2 grows with M; decompress + cuBLAS pays 2 N K bytes of
+    # dense weights instead, so the crossover moves out with the layer size (r02_umma_bench.json)
+    return M <= 128 and N * K >= (32 << 20)      # (129 .. 256 rows: 0.7-0.9x of the dense route at every shape measured)
 
 
 def _mm_umma(x, Qidxs, grid, K, codebook=None, scale=0.0, grid2=None):
@@ -207,23 +210,12 @@ def _mm_umma(x, Qidxs, grid, K, codebook=None, scale=0.0, grid2=None):
     if codebook is None:
         codebook = _native.CB_E8P12
     L = lib()
-    # The kernel accumulates fp32 split-K partials and arrival tickets in the workspace and leaves it zero again; two
-    # launches that overlap in time must not share one.  Launches on one stream are ordered, so the workspace is keyed by
-    # (device, stream, N).  A workspace first needed while a CUDA graph is being captured belongs to the capture stream
-    # (torch captures on a stream of its own, so eager calls never share it): its zero fill is captured with it and
-    # re-runs at the head of every replay, which is harmless because the kernel leaves the workspace zeroed anyway.
-    stream = torch.cuda.current_stream(x.device)
-    key = (x.device.index, stream.cuda_stream, N)
-    ws = _UMMA_WS.get(key)
-    if ws is None:
-        nbytes = L.quipb200_e8p_mm_umma_workspace_bytes(256, N, K)
-        ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=x.device)
-        _UMMA_WS[key] = ws
-    off = (-ws.data_ptr()) % 256
+    # (no workspace: split-K partial tiles are reduced inside the kernel's cluster, so concurrent launches on different
+    # streams share nothing)
     out = torch.empty((M, N), dtype=torch.float16, device=x.device)
     with torch.cuda.device(x.device):
         rc = L.quipb200_mm_umma(int(codebook), _ptr(x), _ptr(Qidxs), _ptr(grid), _ptr(grid2), float(scale), _ptr(out), M, N, K,
-                                ctypes.c_void_p(ws.data_ptr() + off), ws.numel() - 256, _stream())
+                                None, 0, _stream())
     if rc == _native.EUNSUPPORTED:
         return None
     check(rc, "mm_umma")

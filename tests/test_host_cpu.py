@@ -319,7 +319,10 @@ def test_mm_dispatch_policy_and_rotation_coverage():
         assert _native.get_option("umma") == 2
         assert not rl.umma_preferred(1, 4096, 4096) and not rl.umma_preferred(3, 4096, 4096)
         assert rl.umma_preferred(4, 4096, 4096) and rl.umma_preferred(32, 4096, 4096)
-        assert not rl.umma_preferred(33, 4096, 4096) and rl.umma_preferred(64, 4096, 11008)
+        assert rl.umma_preferred(64, 4096, 4096) and rl.umma_preferred(64, 4096, 11008)
+        # 65 .. 128 rows: layers of >= 32 Mi weights; beyond that the dense route
+        assert not rl.umma_preferred(128, 4096, 4096) and rl.umma_preferred(128, 4096, 11008)
+        assert not rl.umma_preferred(129, 8192, 8192) and not rl.umma_preferred(256, 8192, 28672)
         assert not rl.umma_preferred(16, 4096 + 64, 4096) and not rl.umma_preferred(300, 4096, 4096)
 
 
