@@ -54,3 +54,35 @@ for (n, K, fin, fout, M) in ((4096, 1, 4000, 3968, 3), (2816, 11, 2816, 2800, 5)
     y = torch.ops.quip_lib.rotate_fused(x, pre, hk, post, post, n, K, fout, 1.0 / math.sqrt(n // K))
     torch.cuda.synchronize()
     print("rotate", n, K, M, "ok", float(y.float().abs().max()))
+
+# per-linear fused op (round 2 paths): cluster rotations on both sides (K = 3 / 5 / 7 blocks of 256 .. 4096 points), the
+# 4096 / 8192-point warp-first FWHT, replicated-table GEMV (>= 8 Mi weights), grouped launch with a shared input
+from quip_for_all_b200 import QuantLinear  # noqa: E402
+from quip_for_all_b200.modeling import randomize_quantlinear  # noqa: E402
+from quip_for_all_b200.quantizer import apply_load_time_tricks  # noqa: E402
+from quip_for_all_b200.fused import LinearGroup  # noqa: E402
+
+gd = torch.Generator(device=dev)
+gd.manual_seed(0)
+for (fin, fout, M) in ((768, 1280, 1), (3 * 1024, 5 * 512, 2), (7 * 4096, 4096, 1), (4096, 7 * 2048, 1), (8192, 4096, 1), (4096, 4096, 3)):
+    L = QuantLinear(fin, fout, codebook_id["E8P12"](inference=True), bias=True).to(dev)
+    randomize_quantlinear(L, gd)
+    L.eval()
+    apply_load_time_tricks(torch.nn.ModuleList([L]))
+    x = torch.randn(M, fin, generator=g).half().to(dev)
+    with torch.no_grad():
+        y = L(x)
+    torch.cuda.synchronize()
+    print("quantlinear", fin, fout, M, "ok", float(y.float().abs().max()))
+ls = [QuantLinear(1024, 3 * 256, codebook_id["E8P12"](inference=True), bias=False).to(dev) for _ in range(2)]
+for L in ls:
+    randomize_quantlinear(L, gd)
+    L.eval()
+apply_load_time_tricks(torch.nn.ModuleList(ls))
+grp = LinearGroup(ls)
+h = torch.randn(1, 1024, generator=g).half().to(dev)
+w = torch.ones(1024, dtype=torch.float16, device=dev)
+with torch.no_grad():
+    a, b = grp(h, norm_w=w, eps=1e-5)
+torch.cuda.synchronize()
+print("group (cluster epilogue, 2 members in one launch) ok", float(a.float().abs().max()), float(b.float().abs().max()))
