@@ -270,6 +270,20 @@ int quipb200_decode_step_debug_cta(int cta);   /* which CTA writes the stamps (d
  * takes effect for workspaces sized and steps launched afterwards. */
 int quipb200_decode_step_set_splits(int splits);
 
+/* ---------------------------------------------------------------------------------------------
+ * Quantise-time nearest-codeword search
+ *   replaces `E8P12_codebook.round` / `.quantize` (codebook/e8p12.py:125-134: `(2 * X @ grid.T - grid_norm).argmax(-1)`
+ *   over the 65 536 x 8 table, then `grid[idx]`) and, with n_stages = 2, `E8P12RVQ4B_codebook.quantize`
+ *   (codebook/e8p12_rvq4.py:37-46: a second search on `(X - init_vals) / opt_resid_scale`,
+ *   vals = init + resid * scale, idx = (init << 16) + resid) -- the call LDLQ makes once per 8 columns (quant.py:128-129).
+ *   x: fp32 [m, 8]; vals_out: fp32 [m, 8]; idx_out: int64 [m] (torch.argmax's dtype; equal scores resolve to the lowest
+ *   index, torch's first-occurrence rule).  The [m, 65536] score matrix of the reference is never materialised.
+ *   workspace: quipb200_e8p_quantize_workspace_bytes(m) bytes, 16-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+size_t quipb200_e8p_quantize_workspace_bytes(int64_t m);
+int quipb200_e8p_quantize(const float* x, int64_t m, const int64_t* grid_packed_abs, int n_stages, float resid_scale,
+                          float* vals_out, int64_t* idx_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Tuning / introspection hooks used by bench.py and the tests (not part of the reference surface). */
 /* options: "umma" 0|1|2 (tcgen05 decode+GEMM never / whenever covered / where measured faster; default 2),
  *   "rot_warp_rows", "rot_pipe_rows" (row counts from which the many-rows rotation kernels are used),

@@ -571,3 +571,77 @@ def llama_decoder_layer_step(h, layer, k_cache, v_cache, pos, *, n_heads, n_kv_h
     g, u = lin("gate", x), lin("up", x)
     act = rd(rd(g / (1.0 + np.exp(-g))) * u)
     return rd(h + lin("down", act))
+
+
+# --------------------------------------------------------------------------------------
+# Quantise-time path: nearest codeword + LDLQ  -- float64 statements
+# --------------------------------------------------------------------------------------
+
+def e8p_nearest(x: np.ndarray, table: np.ndarray | None = None, chunk: int = 256):
+    """codebook/e8p12.py:125-128 (`round`): argmax_c 2 x.g_c - |g_c|^2 over the 65 536 codewords, FIRST index on equal
+    scores (torch.argmax).  Evaluated in float64 (the codewords are multiples of 1/4: products and norms are exact for
+    fp32 inputs up to the final sum).  Returns (idx int64 [m], best score float64 [m], scores of a given index via
+    `e8p_score`)."""
+    g = e8p_full_grid(table).astype(np.float64)
+    gn = (g * g).sum(1)
+    x = np.asarray(x, dtype=np.float64).reshape(-1, 8)
+    idx = np.empty(x.shape[0], dtype=np.int64)
+    best = np.empty(x.shape[0], dtype=np.float64)
+    for a in range(0, x.shape[0], chunk):
+        s = 2.0 * x[a:a + chunk] @ g.T - gn
+        idx[a:a + chunk] = s.argmax(1)
+        best[a:a + chunk] = s.max(1)
+    return idx, best
+
+
+def e8p_score(x: np.ndarray, idx: np.ndarray, table: np.ndarray | None = None) -> np.ndarray:
+    """float64 score 2 x.g - |g|^2 of the given codeword indices (one per row of x)."""
+    g = e8p_full_grid(table).astype(np.float64)[np.asarray(idx, dtype=np.int64)]
+    x = np.asarray(x, dtype=np.float64).reshape(-1, 8)
+    return 2.0 * (x * g).sum(1) - (g * g).sum(1)
+
+
+def e8prvq4_quantize(x: np.ndarray, scale: float = RVQ4_DEFAULT_RESID_SCALE):
+    """codebook/e8p12_rvq4.py:37-46 with fp32 tensors: init = round(X); resid = (X - init) / fl32(scale) (fp32);
+    resid code = round(resid); vals = init + resid_vals * fl32(scale) (fp32 mul, fp32 add); idx = (init << 16) + resid."""
+    g32 = e8p_full_grid()
+    x32 = np.asarray(x, dtype=np.float32).reshape(-1, 8)
+    s32 = np.float32(scale)
+    i0, _ = e8p_nearest(x32)
+    v0 = g32[i0]
+    r = ((x32 - v0) / s32).astype(np.float32)
+    i1, _ = e8p_nearest(r)
+    vals = (v0 + (g32[i1] * s32).astype(np.float32)).astype(np.float32)
+    return vals, (i0 << 16) + i1, r
+
+
+def block_ldl(L: np.ndarray, b: int) -> np.ndarray:
+    """quant.py:91-104: every b-column block of L is multiplied by the inverse of its diagonal block."""
+    n = L.shape[0]
+    out = np.array(L, dtype=np.float64, copy=True)
+    for i in range(n // b):
+        out[:, i * b:(i + 1) * b] = out[:, i * b:(i + 1) * b] @ np.linalg.inv(L[i * b:(i + 1) * b, i * b:(i + 1) * b])
+    return out
+
+
+def ldlq(W: np.ndarray, H: np.ndarray, L: np.ndarray, tune_iters: int = 0):
+    """quant.py:107-139 (`LDLQ`, E8P12 codebook), float64: the last 8-column group is rounded first, each group sees
+    the error of everything to its right through the block-LDL factor; optional re-rounding sweeps (:131-139)."""
+    g = e8p_full_grid().astype(np.float64)
+    W = np.asarray(W, dtype=np.float64)
+    m, n = W.shape
+    Lb = block_ldl(np.asarray(L, dtype=np.float64), 8)
+    hat = np.zeros_like(W)
+    Q = np.zeros((m, n // 8), dtype=np.int64)
+    for k in range(n // 8 - 1, -1, -1):
+        a, b = 8 * k, 8 * k + 8
+        t = W[:, a:b] + (W[:, b:] - hat[:, b:]) @ Lb[b:, a:b]
+        Q[:, k], _ = e8p_nearest(t)
+        hat[:, a:b] = g[Q[:, k]]
+    for _ in range(tune_iters):
+        for k in range(n // 8 - 1, -1, -1):
+            a, b = 8 * k, 8 * k + 8
+            t = hat[:, a:b] + (W - hat) @ H[:, a:b] @ np.linalg.inv(H[a:b, a:b])
+            Q[:, k], _ = e8p_nearest(t)
+            hat[:, a:b] = g[Q[:, k]]
+    return hat, Q

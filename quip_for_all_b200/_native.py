@@ -26,6 +26,7 @@ EXPORTS = [
     "quipb200_decode_step_workspace_bytes", "quipb200_decode_step", "quipb200_decode_step_debug", "quipb200_decode_step_debug_cta", "quipb200_decode_step_set_splits",
     "quipb200_e8p_mm_umma_workspace_bytes", "quipb200_e8p_mm_umma", "quipb200_mm_umma", "quipb200_rotate_batched",
     "quipb200_lm_tail_workspace_bytes", "quipb200_lm_tail",
+    "quipb200_e8p_quantize_workspace_bytes", "quipb200_e8p_quantize",
     "quipb200_set_option", "quipb200_get_option", "quipb200_launch_count", "quipb200_debug_timeline",
 ]
 
@@ -97,6 +98,10 @@ def lib():
     L.quipb200_lm_tail_workspace_bytes.restype = c_size_t
     L.quipb200_lm_tail.restype = c_int
     L.quipb200_lm_tail.argtypes = [vp, vp, c_float, vp, vp, c_int, c_int, vp, vp, vp, vp, vp, c_size_t, vp]
+    L.quipb200_e8p_quantize_workspace_bytes.restype = c_size_t
+    L.quipb200_e8p_quantize_workspace_bytes.argtypes = [c_int64]
+    L.quipb200_e8p_quantize.restype = c_int
+    L.quipb200_e8p_quantize.argtypes = [vp, c_int64, vp, c_int, c_float, vp, vp, vp, c_size_t, vp]
     L.quipb200_debug_timeline.argtypes = [vp]
     L.quipb200_debug_timeline.restype = c_int
     L.quipb200_set_option.argtypes = [c_char_p, c_int]

@@ -103,7 +103,13 @@ class E8P12_codebook(nn.Module):
         return grid[Xqidx], Xqidx
 
     def quantize(self, X, return_idx=True):
-        vals, idxs = self.round(X, self.grid, self.grid_norm)
+        # CUDA fp32 rows (what LDLQ feeds, quant.py:128-129) go to the fused search kernel (csrc/nearest.cu), which never
+        # materialises the [m, 65536] score matrix; other dtypes / devices evaluate the reference's torch expression
+        from ..nearest import e8p_quantize, native_ok
+        if native_ok(X):
+            vals, idxs = e8p_quantize(X, self.grid_packed_abs)
+        else:
+            vals, idxs = self.round(X, self.grid, self.grid_norm)
         return (vals, idxs) if return_idx else vals
 
     def maybe_pack_idxs(self, idxs):

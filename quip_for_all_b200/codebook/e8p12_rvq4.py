@@ -30,6 +30,10 @@ class E8P12RVQ4B_codebook(nn.Module):
         return grid[Xqidx], Xqidx
 
     def quantize(self, X, return_idx=True):
+        from ..nearest import e8p_quantize, native_ok
+        if native_ok(X):      # both searches + the residual arithmetic in the fused kernels (csrc/nearest.cu)
+            final_vals, final_idxs = e8p_quantize(X, self.grid_packed_abs, 2, self.opt_resid_scale)
+            return (final_vals, final_idxs) if return_idx else final_vals
         init_vals, init_idxs = self.round(X, self.grid, self.grid_norm)
         resid = (X - init_vals) / self.opt_resid_scale
         resid_vals, resid_idxs = self.round(resid, self.grid, self.grid_norm)

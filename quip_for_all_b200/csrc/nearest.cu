@@ -1,0 +1,189 @@
+// Quantise-time nearest-codeword search for the E8P12 family.
+//
+// Reference: `E8P12_codebook.round` (codebook/e8p12.py:125-128) -- `(2 * X @ grid.T - grid_norm).argmax(-1)` over
+// the 65 536 x 8 codeword table -- and `E8P12RVQ4B_codebook.quantize` (codebook/e8p12_rvq4.py:37-46), which runs it
+// twice (second time on `(X - init_vals) / opt_resid_scale`).  The reference materialises the [m, 65536] fp32 score
+// matrix with a library GEMM (1 GB for the 4096 rows of one LDLQ step) and runs argmax over it.  Here the scores are
+// never stored: a CTA decodes a chunk of 1024 codewords into shared memory once (same decode as the inference
+// kernels, common.cuh `e8p_decode_q`), every thread keeps 4 input vectors in registers, streams the chunk through
+// broadcast shared-memory reads (8 FMA + compare per pair) and folds its running (score, index) into one 64-bit
+// atomicMax per vector.  Key = (order-preserving image of the fp32 score) << 32 | (0xffff - index): the maximum is
+// the best score and, on equal scores, the LOWEST index -- torch.argmax's first-occurrence rule.
+//
+// Arithmetic (stated so that the CPU oracle can restate it): score(c) = fl(sum_j (2 x_j) g_j) - fl(fl(sqrt(|g|^2))^2),
+// the sum as an fp32 fma chain over j = 0..7 in element order; |g|^2 is exact in fp32 (multiples of 1/16 below 17), so
+// the norm term equals torch's `grid.norm(dim=-1) ** 2` bit for bit.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace qb {
+
+constexpr int NQ_THREADS = 128;
+constexpr int NQ_VT = 4;        // vectors per thread
+constexpr int NQ_CHUNK = 1024;  // codewords per CTA
+constexpr int NQ_NCHUNK = 65536 / NQ_CHUNK;
+
+__device__ __forceinline__ unsigned long long nq_key(float s, uint32_t c) {
+  uint32_t u = __float_as_uint(s);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)u << 32) | (unsigned long long)(0xffffu - c);
+}
+
+// codeword c -> 8 floats in element order (weight i = packed byte {0,2,1,3,4,6,5,7}[i])
+__device__ __forceinline__ void nq_decode(const uint2* __restrict__ tab, uint32_t c, float (&e)[8]) {
+  uint2 t = __ldg(tab + (c >> 8));
+  t.x |= 0x01010101u;
+  t.y |= 0x01010101u;
+  const uint2 q = e8p_decode_q(t, c & 0xffffu);
+  float w[8];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    w[j] = (float)(int)(signed char)((q.x >> (8 * j)) & 0xffu) * 0.25f;
+    w[4 + j] = (float)(int)(signed char)((q.y >> (8 * j)) & 0xffu) * 0.25f;
+  }
+  e[0] = w[0]; e[1] = w[2]; e[2] = w[1]; e[3] = w[3];
+  e[4] = w[4]; e[5] = w[6]; e[6] = w[5]; e[7] = w[7];
+}
+
+__global__ void __launch_bounds__(NQ_THREADS) e8p_nearest_kernel(const float* __restrict__ x, int64_t m,
+                                                                 const uint2* __restrict__ tab,
+                                                                 unsigned long long* __restrict__ keys) {
+  __shared__ __align__(16) float g[NQ_CHUNK][8];
+  __shared__ float gn[NQ_CHUNK];
+  const int tid = threadIdx.x;
+  const uint32_t c0 = blockIdx.y * NQ_CHUNK;
+  for (int k = tid; k < NQ_CHUNK; k += NQ_THREADS) {
+    float e[8];
+    nq_decode(tab, c0 + k, e);
+    float n2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) n2 = fmaf(e[i], e[i], n2);
+    const float nr = __fsqrt_rn(n2);
+    gn[k] = __fmul_rn(nr, nr);
+    *reinterpret_cast<float4*>(&g[k][0]) = make_float4(e[0], e[1], e[2], e[3]);
+    *reinterpret_cast<float4*>(&g[k][4]) = make_float4(e[4], e[5], e[6], e[7]);
+  }
+  // this thread's vectors: v = (blockIdx.x * NQ_VT + i) * NQ_THREADS + tid  (consecutive lanes -> consecutive 32-byte rows)
+  float xv[NQ_VT][8];
+  int64_t vi[NQ_VT];
+#pragma unroll
+  for (int i = 0; i < NQ_VT; i++) {
+    vi[i] = ((int64_t)blockIdx.x * NQ_VT + i) * NQ_THREADS + tid;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (vi[i] < m) {
+      a = __ldg(reinterpret_cast<const float4*>(x + vi[i] * 8));
+      b = __ldg(reinterpret_cast<const float4*>(x + vi[i] * 8) + 1);
+    }
+    xv[i][0] = 2.f * a.x; xv[i][1] = 2.f * a.y; xv[i][2] = 2.f * a.z; xv[i][3] = 2.f * a.w;
+    xv[i][4] = 2.f * b.x; xv[i][5] = 2.f * b.y; xv[i][6] = 2.f * b.z; xv[i][7] = 2.f * b.w;
+  }
+  __syncthreads();
+  float best[NQ_VT];
+  int bk[NQ_VT];
+#pragma unroll
+  for (int i = 0; i < NQ_VT; i++) { best[i] = -INFINITY; bk[i] = 0; }
+#pragma unroll 4
+  for (int k = 0; k < NQ_CHUNK; k++) {
+    const float4 a = *reinterpret_cast<const float4*>(&g[k][0]);
+    const float4 b = *reinterpret_cast<const float4*>(&g[k][4]);
+    const float nn = gn[k];
+#pragma unroll
+    for (int i = 0; i < NQ_VT; i++) {
+      float s = __fmul_rn(xv[i][0], a.x);
+      s = fmaf(xv[i][1], a.y, s);
+      s = fmaf(xv[i][2], a.z, s);
+      s = fmaf(xv[i][3], a.w, s);
+      s = fmaf(xv[i][4], b.x, s);
+      s = fmaf(xv[i][5], b.y, s);
+      s = fmaf(xv[i][6], b.z, s);
+      s = fmaf(xv[i][7], b.w, s);
+      s = __fsub_rn(s, nn);
+      if (s > best[i]) { best[i] = s; bk[i] = k; }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NQ_VT; i++)
+    if (vi[i] < m) atomicMax(keys + vi[i], nq_key(best[i], c0 + (uint32_t)bk[i]));
+}
+
+// mode 0: single stage          vals = g[c]                          idx = c
+// mode 1: first of two stages   vals = g[c] (held for mode 2)        idx = c (held), xr = (x - g[c]) / resid_scale, key reset
+// mode 2: second of two stages  vals = vals + g[c] * resid_scale     idx = (idx << 16) + c
+__global__ void e8p_nearest_finish_kernel(const float* __restrict__ x, int64_t m, const uint2* __restrict__ tab,
+                                          unsigned long long* __restrict__ keys, float* __restrict__ vals,
+                                          long long* __restrict__ idx, float* __restrict__ xr, float resid_scale, int mode) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= m) return;
+  const uint32_t c = 0xffffu - (uint32_t)(keys[v] & 0xffffull);
+  float e[8];
+  nq_decode(tab, c, e);
+  float4* vo = reinterpret_cast<float4*>(vals + v * 8);
+  if (mode == 0) {
+    vo[0] = make_float4(e[0], e[1], e[2], e[3]);
+    vo[1] = make_float4(e[4], e[5], e[6], e[7]);
+    idx[v] = (long long)c;
+  } else if (mode == 1) {
+    vo[0] = make_float4(e[0], e[1], e[2], e[3]);
+    vo[1] = make_float4(e[4], e[5], e[6], e[7]);
+    idx[v] = (long long)c;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + v * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x + v * 8) + 1);
+    float4* ro = reinterpret_cast<float4*>(xr + v * 8);
+    ro[0] = make_float4(__fdiv_rn(__fsub_rn(a.x, e[0]), resid_scale), __fdiv_rn(__fsub_rn(a.y, e[1]), resid_scale),
+                        __fdiv_rn(__fsub_rn(a.z, e[2]), resid_scale), __fdiv_rn(__fsub_rn(a.w, e[3]), resid_scale));
+    ro[1] = make_float4(__fdiv_rn(__fsub_rn(b.x, e[4]), resid_scale), __fdiv_rn(__fsub_rn(b.y, e[5]), resid_scale),
+                        __fdiv_rn(__fsub_rn(b.z, e[6]), resid_scale), __fdiv_rn(__fsub_rn(b.w, e[7]), resid_scale));
+    keys[v] = 0ull;
+  } else {
+    const float4 a = vo[0], b = vo[1];
+    vo[0] = make_float4(__fadd_rn(a.x, __fmul_rn(e[0], resid_scale)), __fadd_rn(a.y, __fmul_rn(e[1], resid_scale)),
+                        __fadd_rn(a.z, __fmul_rn(e[2], resid_scale)), __fadd_rn(a.w, __fmul_rn(e[3], resid_scale)));
+    vo[1] = make_float4(__fadd_rn(b.x, __fmul_rn(e[4], resid_scale)), __fadd_rn(b.y, __fmul_rn(e[5], resid_scale)),
+                        __fadd_rn(b.z, __fmul_rn(e[6], resid_scale)), __fadd_rn(b.w, __fmul_rn(e[7], resid_scale)));
+    idx[v] = (idx[v] << 16) + (long long)c;
+  }
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" size_t quipb200_e8p_quantize_workspace_bytes(int64_t m) {
+  if (m < 1) return 0;
+  return (size_t)m * (sizeof(unsigned long long) + 8 * sizeof(float));
+}
+
+extern "C" int quipb200_e8p_quantize(const float* x, int64_t m, const int64_t* grid_packed_abs, int n_stages,
+                                     float resid_scale, float* vals_out, int64_t* idx_out, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  if (!x || !grid_packed_abs || !vals_out || !idx_out || !workspace || m < 1 || (n_stages != 1 && n_stages != 2))
+    return QUIPB200_EINVAL;
+  if (n_stages == 2 && !(resid_scale > 0.f)) return QUIPB200_EINVAL;
+  if (!aligned16(x) || !aligned16(vals_out) || !aligned16(workspace) || ((uintptr_t)idx_out & 7)) return QUIPB200_EALIGN;
+  if (workspace_bytes < quipb200_e8p_quantize_workspace_bytes(m)) return QUIPB200_EWORKSPACE;
+  const int64_t gx = (m + NQ_THREADS * NQ_VT - 1) / (NQ_THREADS * NQ_VT);
+  if (gx > 0x7fffffffLL) return QUIPB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(workspace);
+  float* xr = reinterpret_cast<float*>(keys + m);
+  const uint2* tab = reinterpret_cast<const uint2*>(grid_packed_abs);
+  cudaError_t e = cudaMemsetAsync(keys, 0, (size_t)m * sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return (int)e;
+  const dim3 grid((unsigned)gx, NQ_NCHUNK);
+  const int fb = 256;
+  const unsigned fgrid = (unsigned)((m + fb - 1) / fb);
+  e8p_nearest_kernel<<<grid, NQ_THREADS, 0, st>>>(x, m, tab, keys);
+  QB_LAUNCH_CHECK();
+  e8p_nearest_finish_kernel<<<fgrid, fb, 0, st>>>(x, m, tab, keys, vals_out, reinterpret_cast<long long*>(idx_out), xr,
+                                                  resid_scale, n_stages == 1 ? 0 : 1);
+  QB_LAUNCH_CHECK();
+  if (n_stages == 2) {
+    e8p_nearest_kernel<<<grid, NQ_THREADS, 0, st>>>(xr, m, tab, keys);
+    QB_LAUNCH_CHECK();
+    e8p_nearest_finish_kernel<<<fgrid, fb, 0, st>>>(xr, m, tab, keys, vals_out, reinterpret_cast<long long*>(idx_out), xr,
+                                                    resid_scale, 2);
+    QB_LAUNCH_CHECK();
+  }
+  return 0;
+}

@@ -1,0 +1,97 @@
+"""Quantise-time path on CPU: the oracle's nearest-codeword search / LDLQ against vectors produced by the reference's
+own Python (tests/golden/quantize.npz, tests/golden/gen_quantize_golden.py), and the product's host-side LDLQ driver
+(`quip_for_all_b200.ldlq`, CPU tensors take the reference's torch rounding expression) against the same vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import quip_oracle as qo
+
+
+@pytest.fixture(scope="module")
+def gq(golden_dir):
+    return np.load(os.path.join(golden_dir, "quantize.npz"))
+
+
+def _check_idx(x, got, want, max_near_ties=0.005):
+    """Indices equal, except rows where both choices score within 1e-5 of each other (fp32 near-ties)."""
+    got, want = np.asarray(got, dtype=np.int64), np.asarray(want, dtype=np.int64)
+    diff = np.nonzero(got != want)[0]
+    if diff.size:
+        gap = np.abs(qo.e8p_score(x[diff], got[diff]) - qo.e8p_score(x[diff], want[diff]))
+        assert gap.max() < 1e-5, f"{diff.size} rows differ, worst score gap {gap.max()}"
+        assert diff.size <= max_near_ties * got.size
+    return diff.size
+
+
+def test_oracle_nearest_matches_reference_quantize(gq):
+    x = gq["nearest_x"]
+    idx, _ = qo.e8p_nearest(x)
+    _check_idx(x, idx, gq["nearest_idx"])
+    assert np.array_equal(idx[1464:1528], gq["nearest_idx"][1464:1528])      # exact codewords: unique maximum
+    assert np.array_equal(idx[1528:], gq["nearest_idx"][1528:])              # all-zero rows: first index of the tie
+    np.testing.assert_array_equal(qo.e8p_full_grid()[idx[:1400]][idx[:1400] == gq["nearest_idx"][:1400]],
+                                  gq["nearest_vals"][:1400][idx[:1400] == gq["nearest_idx"][:1400]])
+
+
+def test_oracle_rvq4_quantize_matches_reference(gq):
+    x = gq["nearest_x"]
+    vals, idx, _ = qo.e8prvq4_quantize(x, float(gq["rvq4_resid_scale"]))
+    same = idx == gq["nearest_rvq4_idx"]
+    assert same.mean() > 0.995
+    np.testing.assert_array_equal(vals[same], gq["nearest_rvq4_vals"][same])
+
+
+def test_oracle_ldlq_matches_reference(gq):
+    W, H = gq["ldlq_W"], gq["ldlq_H"]
+    L = np.linalg.cholesky(H)
+    hat, Q = qo.ldlq(W, H, L)
+    assert np.array_equal(Q.astype(np.int16), gq["ldlq_f64_Q"])
+    np.testing.assert_allclose(hat, gq["ldlq_f64_hat"], rtol=0, atol=0)
+    assert bool(gq["ldlq_f64_buffered_same"])
+    _, Qt = qo.ldlq(W, H, L, tune_iters=1)
+    assert np.array_equal(Qt.astype(np.int16), gq["ldlq_f64_tune1_Q"])
+
+
+def test_product_ldlq_cpu_matches_reference(gq):
+    from quip_for_all_b200 import codebook_id
+    from quip_for_all_b200.ldlq import ldlq, proxy_loss
+    cb = codebook_id["E8P12"](inference=False)
+    cb.grid = cb.grid.double()
+    cb.grid_norm = cb.grid_norm.double()
+    W, H = torch.from_numpy(gq["ldlq_W"]), torch.from_numpy(gq["ldlq_H"])
+    L = torch.linalg.cholesky(H)
+    for bc in (128, 64, 8, 256):                       # the blocking of the sweep does not change the result
+        hat, Q = ldlq(W, H, L, cb, 0, block_cols=bc)
+        assert np.array_equal(Q.numpy(), gq["ldlq_f64_Q"]), bc
+        assert np.array_equal(hat.numpy(), gq["ldlq_f64_hat"])
+    _, Qt = ldlq(W, H, L, cb, 1)
+    assert np.array_equal(Qt.numpy(), gq["ldlq_f64_tune1_Q"])
+    # LDLQ beats plain nearest rounding on the proxy objective it minimises
+    near = cb.quantize(W.reshape(-1, 8), return_idx=False).reshape(W.shape)
+    assert proxy_loss(W, hat, H) < proxy_loss(W, near, H)
+
+
+def test_product_layer_quantizer_cpu_matches_reference(gq):
+    """`LayerQuantizer` (reference: quip.py QUIP.add_batch / .quant) on the reference's layer, calibration batches and
+    sign vectors: same packed indices, scale and de-rotated weight."""
+    from quip_for_all_b200 import codebook_id
+    from quip_for_all_b200.ldlq import LayerQuantizer
+    lin = torch.nn.Linear(256, 64, bias=True)
+    lin.weight.data = torch.from_numpy(gq["quip_w"]).clone()
+    lin.bias.data = torch.from_numpy(gq["quip_bias"]).clone()
+    cb = codebook_id["E8P12"](inference=False)
+    cb.grid = cb.grid.double()
+    cb.grid_norm = cb.grid_norm.double()
+    lq = LayerQuantizer(lin, cb)
+    calib = torch.from_numpy(gq["quip_calib"])
+    for b in range(calib.shape[0]):
+        lq.add_batch(calib[b])
+    attr = lq.quantize(use_fp64=True, sigma_reg=0.01, SU=torch.from_numpy(gq["quip_SU"]), SV=torch.from_numpy(gq["quip_SV"]))
+    assert np.array_equal(attr["Qidxs"].numpy(), gq["quip_Qidxs"])
+    assert abs(float(attr["w_scale"]) - float(gq["quip_w_scale"])) < 1e-12 * float(gq["quip_w_scale"]) + 1e-15
+    np.testing.assert_allclose(lin.weight.data.numpy(), gq["quip_w_hat"], rtol=0, atol=1e-7)
+    assert attr["merge_su"] and attr["merge_sv"] and attr["left_hadK"] is None and attr["scaleWH"] is None
+    assert 0 < lq.last_proxy_loss < 0.2
