@@ -411,14 +411,15 @@ def hf_dropin_bench(model, torch, prompt, steps, warmup):
         return {"unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
 
 
-def single_gpu_70b(a, torch, dev, peak):
+def single_gpu_70b(a, torch, dev, peak, model_name=None):
     """BASELINE config 5 on ONE GPU (17.1 GB of packed codes fit): the N = 1 point of the 70B layer-pipeline scaling that
     `--gpus N` (N > 1) measures.  Same engine as a pipeline stage (grouped launches: the persistent kernel does not cover
     hidden 8192 / 7 x 4096 blocks), CUDA-graph replay, CUDA events."""
     try:
         from quip_for_all_b200.modeling import LlamaDecodeEngine, make_random_quantized_llama, quantized_bytes
         steps, warm = min(a.steps, 48), 4
-        model = make_random_quantized_llama("llama2-70b", a.codebook, seed=0, device=dev)
+        model_name = model_name or "llama2-70b"
+        model = make_random_quantized_llama(model_name, a.codebook, seed=0, device=dev)
         code_bytes = quantized_bytes(model)
         eng = LlamaDecodeEngine(model, max_cache_len=a.prompt_len + 2 * (steps + warm) + 16, use_cuda_graph=not a.no_graph)
         g = torch.Generator().manual_seed(0)
@@ -433,7 +434,7 @@ def single_gpu_70b(a, torch, dev, peak):
         e1.record()
         e1.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        out = {"workload": f"llama2-70b {a.codebook} bs=1 greedy decode on one GPU, random-init packed weights",
+        out = {"workload": f"{model_name} {a.codebook} bs=1 greedy decode on one GPU, random-init packed weights",
                "value": 1000.0 / ms, "unit": "tokens/s", "ms_per_step": ms, "steps": steps,
                "engine": "persistent whole-step kernel" if eng.persistent is not None else "grouped launches (6 per decoder layer)",
                "packed_code_bytes_per_token": code_bytes, "frac_of_hbm_roofline": (1000.0 / ms) * code_bytes / (peak * 1e9)}
@@ -452,7 +453,8 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from quip_for_all_b200.parallel import run_pipeline_bench
-        return run_pipeline_bench(a, METRIC, ClockSampler, peak_gbs=measured_peaks()[0])
+        return run_pipeline_bench(a, METRIC, ClockSampler, peak_gbs=measured_peaks()[0],
+                                  single_gpu_fn=None if a.no_70b else single_gpu_70b)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     from quip_for_all_b200 import _native

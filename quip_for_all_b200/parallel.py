@@ -197,7 +197,7 @@ def _pipeline_measure(a, model_name, world, rank, local, dev, clock_sampler_cls=
     return out
 
 
-def run_pipeline_bench(a, metric, clock_sampler_cls=None, peak_gbs=None):
+def run_pipeline_bench(a, metric, clock_sampler_cls=None, peak_gbs=None, single_gpu_fn=None):
     """bench.py body for WORLD_SIZE > 1 (launched by torchrun, one rank per GPU).  Workload = BASELINE config 5: the
     Llama-2-70B layer pipeline; the 7B pipeline of round 1 is measured as well and reported under `secondary`."""
     import json
@@ -211,6 +211,14 @@ def run_pipeline_bench(a, metric, clock_sampler_cls=None, peak_gbs=None):
     second = None
     if a.model != "llama2-7b" and not getattr(a, "no_secondary", False):
         second = _pipeline_measure(a, "llama2-7b", world, rank, local, dev, None)
+    # the N = 1 point of the SAME workload, measured in this run on rank 0's GPU (the other ranks wait): the whole model on
+    # one device through the same engine -- the denominator of the scaling efficiency of this line
+    single = None
+    if single_gpu_fn is not None and not getattr(a, "no_single", False):
+        torch.cuda.synchronize()
+        if rank == 0:
+            single = single_gpu_fn(a, torch, dev, peak_gbs, a.model)
+        dist.barrier()
     if rank == 0:
         line = {
             "metric": metric, "value": main["tok_s"], "unit": "tokens/s", "n_gpus": world,
@@ -236,6 +244,11 @@ def run_pipeline_bench(a, metric, clock_sampler_cls=None, peak_gbs=None):
             roof = world * peak_gbs * 1e9 / main["code_bytes"]
             line["model_roofline"] = {"packed_code_bytes_per_token": main["code_bytes"],
                                       "tok_s_at_hbm_peak_all_gpus": roof, "frac_of_hbm_roofline": main["tok_s"] / roof}
+        if single is not None:
+            line["single_gpu_same_workload"] = single
+            if "value" in single:
+                line["scaling_vs_single_gpu"] = {"speedup": main["tok_s"] / single["value"],
+                                                 "efficiency": main["tok_s"] / single["value"] / world}
         if second is not None:
             line["secondary"] = {"workload": f"llama2-7b {a.codebook} bs=1 decode, same pipeline ({second['engine']})",
                                  "value": second["tok_s"], "unit": "tokens/s", "ms_per_step": second["ms_per_step"],

@@ -114,11 +114,140 @@ class QuipQuantizer(object):
             parent = recurse_getattr(model, parent_name) if parent_name else model
             setattr(parent, attr, new)
 
-    def quantize_model(self, *a, **k):
-        raise NotImplementedError("offline quantisation (calibration + LDLQ + fine-tuning) is out of scope of "
-                                  "the B200 inference build; quantise with the reference and load the result")
+    # ---------------------------------------------------------------------------------------------
+    # offline quantisation (reference: quantizer.py:250-600).  Calibration data: the reference tokenises a hub dataset
+    # (data.py); there is no network here, so `calib` is an iterable of ready batches -- LongTensor input_ids [B, T] or
+    # dicts of model kwargs.  Block-wise fine-tuning (ft_epochs > 0, quantizer.py:501-567) is not part of this build.
+    # ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def _sublayer_groups(names):
+        """Order in which the linears of a block are quantised: q/k/v -> attention out -> MLP in -> MLP out, each group
+        seeing the already-quantised groups before it (reference: utils.split_block_to_sublayers); unknown layouts are
+        treated as one group."""
+        roles = (("q_proj", "k_proj", "v_proj", "query_key_value", "c_attn", "qkv_proj", "W_pack"),
+                 ("o_proj", "out_proj", "attn.c_proj", "attention.dense", "self_attention.dense"),
+                 ("gate_proj", "up_proj", "dense_h_to_4h", "c_fc", "fc_in", "fc1"),
+                 ("down_proj", "dense_4h_to_h", "mlp.c_proj", "fc_out", "fc2"))
+        groups = [[n for n in names if any(n.endswith(r) for r in role)] for role in roles]
+        if sum(len(g) for g in groups) != len(names) or len({n for g in groups for n in g}) != len(names):
+            return [list(names)]
+        return [g for g in groups if g]
 
-    save = quantize_model
+    @torch.no_grad()
+    def quantize_model(self, model: nn.Module, calib, save_dir: str = ""):
+        from .ldlq import LayerQuantizer
+        if isinstance(calib, str) or hasattr(calib, "encode") or hasattr(calib, "tokenize"):
+            raise ValueError("quantize_model: pass calibration batches (input_ids tensors or kwargs dicts); fetching and "
+                             "tokenising a hub dataset (reference data.py) needs network access")
+        if self.ft_epochs and self.ft_epochs > 0:
+            raise NotImplementedError("block-wise fine-tuning (ft_epochs > 0) is not part of this build: pass ft_epochs=0")
+        if getattr(self.codebook, "grid", None) is None:
+            raise ValueError("quantize_model needs the full codebook: construct QuipQuantizer(..., inference=False)")
+        model.eval()
+        use_cache = getattr(getattr(model, "config", None), "use_cache", None)
+        if use_cache is not None:
+            model.config.use_cache = False
+        if self.block_name_to_quantize is None:
+            self.block_name_to_quantize = get_block_name_with_pattern(model)
+        blocks = recurse_getattr(model, self.block_name_to_quantize)
+        dev = next(model.parameters()).device
+        origin_dtype = next(model.parameters()).dtype
+
+        # inputs of the first block: run the model until the block is entered
+        class _Stop(Exception):
+            pass
+
+        inputs, in_kwargs = [], []
+
+        def grab(_, args, kwargs):
+            x = args[0] if args else kwargs["hidden_states"]
+            inputs.append(x.detach())
+            in_kwargs.append({k: v for k, v in kwargs.items() if k != "hidden_states"})
+            raise _Stop
+
+        h = blocks[0].register_forward_pre_hook(grab, with_kwargs=True)
+        for batch in calib:
+            data = batch if isinstance(batch, dict) else {"input_ids": batch}
+            try:
+                model(**{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in data.items()})
+            except _Stop:
+                pass
+        h.remove()
+        if not inputs:
+            raise ValueError("quantize_model: no calibration batch reached the first block")
+
+        for bi, block in enumerate(blocks):
+            block.float()
+            layers = get_layers(block, skip=self.modules_to_not_convert)
+            acc = {n: LayerQuantizer(l, codebook_id[self.codebook.id](inference=False, opt_resid_scale=self.opt_resid_scale))
+                   for n, l in layers.items() if isinstance(l, nn.Linear)}
+            hooks = [layers[n].register_forward_hook(lambda _, i, o, n=n: acc[n].add_batch(i[0].data)) for n in acc]
+            outs = []
+            for x, kw in zip(inputs, in_kwargs):
+                y = block(x.float(), **kw)
+                outs.append((y[0] if isinstance(y, tuple) else y).detach())
+            for hk in hooks:
+                hk.remove()
+            for group in self._sublayer_groups(list(acc)):
+                for n in group:
+                    attr = acc[n].quantize(rescale_WH=self.rescale_WH, sigma_reg=self.sigma_reg,
+                                           quip_tune_iters=self.quip_tune_iters,
+                                           scale_override=getattr(self, "scale_override", 0) or 0,
+                                           use_rand=self.use_rand, per_channel=self.per_channel)
+                    lin = layers[n]
+                    self._replace_by_quant_layers(block, {n: lin})
+                    q = recurse_getattr(block, n)
+                    q.cpu()
+                    q.pack(lin.cpu(), attr)
+                    q.to(dev)
+                    q.proxy_loss = acc[n].last_proxy_loss
+                    q._w_scale_f32 = attr["w_scale"].to(torch.float32)
+                    acc[n].H = None
+            block.to(origin_dtype)
+            for q in get_layers(block, [QuantLinear]).values():
+                q.weight_dtype = origin_dtype
+                if not q.per_channel and hasattr(q, "_w_scale_f32"):      # the scalar scale stays fp32 (SURVEY A.4)
+                    q.Wscale = q._w_scale_f32.to(dev).reshape(())
+                    del q._w_scale_f32
+            apply_load_time_tricks(block, self.merge_suv)
+            inputs = outs            # the next block is calibrated on the un-quantised stream, as the reference does
+        model.is_quantized = True
+        if use_cache is not None:
+            model.config.use_cache = use_cache
+        if hasattr(model, "config"):
+            model.config.quantization_config = self.to_dict()
+        if save_dir:
+            self.save(model, save_dir)
+        return model
+
+    def save(self, model: nn.Module, save_dir: str, max_shard_size: str = "10GB", safe_serialization: bool = False):
+        """Write the checkpoint folder `load_quantized_model` reads: weights under the model's state-dict keys
+        (`pytorch_model.bin` or `model.safetensors`, what `Accelerator.save_model` writes for a model below the shard
+        size, reference quantizer.py:718-756), the HF config and quantization_config.json."""
+        import json
+        os.makedirs(save_dir, exist_ok=True)
+        sd = {}
+        for k, v in model.state_dict().items():
+            t = v.detach().cpu().contiguous()
+            lay = recurse_getattr(model, k.rpartition(".")[0]) if "." in k else model
+            if isinstance(lay, QuantLinear) and k.endswith(".Wscale") and lay.per_channel:
+                t = t * lay.wscale_float          # undo the load-time normalisation (quantizer.py:838-839)
+            sd[k] = t
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file(sd, os.path.join(save_dir, "model.safetensors"), metadata={"format": "pt"})
+        else:
+            torch.save(sd, os.path.join(save_dir, "pytorch_model.bin"))
+        if hasattr(model, "config"):
+            qc = getattr(model.config, "quantization_config", None)
+            if qc is not None:
+                del model.config.quantization_config      # read back from quantization_config.json; recent transformers
+                                                          # validate `quant_method` of a config.json entry on load
+            model.config.save_pretrained(save_dir)
+            if qc is not None:
+                model.config.quantization_config = qc
+        with open(os.path.join(save_dir, QUIP_CONFIG), "w", encoding="utf-8") as f:
+            json.dump(self.to_dict(), f, indent=2)
 
 
 # --------------------------------------------------------------------------------------------------

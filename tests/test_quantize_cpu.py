@@ -95,3 +95,41 @@ def test_product_layer_quantizer_cpu_matches_reference(gq):
     np.testing.assert_allclose(lin.weight.data.numpy(), gq["quip_w_hat"], rtol=0, atol=1e-7)
     assert attr["merge_su"] and attr["merge_sv"] and attr["left_hadK"] is None and attr["scaleWH"] is None
     assert 0 < lq.last_proxy_loss < 0.2
+
+
+def _tiny_llama(dtype=torch.float32):
+    from transformers import LlamaConfig, LlamaForCausalLM
+    torch.manual_seed(0)
+    cfg = LlamaConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                      num_key_value_heads=2, vocab_size=100, max_position_embeddings=64)
+    return LlamaForCausalLM(cfg).eval().to(dtype)
+
+
+def test_quantize_model_save_load_round_trip_cpu(tmp_path):
+    """`QuipQuantizer.quantize_model` (reference: quantizer.py:250-600, without the fine-tuning stage) on a tiny Llama with
+    ready calibration batches, `save`, then `load_quantized_model`'s body: same module tree, same tensors, the
+    reference's state-dict key layout."""
+    from quip_for_all_b200 import QuantLinear, QuipQuantizer
+    from quip_for_all_b200.quantizer import _load_quantized_model
+    m = _tiny_llama()
+    qz = QuipQuantizer("E8P12", quip_tune_iters=0, ft_epochs=0, inference=False)
+    calib = [torch.randint(0, 100, (2, 16), generator=torch.Generator().manual_seed(i)) for i in range(3)]
+    m = qz.quantize_model(m, calib, save_dir=str(tmp_path))
+    qls = {n: x for n, x in m.named_modules() if isinstance(x, QuantLinear)}
+    assert len(qls) == 14 and not any(isinstance(x, torch.nn.Linear) for n, x in m.named_modules() if "layers" in n)
+    for n, q in qls.items():
+        assert q.Wscale.dtype == torch.float32 and abs(q.wscale_float - float(q.Wscale)) < 1e-9
+        assert 0 < q.proxy_loss < 0.2 and q.Qidxs.abs().max() > 0
+    assert sorted(os.listdir(tmp_path)) == ["config.json", "pytorch_model.bin", "quantization_config.json"]
+    sd = torch.load(tmp_path / "pytorch_model.bin")
+    pre = "model.layers.0.self_attn.q_proj."
+    assert {k[len(pre):] for k in sd if k.startswith(pre)} == {"SU", "SV", "Qidxs", "Wscale", "weight"}
+    m2 = _load_quantized_model(str(tmp_path), torch_dtype=torch.float32)
+    sd1, sd2 = m.state_dict(), m2.state_dict()
+    assert sd1.keys() == sd2.keys()
+    for k in sd1:
+        assert torch.equal(sd1[k], sd2[k]), k
+    with pytest.raises(NotImplementedError):
+        QuipQuantizer("E8P12", ft_epochs=2, inference=False).quantize_model(_tiny_llama(), calib)
+    with pytest.raises(ValueError):
+        QuipQuantizer("E8P12", ft_epochs=0, inference=False).quantize_model(_tiny_llama(), "wikitext2")

@@ -120,7 +120,8 @@ def test_quantize_linear_round_trip(codebook, fin, fout):
     calib = [torch.randn(2, 64, fin, device=dev) for _ in range(3)]
     ql = quantize_linear(lin, calib, codebook=codebook).eval()
     x = torch.randn(5, fin, device=dev).half()
-    y_q = ql(x).float()
+    with torch.no_grad():
+        y_q = ql(x).float()
     y_hat = torch.nn.functional.linear(x.float(), lin.weight.data.float(), lin.bias.data.float())
     y_0 = torch.nn.functional.linear(x.float(), w0.float(), lin.bias.data.float())
     tol = 2.0 ** -7 * float(y_hat.abs().max())
@@ -130,3 +131,32 @@ def test_quantize_linear_round_trip(codebook, fin, fout):
     rel = float((y_hat - y_0).norm() / (y_0 - lin.bias.data.float()).norm())
     assert rel < (0.40 if codebook == "E8P12" else 0.12), rel        # 2-bit ~0.30, 4-bit ~0.07 relative error on iid weights
     assert ql.proxy_loss < (0.13 if codebook == "E8P12" else 0.015)
+
+
+@pytest.mark.parametrize("codebook,min_corr", [("E8P12RVQ4B", 0.97), ("E8P12", 0.70)])
+def test_quantize_model_end_to_end(tmp_path, codebook, min_corr):
+    """tiny Llama: quantize_model on the GPU (search kernel inside LDLQ) -> logits through the CUDA inference path track the
+    fp32 model's at the codebook's rate; save -> load_quantized_model reproduces the quantised model's logits exactly."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from quip_for_all_b200 import QuipQuantizer, load_quantized_model
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    cfg = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                      num_key_value_heads=2, vocab_size=128, max_position_embeddings=64)
+    m = LlamaForCausalLM(cfg).eval().half().to(dev)
+    ids = torch.randint(0, 128, (2, 24), device=dev)
+    with torch.no_grad():
+        ref = m(ids).logits.float()
+    qz = QuipQuantizer(codebook, quip_tune_iters=0, ft_epochs=0, inference=False)
+    calib = [torch.randint(0, 128, (4, 32)) for _ in range(4)]
+    m = qz.quantize_model(m, calib, save_dir=str(tmp_path))
+    with torch.no_grad():
+        got = m(ids).logits.float()
+    assert torch.isfinite(got).all()
+    a, b = (got - got.mean()).flatten(), (ref - ref.mean()).flatten()
+    corr = float((a @ b) / (a.norm() * b.norm()))
+    assert corr > min_corr, corr
+    m2 = load_quantized_model(str(tmp_path)).to(dev).eval()
+    with torch.no_grad():
+        again = m2(ids).logits.float()
+    assert torch.equal(again, got)
