@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-hf-dropin", action="store_true")
     ap.add_argument("--no-70b", action="store_true", help="N = 1: skip the single-GPU Llama-2-70B leg (the base of the N > 1 scaling)")
+    ap.add_argument("--handoff", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: stage hand-off through NVLink peer memory (device-side store + flag) or host-issued NCCL p2p")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--engine", default="auto", choices=["auto", "persistent", "grouped"],
                     help="decode engine: one persistent whole-step kernel, or one launch per linear group")

@@ -284,6 +284,23 @@ size_t quipb200_e8p_quantize_workspace_bytes(int64_t m);
 int quipb200_e8p_quantize(const float* x, int64_t m, const int64_t* grid_packed_abs, int n_stages, float resid_scale,
                           float* vals_out, int64_t* idx_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU layer pipeline: stage-to-stage hand-off over NVLink peer memory (the reference's only
+ * multi-device facility keeps whole decoder blocks per device, quantizer.py:180-191, :831, and moves the activation with
+ * accelerate's hooks).  A mailbox is device memory of THIS process exported by CUDA IPC; the upstream process maps it and
+ * stores the payload + a sequence number into it (send); the owner polls the sequence number locally and copies the
+ * payload into its engine's input buffer (wait).  Both are enqueued on `stream`, involve no host synchronisation and
+ * advance a caller-owned device counter (uint64, zero-initialised unless the first wait is to pass without a send: -1).
+ * bytes: multiple of 8 (8-byte aligned buffers); a wait whose sequence number is 0 copies nothing.  A wait not satisfied within ~2 s of GPU time increments *err_flag (uint32) and returns.
+ * ------------------------------------------------------------------------------------------- */
+int quipb200_mailbox_create(size_t bytes, void** dev_ptr, void* ipc_handle_64);   /* zero-filled; 64-byte cudaIpcMemHandle_t out */
+int quipb200_mailbox_open(const void* ipc_handle_64, void** peer_ptr);
+int quipb200_mailbox_close(void* peer_ptr);
+int quipb200_mailbox_destroy(void* dev_ptr);
+int quipb200_handoff_send(const void* src, void* peer_dst, size_t bytes, void* peer_flag, void* seq_counter, void* stream);
+int quipb200_handoff_wait(const void* flag, void* seq_counter, const void* inbox, void* dst, size_t bytes, void* err_flag,
+                          void* stream);
+
 /* Tuning / introspection hooks used by bench.py and the tests (not part of the reference surface). */
 /* options: "umma" 0|1|2 (tcgen05 decode+GEMM never / whenever covered / where measured faster; default 2),
  *   "rot_warp_rows", "rot_pipe_rows" (row counts from which the many-rows rotation kernels are used),

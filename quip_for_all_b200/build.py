@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libquipb200.so")
 SOURCES = ["api.cu", "decompress.cu", "hadamard.cu", "quantlinear.cu", "glue.cu", "decode_step.cu", "umma_gemm.cu",
-           "rotate_batched.cu", "lm_tail.cu", "nearest.cu"]
+           "rotate_batched.cu", "lm_tail.cu", "nearest.cu", "handoff.cu"]
 # (hook for translation units that need relocatable device code; none at present)
 RDC_SOURCES = set()
 RDC_FLAGS = {}

@@ -33,6 +33,66 @@ def partition_layers(n_layers: int, world: int) -> List[range]:
     return out
 
 
+class PeerMailbox:
+    """Device-side hand-off over NVLink peer memory (csrc/handoff.cu).  Every rank owns a mailbox with one slot per
+    in-flight sequence ([payload | flag]); the upstream rank maps it through CUDA IPC and stores into it.  No host
+    synchronisation and no NCCL call on the tick path."""
+    FLAG_OFF = 32768          # payload capacity per slot (>= 2 * hidden bytes of any supported model)
+    SLOT = FLAG_OFF + 256
+
+    def __init__(self, rank, world, n_slots, device, group=None):
+        import ctypes
+        from ._native import check, lib
+        self.L, self.check, self.ct = lib(), check, ctypes
+        self.rank, self.world, self.S, self.dev = rank, world, n_slots, device
+        own, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        with torch.cuda.device(device):
+            check(self.L.quipb200_mailbox_create(self.SLOT * n_slots, ctypes.byref(own), handle), "mailbox_create")
+        self.own = own.value
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        peer = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            check(self.L.quipb200_mailbox_open(handles[(rank + 1) % world], ctypes.byref(peer)), "mailbox_open")
+        self.peer = peer.value
+        # per-slot sequence counters (device uint64): sends start at 0; waits start at 0, except on stage 0 whose first
+        # run of a slot consumes the token left by the prefill (counter -1: the first wait passes and copies nothing)
+        self.send_ctr = torch.zeros(n_slots, dtype=torch.int64, device=device)
+        self.wait_ctr = torch.full((n_slots,), -1 if rank == 0 else 0, dtype=torch.int64, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier(group=group)
+
+    def _st(self):
+        return self.ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def send(self, slot, src: torch.Tensor):
+        nbytes = src.numel() * src.element_size()
+        assert nbytes <= self.FLAG_OFF and nbytes % 8 == 0
+        base = self.peer + slot * self.SLOT
+        self.check(self.L.quipb200_handoff_send(src.data_ptr(), base, nbytes, base + self.FLAG_OFF,
+                                                self.send_ctr.data_ptr() + 8 * slot, self._st()), "handoff_send")
+
+    def wait_into(self, slot, dst: torch.Tensor):
+        nbytes = dst.numel() * dst.element_size()
+        base = self.own + slot * self.SLOT
+        self.check(self.L.quipb200_handoff_wait(base + self.FLAG_OFF, self.wait_ctr.data_ptr() + 8 * slot, base,
+                                                dst.data_ptr(), nbytes, self.err.data_ptr(), self._st()), "handoff_wait")
+
+    def errors(self):
+        return int(self.err.item())
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier()
+        if self.peer:
+            self.L.quipb200_mailbox_close(self.peer)
+            self.peer = None
+        dist.barrier()
+        if self.own:
+            self.L.quipb200_mailbox_destroy(self.own)
+            self.own = None
+
+
 class RingPipeline:
     """Tick driver.  `stage` must provide, for slot s in [0, S):
          step(s)                      run one decode step of slot s in place
@@ -40,8 +100,9 @@ class RingPipeline:
          scratch_in()                 a tensor shaped like in_buffer for discarded fill-phase traffic
     """
 
-    def __init__(self, stage, rank: int, world: int, n_slots: int = None, group=None):
+    def __init__(self, stage, rank: int, world: int, n_slots: int = None, group=None, mailbox: "PeerMailbox" = None):
         self.stage, self.rank, self.world = stage, rank, world
+        self.mailbox = mailbox       # device-side hand-off (GPU runs); None: one grouped isend/irecv per tick
         self.S = n_slots or world
         assert world % self.S == 0 or self.S == world, "token feedback needs S | P"
         self.group = group
@@ -57,11 +118,24 @@ class RingPipeline:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
 
-    def tick(self):
+    def tick(self, pre_step=None):
+        """`pre_step(slot)`: called after this tick's input has arrived and before the step consumes it (the e2e
+        harness overrides the input token there)."""
         t, r, S = self.t, self.rank, self.S
         active = t >= r
         s = (t - r) % S
+        if self.mailbox is not None:
+            if active:
+                self.mailbox.wait_into(s, self.stage.in_buffer(s))
+                if pre_step is not None:
+                    pre_step(s)
+                self.stage.step(s)
+                self.mailbox.send(s, self.stage.out_buffer(s))
+            self.t += 1
+            return active and r == self.world - 1
         if active:
+            if pre_step is not None:
+                pre_step(s)
             self.stage.step(s)
         s_next = (t + 1 - r) % S
         sender_active = t >= ((r - 1) % self.world)      # was my upstream neighbour active this tick?
@@ -75,9 +149,10 @@ class RingPipeline:
 # the real stage: a slice of a random-init quantised Llama, one decode engine per in-flight sequence
 # --------------------------------------------------------------------------------------------------
 class LlamaStage:
-    def __init__(self, model_name, codebook, rank, world, device, n_slots, cache_len, seed=0, use_graph=True):
+    def __init__(self, model_name, codebook, rank, world, device, n_slots, cache_len, seed=0, use_graph=True,
+                 **cfg_overrides):
         from .modeling import LlamaDecodeEngine, llama_config, make_random_quantized_llama
-        cfg = llama_config(model_name)
+        cfg = llama_config(model_name, **cfg_overrides)
         self.layers = partition_layers(cfg.num_hidden_layers, world)[rank]
         self.first, self.last = rank == 0, rank == world - 1
         self.model = make_random_quantized_llama(cfg, codebook, seed=seed + rank, device=device,
@@ -140,7 +215,20 @@ def _pipeline_measure(a, model_name, world, rank, local, dev, clock_sampler_cls=
     S = world
     cache_len = a.cache_len or (a.prompt_len + (a.steps * 2 + a.warmup) // S * 2 + 4 * S + 32)
     stage = LlamaStage(model_name, a.codebook, rank, world, dev, S, cache_len, use_graph=not a.no_graph)
-    pipe = RingPipeline(stage, rank, world, S)
+    mailbox = None
+    if getattr(a, "handoff", "peer") == "peer":
+        try:
+            mailbox = PeerMailbox(rank, world, S, dev)
+        except Exception as e:       # CUDA IPC unavailable (container policy): every rank must agree on the mode
+            mailbox = None
+            if rank == 0:
+                print(f"[parallel] peer-memory hand-off unavailable ({type(e).__name__}: {e}); using NCCL p2p", flush=True)
+        okt = torch.tensor([1 if mailbox is not None else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if okt.item() == 0 and mailbox is not None:
+            mailbox.close()
+            mailbox = None
+    pipe = RingPipeline(stage, rank, world, S, mailbox=mailbox)
     g = torch.Generator().manual_seed(0)
     vocab = stage.model.config.vocab_size
     prompts = [torch.randint(0, vocab, (1, a.prompt_len), generator=g) for _ in range(S)]
@@ -175,11 +263,9 @@ def _pipeline_measure(a, model_name, world, rank, local, dev, clock_sampler_cls=
     h_tok = torch.randint(0, vocab, (1, 1), generator=g).pin_memory()
     dist.barrier()
     t0 = time.perf_counter()
+    feed = (lambda slot: stage.engines[slot].tok.copy_(h_tok, non_blocking=True)) if stage.first else None
     for _ in range(a.steps):
-        if stage.first:
-            slot = (pipe.t - rank) % S
-            stage.engines[slot].tok.copy_(h_tok, non_blocking=True)
-        pipe.tick()
+        pipe.tick(pre_step=feed)
         if stage.last:
             h_tok.copy_(stage.engines[(pipe.t - 1 - rank) % S].tok, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -189,7 +275,15 @@ def _pipeline_measure(a, model_name, world, rank, local, dev, clock_sampler_cls=
     code_bytes = torch.tensor([float(quantized_bytes(stage.model))], device=dev)
     dist.all_reduce(code_bytes, op=dist.ReduceOp.SUM)
     persistent = stage.engines[0].persistent is not None
-    out = {"tok_s": a.steps / (ms * 1e-3), "ms_per_step": ms / a.steps, "e2e_tok_s": a.steps / t_e2e.item(),
+    handoff = "NCCL p2p ring exchange per tick (host-issued)"
+    if mailbox is not None:
+        nerr = torch.tensor([mailbox.errors()], device=dev)
+        dist.all_reduce(nerr, op=dist.ReduceOp.SUM)
+        if nerr.item():
+            raise RuntimeError(f"peer-memory hand-off: {int(nerr.item())} waits timed out")
+        handoff = "device-side hand-off over NVLink peer memory (store + flag, no host sync, no NCCL on the tick path)"
+        mailbox.close()
+    out = {"handoff": handoff,"tok_s": a.steps / (ms * 1e-3), "ms_per_step": ms / a.steps, "e2e_tok_s": a.steps / t_e2e.item(),
            "launches": int(launches.item()) * a.steps, "clocks": ck, "code_bytes": code_bytes.item(),
            "engine": "persistent whole-step kernel per stage" if persistent else "grouped launches (6 per decoder layer)"}
     del stage, pipe
@@ -229,7 +323,7 @@ def run_pipeline_bench(a, metric, clock_sampler_cls=None, peak_gbs=None, single_
             "config": {"workload": f"{a.model} {a.codebook} bs=1 greedy decode, layer pipeline over {world} GPUs "
                                    f"({world} independent bs=1 sequences in flight, one per stage), random-init "
                                    f"packed weights, synthetic {a.prompt_len}-token prompts",
-                       "parallelism": f"pp{world} (whole decoder layers per stage, NCCL p2p ring exchange per tick)",
+                       "parallelism": f"pp{world} (whole decoder layers per stage; {main['handoff']})",
                        "engine": main["engine"],
                        "l2": "inputs larger than L2 (each stage streams its slice of the %.1f GB of codes per tick)"
                              % (main["code_bytes"] / 1e9)},
