@@ -151,7 +151,7 @@ using namespace qb;
 
 extern "C" size_t quipb200_e8p_quantize_workspace_bytes(int64_t m) {
   if (m < 1) return 0;
-  return (size_t)m * (sizeof(unsigned long long) + 8 * sizeof(float));
+  return (((size_t)m * sizeof(unsigned long long) + 15) & ~(size_t)15) + (size_t)m * 8 * sizeof(float);
 }
 
 extern "C" int quipb200_e8p_quantize(const float* x, int64_t m, const int64_t* grid_packed_abs, int n_stages,
@@ -159,14 +159,16 @@ extern "C" int quipb200_e8p_quantize(const float* x, int64_t m, const int64_t* g
                                      size_t workspace_bytes, void* stream) {
   if (!x || !grid_packed_abs || !vals_out || !idx_out || !workspace || m < 1 || (n_stages != 1 && n_stages != 2))
     return QUIPB200_EINVAL;
-  if (n_stages == 2 && !(resid_scale > 0.f)) return QUIPB200_EINVAL;
+  if (n_stages == 2 && !(resid_scale != 0.f && resid_scale == resid_scale)) return QUIPB200_EINVAL;   // (the reference's
+  // quantizer default of -1 reaches the codebook unchanged, quantizer.py:69,127: negative scales are legal)
   if (!aligned16(x) || !aligned16(vals_out) || !aligned16(workspace) || ((uintptr_t)idx_out & 7)) return QUIPB200_EALIGN;
   if (workspace_bytes < quipb200_e8p_quantize_workspace_bytes(m)) return QUIPB200_EWORKSPACE;
   const int64_t gx = (m + NQ_THREADS * NQ_VT - 1) / (NQ_THREADS * NQ_VT);
   if (gx > 0x7fffffffLL) return QUIPB200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(workspace);
-  float* xr = reinterpret_cast<float*>(keys + m);
+  float* xr = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) +
+                                       (((size_t)m * sizeof(unsigned long long) + 15) & ~(size_t)15));   // 16-byte aligned rows
   const uint2* tab = reinterpret_cast<const uint2*>(grid_packed_abs);
   cudaError_t e = cudaMemsetAsync(keys, 0, (size_t)m * sizeof(unsigned long long), st);
   if (e != cudaSuccess) return (int)e;

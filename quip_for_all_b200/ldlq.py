@@ -204,7 +204,7 @@ def quantize_linear(layer: nn.Linear, calib_inputs, codebook: str = "E8P12", wei
     ql = QuantLinear(layer.in_features, layer.out_features, codebook_id[codebook](inference=True),
                      bias=layer.bias is not None, use_rand=use_rand, per_channel=per_channel, weight_dtype=weight_dtype)
     ql.pack(layer, attr)
-    ql = ql.to(dev)
+    ql = ql.to(dev).train(layer.training)
     ql.wscale_float = float(ql.Wscale.float().mean().item())        # quantizer.py:837
     if per_channel:
         ql.Wscale.data = ql.Wscale.data / ql.wscale_float

@@ -200,6 +200,7 @@ class QuipQuantizer(object):
                     q.cpu()
                     q.pack(lin.cpu(), attr)
                     q.to(dev)
+                    q.train(block.training)        # a fresh module is in training mode (the dense calc_weight branch)
                     q.proxy_loss = acc[n].last_proxy_loss
                     q._w_scale_f32 = attr["w_scale"].to(torch.float32)
                     acc[n].H = None

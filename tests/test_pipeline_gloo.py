@@ -1,5 +1,7 @@
 """Layer-pipeline tick schedule on CPU: world_size 2 and 4 over gloo with a fake stage, checked against a
-sequential single-process evaluation of the same per-sequence recurrences."""
+sequential single-process evaluation of the same per-sequence recurrences -- in both hand-off modes of
+`RingPipeline.tick`: the grouped exchange per tick, and the mailbox order (wait -> step -> send, per-slot sequence
+numbers) that the GPU runs use over NVLink peer memory (`parallel.PeerMailbox`)."""
 import os
 import socket
 
@@ -69,7 +71,31 @@ def _sequential(world, S, first_tokens, n_tokens):
     return out
 
 
-def _worker(rank, world, port, n_ticks, q):
+class GlooMailbox:
+    """CPU stand-in for parallel.PeerMailbox with the same interface and the same sequence-number rule: `send` posts the
+    payload to the next rank (tag = slot), `wait_into` blocks on the upstream's k-th send for that slot -- except on
+    stage 0, whose first wait per slot passes without a send and leaves the buffer alone (the prefill's token)."""
+
+    def __init__(self, rank, world, S):
+        self.rank, self.nxt, self.prv = rank, (rank + 1) % world, (rank - 1) % world
+        self.waits = [-1 if rank == 0 else 0] * S
+        self.pending = []
+
+    def send(self, slot, src):
+        self.pending.append(dist.isend(src.clone(), self.nxt, tag=slot))
+
+    def wait_into(self, slot, dst):
+        self.waits[slot] += 1
+        if self.waits[slot] == 0:
+            return
+        dist.recv(dst, self.prv, tag=slot)
+
+    def drain(self):
+        for w in self.pending:
+            w.wait()
+
+
+def _worker(rank, world, port, n_ticks, q, mode="collective"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -79,18 +105,25 @@ def _worker(rank, world, port, n_ticks, q):
     if st.first:
         for s in range(S):
             st.tok[s] = torch.tensor([first[s]])      # what the prefill phase leaves behind
-    pipe = RingPipeline(st, rank, world, S)
+    mailbox = GlooMailbox(rank, world, S) if mode == "mailbox" else None
+    pipe = RingPipeline(st, rank, world, S, mailbox=mailbox)
     emitted = 0
     for _ in range(n_ticks):
         emitted += bool(pipe.tick())
     if st.last:
         q.put((st.emitted, emitted))
+    if mailbox is not None:
+        # the upstream's send of its last tick has no tick left to consume it: receive it, then retire the own sends
+        prv = (rank - 1) % world
+        s_last = (n_ticks - 1 - prv) % S
+        dist.recv(st.in_buffer(s_last).clone(), prv, tag=s_last)
+        mailbox.drain()
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_ring_pipeline_matches_sequential(world):
+@pytest.mark.parametrize("world,mode", [(2, "collective"), (4, "collective"), (2, "mailbox"), (4, "mailbox")])
+def test_ring_pipeline_matches_sequential(world, mode):
     sock = socket.socket()
     sock.bind(("127.0.0.1", 0))
     port = sock.getsockname()[1]
@@ -98,7 +131,7 @@ def test_ring_pipeline_matches_sequential(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     n_ticks = world - 1 + 3 * world                      # fill + 3 tokens per sequence
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_ticks, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_ticks, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     emitted, count = q.get(timeout=120)

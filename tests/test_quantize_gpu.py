@@ -117,7 +117,7 @@ def test_quantize_linear_round_trip(codebook, fin, fout):
     torch.manual_seed(1)
     lin = torch.nn.Linear(fin, fout, bias=True).to(dev)
     w0 = lin.weight.data.clone()
-    calib = [torch.randn(2, 64, fin, device=dev) for _ in range(3)]
+    calib = [torch.randn(8, 256, fin, device=dev) for _ in range(3)]      # 6144 tokens: a full-rank proxy Hessian
     ql = quantize_linear(lin, calib, codebook=codebook).eval()
     x = torch.randn(5, fin, device=dev).half()
     with torch.no_grad():
@@ -137,17 +137,19 @@ def test_quantize_linear_round_trip(codebook, fin, fout):
 def test_quantize_model_end_to_end(tmp_path, codebook, min_corr):
     """tiny Llama: quantize_model on the GPU (search kernel inside LDLQ) -> logits through the CUDA inference path track the
     fp32 model's at the codebook's rate; save -> load_quantized_model reproduces the quantised model's logits exactly."""
-    from transformers import LlamaConfig, LlamaForCausalLM
+    from transformers import AutoModelForCausalLM, LlamaConfig
     from quip_for_all_b200 import QuipQuantizer, load_quantized_model
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     cfg = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
                       num_key_value_heads=2, vocab_size=128, max_position_embeddings=64)
-    m = LlamaForCausalLM(cfg).eval().half().to(dev)
+    # built the way the loader builds it (fp16 parameters, computed buffers such as the rotary inv_freq stay fp32);
+    # `.half()` on an fp32 model would round inv_freq and the two models would differ in RoPE, not in the linears
+    m = AutoModelForCausalLM.from_config(cfg, dtype=torch.float16).eval().to(dev)
     ids = torch.randint(0, 128, (2, 24), device=dev)
     with torch.no_grad():
         ref = m(ids).logits.float()
-    qz = QuipQuantizer(codebook, quip_tune_iters=0, ft_epochs=0, inference=False)
+    qz = QuipQuantizer(codebook, quip_tune_iters=0, ft_epochs=0, inference=False, opt_resid_scale=None)
     calib = [torch.randint(0, 128, (4, 32)) for _ in range(4)]
     m = qz.quantize_model(m, calib, save_dir=str(tmp_path))
     with torch.no_grad():

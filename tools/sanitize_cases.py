@@ -86,3 +86,12 @@ with torch.no_grad():
     a, b = grp(h, norm_w=w, eps=1e-5)
 torch.cuda.synchronize()
 print("group (cluster epilogue, 2 members in one launch) ok", float(a.float().abs().max()), float(b.float().abs().max()))
+
+# quantise-time nearest-codeword search (csrc/nearest.cu): partial thread tiles, several CTAs in x, both RVQ4B stages
+for name in ("E8P12", "E8P12RVQ4B"):
+    cb = codebook_id[name](inference=False).to(dev)
+    for m in (3, 700):
+        xq = (torch.randn(m, 8, generator=g) * 1.1).to(dev)
+        vals, idx = cb.quantize(xq)
+        torch.cuda.synchronize()
+        print("nearest", name, m, "ok", int(idx.max()), float((vals - xq).square().mean()))
