@@ -141,6 +141,10 @@ class QuipQuantizer(object):
                              "tokenising a hub dataset (reference data.py) needs network access")
         if self.ft_epochs and self.ft_epochs > 0:
             raise NotImplementedError("block-wise fine-tuning (ft_epochs > 0) is not part of this build: pass ft_epochs=0")
+        if self.merge_suv:
+            raise NotImplementedError("merge_suv=True at quantisation time (sharing sign vectors between consecutive "
+                                      "layers, quantizer.py:409-421) is not part of this build; checkpoints written that "
+                                      "way by the reference load fine")
         if getattr(self.codebook, "grid", None) is None:
             raise ValueError("quantize_model needs the full codebook: construct QuipQuantizer(..., inference=False)")
         model.eval()
