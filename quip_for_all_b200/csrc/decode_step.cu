@@ -401,6 +401,7 @@ __device__ __forceinline__ void gemv_store_mix(const GemvCfg& c, const int* red,
                                                const __half* wpc, const __half* M, int K, float* vbuf, int tid) {
   using T = CbTraits<CB>;
   const int Kp = (K + 15) / 16 * 16;
+  if (tid < 8 * (Kp - K)) vbuf[(tid / (Kp - K)) * 64 + K + tid % (Kp - K)] = 0.f;   // the padded columns of M meet zeros
   __syncthreads();
   const float xs = xscale * (CB == QUIPB200_CB_D4 ? 0.5f : 0.25f);
   const float rs = __half2float(__float2half_rn(resid_scale));
@@ -421,8 +422,19 @@ __device__ __forceinline__ void gemv_store_mix(const GemvCfg& c, const int* red,
   __syncthreads();
   const int i = tid >> 6, ko = tid & 63;
   if (i < c.nu && ko < K) {
+    // row ko of M as 16-byte loads (row pitch Kp halfs = a multiple of 32 bytes), v[.][i] as broadcast float4 loads: the
+    // 2-byte form of this loop ran with 8-way bank conflicts (lane stride 96 bytes) on the critical path of the grid barrier
     float a = 0.f;
-    for (int k = 0; k < K; k++) a = fmaf(__half2float(M[ko * Kp + k]), vbuf[i * 64 + k], a);
+    const uint4* mrow = reinterpret_cast<const uint4*>(M + ko * Kp);
+    const float4* vrow = reinterpret_cast<const float4*>(vbuf + i * 64);
+    for (int k8 = 0; k8 < Kp; k8 += 8) {          // columns K .. Kp-1 of M are zero (padded blob), vbuf is finite there
+      const uint4 m8 = mrow[k8 >> 3];
+      const float4 v0 = vrow[k8 >> 2], v1 = vrow[(k8 >> 2) + 1];
+      const float2 m01 = __half22float2(as_h2(m8.x)), m23 = __half22float2(as_h2(m8.y));
+      const float2 m45 = __half22float2(as_h2(m8.z)), m67 = __half22float2(as_h2(m8.w));
+      a = fmaf(m01.x, v0.x, a); a = fmaf(m01.y, v0.y, a); a = fmaf(m23.x, v0.z, a); a = fmaf(m23.y, v0.w, a);
+      a = fmaf(m45.x, v1.x, a); a = fmaf(m45.y, v1.y, a); a = fmaf(m67.x, v1.z, a); a = fmaf(m67.y, v1.w, a);
+    }
     acc[ko * c.rstride + c.row_begin + i] = __float2half_rn(a);
   }
 }

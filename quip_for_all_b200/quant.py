@@ -4,8 +4,7 @@
 
 `matmul_hadU` / `matmul_hadUt` are the device-agnostic pure-torch transforms (the reference's only
 CPU-runnable ones, used at quantisation time); `matmul_hadU_cuda` / `matmul_hadUt_cuda` run the
-`quip_lib::hadamard` CUDA op.  The LDLQ solvers of the reference's quant.py are quantise-time only and
-out of scope.
+`quip_lib::hadamard` CUDA op.  The LDLQ solvers of the reference's quant.py (:91-232) live in `ldlq.py`.
 """
 import math
 import os

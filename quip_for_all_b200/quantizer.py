@@ -1,8 +1,10 @@
-"""Inference-side model surgery and checkpoint loading (reference: quantizer.py:53-248, 760-848).
+"""Model surgery, checkpoint loading and the offline quantisation driver (reference: quantizer.py:53-848).
 
 `QuipQuantizer` keeps the reference's constructor keywords / `to_dict` / `from_dict` / `convert_model` /
-`get_no_split_module_classes`; the offline quantisation driver (`quantize_model`, LDLQ, fine-tuning,
-`save`) is out of scope for this build and raises NotImplementedError.
+`get_no_split_module_classes`.  `quantize_model` (block-wise calibration -> LDLQ per sub-layer group with the GPU
+codeword search, `ldlq.py` / `csrc/nearest.cu` -> packed `QuantLinear`s) and `save` (the reference's checkpoint layout) are
+here too; what is NOT part of this build: fetching / tokenising a calibration dataset (no network: ready batches are
+passed in), block-wise fine-tuning (`ft_epochs > 0`) and `merge_suv` at quantisation time -- each raises.
 
 `load_quantized_model` has the reference signature but does not need `accelerate`: the HF model is
 instantiated on the meta device, every block linear is swapped for a `QuantLinear`, and the
