@@ -10,7 +10,7 @@ import sys
 KEYS = ['UTCHMMA', 'LDTM', 'UTCBAR', 'UTMALDG', 'UBLKCP', 'SYNCS', 'UCGABAR', 'IDP.4A', 'HMMA', 'LDSM', 'REDUX', 'SHFL', 'LDGSTS', 'ATOM', 'RED',
         'MEMBAR', 'LDS', 'STS']
 WANT = ('e8p_umma_kernel', 'rotblk_pipe', 'rot4096', 'decode_step_kernel', 'ql_gemv_kernel', 'cluster_kernel', 'lm_tail', 'decompress_e8',
-        'attn_decode', 'ql_prologue_kernel', 'ql_epilogue_kernel')
+        'attn_decode', 'ql_prologue_kernel', 'ql_epilogue_kernel', 'e8p_nearest', 'handoff_')
 
 
 def main(path):
