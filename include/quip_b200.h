@@ -283,6 +283,12 @@ int quipb200_decode_step_set_splits(int splits);
 size_t quipb200_e8p_quantize_workspace_bytes(int64_t m);
 int quipb200_e8p_quantize(const float* x, int64_t m, const int64_t* grid_packed_abs, int n_stages, float resid_scale,
                           float* vals_out, int64_t* idx_out, void* workspace, size_t workspace_bytes, void* stream);
+/* `E8P12RVQ3B_codebook.quantize` (codebook/e8p12_rvq3.py:91-101): E8P12 search, then the residual `(X - init) / scale`
+ * against the 256-entry e81b grid (fp32 [256, 8], :16-50); vals = init + resid * scale, idx = (init << 8) + resid.
+ * Same workspace size. */
+int quipb200_e8prvq3_quantize(const float* x, int64_t m, const int64_t* grid_packed_abs, const float* e81b_grid,
+                              float resid_scale, float* vals_out, int64_t* idx_out, void* workspace, size_t workspace_bytes,
+                              void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU layer pipeline: stage-to-stage hand-off over NVLink peer memory (the reference's only

@@ -645,3 +645,20 @@ def ldlq(W: np.ndarray, H: np.ndarray, L: np.ndarray, tune_iters: int = 0):
             Q[:, k], _ = e8p_nearest(t)
             hat[:, a:b] = g[Q[:, k]]
     return hat, Q
+
+
+def e8prvq3_quantize(x: np.ndarray, scale: float = RVQ3_DEFAULT_RESID_SCALE):
+    """codebook/e8p12_rvq3.py:91-101 with fp32 tensors: init = E8P12 round(X); resid = (X - init) / fl32(scale); the
+    residual code is the nearest of the 256 e81b points (argmax 2 r.g - |g|^2, first index on ties);
+    vals = init + e81b[resid] * fl32(scale); idx = (init << 8) + resid."""
+    g32 = e8p_full_grid()
+    e = e81b_grid().astype(np.float64)
+    x32 = np.asarray(x, dtype=np.float32).reshape(-1, 8)
+    s32 = np.float32(scale)
+    i0, _ = e8p_nearest(x32)
+    v0 = g32[i0]
+    r = ((x32 - v0) / s32).astype(np.float32)
+    sc = 2.0 * r.astype(np.float64) @ e.T - (e * e).sum(1)
+    i1 = sc.argmax(1)
+    vals = (v0 + (e81b_grid().astype(np.float32)[i1] * s32).astype(np.float32)).astype(np.float32)
+    return vals, (i0 << 8) + i1

@@ -26,7 +26,7 @@ EXPORTS = [
     "quipb200_decode_step_workspace_bytes", "quipb200_decode_step", "quipb200_decode_step_debug", "quipb200_decode_step_debug_cta", "quipb200_decode_step_set_splits",
     "quipb200_e8p_mm_umma_workspace_bytes", "quipb200_e8p_mm_umma", "quipb200_mm_umma", "quipb200_rotate_batched",
     "quipb200_lm_tail_workspace_bytes", "quipb200_lm_tail",
-    "quipb200_e8p_quantize_workspace_bytes", "quipb200_e8p_quantize",
+    "quipb200_e8p_quantize_workspace_bytes", "quipb200_e8p_quantize", "quipb200_e8prvq3_quantize",
     "quipb200_mailbox_create", "quipb200_mailbox_open", "quipb200_mailbox_close", "quipb200_mailbox_destroy",
     "quipb200_handoff_send", "quipb200_handoff_wait",
     "quipb200_set_option", "quipb200_get_option", "quipb200_launch_count", "quipb200_debug_timeline",
@@ -104,6 +104,8 @@ def lib():
     L.quipb200_e8p_quantize_workspace_bytes.argtypes = [c_int64]
     L.quipb200_e8p_quantize.restype = c_int
     L.quipb200_e8p_quantize.argtypes = [vp, c_int64, vp, c_int, c_float, vp, vp, vp, c_size_t, vp]
+    L.quipb200_e8prvq3_quantize.restype = c_int
+    L.quipb200_e8prvq3_quantize.argtypes = [vp, c_int64, vp, vp, c_float, vp, vp, vp, c_size_t, vp]
     L.quipb200_mailbox_create.argtypes = [c_size_t, POINTER(c_void_p), vp]
     L.quipb200_mailbox_open.argtypes = [vp, POINTER(c_void_p)]
     L.quipb200_mailbox_close.argtypes = [vp]

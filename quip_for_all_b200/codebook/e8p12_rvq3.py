@@ -74,6 +74,10 @@ class E8P12RVQ3B_codebook(nn.Module):
         return grid[Xqidx], Xqidx
 
     def quantize(self, X, return_idx=True):
+        from ..nearest import e8p_quantize, native_ok
+        if native_ok(X):      # E8P12 search + the 256-entry residual search in the fused kernels (csrc/nearest.cu)
+            final_vals, final_idxs = e8p_quantize(X, self.grid_packed_abs, 2, self.opt_resid_scale, resid_grid=self.e81b_grid)
+            return (final_vals, final_idxs) if return_idx else final_vals
         init_vals, init_idxs = self.round(X, self.grid, self.grid_norm)
         resid = (X - init_vals) / self.opt_resid_scale
         resid_vals, resid_idxs = self.round(resid, self.e81b_grid, self.e81b_grid_norm)

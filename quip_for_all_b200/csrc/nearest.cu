@@ -46,16 +46,28 @@ __device__ __forceinline__ void nq_decode(const uint2* __restrict__ tab, uint32_
   e[4] = w[4]; e[5] = w[6]; e[6] = w[5]; e[7] = w[7];
 }
 
+// TABLE = false: the 65 536 E8P12 codewords, decoded from the abs table (tab), 64 chunks in grid.y.
+// TABLE = true : an explicit codebook `table` = float [ncode][8] (ncode <= NQ_CHUNK: one chunk), e.g. the 256-entry e81b
+//                residual grid of E8P12RVQ3B (codebook/e8p12_rvq3.py:16-50).
+template <bool TABLE>
 __global__ void __launch_bounds__(NQ_THREADS) e8p_nearest_kernel(const float* __restrict__ x, int64_t m,
                                                                  const uint2* __restrict__ tab,
+                                                                 const float* __restrict__ table, int ncode,
                                                                  unsigned long long* __restrict__ keys) {
   __shared__ __align__(16) float g[NQ_CHUNK][8];
   __shared__ float gn[NQ_CHUNK];
   const int tid = threadIdx.x;
   const uint32_t c0 = blockIdx.y * NQ_CHUNK;
-  for (int k = tid; k < NQ_CHUNK; k += NQ_THREADS) {
+  const int nk = TABLE ? ncode : NQ_CHUNK;
+  for (int k = tid; k < nk; k += NQ_THREADS) {
     float e[8];
-    nq_decode(tab, c0 + k, e);
+    if (TABLE) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(table + (size_t)k * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(table + (size_t)k * 8) + 1);
+      e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
+    } else {
+      nq_decode(tab, c0 + k, e);
+    }
     float n2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) n2 = fmaf(e[i], e[i], n2);
@@ -84,7 +96,7 @@ __global__ void __launch_bounds__(NQ_THREADS) e8p_nearest_kernel(const float* __
 #pragma unroll
   for (int i = 0; i < NQ_VT; i++) { best[i] = -INFINITY; bk[i] = 0; }
 #pragma unroll 4
-  for (int k = 0; k < NQ_CHUNK; k++) {
+  for (int k = 0; k < nk; k++) {
     const float4 a = *reinterpret_cast<const float4*>(&g[k][0]);
     const float4 b = *reinterpret_cast<const float4*>(&g[k][4]);
     const float nn = gn[k];
@@ -110,14 +122,21 @@ __global__ void __launch_bounds__(NQ_THREADS) e8p_nearest_kernel(const float* __
 // mode 0: single stage          vals = g[c]                          idx = c
 // mode 1: first of two stages   vals = g[c] (held for mode 2)        idx = c (held), xr = (x - g[c]) / resid_scale, key reset
 // mode 2: second of two stages  vals = vals + g[c] * resid_scale     idx = (idx << 16) + c
+// mode 3: second stage against an explicit table (E8P12RVQ3B): vals = vals + table[c] * resid_scale, idx = (idx << 8) + c
 __global__ void e8p_nearest_finish_kernel(const float* __restrict__ x, int64_t m, const uint2* __restrict__ tab,
                                           unsigned long long* __restrict__ keys, float* __restrict__ vals,
-                                          long long* __restrict__ idx, float* __restrict__ xr, float resid_scale, int mode) {
+                                          long long* __restrict__ idx, float* __restrict__ xr, float resid_scale, int mode,
+                                          const float* __restrict__ table) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= m) return;
   const uint32_t c = 0xffffu - (uint32_t)(keys[v] & 0xffffull);
   float e[8];
-  nq_decode(tab, c, e);
+  if (mode == 3) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) e[j] = __ldg(table + (size_t)c * 8 + j);
+  } else {
+    nq_decode(tab, c, e);
+  }
   float4* vo = reinterpret_cast<float4*>(vals + v * 8);
   if (mode == 0) {
     vo[0] = make_float4(e[0], e[1], e[2], e[3]);
@@ -141,7 +160,7 @@ __global__ void e8p_nearest_finish_kernel(const float* __restrict__ x, int64_t m
                         __fadd_rn(a.z, __fmul_rn(e[2], resid_scale)), __fadd_rn(a.w, __fmul_rn(e[3], resid_scale)));
     vo[1] = make_float4(__fadd_rn(b.x, __fmul_rn(e[4], resid_scale)), __fadd_rn(b.y, __fmul_rn(e[5], resid_scale)),
                         __fadd_rn(b.z, __fmul_rn(e[6], resid_scale)), __fadd_rn(b.w, __fmul_rn(e[7], resid_scale)));
-    idx[v] = (idx[v] << 16) + (long long)c;
+    idx[v] = (idx[v] << (mode == 3 ? 8 : 16)) + (long long)c;
   }
 }
 
@@ -154,13 +173,14 @@ extern "C" size_t quipb200_e8p_quantize_workspace_bytes(int64_t m) {
   return (((size_t)m * sizeof(unsigned long long) + 15) & ~(size_t)15) + (size_t)m * 8 * sizeof(float);
 }
 
-extern "C" int quipb200_e8p_quantize(const float* x, int64_t m, const int64_t* grid_packed_abs, int n_stages,
-                                     float resid_scale, float* vals_out, int64_t* idx_out, void* workspace,
-                                     size_t workspace_bytes, void* stream) {
+static int nearest_run(const float* x, int64_t m, const int64_t* grid_packed_abs, int n_stages, float resid_scale,
+                       const float* table2, int ncode2, float* vals_out, int64_t* idx_out, void* workspace,
+                       size_t workspace_bytes, void* stream) {
   if (!x || !grid_packed_abs || !vals_out || !idx_out || !workspace || m < 1 || (n_stages != 1 && n_stages != 2))
     return QUIPB200_EINVAL;
   if (n_stages == 2 && !(resid_scale != 0.f && resid_scale == resid_scale)) return QUIPB200_EINVAL;   // (the reference's
   // quantizer default of -1 reaches the codebook unchanged, quantizer.py:69,127: negative scales are legal)
+  if (table2 && (n_stages != 2 || ncode2 < 1 || ncode2 > NQ_CHUNK || !aligned16(table2))) return QUIPB200_EINVAL;
   if (!aligned16(x) || !aligned16(vals_out) || !aligned16(workspace) || ((uintptr_t)idx_out & 7)) return QUIPB200_EALIGN;
   if (workspace_bytes < quipb200_e8p_quantize_workspace_bytes(m)) return QUIPB200_EWORKSPACE;
   const int64_t gx = (m + NQ_THREADS * NQ_VT - 1) / (NQ_THREADS * NQ_VT);
@@ -175,17 +195,36 @@ extern "C" int quipb200_e8p_quantize(const float* x, int64_t m, const int64_t* g
   const dim3 grid((unsigned)gx, NQ_NCHUNK);
   const int fb = 256;
   const unsigned fgrid = (unsigned)((m + fb - 1) / fb);
-  e8p_nearest_kernel<<<grid, NQ_THREADS, 0, st>>>(x, m, tab, keys);
+  long long* idx = reinterpret_cast<long long*>(idx_out);
+  e8p_nearest_kernel<false><<<grid, NQ_THREADS, 0, st>>>(x, m, tab, nullptr, 0, keys);
   QB_LAUNCH_CHECK();
-  e8p_nearest_finish_kernel<<<fgrid, fb, 0, st>>>(x, m, tab, keys, vals_out, reinterpret_cast<long long*>(idx_out), xr,
-                                                  resid_scale, n_stages == 1 ? 0 : 1);
+  e8p_nearest_finish_kernel<<<fgrid, fb, 0, st>>>(x, m, tab, keys, vals_out, idx, xr, resid_scale, n_stages == 1 ? 0 : 1, nullptr);
   QB_LAUNCH_CHECK();
-  if (n_stages == 2) {
-    e8p_nearest_kernel<<<grid, NQ_THREADS, 0, st>>>(xr, m, tab, keys);
+  if (n_stages == 2 && !table2) {
+    e8p_nearest_kernel<false><<<grid, NQ_THREADS, 0, st>>>(xr, m, tab, nullptr, 0, keys);
     QB_LAUNCH_CHECK();
-    e8p_nearest_finish_kernel<<<fgrid, fb, 0, st>>>(xr, m, tab, keys, vals_out, reinterpret_cast<long long*>(idx_out), xr,
-                                                    resid_scale, 2);
+    e8p_nearest_finish_kernel<<<fgrid, fb, 0, st>>>(xr, m, tab, keys, vals_out, idx, xr, resid_scale, 2, nullptr);
+    QB_LAUNCH_CHECK();
+  } else if (n_stages == 2) {
+    e8p_nearest_kernel<true><<<dim3((unsigned)gx, 1), NQ_THREADS, 0, st>>>(xr, m, tab, table2, ncode2, keys);
+    QB_LAUNCH_CHECK();
+    e8p_nearest_finish_kernel<<<fgrid, fb, 0, st>>>(xr, m, tab, keys, vals_out, idx, xr, resid_scale, 3, table2);
     QB_LAUNCH_CHECK();
   }
   return 0;
+}
+
+extern "C" int quipb200_e8p_quantize(const float* x, int64_t m, const int64_t* grid_packed_abs, int n_stages,
+                                     float resid_scale, float* vals_out, int64_t* idx_out, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  return nearest_run(x, m, grid_packed_abs, n_stages, resid_scale, nullptr, 0, vals_out, idx_out, workspace, workspace_bytes,
+                     stream);
+}
+
+extern "C" int quipb200_e8prvq3_quantize(const float* x, int64_t m, const int64_t* grid_packed_abs, const float* e81b_grid,
+                                         float resid_scale, float* vals_out, int64_t* idx_out, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  if (!e81b_grid) return QUIPB200_EINVAL;
+  return nearest_run(x, m, grid_packed_abs, 2, resid_scale, e81b_grid, 256, vals_out, idx_out, workspace, workspace_bytes,
+                     stream);
 }

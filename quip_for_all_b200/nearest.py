@@ -13,8 +13,10 @@ def native_ok(X: torch.Tensor) -> bool:
     return X.is_cuda and X.dtype == torch.float32 and X.dim() >= 1 and X.shape[-1] == 8 and X.numel() > 0
 
 
-def e8p_quantize(X: torch.Tensor, grid_packed_abs: torch.Tensor, n_stages: int = 1, resid_scale: float = 1.0):
-    """X: CUDA fp32 [..., 8].  Returns (vals fp32 [..., 8], idx int64 [...]) exactly as the reference's `quantize`."""
+def e8p_quantize(X: torch.Tensor, grid_packed_abs: torch.Tensor, n_stages: int = 1, resid_scale: float = 1.0,
+                 resid_grid: torch.Tensor = None):
+    """X: CUDA fp32 [..., 8].  Returns (vals fp32 [..., 8], idx int64 [...]) exactly as the reference's `quantize`.
+    `resid_grid` (fp32 [256, 8]): the second search runs against this table (E8P12RVQ3B's e81b grid)."""
     if not native_ok(X):
         raise ValueError("e8p_quantize: CUDA float32 [..., 8] input required")
     if grid_packed_abs.device != X.device or grid_packed_abs.dtype != torch.int64 or grid_packed_abs.numel() != 256:
@@ -30,6 +32,13 @@ def e8p_quantize(X: torch.Tensor, grid_packed_abs: torch.Tensor, n_stages: int =
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        check(L.quipb200_e8p_quantize(x.data_ptr(), m, grid_packed_abs.data_ptr(), int(n_stages), float(resid_scale),
-                                      vals.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws_bytes, st), "e8p_quantize")
+        if resid_grid is not None:
+            rg = resid_grid.to(device=x.device, dtype=torch.float32).contiguous()
+            if rg.shape != (256, 8):
+                raise ValueError("e8p_quantize: resid_grid must be [256, 8]")
+            check(L.quipb200_e8prvq3_quantize(x.data_ptr(), m, grid_packed_abs.data_ptr(), rg.data_ptr(), float(resid_scale),
+                                              vals.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws_bytes, st), "e8prvq3_quantize")
+        else:
+            check(L.quipb200_e8p_quantize(x.data_ptr(), m, grid_packed_abs.data_ptr(), int(n_stages), float(resid_scale),
+                                          vals.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws_bytes, st), "e8p_quantize")
     return vals.view(*X.shape), idx.view(*X.shape[:-1])

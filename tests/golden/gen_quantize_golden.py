@@ -6,6 +6,7 @@ Needs /root/reference (read-only; absent on the GPU box -- tests only read the c
 Executed from the reference, on CPU tensors (these pieces are pure torch):
   * codebook/e8p12.py        E8P12_codebook(inference=False).quantize            (:125-134)
   * codebook/e8p12_rvq4.py   E8P12RVQ4B_codebook(inference=False).quantize       (:32-46)
+  * codebook/e8p12_rvq3.py   E8P12RVQ3B_codebook(inference=False).quantize       (:91-101)
   * quant.py                 LDLQ (:107-139), LDLQ_buffered (:142-232), block_LDL (:91-104)
   * quip.py                  QUIP.add_batch / QUIP.quant                         (:43-184)
 The same numpy-2 shim as gen_golden.py is applied to codebook/e8p12.py:96.
@@ -35,6 +36,7 @@ def main():
     import codebook.e8p12 as e8p12
     e8p12.np = _NpProxy()
     import codebook.e8p12_rvq4 as rvq4
+    import codebook.e8p12_rvq3 as rvq3
     import quant
     import quip
     torch.manual_seed(0)
@@ -57,6 +59,11 @@ def main():
     out["nearest_rvq4_idx"] = idx4.numpy().astype(np.int64)
     out["nearest_rvq4_vals"] = vals4.numpy()
     out["rvq4_resid_scale"] = np.float64(cb4.opt_resid_scale)
+    cb3 = rvq3.E8P12RVQ3B_codebook(inference=False)
+    vals3, idx3 = cb3.quantize(X)
+    out["nearest_rvq3_idx"] = idx3.numpy().astype(np.int64)
+    out["nearest_rvq3_vals"] = vals3.numpy()
+    out["rvq3_resid_scale"] = np.float64(cb3.opt_resid_scale)
 
     # ---- LDLQ on a small problem, float64 (ties / near-ties out of the picture) and float32
     m, n = 48, 256

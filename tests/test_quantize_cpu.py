@@ -133,3 +133,11 @@ def test_quantize_model_save_load_round_trip_cpu(tmp_path):
         QuipQuantizer("E8P12", ft_epochs=2, inference=False).quantize_model(_tiny_llama(), calib)
     with pytest.raises(ValueError):
         QuipQuantizer("E8P12", ft_epochs=0, inference=False).quantize_model(_tiny_llama(), "wikitext2")
+
+
+def test_oracle_rvq3_quantize_matches_reference(gq):
+    x = gq["nearest_x"]
+    vals, idx = qo.e8prvq3_quantize(x, float(gq["rvq3_resid_scale"]))
+    same = idx == gq["nearest_rvq3_idx"]
+    assert same.mean() > 0.995
+    np.testing.assert_array_equal(vals[same], gq["nearest_rvq3_vals"][same])

@@ -63,6 +63,34 @@ def test_nearest_kernel_rvq4_vs_reference_golden(gq):
     assert (err <= gerr + 1e-4).all()
 
 
+def test_nearest_kernel_rvq3_vs_reference_golden(gq):
+    """E8P12RVQ3B: the second search runs against the 256-entry e81b table (csrc/nearest.cu, TABLE variant)"""
+    from quip_for_all_b200 import codebook_id
+    dev = torch.device("cuda:0")
+    cb = codebook_id["E8P12RVQ3B"](inference=False).to(dev)
+    x = gq["nearest_x"]
+    vals, idx = cb.quantize(torch.from_numpy(x).to(dev))
+    idx, vals = idx.cpu().numpy(), vals.cpu().numpy()
+    same = idx == gq["nearest_rvq3_idx"]
+    assert same.mean() > 0.99
+    np.testing.assert_array_equal(vals[same], gq["nearest_rvq3_vals"][same])
+    ovals, oidx = qo.e8prvq3_quantize(x, float(gq["rvq3_resid_scale"]))
+    osame = idx == oidx
+    assert osame.mean() > 0.99
+    np.testing.assert_array_equal(vals[osame], ovals[osame])
+    assert (idx >> 8).max() < 65536 and (idx & 0xff).max() < 256
+    err = ((vals - x) ** 2).sum(1)
+    gerr = ((gq["nearest_rvq3_vals"] - x) ** 2).sum(1)
+    assert (err <= gerr + 1e-4).all()
+    # ragged size against the torch expression of the same device
+    xr = (torch.randn(777, 8, generator=torch.Generator().manual_seed(5)) * 1.1).to(dev)
+    v1, i1 = cb.quantize(xr)
+    iv, ii = cb.round(xr, cb.grid, cb.grid_norm)
+    rr = (xr - iv) / cb.opt_resid_scale
+    rv, ri = cb.round(rr, cb.e81b_grid, cb.e81b_grid_norm)
+    assert ((i1 == (ii << 8) + ri).float().mean()) > 0.99
+
+
 @pytest.mark.parametrize("m", [1, 7, 511, 513, 5000])
 def test_nearest_kernel_vs_torch_expression_same_device(m):
     """ragged sizes (one vector, partial thread tiles, several CTAs in x) against `round` (codebook/e8p12.py:125-128)

@@ -87,8 +87,9 @@ with torch.no_grad():
 torch.cuda.synchronize()
 print("group (cluster epilogue, 2 members in one launch) ok", float(a.float().abs().max()), float(b.float().abs().max()))
 
-# quantise-time nearest-codeword search (csrc/nearest.cu): partial thread tiles, several CTAs in x, both RVQ4B stages
-for name in ("E8P12", "E8P12RVQ4B"):
+# quantise-time nearest-codeword search (csrc/nearest.cu): partial thread tiles, several CTAs in x, both RVQ4B stages,
+# the explicit-table second stage of RVQ3B
+for name in ("E8P12", "E8P12RVQ4B", "E8P12RVQ3B"):
     cb = codebook_id[name](inference=False).to(dev)
     for m in (3, 700):
         xq = (torch.randn(m, 8, generator=g) * 1.1).to(dev)
