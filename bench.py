@@ -502,19 +502,33 @@ def run_ours(a):
     tok_s = a.steps / (ms * 1e-3)
 
     # ---- e2e: token id travels host -> device and back every step (pinned buffers) --------------------
-    h_tok_in = torch.zeros(1, 1, dtype=torch.long).pin_memory()
-    h_tok_out = torch.zeros(1, 1, dtype=torch.long).pin_memory()
-    h_tok_in.copy_(eng.tok.cpu())
+    # public API: LlamaDecodeEngine.step_host() -- one graph replay whose first / last nodes are the 8-byte copies from /
+    # to pinned host memory, then a stream synchronisation and the host-side read of the token
     e2e_steps = a.steps
+    e2e_how = "per step: pinned host token id -> device, graph replay, next token id -> pinned host, stream sync"
     torch.cuda.synchronize()
-    t_e2e0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.tok.copy_(h_tok_in, non_blocking=True)      # H2D: this step's input token
-        eng.step()
-        h_tok_out.copy_(eng.tok, non_blocking=True)     # D2H: the sampled token
-        torch.cuda.current_stream().synchronize()
-        h_tok_in.copy_(h_tok_out)
-    t_e2e = time.perf_counter() - t_e2e0
+    if not a.no_graph:
+        eng.capture_host_io()
+        eng.step_host()
+        torch.cuda.synchronize()
+        t_e2e0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.step_host()                                 # H2D of this step's token, the step, D2H of the sampled token, sync
+        t_e2e = time.perf_counter() - t_e2e0
+        e2e_how = ("per step: LlamaDecodeEngine.step_host(): ONE graph replay = [pinned host token id -> device] + decode step + "
+                   "[next token id -> pinned host], stream sync, host reads the token")
+    else:
+        h_tok_in = torch.zeros(1, 1, dtype=torch.long).pin_memory()
+        h_tok_out = torch.zeros(1, 1, dtype=torch.long).pin_memory()
+        h_tok_in.copy_(eng.tok.cpu())
+        t_e2e0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.tok.copy_(h_tok_in, non_blocking=True)      # H2D: this step's input token
+            eng.step()
+            h_tok_out.copy_(eng.tok, non_blocking=True)     # D2H: the sampled token
+            torch.cuda.current_stream().synchronize()
+            h_tok_in.copy_(h_tok_out)
+        t_e2e = time.perf_counter() - t_e2e0
     e2e_tok_s = e2e_steps / t_e2e
 
     line = {
@@ -530,7 +544,7 @@ def run_ours(a):
                              ("persistent whole-step kernel" if eng.persistent is not None else "grouped launches")},
         "clocks": ck,
         "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8,
-                "how": "per step: pinned host token id -> device, graph replay, next token id -> pinned host, stream sync"},
+                "how": e2e_how},
         "gpu_launches": (launches_per_step * a.steps) if launches_per_step else None,
         "launches_per_step_own_kernels": launches_per_step,
         "model_roofline": {"packed_code_bytes_per_token": code_bytes,

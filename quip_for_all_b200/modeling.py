@@ -340,6 +340,44 @@ class LlamaDecodeEngine:
         self.k_cache.copy_(saved[2]); self.v_cache.copy_(saved[3])
 
     @torch.no_grad()
+    def capture_host_io(self):
+        """A second CUDA graph for callers that keep the token on the host: [pinned host token -> device] -> the decode step ->
+        [next token -> pinned host], i.e. the two 8-byte copies ride inside the replay instead of being two more API calls
+        per step.  Returns the pinned (input, output) buffers; use `step_host()`."""
+        assert self.first and self.last, "host token I/O belongs to an engine that holds the whole model"
+        if getattr(self, "graph_io", None) is not None:
+            return self.h_tok_in, self.h_tok_out
+        if self.use_graph and self.graph is None:
+            self.capture()
+        self.h_tok_in = torch.zeros(1, 1, dtype=torch.long).pin_memory()
+        self.h_tok_out = torch.zeros(1, 1, dtype=torch.long).pin_memory()
+        self.h_tok_in.copy_(self.tok.cpu())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.tok.copy_(self.h_tok_in, non_blocking=True)
+            self._step_body()
+            self.h_tok_out.copy_(self.tok, non_blocking=True)
+        self.graph_io = g
+        return self.h_tok_in, self.h_tok_out
+
+    @torch.no_grad()
+    def step_host(self, token_id=None):
+        """One decode step with host-resident token ids: feeds `token_id` (default: the previous output), returns the next
+        token id as a Python int after a stream synchronisation."""
+        if getattr(self, "graph_io", None) is None:
+            self.capture_host_io()
+        if self._host_pos >= self.max_len:
+            raise RuntimeError(f"KV cache is full ({self.max_len} positions): allocate a larger max_cache_len")
+        self._host_pos += 1
+        if token_id is not None:
+            self.h_tok_in[0, 0] = int(token_id)
+        self.graph_io.replay()
+        torch.cuda.current_stream(self.dev).synchronize()
+        nxt = int(self.h_tok_out[0, 0])
+        self.h_tok_in[0, 0] = nxt
+        return nxt
+
+    @torch.no_grad()
     def step(self):
         """One decode step: consumes self.tok / self.pos, leaves the next token in self.tok."""
         if self._host_pos >= self.max_len:          # the kernels clamp the position: refuse instead of overwriting the last slot

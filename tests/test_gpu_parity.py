@@ -689,6 +689,35 @@ def test_persistent_decode_step_under_cuda_graph_generates_same_tokens():
     assert torch.equal(o1[:, :4], o2[:, :4])      # later tokens may differ by an fp16 near-tie
 
 
+def test_decode_engine_host_token_io_graph():
+    """`step_host()`: the token id comes from / returns to pinned host memory inside ONE graph replay (what bench.py's e2e
+    leg times); same tokens as the device-resident loop, and an overridden input token is what the step consumes."""
+    from quip_for_all_b200.modeling import LlamaDecodeEngine, make_random_quantized_llama
+    model = make_random_quantized_llama("tiny256", "E8P12", seed=3, device=DEV)
+    ids = torch.randint(0, 32000, (1, 10), generator=torch.Generator().manual_seed(2)).to(DEV)
+    e1 = LlamaDecodeEngine(model, max_cache_len=64, persistent=True)
+    ref = e1.generate(ids, 9)[0].tolist()
+    e2 = LlamaDecodeEngine(model, max_cache_len=64, persistent=True)
+    e2.prefill(ids)
+    e2.capture()
+    first = int(e2.tok.item())
+    got = [first] + [e2.step_host() for _ in range(8)]
+    assert got == ref
+    # feed a different token: the continuation must equal the device loop started from that token
+    e3 = LlamaDecodeEngine(model, max_cache_len=64, persistent=True)
+    e3.prefill(ids)
+    e3.capture()
+    e3.tok.fill_(123)
+    e3.step()
+    want = int(e3.tok.item())
+    e4 = LlamaDecodeEngine(model, max_cache_len=64, persistent=True)
+    e4.prefill(ids)
+    assert e4.step_host(123) == want
+    with pytest.raises(RuntimeError):
+        for _ in range(100):
+            e4.step_host()
+
+
 # ------------------------------------------------------------------------------------------------
 # tcgen05 decode + GEMM (umma_gemm.cu): 17 <= M <= 256
 # ------------------------------------------------------------------------------------------------
