@@ -37,6 +37,7 @@ int g_opt_fuse = 3;          // bit0: fuse prologue into the GEMV kernel, bit1: 
 int g_opt_rot_cluster = 1;  // block rotations with an orthogonal mix run on a thread-block cluster (rot_cluster.cuh); 0: one CTA
 int g_opt_lean = 1;          // use the instruction-cache-lean kernel instantiation when eligible
 int g_opt_phase0 = 1;        // experiment: 0 = no early code prefetch
+int g_opt_epi_mma = 1;       // 4096-point output rotations of the per-linear kernels on the tensor path (0: shuffle form)
 long long* g_dbg_timeline = nullptr;   // profiling hook: per-CTA clock64 stamps of the GEMV kernel phases
 
 // tickets for the last-CTA-done epilogue: zero at module load, reset by the CTA that consumes them.
@@ -661,6 +662,7 @@ static int member_from_layer(const quipb200_linear_t* L, const quipb200_fusion_t
   ea.scale = 1.0f / sqrtf((float)(L->q_out / L->K_right));
   ea.SV = (const __half*)L->SV; ea.bias = (const __half*)L->bias; ea.y = (__half*)y; ea.ldy = ldy;
   if (fu) { ea.residual = (const __half*)fu->residual; ea.ldres = fu->ldres; }
+  ea.mma = (g_opt_epi_mma && L->K_right == 1 && L->q_out == 4096) ? 1 : 0;
   m->pa = pa; m->ea = ea;
   return 0;
 }
