@@ -588,68 +588,94 @@ __device__ __forceinline__ void epilogue_body(const EpilogueArgs& a, unsigned ch
                                (!a.bias || al16(a.bias)) && (!rr || al16(rr)) && ((a.K == 1) || L >= 8));
   const int noct_out = a.out_features >> 3;
   if (a.mma && nt == 512 && vec_in && vec_out) {
-    // 4096-point output rotation as three H_16 factors on the (legacy) tensor path, register resident, ONE exchange through
-    // shared memory (fwht4096_frag; decode_step.cu's out_side_m for a standalone linear).  The shuffle form below needs
-    // 40 shuffles per thread and two passes through shared memory with two CTA barriers.  Block layout in (thread = octet
-    // tid), spread layout out (4 consecutive halfs per position), same fp16 rounding points as the path below.
+    // 4096- and 8192-point output rotations as H_16 factors on the (legacy) tensor path, register resident, ONE exchange
+    // through shared memory per 4096 points (fwht4096_frag; decode_step.cu's out_side_m for a standalone linear).  The
+    // shuffle form below needs 40 shuffles per thread and two passes through shared memory with two CTA barriers.
+    // Block layout in (thread = octet tid of each 4096-point half), spread layout out (4 consecutive halfs per position),
+    // same fp16 rounding points as the path below.  8192 = H_2 (x) H_4096: both halves are transformed, then one butterfly.
     const int warp = tid >> 5, lane = tid & 31;
-    uint2 sv2[2], bi2[2], re2[2];
-    int pos[2];
+    const int NH = a.mma;                         // 1: q_out = 4096, 2: q_out = 8192
+    const HFrag A = make_hfrag(lane);
+    float r[2][8];
+    // SV / bias / skip connection at this thread's output positions: requested first, they travel during the rotation
+    uint2 sv2[2][2], bi2[2][2], re2[2][2];
 #pragma unroll
-    for (int xh = 0; xh < 2; xh++) {
-      pos[xh] = idx_spread(warp, lane, xh);
-      sv2[xh] = bi2[xh] = re2[xh] = make_uint2(0, 0);
-      if (pos[xh] < a.out_features) {
-        if (a.SV) sv2[xh] = __ldg(reinterpret_cast<const uint2*>(a.SV + pos[xh]));
-        if (a.bias) bi2[xh] = __ldg(reinterpret_cast<const uint2*>(a.bias + pos[xh]));
-        if (rr) re2[xh] = __ldcg(reinterpret_cast<const uint2*>(rr + pos[xh]));
+    for (int hh = 0; hh < 2; hh++) {
+#pragma unroll
+      for (int xh = 0; xh < 2; xh++) {
+        sv2[hh][xh] = bi2[hh][xh] = re2[hh][xh] = make_uint2(0, 0);
+        const int pos = hh * 4096 + idx_spread(warp, lane, xh);
+        if (hh < NH && pos < a.out_features) {
+          if (a.SV) sv2[hh][xh] = __ldg(reinterpret_cast<const uint2*>(a.SV + pos));
+          if (a.bias) bi2[hh][xh] = __ldg(reinterpret_cast<const uint2*>(a.bias + pos));
+          if (rr) re2[hh][xh] = __ldcg(reinterpret_cast<const uint2*>(rr + pos));
+        }
       }
     }
-    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(ar + (size_t)tid * 8));
-    const float4 v1 = __ldcg(reinterpret_cast<const float4*>(ar + (size_t)tid * 8) + 1);
-    float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    if (ar2) {
-      const float4 w0 = __ldcg(reinterpret_cast<const float4*>(ar2 + (size_t)tid * 8));
-      const float4 w1 = __ldcg(reinterpret_cast<const float4*>(ar2 + (size_t)tid * 8) + 1);
-      const float r2[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-      for (int j = 0; j < 8; j++) f[j] = fmaf(a.resid_scale, r2[j], f[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] * xs);                          // origin_order.cu:129
-    if (a.wscale_pc) {
-      float w8[8];
-      unpack_h8(__ldg(reinterpret_cast<const uint4*>(a.wscale_pc) + tid), w8);
-#pragma unroll
-      for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] * w8[j]);                     // qlinear.py:107
-    }
-    const uint4 oct = pack_h8(f);
-    const uint32_t p[4] = {oct.x, oct.z, oct.y, oct.w};
-    const HFrag A = make_hfrag(lane);
-    float r[8];
     QB_DSTAMP(13);
-    fwht4096_frag(p, A, sm.s, warp, lane, r);                                         // x 1/64 = 1/sqrt(4096), quant.py:75
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+      if (hh < NH) {
+        const size_t o = (size_t)hh * 512 + tid;
+        const float4 v0 = __ldcg(reinterpret_cast<const float4*>(ar + o * 8));
+        const float4 v1 = __ldcg(reinterpret_cast<const float4*>(ar + o * 8) + 1);
+        float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        if (ar2) {
+          const float4 w0 = __ldcg(reinterpret_cast<const float4*>(ar2 + o * 8));
+          const float4 w1 = __ldcg(reinterpret_cast<const float4*>(ar2 + o * 8) + 1);
+          const float r2[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int j = 0; j < 8; j++) f[j] = fmaf(a.resid_scale, r2[j], f[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] * xs);                        // origin_order.cu:129
+        if (a.wscale_pc) {
+          float w8[8];
+          unpack_h8(__ldg(reinterpret_cast<const uint4*>(a.wscale_pc) + o), w8);
+#pragma unroll
+          for (int j = 0; j < 8; j++) f[j] = f16_round(f[j] * w8[j]);                   // qlinear.py:107
+        }
+        const uint4 oct = pack_h8(f);
+        const uint32_t p[4] = {oct.x, oct.z, oct.y, oct.w};
+        if (hh) __syncthreads();                                                        // the exchange buffer is reused
+        fwht4096_frag(p, A, sm.s, warp, lane, r[hh]);                                   // x 1/64
+      }
+    }
+    if (NH == 2) {                                                                      // x 1/sqrt(2): 1/sqrt(8192) in total
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float u = r[0][j], v = r[1][j];
+        r[0][j] = (u + v) * 0.70710678118654752f;
+        r[1][j] = (u - v) * 0.70710678118654752f;
+      }
+    }
     QB_DSTAMP(14);
 #pragma unroll
-    for (int xh = 0; xh < 2; xh++) {
-      if (pos[xh] < a.out_features) {
-        uint32_t ow[2];
+    for (int hh = 0; hh < 2; hh++) {
+      if (hh < NH) {
 #pragma unroll
-        for (int yh = 0; yh < 2; yh++) {
-          const int q = xh + 2 * yh;
-          __half2 h = __floats2half2_rn(r[2 * q], r[2 * q + 1]);
-          if (a.SV) h = __hmul2(h, as_h2(yh ? sv2[xh].y : sv2[xh].x));                 // qlinear.py:112
-          if (a.bias) h = __hadd2_rn(h, as_h2(yh ? bi2[xh].y : bi2[xh].x));            // qlinear.py:114
-          if (rr) {
-            float2 v = __half22float2(h);
-            const float2 e = __half22float2(as_h2(yh ? re2[xh].y : re2[xh].x));
-            v.x += e.x;
-            v.y += e.y;
-            h = __floats2half2_rn(v.x, v.y);
+        for (int xh = 0; xh < 2; xh++) {
+          const int pos = hh * 4096 + idx_spread(warp, lane, xh);
+          if (pos < a.out_features) {
+            uint32_t ow[2];
+#pragma unroll
+            for (int yh = 0; yh < 2; yh++) {
+              const int q = xh + 2 * yh;
+              __half2 h = __floats2half2_rn(r[hh][2 * q], r[hh][2 * q + 1]);
+              if (a.SV) h = __hmul2(h, as_h2(yh ? sv2[hh][xh].y : sv2[hh][xh].x));       // qlinear.py:112
+              if (a.bias) h = __hadd2_rn(h, as_h2(yh ? bi2[hh][xh].y : bi2[hh][xh].x));  // qlinear.py:114
+              if (rr) {
+                float2 v = __half22float2(h);
+                const float2 e = __half22float2(as_h2(yh ? re2[hh][xh].y : re2[hh][xh].x));
+                v.x += e.x;
+                v.y += e.y;
+                h = __floats2half2_rn(v.x, v.y);
+              }
+              ow[yh] = as_u32(h);
+            }
+            *reinterpret_cast<uint2*>(yr + pos) = make_uint2(ow[0], ow[1]);
           }
-          ow[yh] = as_u32(h);
         }
-        *reinterpret_cast<uint2*>(yr + pos[xh]) = make_uint2(ow[0], ow[1]);
       }
     }
     return;

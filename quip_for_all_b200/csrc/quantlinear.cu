@@ -662,7 +662,7 @@ static int member_from_layer(const quipb200_linear_t* L, const quipb200_fusion_t
   ea.scale = 1.0f / sqrtf((float)(L->q_out / L->K_right));
   ea.SV = (const __half*)L->SV; ea.bias = (const __half*)L->bias; ea.y = (__half*)y; ea.ldy = ldy;
   if (fu) { ea.residual = (const __half*)fu->residual; ea.ldres = fu->ldres; }
-  ea.mma = (g_opt_epi_mma && L->K_right == 1 && L->q_out == 4096) ? 1 : 0;
+  ea.mma = (g_opt_epi_mma && L->K_right == 1) ? (L->q_out == 4096 ? 1 : (L->q_out == 8192 ? 2 : 0)) : 0;
   m->pa = pa; m->ea = ea;
   return 0;
 }
