@@ -38,7 +38,7 @@ class QuipQuantizer(object):
                  merge_suv: bool = False, per_channel: bool = False, opt_resid_scale: Optional[float] = -1,
                  inference: bool = False, ft_epochs: int = 5, ft_lr: float = 5e-5, ft_susv_lr: float = 5e-4,
                  ft_valid_size: int = 128, ft_bs: int = 8, ft_update_freq: int = 2, ft_early_stop: int = 3,
-                 *args, **kwargs):
+                 cache_on_gpu: bool = False, scale_override: float = -1, *args, **kwargs):
         if codebook not in codebook_id:
             raise ValueError(f"unknown codebook {codebook!r}; expected one of {sorted(codebook_id)}")
         self.codebook = codebook_id[codebook](inference=inference, opt_resid_scale=opt_resid_scale)
@@ -60,6 +60,8 @@ class QuipQuantizer(object):
         self.ft_valid_size, self.ft_bs = ft_valid_size, ft_bs
         self.ft_update_freq, self.ft_early_stop = ft_update_freq, ft_early_stop
         self.quant_method = "QUiP"
+        self.cache_on_gpu = cache_on_gpu        # calibration activations stay on the device between blocks (quantizer.py:75)
+        self.scale_override = scale_override
 
     def to_dict(self):
         """quantization_config.json contents (reference: quantizer.py:132-147)."""
@@ -165,9 +167,11 @@ class QuipQuantizer(object):
 
         inputs, in_kwargs = [], []
 
+        keep = (lambda t: t) if self.cache_on_gpu else (lambda t: t.cpu())   # host RAM unless cache_on_gpu, as the reference
+
         def grab(_, args, kwargs):
             x = args[0] if args else kwargs["hidden_states"]
-            inputs.append(x.detach())
+            inputs.append(keep(x.detach()))
             in_kwargs.append({k: v for k, v in kwargs.items() if k != "hidden_states"})
             raise _Stop
 
@@ -190,15 +194,15 @@ class QuipQuantizer(object):
             hooks = [layers[n].register_forward_hook(lambda _, i, o, n=n: acc[n].add_batch(i[0].data)) for n in acc]
             outs = []
             for x, kw in zip(inputs, in_kwargs):
-                y = block(x.float(), **kw)
-                outs.append((y[0] if isinstance(y, tuple) else y).detach())
+                y = block(x.to(dev).float(), **kw)
+                outs.append(keep((y[0] if isinstance(y, tuple) else y).detach()))
             for hk in hooks:
                 hk.remove()
             for group in self._sublayer_groups(list(acc)):
                 for n in group:
                     attr = acc[n].quantize(rescale_WH=self.rescale_WH, sigma_reg=self.sigma_reg,
                                            quip_tune_iters=self.quip_tune_iters,
-                                           scale_override=getattr(self, "scale_override", 0) or 0,
+                                           scale_override=self.scale_override if self.scale_override and self.scale_override > 0 else 0,
                                            use_rand=self.use_rand, per_channel=self.per_channel)
                     lin = layers[n]
                     self._replace_by_quant_layers(block, {n: lin})
