@@ -142,7 +142,7 @@ class LayerQuantizer:
         if rescale_WH:
             H /= H.abs().max()
             dH = torch.diag(H).clamp(min=1e-8)
-            dW = (w * w).sum(dim=0).clamp(min=1e-8)
+            dW = torch.diag(w.T @ w).clamp(min=1e-8)      # (the reference's expression, quip.py:104: same summation order)
             scaleWH = (dH / dW).sqrt().sqrt().to(torch.float32).clamp(min=1e-8)
             w *= scaleWH[None, :]
             H /= scaleWH[None, :]

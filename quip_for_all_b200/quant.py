@@ -93,7 +93,9 @@ def matmul_hadU(X, hadK, K, padN, transpose=False):
     if K > 1:
         hk = hadK.T if transpose else hadK
         y = hk.to(device=y.device, dtype=y.dtype) @ y
-    return y.reshape(*lead, padN) / math.sqrt(padN // K)
+    # the reference divides by `torch.tensor(padN / K).sqrt()` (quant.py:65), an fp32 scalar: for block lengths that are not
+    # powers of 4 (128, 8192, ...) the divisor is the fp32-rounded root also when X is fp64 (quantise-time Hessians)
+    return y.reshape(*lead, padN) / float(torch.tensor(padN / K).sqrt())
 
 
 def matmul_hadUt(X, hadK, K, padN):

@@ -113,6 +113,33 @@ def main():
     out["quip_Qidxs"] = attr["Qidxs"].numpy().astype(np.int16)
     out["quip_w_scale"] = np.float64(attr["w_scale"].item())
     out["quip_w_hat"] = lin.weight.data.numpy()         # the de-rotated quantised weight QUIP.quant writes back (:160-168)
+    # ---- second driver case: W/H rescaling, per-channel scales, one re-rounding sweep (unbuffered LDLQ)
+    torch.manual_seed(1)
+    lin2 = torch.nn.Linear(128, 48, bias=False)
+    lin2.weight.data = torch.randn(48, 128) * 0.02 * (1 + torch.rand(48, 1))
+    SU2 = (torch.randn(128).sign() + 1e-5).sign()
+    SV2 = (torch.randn(48).sign() + 1e-5).sign()      # 48 = 3 * 16: random orthogonal 3 x 3 block on the output side
+    lin2.SU, lin2.SV = SU2.clone(), SV2.clone()
+    w2 = lin2.weight.data.clone()
+    cb64b = e8p12.E8P12_codebook(inference=False)
+    cb64b.grid = cb64b.grid.double()
+    cb64b.grid_norm = cb64b.grid_norm.double()
+    q2 = quip.QUIP(lin2, cb64b)
+    calib2 = torch.randn(3, 200, 128) * (0.5 + torch.rand(128))
+    for b in range(3):
+        q2.add_batch(calib2[b], None)
+    np.random.seed(3)                                  # get_hadK(use_rand=True) draws scipy special_ortho_group for 48 rows
+    attr2 = q2.quant(rescale_WH=True, use_fp64=True, sigma_reg=0.01, scale_override=0, use_buffered=False, use_rand=True,
+                     per_channel=True, quip_tune_iters=1)
+    out["quip2_w"] = w2.numpy()
+    out["quip2_calib"] = calib2.numpy()
+    out["quip2_SU"] = SU2.numpy()
+    out["quip2_SV"] = SV2.numpy()
+    out["quip2_Qidxs"] = attr2["Qidxs"].numpy().astype(np.int16)
+    out["quip2_w_scale"] = attr2["w_scale"].numpy().astype(np.float64)
+    out["quip2_scaleWH"] = attr2["scaleWH"].numpy().astype(np.float64)
+    out["quip2_right_hadK"] = attr2["right_hadK"].numpy().astype(np.float64)
+    out["quip2_w_hat"] = lin2.weight.data.numpy()
     np.savez_compressed(os.path.join(OUT, "quantize.npz"), **out)
     for k, v in out.items():
         print(k, getattr(v, "shape", v), getattr(v, "dtype", ""))

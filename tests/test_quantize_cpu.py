@@ -141,3 +141,29 @@ def test_oracle_rvq3_quantize_matches_reference(gq):
     same = idx == gq["nearest_rvq3_idx"]
     assert same.mean() > 0.995
     np.testing.assert_array_equal(vals[same], gq["nearest_rvq3_vals"][same])
+
+
+def test_product_layer_quantizer_rescale_per_channel_tune_matches_reference(gq):
+    """second driver case of the reference (quip.py QUIP.quant): W/H rescaling, per-channel scales, a random orthogonal
+    3 x 3 block on the 48-row output side (same numpy seed -> same draw), one re-rounding sweep, unbuffered LDLQ."""
+    from quip_for_all_b200 import codebook_id
+    from quip_for_all_b200.ldlq import LayerQuantizer
+    lin = torch.nn.Linear(128, 48, bias=False)
+    lin.weight.data = torch.from_numpy(gq["quip2_w"]).clone()
+    cb = codebook_id["E8P12"](inference=False)
+    cb.grid = cb.grid.double()
+    cb.grid_norm = cb.grid_norm.double()
+    lq = LayerQuantizer(lin, cb)
+    calib = torch.from_numpy(gq["quip2_calib"])
+    for b in range(calib.shape[0]):
+        lq.add_batch(calib[b])
+    np.random.seed(3)
+    attr = lq.quantize(rescale_WH=True, use_fp64=True, sigma_reg=0.01, per_channel=True, quip_tune_iters=1,
+                       SU=torch.from_numpy(gq["quip2_SU"]), SV=torch.from_numpy(gq["quip2_SV"]))
+    np.testing.assert_array_equal(attr["right_hadK"].double().numpy(), gq["quip2_right_hadK"])
+    np.testing.assert_allclose(attr["scaleWH"].double().numpy(), gq["quip2_scaleWH"], rtol=1e-6)
+    np.testing.assert_allclose(attr["w_scale"].double().numpy(), gq["quip2_w_scale"], rtol=1e-12)
+    same_rows = (attr["Qidxs"].numpy() == gq["quip2_Qidxs"]).all(1).mean()
+    assert same_rows == 1.0, same_rows
+    np.testing.assert_allclose(lin.weight.data.numpy(), gq["quip2_w_hat"], rtol=0, atol=2e-7)
+    assert attr["left_hadK"] is None and attr["w_scale"].shape == (48, 1)
