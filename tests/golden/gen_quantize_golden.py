@@ -6,7 +6,8 @@ Needs /root/reference (read-only; absent on the GPU box -- tests only read the c
 Executed from the reference, on CPU tensors (these pieces are pure torch):
   * codebook/e8p12.py        E8P12_codebook(inference=False).quantize            (:125-134)
   * codebook/e8p12_rvq4.py   E8P12RVQ4B_codebook(inference=False).quantize       (:32-46)
-  * codebook/e8p12_rvq3.py   E8P12RVQ3B_codebook(inference=False).quantize       (:91-101)
+  * codebook/e8p12_rvq3.py   E8P12RVQ3B_codebook(inference=False).quantize       (:91-101), maybe_pack_idxs (:103-108)
+  * codebook/d4.py, hi.py    D4_codebook.quantize, HI4B1C_codebook.quantize / maybe_pack_idxs
   * quant.py                 LDLQ (:107-139), LDLQ_buffered (:142-232), block_LDL (:91-104)
   * quip.py                  QUIP.add_batch / QUIP.quant                         (:43-184)
 The same numpy-2 shim as gen_golden.py is applied to codebook/e8p12.py:96.
@@ -37,6 +38,8 @@ def main():
     e8p12.np = _NpProxy()
     import codebook.e8p12_rvq4 as rvq4
     import codebook.e8p12_rvq3 as rvq3
+    import codebook.d4 as d4
+    import codebook.hi as hi
     import quant
     import quip
     torch.manual_seed(0)
@@ -113,6 +116,22 @@ def main():
     out["quip_Qidxs"] = attr["Qidxs"].numpy().astype(np.int16)
     out["quip_w_scale"] = np.float64(attr["w_scale"].item())
     out["quip_w_hat"] = lin.weight.data.numpy()         # the de-rotated quantised weight QUIP.quant writes back (:160-168)
+    # ---- the two small codebooks and the index packing of the two packed formats
+    torch.manual_seed(7)
+    cbd = d4.D4_codebook(inference=False)
+    X4 = torch.randn(600, 4) * 1.21
+    X4[:16] = cbd.grid[torch.randint(0, 256, (16,))]
+    vd, idd = cbd.quantize(X4)
+    out["d4_x"], out["d4_idx"], out["d4_vals"] = X4.numpy(), idd.numpy().astype(np.int64), vd.numpy()
+    cbh = hi.HI4B1C_codebook(inference=False)
+    X1 = torch.randn(800, 1) * 2.97
+    vh, idh = cbh.quantize(X1)
+    out["hi_x"], out["hi_idx"], out["hi_vals"] = X1.numpy(), idh.numpy().astype(np.int64), vh.numpy()
+    raw_hi = torch.randint(0, 16, (6, 64), dtype=torch.int32)
+    out["hi_pack_in"], out["hi_pack_out"] = raw_hi.numpy(), cbh.maybe_pack_idxs(raw_hi).numpy()
+    raw3 = ((torch.randint(0, 65536, (5, 16)) << 8) + torch.randint(0, 256, (5, 16))).to(torch.int32)
+    out["rvq3_pack_in"], out["rvq3_pack_out"] = raw3.numpy(), cb3.maybe_pack_idxs(raw3).numpy()
+
     # ---- second driver case: W/H rescaling, per-channel scales, one re-rounding sweep (unbuffered LDLQ)
     torch.manual_seed(1)
     lin2 = torch.nn.Linear(128, 48, bias=False)

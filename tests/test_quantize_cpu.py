@@ -167,3 +167,18 @@ def test_product_layer_quantizer_rescale_per_channel_tune_matches_reference(gq):
     assert same_rows == 1.0, same_rows
     np.testing.assert_allclose(lin.weight.data.numpy(), gq["quip2_w_hat"], rtol=0, atol=2e-7)
     assert attr["left_hadK"] is None and attr["w_scale"].shape == (48, 1)
+
+
+def test_small_codebooks_and_index_packing_match_reference(gq):
+    """D4 / HI `quantize` and the packed index formats of HI (8 nibbles per int32) and E8P12RVQ3B (3 bytes per code)
+    against outputs of the reference's codebook classes."""
+    from quip_for_all_b200 import codebook_id
+    d = codebook_id["D4"](inference=False)
+    vals, idx = d.quantize(torch.from_numpy(gq["d4_x"]))
+    assert np.array_equal(idx.numpy().astype(np.int64), gq["d4_idx"]) and np.array_equal(vals.numpy(), gq["d4_vals"])
+    h = codebook_id["HI"](inference=False)
+    vals, idx = h.quantize(torch.from_numpy(gq["hi_x"]))
+    assert np.array_equal(idx.numpy().astype(np.int64), gq["hi_idx"]) and np.array_equal(vals.numpy(), gq["hi_vals"])
+    assert np.array_equal(h.maybe_pack_idxs(torch.from_numpy(gq["hi_pack_in"])).numpy(), gq["hi_pack_out"])
+    r3 = codebook_id["E8P12RVQ3B"](inference=True)
+    assert np.array_equal(r3.maybe_pack_idxs(torch.from_numpy(gq["rvq3_pack_in"])).numpy(), gq["rvq3_pack_out"])
