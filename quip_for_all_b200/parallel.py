@@ -339,6 +339,9 @@ def run_pipeline_bench(a, metric, clock_sampler_cls=None, peak_gbs=None, single_
             line["model_roofline"] = {"packed_code_bytes_per_token": main["code_bytes"],
                                       "tok_s_at_hbm_peak_all_gpus": roof, "frac_of_hbm_roofline": main["tok_s"] / roof}
         if single is not None:
+            line["config"]["scaling_note"] = ("the N = 1 bench line is the metric's own workload (llama2-7b on one GPU); the N = 1 "
+                                              "point of THIS workload is measured in this run: single_gpu_same_workload / "
+                                              "scaling_vs_single_gpu")
             line["single_gpu_same_workload"] = single
             if "value" in single:
                 line["scaling_vs_single_gpu"] = {"speedup": main["tok_s"] / single["value"],
