@@ -45,16 +45,39 @@ class PeerMailbox:
         from ._native import check, lib
         self.L, self.check, self.ct = lib(), check, ctypes
         self.rank, self.world, self.S, self.dev = rank, world, n_slots, device
+        # Every rank takes part in every collective below whatever happens locally, and all ranks reach the same verdict:
+        # a rank that failed to create / map a mailbox must not leave the others waiting in a barrier.
         own, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        self.own = self.peer = None
+        why = ""
         with torch.cuda.device(device):
-            check(self.L.quipb200_mailbox_create(self.SLOT * n_slots, ctypes.byref(own), handle), "mailbox_create")
-        self.own = own.value
+            rc = self.L.quipb200_mailbox_create(self.SLOT * n_slots, ctypes.byref(own), handle)
+        if rc == 0:
+            self.own = own.value
+        else:
+            why = f"mailbox_create rc={rc}"
         handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle.raw), group=group)
-        peer = ctypes.c_void_p()
-        with torch.cuda.device(device):
-            check(self.L.quipb200_mailbox_open(handles[(rank + 1) % world], ctypes.byref(peer)), "mailbox_open")
-        self.peer = peer.value
+        dist.all_gather_object(handles, bytes(handle.raw) if rc == 0 else b"", group=group)
+        if rc == 0 and all(handles):
+            peer = ctypes.c_void_p()
+            with torch.cuda.device(device):
+                rc = self.L.quipb200_mailbox_open(handles[(rank + 1) % world], ctypes.byref(peer))
+            if rc == 0:
+                self.peer = peer.value
+            else:
+                why = f"mailbox_open rc={rc}"
+        elif rc == 0:
+            rc, why = -1, "a peer could not create its mailbox"
+        okt = torch.tensor([1 if rc == 0 else 0], device=device)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN, group=group)
+        if okt.item() == 0:
+            if self.peer:
+                self.L.quipb200_mailbox_close(self.peer)
+            dist.barrier(group=group)            # nobody frees a mailbox a neighbour still maps
+            if self.own:
+                self.L.quipb200_mailbox_destroy(self.own)
+            self.own = self.peer = None
+            raise RuntimeError("peer-memory mailboxes unavailable on at least one rank" + (f" ({why})" if why else ""))
         # per-slot sequence counters (device uint64): sends start at 0; waits start at 0, except on stage 0 whose first
         # run of a slot consumes the token left by the prefill (counter -1: the first wait passes and copies nothing)
         self.send_ctr = torch.zeros(n_slots, dtype=torch.int64, device=device)
@@ -217,17 +240,12 @@ def _pipeline_measure(a, model_name, world, rank, local, dev, clock_sampler_cls=
     stage = LlamaStage(model_name, a.codebook, rank, world, dev, S, cache_len, use_graph=not a.no_graph)
     mailbox = None
     if getattr(a, "handoff", "peer") == "peer":
-        try:
+        try:       # raises on EVERY rank or on none (the constructor agrees on the outcome through an all-reduce)
             mailbox = PeerMailbox(rank, world, S, dev)
-        except Exception as e:       # CUDA IPC unavailable (container policy): every rank must agree on the mode
+        except RuntimeError as e:
             mailbox = None
             if rank == 0:
-                print(f"[parallel] peer-memory hand-off unavailable ({type(e).__name__}: {e}); using NCCL p2p", flush=True)
-        okt = torch.tensor([1 if mailbox is not None else 0], device=dev)
-        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-        if okt.item() == 0 and mailbox is not None:
-            mailbox.close()
-            mailbox = None
+                print(f"[parallel] {e}; using NCCL p2p", flush=True)
     pipe = RingPipeline(stage, rank, world, S, mailbox=mailbox)
     g = torch.Generator().manual_seed(0)
     vocab = stage.model.config.vocab_size
