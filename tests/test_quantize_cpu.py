@@ -182,3 +182,15 @@ def test_small_codebooks_and_index_packing_match_reference(gq):
     assert np.array_equal(h.maybe_pack_idxs(torch.from_numpy(gq["hi_pack_in"])).numpy(), gq["hi_pack_out"])
     r3 = codebook_id["E8P12RVQ3B"](inference=True)
     assert np.array_equal(r3.maybe_pack_idxs(torch.from_numpy(gq["rvq3_pack_in"])).numpy(), gq["rvq3_pack_out"])
+
+
+def test_structured_search_equals_brute_force(gq):
+    """the 512-candidate search derived from the codebook's structure picks the brute-force argmax on generic inputs
+    (random and outlier rows; exact-tie rows are excluded by construction of the method)"""
+    x = gq["nearest_x"][:1464]
+    i_bf, s_bf = qo.e8p_nearest(x)
+    i_st, s_st = qo.e8p_nearest_structured(x)
+    np.testing.assert_allclose(s_st, s_bf, rtol=0, atol=1e-9)
+    diff = np.nonzero(i_st != i_bf)[0]
+    assert diff.size == 0 or np.abs(qo.e8p_score(x[diff], i_st[diff]) - s_bf[diff]).max() < 1e-9
+    assert (i_st[1400:] == i_bf[1400:]).all()                # outliers and exact codewords
