@@ -16,6 +16,7 @@ extern int g_ds_flags;
 extern int g_opt_phase0;
 extern int g_opt_lean;
 extern int g_opt_epi_mma;
+extern int g_opt_nearest_struct;
 extern int g_opt_rot_warp_rows;
 extern int g_opt_rot_pipe_rows;
 int g_opt_umma_rt = 0;       // experiments: 1 = one 128-row tile per CTA at every M (0 = auto: two when M > 64)
@@ -88,6 +89,10 @@ extern "C" int quipb200_set_option(const char* name, int value) {
     qb::g_opt_epi_mma = value ? 1 : 0;
     return 0;
   }
+  if (!strcmp(name, "nearest_struct")) {
+    qb::g_opt_nearest_struct = value ? 1 : 0;
+    return 0;
+  }
   if (!strcmp(name, "pdl")) {
     qb::g_opt_pdl = value ? 1 : 0;
     return 0;
@@ -133,6 +138,7 @@ extern "C" int quipb200_get_option(const char* name) {
   if (!strcmp(name, "gemv_table_repl")) return qb::g_opt_table_repl;
   if (!strcmp(name, "rot_cluster")) return qb::g_opt_rot_cluster;
   if (!strcmp(name, "epi_mma")) return qb::g_opt_epi_mma;
+  if (!strcmp(name, "nearest_struct")) return qb::g_opt_nearest_struct;
   if (!strcmp(name, "gemv_warps")) return qb::g_opt_gemv_warps;
   if (!strcmp(name, "gemv_ctas_per_sm")) return qb::g_opt_gemv_ctas_per_sm;
   if (!strcmp(name, "stage_mask")) return qb::g_opt_stage_mask;

