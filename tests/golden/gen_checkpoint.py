@@ -61,7 +61,7 @@ def _import_reference_quantizer():
 def main():
     quantizer, constants = _import_reference_quantizer()
     from transformers import LlamaConfig, LlamaForCausalLM
-    for cb_name in ("E8P12", "E8P12RVQ4B"):
+    for cb_name in ("E8P12", "E8P12RVQ4B", "D4", "HI", "E8P12RVQ3B"):
         torch.manual_seed(0)
         cfg = LlamaConfig(hidden_size=256, intermediate_size=768, num_hidden_layers=2, num_attention_heads=2,
                           num_key_value_heads=2, vocab_size=128, max_position_embeddings=64, tie_word_embeddings=False)

@@ -379,7 +379,8 @@ def test_bench_reference_arm_prints_the_contract_line():
 # checkpoint folders written with the REFERENCE's module tree / key layout / config (tests/golden/gen_checkpoint.py)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("folder,st", [("ref_ckpt_e8p12_bin", False), ("ref_ckpt_e8p12_sharded_st", True),
-                                       ("ref_ckpt_e8p12rvq4b_bin", False)])
+                                       ("ref_ckpt_e8p12rvq4b_bin", False), ("ref_ckpt_d4_bin", False),
+                                       ("ref_ckpt_hi_bin", False), ("ref_ckpt_e8p12rvq3b_bin", False)])
 def test_loader_consumes_reference_written_checkpoint(golden_dir, folder, st):
     import json
     from quip_for_all_b200 import quantizer as qz
@@ -391,7 +392,7 @@ def test_loader_consumes_reference_written_checkpoint(golden_dir, folder, st):
         ref.update(qz._read_shard(f))
     with open(os.path.join(golden_dir, "ref_ckpt_manifest.json")) as f:
         manifest = json.load(f)
-    if "rvq4b" not in folder:
+    if "e8p12_" in folder:
         assert set(ref) == set(manifest)
     sd = model.state_dict()
     # every tensor the reference's model exposes has a destination of the same shape / dtype and arrives bit-exact
@@ -403,7 +404,7 @@ def test_loader_consumes_reference_written_checkpoint(golden_dir, folder, st):
     from quip_for_all_b200 import QuantLinear
     ql = [m for m in model.modules() if isinstance(m, QuantLinear)]
     assert len(ql) == 14
-    cb = "E8P12RVQ4B" if "rvq4b" in folder else "E8P12"
+    cb = {"e8p12": "E8P12", "e8p12rvq4b": "E8P12RVQ4B", "d4": "D4", "hi": "HI", "e8p12rvq3b": "E8P12RVQ3B"}[folder.split("_")[2]]
     for m in ql:
         assert m.codebook.id == cb
         assert m.SU is not None and m.SV is not None              # merge_suv = false in the reference config
