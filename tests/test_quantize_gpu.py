@@ -110,7 +110,6 @@ def test_structured_search_kernel_equals_brute_force_kernel(gq):
         _near_tie_ok(x.numpy(), i1.cpu().numpy(), i0.cpu().numpy(), frac=0.002)
         same = (i1 == i0)
         assert torch.equal(v1[same], v0[same])
-    assert torch.equal(i1[-1:], i0[-1:]) or True
     x = gq["nearest_x"]
     _, i1 = cb.quantize(torch.from_numpy(x).to(dev))
     assert np.array_equal(i1.cpu().numpy()[1464:], gq["nearest_idx"][1464:])
